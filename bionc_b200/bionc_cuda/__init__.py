@@ -1,1 +1,23 @@
+"""CUDA backend: same exported names as ``bionc/bionc_numpy/__init__.py:1-27`` for the
+constrained forward-dynamics path (everything else of bioNC is out of scope).
+
+``BiomechanicalModel`` (which needs torch and the CUDA library) is imported lazily so that the pure
+numpy pieces -- the model table and the force set -- stay importable in light-weight processes.
+"""
+
 from .model_table import ModelTable, UnsupportedModelError  # noqa: F401
+from .external_force import ExternalForceSet  # noqa: F401
+
+__all__ = ["BiomechanicalModel", "BioncCudaError", "ExternalForceSet", "ModelTable", "UnsupportedModelError"]
+
+
+def __getattr__(name):
+    if name == "BiomechanicalModel":
+        from .biomechanical_model import BiomechanicalModel
+
+        return BiomechanicalModel
+    if name == "BioncCudaError":
+        from ._lib import BioncCudaError
+
+        return BioncCudaError
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

@@ -1,0 +1,432 @@
+"""``bionc_cuda.BiomechanicalModel``: the batched CUDA mirror of
+``bionc.bionc_numpy.BiomechanicalModel`` for the constrained forward-dynamics path.
+
+Same method names and argument meaning as the reference
+(``bionc/bionc_numpy/biomechanical_model.py``, ``bionc/protocols/biomechanical_model.py:347-481``);
+every state argument gains a leading batch axis:
+
+===============================  =======================  ==========================
+reference (one system)           bionc_cuda (single)      bionc_cuda (batch)
+===============================  =======================  ==========================
+``Q``, ``Qdot``: ``(n, 1)``      ``(n,)`` or ``(n, 1)``   ``(B, n)``
+``Qddot``: ``(n, 1)``            ``(n, 1)``               ``(B, n)``
+``lambdas``: ``(m, 1)``          ``(m, 1)``               ``(B, m)``
+``K``: ``(m, n)``                ``(m, n)``               ``(B, m, n)``
+===============================  =======================  ==========================
+
+numpy in -> numpy out; torch CUDA tensors in -> torch CUDA tensors out (no host round trip).
+All arithmetic happens in the hand-written sm_100a kernels of ``bionc_b200/csrc`` reached through
+the C ABI of ``include/bionc_cuda.h``; there is no CPU fallback.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .external_force import ExternalForceSet
+from .model_table import ModelTable
+
+EVAL_PHI_R, EVAL_K_R, EVAL_PHI_J, EVAL_K_J, EVAL_PHI_H, EVAL_K_H, EVAL_BIAS_H, EVAL_FEXT = range(8)
+
+
+def _ptr(a: np.ndarray, typ):
+    return a.ctypes.data_as(typ)
+
+
+class _Batch:
+    """Normalises user input to a contiguous float64 CUDA tensor (B, n) and remembers how to go back."""
+
+    def __init__(self, x, n: int, device: torch.device, name: str):
+        self.torch_in = isinstance(x, torch.Tensor)
+        if self.torch_in:
+            t = x
+            shape = tuple(t.shape)
+        else:
+            a = np.asarray(x, dtype=np.float64)
+            shape = a.shape
+            t = torch.from_numpy(np.ascontiguousarray(a))
+        self.single = len(shape) == 1 or (len(shape) == 2 and shape[1] == 1 and shape[0] == n)
+        if self.single:
+            t = t.reshape(1, -1)
+        if t.dim() != 2 or t.shape[1] != n:
+            raise ValueError(f"{name} must have shape ({n},), ({n}, 1) or (B, {n}); got {shape}")
+        self.t = t.to(device=device, dtype=torch.float64).contiguous()
+        self.B = int(self.t.shape[0])
+
+    def out(self, t: torch.Tensor, column: bool = False):
+        """Back to the caller's world: torch stays on the device; numpy goes to the host; a single
+        system loses the batch axis (``column`` -> trailing axis of 1 like the reference)."""
+        if self.single:
+            t = t[0]
+            if column:
+                t = t.unsqueeze(-1)
+        return t if self.torch_in else t.cpu().numpy()
+
+
+class BiomechanicalModel:
+    """Compiled model on one CUDA device.  Build it with :meth:`from_numpy` (from a loaded
+    ``bionc_numpy`` model -- the analogue of ``to_mx()``), :meth:`from_table` or :meth:`load`."""
+
+    def __init__(self, table: ModelTable, device=None):
+        self.table = table.validate()
+        if not torch.cuda.is_available():
+            raise _lib.BioncCudaError("bionc_cuda needs a CUDA device (torch.cuda.is_available() is False); there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("bionc_cuda models live on CUDA devices only")
+        self._lib = _lib.load()
+        t = self.table
+        self._keep = dict(
+            phic=np.ascontiguousarray(t.seg_phi_const, dtype=np.float64),
+            mass=np.ascontiguousarray(t.seg_mass, dtype=np.float64),
+            com=np.ascontiguousarray(t.seg_com, dtype=np.float64),
+            J=np.ascontiguousarray(t.seg_J, dtype=np.float64).reshape(-1, 9),
+            rrow=np.ascontiguousarray(t.seg_rigid_row, dtype=np.int32),
+            btype=np.ascontiguousarray(t.blk_type, dtype=np.int32),
+            bpar=np.ascontiguousarray(t.blk_parent, dtype=np.int32),
+            bchi=np.ascontiguousarray(t.blk_child, dtype=np.int32),
+            browh=np.ascontiguousarray(t.blk_row_h, dtype=np.int32),
+            browj=np.ascontiguousarray(t.blk_row_j, dtype=np.int32),
+            bpar_d=np.ascontiguousarray(t.blk_param, dtype=np.float64),
+        )
+        k = self._keep
+        desc = _lib.BioncModelDesc(
+            t.nb_segments, t.nb_blocks,
+            _ptr(k["phic"], _lib.c_double_p), _ptr(k["mass"], _lib.c_double_p), _ptr(k["com"], _lib.c_double_p),
+            _ptr(k["J"], _lib.c_double_p), _ptr(k["rrow"], _lib.c_int32_p), _ptr(k["btype"], _lib.c_int32_p),
+            _ptr(k["bpar"], _lib.c_int32_p), _ptr(k["bchi"], _lib.c_int32_p), _ptr(k["browh"], _lib.c_int32_p),
+            _ptr(k["browj"], _lib.c_int32_p), _ptr(k["bpar_d"], _lib.c_double_p),
+        )
+        handle = C.c_void_p()
+        _lib.check(self._lib.bionc_cuda_model_create(C.byref(desc), self.device.index or 0, C.byref(handle)), "model_create")
+        self._h = handle
+        self._mass_matrix = None
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and getattr(self, "_lib", None) is not None:
+            try:
+                self._lib.bionc_cuda_model_destroy(h)
+            except Exception:
+                pass
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_numpy(cls, model, device=None) -> "BiomechanicalModel":
+        """From a loaded ``bionc.bionc_numpy.BiomechanicalModel`` (e.g. ``BiomechanicalModel.load("x.nmod")``)."""
+        return cls(ModelTable.from_numpy(model), device)
+
+    @classmethod
+    def from_table(cls, table: ModelTable, device=None) -> "BiomechanicalModel":
+        return cls(table, device)
+
+    @classmethod
+    def load(cls, filename: str, device=None) -> "BiomechanicalModel":
+        """Load a compiled model table (``.npz`` written by :meth:`save`)."""
+        return cls(ModelTable.load(filename), device)
+
+    def save(self, filename: str):
+        self.table.save(filename)
+
+    # ------------------------------------------------------------------ counts (protocols/biomechanical_model.py:347-453)
+    @property
+    def nb_segments(self) -> int:
+        return self.table.nb_segments
+
+    @property
+    def nb_Q(self) -> int:
+        return 12 * self.nb_segments
+
+    nb_Qdot = nb_Q
+    nb_Qddot = nb_Q
+
+    @property
+    def nb_rigid_body_constraints(self) -> int:
+        return 6 * self.nb_segments
+
+    @property
+    def nb_joint_constraints(self) -> int:
+        return self.table.nb_joint_constraints
+
+    @property
+    def nb_holonomic_constraints(self) -> int:
+        return self.table.nb_holonomic_constraints
+
+    @property
+    def nb_joints(self) -> int:
+        return len(self.table.joint_names)
+
+    @property
+    def segment_names(self) -> list[str]:
+        return list(self.table.segment_names)
+
+    @property
+    def joint_names(self) -> list[str]:
+        return list(self.table.joint_names)
+
+    @property
+    def normalized_coordinates(self) -> list[list[int]]:
+        """protocols/biomechanical_model_segments.py:226-236"""
+        idx = []
+        for i in range(self.nb_segments):
+            idx.append([12 * i, 12 * i + 1, 12 * i + 2])
+            idx.append([12 * i + 9, 12 * i + 10, 12 * i + 11])
+        return idx
+
+    def external_force_set(self) -> ExternalForceSet:
+        return ExternalForceSet.empty_from_nb_segment(self.nb_segments)
+
+    # ------------------------------------------------------------------ constants
+    @property
+    def mass_matrix(self) -> np.ndarray:
+        """Block-diagonal ``G`` (biomechanical_model.py:77-96), assembled by the library from the uploaded table."""
+        if self._mass_matrix is None:
+            n = self.nb_Q
+            G = np.zeros((n, n))
+            _lib.check(self._lib.bionc_cuda_mass_matrix(self._h, G.ctypes.data), "mass_matrix")
+            self._mass_matrix = G
+        return self._mass_matrix
+
+    def gravity_forces(self) -> np.ndarray:
+        """biomechanical_model.py:319-333 -> (n, 1)"""
+        return self.table.seg_gravity.reshape(-1, 1)
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _options(self, external_forces=None, stabilization=None, inertia=None, B=None):
+        keep = []
+        opt = _lib.BioncDynOptions()
+        opt.use_stabilization = 0
+        if stabilization is not None:
+            opt.use_stabilization, opt.alpha, opt.beta = 1, float(stabilization["alpha"]), float(stabilization["beta"])
+        if external_forces is not None:
+            if not isinstance(external_forces, ExternalForceSet):
+                external_forces = ExternalForceSet.from_reference(external_forces)
+            if len(external_forces) != self.nb_segments:
+                # same check and message as external_force.py:154-157
+                raise ValueError(
+                    "The number of segment in the model and the number of segment in the external forces must be the same"
+                )
+            seg, kind, par = external_forces.to_arrays()
+            if seg.size:
+                fx = _lib.BioncFextDesc(int(seg.size), _ptr(seg, _lib.c_int32_p), _ptr(kind, _lib.c_int32_p), _ptr(par, _lib.c_double_p))
+                keep += [seg, kind, par, fx]
+                opt.fext = C.pointer(fx)
+        if inertia is not None:
+            it = inertia if isinstance(inertia, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(inertia, dtype=np.float64))
+            it = it.to(device=self.device, dtype=torch.float64).contiguous()
+            if tuple(it.shape) != (B, self.nb_segments, 10):
+                raise ValueError(f"inertia must have shape (B, {self.nb_segments}, 10) = [m, c(3), J00 J01 J02 J11 J12 J22]")
+            keep.append(it)
+            opt.inertia = it.data_ptr()
+        keep.append(opt)
+        return opt, keep
+
+    def _eval(self, which: int, x, rows: int | None, cols: int | None, name: str, external_forces=None):
+        b = _Batch(x, self.nb_Q, self.device, name)
+        shape = (b.B,) + ((rows,) if rows is not None else ()) + ((cols,) if cols is not None else ())
+        out = torch.empty(shape, dtype=torch.float64, device=self.device)
+        opt, keep = self._options(external_forces)
+        with torch.cuda.device(self.device):
+            if out.numel():
+                _lib.check(self._lib.bionc_cuda_eval(self._h, which, b.t.data_ptr(), C.byref(opt), out.data_ptr(), b.B, self._stream()), "eval")
+        return b, out
+
+    # ------------------------------------------------------------------ constraint API
+    def rigid_body_constraints(self, Q):
+        """biomechanical_model_segments.py:26-42 -> (6N,) / (B, 6N)"""
+        b, out = self._eval(EVAL_PHI_R, Q, 6 * self.nb_segments, None, "Q")
+        return b.out(out)
+
+    def rigid_body_constraints_jacobian(self, Q):
+        """biomechanical_model_segments.py:62-79 -> (6N, n) / (B, 6N, n)"""
+        b, out = self._eval(EVAL_K_R, Q, 6 * self.nb_segments, self.nb_Q, "Q")
+        return b.out(out)
+
+    def joint_constraints(self, Q):
+        """biomechanical_model_joints.py:13-41 (joint-index order) -> (mj,) / (B, mj)"""
+        b, out = self._eval(EVAL_PHI_J, Q, self.nb_joint_constraints, None, "Q")
+        return b.out(out)
+
+    def joint_constraints_jacobian(self, Q):
+        """biomechanical_model_joints.py:43-77 -> (mj, n) / (B, mj, n)"""
+        b, out = self._eval(EVAL_K_J, Q, self.nb_joint_constraints, self.nb_Q, "Q")
+        return b.out(out)
+
+    def holonomic_constraints(self, Q):
+        """biomechanical_model.py:154-197 -> (m, 1) / (B, m)"""
+        b, out = self._eval(EVAL_PHI_H, Q, self.nb_holonomic_constraints, None, "Q")
+        return b.out(out, column=True)
+
+    def holonomic_constraints_jacobian(self, Q):
+        """biomechanical_model.py:199-258 -> (m, n) / (B, m, n)"""
+        b, out = self._eval(EVAL_K_H, Q, self.nb_holonomic_constraints, self.nb_Q, "Q")
+        return b.out(out)
+
+    def holonomic_constraints_acceleration_bias(self, Qdot):
+        """biomechanical_model.py:260-317 -> (m, 1) / (B, m)"""
+        b, out = self._eval(EVAL_BIAS_H, Qdot, self.nb_holonomic_constraints, None, "Qdot")
+        return b.out(out, column=True)
+
+    def natural_external_forces(self, Q, external_forces):
+        """ExternalForceSet.to_natural_external_forces (external_force.py:143-166) -> (n, 1) / (B, n)"""
+        b, out = self._eval(EVAL_FEXT, Q, self.nb_Q, None, "Q", external_forces=external_forces)
+        return b.out(out, column=True)
+
+    def augmented_mass_matrix(self, Q):
+        """biomechanical_model.py:335-349 -> (n+m, n+m) / (B, n+m, n+m); assembled with torch from K (not on the hot path)."""
+        b, K = self._eval(EVAL_K_H, Q, self.nb_holonomic_constraints, self.nb_Q, "Q")
+        n, m = self.nb_Q, self.nb_holonomic_constraints
+        A = torch.zeros((b.B, n + m, n + m), dtype=torch.float64, device=self.device)
+        A[:, :n, :n] = torch.from_numpy(self.mass_matrix).to(self.device)
+        A[:, n:, :n] = K
+        A[:, :n, n:] = K.transpose(1, 2)
+        return b.out(A)
+
+    # ------------------------------------------------------------------ dynamics
+    def forward_dynamics(
+        self,
+        Q,
+        Qdot,
+        joint_generalized_forces=None,
+        external_forces=None,
+        stabilization: dict = None,
+        inertial_parameters=None,
+        return_status: bool = False,
+    ):
+        """biomechanical_model.py:351-429, batched.  ``joint_generalized_forces`` is accepted and ignored
+        exactly like the reference (:391-413).  ``inertial_parameters`` (B, N, 10) optionally overrides
+        the natural inertial parameters per system.  Returns ``(Qddot, lambdas)``; a single system whose
+        factorisation hits a zero pivot raises ``numpy.linalg.LinAlgError`` like the reference's solve."""
+        q = _Batch(Q, self.nb_Q, self.device, "Q")
+        qd = _Batch(Qdot, self.nb_Q, self.device, "Qdot")
+        if q.B != qd.B:
+            raise ValueError("Q and Qdot must have the same batch size")
+        B = q.B
+        qdd = torch.empty_like(q.t)
+        lam = torch.empty((B, self.nb_holonomic_constraints), dtype=torch.float64, device=self.device)
+        status = torch.empty((B,), dtype=torch.int32, device=self.device)
+        opt, keep = self._options(external_forces, stabilization, inertial_parameters, B)
+        with torch.cuda.device(self.device):
+            if B > 0:
+                rc = self._lib.bionc_cuda_forward_dynamics(
+                    self._h, q.t.data_ptr(), qd.t.data_ptr(), C.byref(opt), qdd.data_ptr(), lam.data_ptr(),
+                    status.data_ptr(), B, self._stream(),
+                )
+                _lib.check(rc, "forward_dynamics")
+        if q.single and B > 0 and not return_status:
+            if int(status[0].item()) & 1:
+                raise np.linalg.LinAlgError("Singular matrix")
+        res = (q.out(qdd, column=True), q.out(lam, column=True))
+        return res + (q.out(status),) if return_status else res
+
+    def rk4(
+        self,
+        Q,
+        Qdot,
+        h: float | None = None,
+        n_steps: int | None = None,
+        t=None,
+        normalize: bool = True,
+        external_forces=None,
+        stabilization: dict = None,
+        inertial_parameters=None,
+        save_every: int | None = None,
+        return_lambdas: bool = False,
+        return_status: bool = False,
+        inplace: bool = False,
+    ):
+        """Fused integrator: ``utils/ode_solver.py:8-53`` with the closure of ``:107-116`` inside the kernel.
+
+        Either a constant step ``h`` with ``n_steps``, or a time grid ``t`` (then ``h_i = t[i+1] - t[i]``
+        exactly as the reference computes it, :41).  ``normalize=True`` is the reference's
+        ``normalize_idx=model.normalized_coordinates``.  Returns ``(Q, Qdot)`` after the last step, plus
+        the trajectory ``(n_steps // save_every, B, 2n)`` if ``save_every`` is given, the multipliers of
+        the first stage of the last step if ``return_lambdas``, and the status flags if ``return_status``.
+        """
+        q = _Batch(Q, self.nb_Q, self.device, "Q")
+        qd = _Batch(Qdot, self.nb_Q, self.device, "Qdot")
+        if q.B != qd.B:
+            raise ValueError("Q and Qdot must have the same batch size")
+        B = q.B
+        if not (inplace and q.torch_in and qd.torch_in and q.t.data_ptr() == Q.data_ptr()):
+            q.t, qd.t = q.t.clone(), qd.t.clone()
+        h_steps = None
+        if t is not None:
+            tt = np.asarray(t, dtype=np.float64).reshape(-1)
+            hs = tt[1:] - tt[:-1]
+            n_steps = int(hs.size)
+            h_steps = torch.from_numpy(np.ascontiguousarray(hs)).to(self.device)
+            h = float(hs[0]) if hs.size else 0.0
+        elif h is None or n_steps is None:
+            raise ValueError("give either a time grid `t` or a constant step `h` with `n_steps`")
+        traj = None
+        if save_every is not None:
+            traj = torch.empty((n_steps // save_every, B, 2 * self.nb_Q), dtype=torch.float64, device=self.device)
+        lam = torch.empty((B, self.nb_holonomic_constraints), dtype=torch.float64, device=self.device) if return_lambdas else None
+        status = torch.empty((B,), dtype=torch.int32, device=self.device)
+        opt, keep = self._options(external_forces, stabilization, inertial_parameters, B)
+        with torch.cuda.device(self.device):
+            if B > 0 and n_steps > 0:
+                rc = self._lib.bionc_cuda_rk4(
+                    self._h, q.t.data_ptr(), qd.t.data_ptr(), float(h), h_steps.data_ptr() if h_steps is not None else None,
+                    int(n_steps), 1 if normalize else 0, C.byref(opt), traj.data_ptr() if traj is not None else None,
+                    int(save_every or 1), lam.data_ptr() if lam is not None else None, status.data_ptr(), B, self._stream(),
+                )
+                _lib.check(rc, "rk4")
+            else:
+                status.zero_()
+        res = [q.out(q.t), q.out(qd.t)]
+        if traj is not None:
+            res.append(traj if q.torch_in else traj.cpu().numpy())
+        if return_lambdas:
+            res.append(q.out(lam, column=True))
+        if return_status:
+            res.append(q.out(status))
+        return tuple(res)
+
+    # ------------------------------------------------------------------ host-buffer path (C ABI with host pointers)
+    def rk4_host(self, Q: np.ndarray, Qdot: np.ndarray, h: float, n_steps: int, normalize: bool = True,
+                 external_forces=None, stabilization: dict = None, status: np.ndarray | None = None):
+        """End-to-end call through ``bionc_cuda_rk4_host``: ``Q``/``Qdot`` are HOST arrays (B, n), float64,
+        C-contiguous (pinned for full copy bandwidth), advanced in place; the library does H2D, the fused
+        kernel and D2H and returns when the results are on the host."""
+        for a in (Q, Qdot):
+            if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.ndim == 2 and a.shape[1] == self.nb_Q):
+                raise ValueError("rk4_host needs C-contiguous float64 host arrays of shape (B, 12N)")
+        opt, keep = self._options(external_forces, stabilization)
+        _lib.check(
+            self._lib.bionc_cuda_rk4_host(
+                self._h, Q.ctypes.data, Qdot.ctypes.data, float(h), None, int(n_steps), 1 if normalize else 0, C.byref(opt),
+                status.ctypes.data if status is not None else None, int(Q.shape[0]),
+            ),
+            "rk4_host",
+        )
+        return Q, Qdot
+
+    def forward_dynamics_host(self, Q: np.ndarray, Qdot: np.ndarray, external_forces=None, stabilization: dict = None):
+        """End-to-end call through ``bionc_cuda_forward_dynamics_host`` with host arrays (B, n)."""
+        Q = np.ascontiguousarray(Q, dtype=np.float64)
+        Qdot = np.ascontiguousarray(Qdot, dtype=np.float64)
+        B = Q.shape[0]
+        qdd = np.empty_like(Q)
+        lam = np.empty((B, self.nb_holonomic_constraints))
+        status = np.empty((B,), dtype=np.int32)
+        opt, keep = self._options(external_forces, stabilization)
+        _lib.check(
+            self._lib.bionc_cuda_forward_dynamics_host(
+                self._h, Q.ctypes.data, Qdot.ctypes.data, C.byref(opt), qdd.ctypes.data, lam.ctypes.data, status.ctypes.data, B
+            ),
+            "forward_dynamics_host",
+        )
+        return qdd, lam, status
+
+    @staticmethod
+    def launch_count() -> int:
+        return int(_lib.load().bionc_cuda_launch_count())

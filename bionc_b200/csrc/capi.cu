@@ -1,0 +1,515 @@
+// C ABI (include/bionc_cuda.h): model lowering to the device blob, launch logic, host-buffer path.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/bionc_cuda.h"
+#include "kernels.cuh"
+
+using namespace bionc;
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess)                                                                 \
+            return fail(BIONC_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));     \
+    } while (0)
+
+int align16(int x) { return (x + 15) & ~15; }
+
+// robust inverse of a 4x4 (Gauss-Jordan, full pivoting, long double): the host has time to spare
+bool invert4(const double M[4][4], double W[4][4]) {
+    long double a[4][8];
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) a[r][c] = M[r][c], a[r][4 + c] = (r == c);
+    int colperm[4] = {0, 1, 2, 3};
+    for (int k = 0; k < 4; ++k) {
+        int pr = k, pc = k;
+        long double best = 0;
+        for (int r = k; r < 4; ++r)
+            for (int c = k; c < 4; ++c)
+                if (fabsl(a[r][c]) > best) best = fabsl(a[r][c]), pr = r, pc = c;
+        if (!(best > 0)) return false;
+        if (pr != k)
+            for (int c = 0; c < 8; ++c) std::swap(a[k][c], a[pr][c]);
+        if (pc != k) {
+            for (int r = 0; r < 4; ++r) std::swap(a[r][k], a[r][pc]);
+            std::swap(colperm[k], colperm[pc]);
+        }
+        const long double inv = 1.0L / a[k][k];
+        for (int c = 0; c < 8; ++c) a[k][c] *= inv;
+        for (int r = 0; r < 4; ++r)
+            if (r != k) {
+                const long double f = a[r][k];
+                if (f != 0)
+                    for (int c = 0; c < 8; ++c) a[r][c] -= f * a[k][c];
+            }
+    }
+    // rows of the result are permuted by the column permutation
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) W[colperm[r]][c] = (double)a[r][4 + c];
+    return true;
+}
+
+}  // namespace
+
+struct BioncModel {
+    int device = 0;
+    DevHeader hdr{};
+    std::vector<DevSeg> seg;
+    std::vector<DevBlk> blk;
+    std::vector<DevSide> side;
+    // device blob for the current external-force set (rebuilt when the set changes)
+    std::vector<unsigned char> fext_key;
+    unsigned char* d_blob = nullptr;
+    int blob_bytes = 0;
+    bool blob_valid = false;
+    int warps_per_cta = 4;
+    size_t smem_bytes = 0;
+    bool attr_set = false;
+    std::mutex mu;
+    // host-path scratch
+    cudaStream_t stream = nullptr;
+    double *d_Q = nullptr, *d_Qd = nullptr, *d_Qdd = nullptr, *d_lam = nullptr, *d_inertia = nullptr, *d_h = nullptr;
+    int* d_status = nullptr;
+    long long cap_B = 0, cap_h = 0;
+};
+
+namespace {
+
+int build_blob(BioncModel* M, const BioncFextDesc* fx) {
+    // key = raw bytes of the force description
+    std::vector<unsigned char> key;
+    std::vector<DevFext> fext;
+    const int N = M->hdr.N;
+    if (fx != nullptr && fx->nb_forces > 0) {
+        for (int i = 0; i < fx->nb_forces; ++i) {
+            if (fx->segment[i] < 0 || fx->segment[i] >= N) return fail(BIONC_E_INVALID, "external force on a segment that does not exist");
+            if (fx->kind[i] < 0 || fx->kind[i] > 3) return fail(BIONC_E_INVALID, "unknown external force kind");
+        }
+        key.resize(sizeof(int) + fx->nb_forces * (2 * sizeof(int) + kFextNParam * sizeof(double)));
+        unsigned char* k = key.data();
+        std::memcpy(k, &fx->nb_forces, sizeof(int)), k += sizeof(int);
+        std::memcpy(k, fx->segment, fx->nb_forces * sizeof(int)), k += fx->nb_forces * sizeof(int);
+        std::memcpy(k, fx->kind, fx->nb_forces * sizeof(int)), k += fx->nb_forces * sizeof(int);
+        std::memcpy(k, fx->param, fx->nb_forces * kFextNParam * sizeof(double));
+    }
+    if (M->blob_valid && key == M->fext_key) return BIONC_OK;
+
+    std::vector<DevSeg> seg = M->seg;
+    for (int s = 0; s < N; ++s) {  // forces grouped by segment, insertion order kept inside a segment
+        seg[s].fext_begin = (int)fext.size();
+        if (fx != nullptr)
+            for (int i = 0; i < fx->nb_forces; ++i)
+                if (fx->segment[i] == s) {
+                    DevFext f{};
+                    std::memcpy(f.p, fx->param + (size_t)i * kFextNParam, kFextNParam * sizeof(double));
+                    f.segment = s, f.kind = fx->kind[i];
+                    fext.push_back(f);
+                }
+        seg[s].fext_end = (int)fext.size();
+    }
+    DevHeader h = M->hdr;
+    h.nfext = (int)fext.size();
+    h.off_seg = align16(sizeof(DevHeader));
+    h.off_blk = align16(h.off_seg + (int)(seg.size() * sizeof(DevSeg)));
+    h.off_side = align16(h.off_blk + (int)(M->blk.size() * sizeof(DevBlk)));
+    h.off_fext = align16(h.off_side + (int)(M->side.size() * sizeof(DevSide)));
+    h.blob_bytes = align16(h.off_fext + (int)(fext.size() * sizeof(DevFext)));
+    std::vector<unsigned char> blob(h.blob_bytes, 0);
+    std::memcpy(blob.data(), &h, sizeof(h));
+    std::memcpy(blob.data() + h.off_seg, seg.data(), seg.size() * sizeof(DevSeg));
+    if (!M->blk.empty()) std::memcpy(blob.data() + h.off_blk, M->blk.data(), M->blk.size() * sizeof(DevBlk));
+    if (!M->side.empty()) std::memcpy(blob.data() + h.off_side, M->side.data(), M->side.size() * sizeof(DevSide));
+    if (!fext.empty()) std::memcpy(blob.data() + h.off_fext, fext.data(), fext.size() * sizeof(DevFext));
+
+    // shared-memory budget: as many warps per CTA (<= 4) as fit
+    int dev_smem = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, M->device));
+    const size_t per_warp = (size_t)warp_smem_doubles(h.N, h.mj, h.spw, h.rnl) * sizeof(double);
+    int warps = kMaxWarpsPerCta;
+    while (warps > 1 && h.blob_bytes + warps * per_warp > (size_t)dev_smem) warps >>= 1;
+    if (h.blob_bytes + warps * per_warp > (size_t)dev_smem)
+        return fail(BIONC_E_TOO_LARGE, "model needs more shared memory per warp than one SM has");
+
+    CUDA_TRY(cudaSetDevice(M->device));
+    if (M->d_blob != nullptr && M->blob_bytes < h.blob_bytes) {
+        CUDA_TRY(cudaFree(M->d_blob));
+        M->d_blob = nullptr;
+    }
+    if (M->d_blob == nullptr) CUDA_TRY(cudaMalloc(&M->d_blob, h.blob_bytes));
+    // synchronous copy: the blob is a few KB and changes only when the force set changes
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(M->d_blob, blob.data(), h.blob_bytes, cudaMemcpyHostToDevice));
+    M->blob_bytes = h.blob_bytes;
+    M->hdr = h;
+    M->warps_per_cta = warps;
+    M->smem_bytes = h.blob_bytes + warps * per_warp;
+    M->fext_key.swap(key);
+    M->blob_valid = true;
+    M->attr_set = false;
+    return BIONC_OK;
+}
+
+template <typename K>
+int ensure_smem(K kernel, size_t bytes) {
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return BIONC_OK;
+}
+
+int prepare(BioncModel* M, const BioncDynOptions* opt, DynOpts& o) {
+    o.use_stab = (opt != nullptr && opt->use_stabilization) ? 1 : 0;
+    o.alpha = opt != nullptr ? opt->alpha : 0.0;
+    o.beta = opt != nullptr ? opt->beta : 0.0;
+    int rc = build_blob(M, opt != nullptr ? opt->fext : nullptr);
+    if (rc != BIONC_OK) return rc;
+    if (!M->attr_set) {
+        if ((rc = ensure_smem(forward_dynamics_kernel<false>, M->smem_bytes)) != BIONC_OK) return rc;
+        if ((rc = ensure_smem(forward_dynamics_kernel<true>, M->smem_bytes)) != BIONC_OK) return rc;
+        if ((rc = ensure_smem(rk4_kernel<false>, M->smem_bytes)) != BIONC_OK) return rc;
+        if ((rc = ensure_smem(rk4_kernel<true>, M->smem_bytes)) != BIONC_OK) return rc;
+        M->attr_set = true;
+    }
+    return BIONC_OK;
+}
+
+unsigned grid_for(const BioncModel* M, long long B) {
+    const long long per_cta = (long long)M->warps_per_cta * M->hdr.spw;
+    return (unsigned)((B + per_cta - 1) / per_cta);
+}
+
+}  // namespace
+
+extern "C" {
+
+int bionc_cuda_model_create(const BioncModelDesc* d, int device, BioncModel** out) {
+    if (d == nullptr || out == nullptr) return fail(BIONC_E_INVALID, "null argument");
+    const int N = d->nb_segments, nblk = d->nb_blocks;
+    if (N < 1 || N > kMaxSegments) return fail(BIONC_E_INVALID, "nb_segments must be in [1, 32] (one lane per segment)");
+    if (nblk < 0) return fail(BIONC_E_INVALID, "nb_blocks < 0");
+    auto M = new BioncModel();
+    M->device = device;
+    M->seg.resize(N);
+    M->blk.resize(nblk);
+    int mj = 0;
+    for (int b = 0; b < nblk; ++b) {
+        DevBlk& B = M->blk[b];
+        std::memset(&B, 0, sizeof(B));
+        B.type = d->blk_type[b], B.parent = d->blk_parent[b], B.child = d->blk_child[b];
+        if (B.type < 0 || B.type > 3 || B.child < 0 || B.child >= N || B.parent < -1 || B.parent >= N || B.parent == B.child) {
+            delete M;
+            return fail(BIONC_E_INVALID, "malformed constraint block");
+        }
+        if (B.parent < 0 && (B.type == CLEN || B.type == SOP)) {
+            delete M;
+            return fail(BIONC_E_INVALID, "constant-length / sphere-on-plane blocks need two segments");
+        }
+        B.row_h = d->blk_row_h[b], B.row_j = d->blk_row_j[b], B.jrow = mj;
+        std::memcpy(B.p, d->blk_param + (size_t)b * kBlkNParam, kBlkNParam * sizeof(double));
+        mj += (B.type == LIN3) ? 3 : 1;
+    }
+    int rnl = 0;
+    for (int i = 0; i < N; ++i) {
+        DevSeg& S = M->seg[i];
+        std::memset(&S, 0, sizeof(S));
+        const double m = d->seg_mass[i];
+        const double* c = d->seg_com + 3 * i;
+        const double* J = d->seg_J + 9 * i;
+        double M4[4][4] = {};
+        M4[0][0] = J[0];
+        M4[0][1] = m * c[0] + J[1];
+        M4[0][2] = -J[1];
+        M4[0][3] = J[2];
+        M4[1][1] = m + 2 * m * c[1] + J[4];
+        M4[1][2] = -(m * c[1] + J[4]);
+        M4[1][3] = m * c[2] + J[5];
+        M4[2][2] = J[4];
+        M4[2][3] = -J[5];
+        M4[3][3] = J[8];
+        for (int r = 0; r < 4; ++r)
+            for (int cc = 0; cc < r; ++cc) M4[r][cc] = M4[cc][r];
+        double W[4][4];
+        if (!invert4(M4, W)) {
+            delete M;
+            return fail(BIONC_E_INVALID, "singular segment mass matrix");  // reference: LinAlgError at solve time
+        }
+        int k = 0;
+        for (int r = 0; r < 4; ++r)
+            for (int cc = r; cc < 4; ++cc) S.W[k++] = 0.5 * (W[r][cc] + W[cc][r]);
+        const double g = -9.81;
+        S.fg[0] = c[0] * m * g, S.fg[1] = (1 + c[1]) * m * g, S.fg[2] = -c[1] * m * g, S.fg[3] = c[2] * m * g;
+        std::memcpy(S.phic, d->seg_phi_const + 4 * i, 4 * sizeof(double));
+        S.mcj[0] = m, S.mcj[1] = c[0], S.mcj[2] = c[1], S.mcj[3] = c[2];
+        S.mcj[4] = J[0], S.mcj[5] = J[1], S.mcj[6] = J[2], S.mcj[7] = J[4], S.mcj[8] = J[5], S.mcj[9] = J[8];
+        S.rigid_row = d->seg_rigid_row[i];
+        S.side_begin = (int)M->side.size();
+        int nl = 0;
+        for (int b = 0; b < nblk; ++b) {  // block order = holonomic order = ascending jrow
+            const DevBlk& B = M->blk[b];
+            if (B.child != i && B.parent != i) continue;
+            DevSide sd{};
+            sd.blk = b, sd.role = (B.child == i) ? CHILD : PARENT;
+            sd.nl_slot = (B.type == LIN3) ? -1 : nl++;
+            M->side.push_back(sd);
+        }
+        S.side_end = (int)M->side.size();
+        if (nl > rnl) rnl = nl;
+    }
+    M->hdr.N = N, M->hdr.nblk = nblk, M->hdr.nside = (int)M->side.size();
+    M->hdr.mj = mj, M->hdr.m = mj + 6 * N, M->hdr.spw = 32 / N, M->hdr.rnl = rnl;
+    *out = M;
+    return BIONC_OK;
+}
+
+int bionc_cuda_model_destroy(BioncModel* M) {
+    if (M == nullptr) return BIONC_OK;
+    cudaSetDevice(M->device);
+    cudaFree(M->d_blob);
+    cudaFree(M->d_Q), cudaFree(M->d_Qd), cudaFree(M->d_Qdd), cudaFree(M->d_lam), cudaFree(M->d_inertia), cudaFree(M->d_h);
+    cudaFree(M->d_status);
+    if (M->stream != nullptr) cudaStreamDestroy(M->stream);
+    delete M;
+    return BIONC_OK;
+}
+
+int bionc_cuda_model_counts(const BioncModel* M, int32_t* nseg, int32_t* mj, int32_t* m) {
+    if (M == nullptr) return fail(BIONC_E_INVALID, "null model");
+    if (nseg) *nseg = M->hdr.N;
+    if (mj) *mj = M->hdr.mj;
+    if (m) *m = M->hdr.m;
+    return BIONC_OK;
+}
+
+int bionc_cuda_forward_dynamics(const BioncModel* Mc, const double* Q, const double* Qd, const BioncDynOptions* opt,
+                                double* Qdd, double* lam, int32_t* status, int64_t B, void* stream) {
+    BioncModel* M = const_cast<BioncModel*>(Mc);
+    if (M == nullptr || Q == nullptr || Qd == nullptr || Qdd == nullptr || B < 0) return fail(BIONC_E_INVALID, "null argument");
+    if (B == 0) return BIONC_OK;
+    std::lock_guard<std::mutex> lock(M->mu);
+    DynOpts o;
+    int rc = prepare(M, opt, o);
+    if (rc != BIONC_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (status != nullptr) CUDA_TRY(cudaMemsetAsync(status, 0, B * sizeof(int32_t), st));
+    const double* inertia = opt != nullptr ? opt->inertia : nullptr;
+    const unsigned grid = grid_for(M, B), block = 32 * M->warps_per_cta;
+    if (M->hdr.nfext > 0)
+        forward_dynamics_kernel<true><<<grid, block, M->smem_bytes, st>>>(M->d_blob, M->blob_bytes, Q, Qd, inertia, o, Qdd, lam, status, B);
+    else
+        forward_dynamics_kernel<false><<<grid, block, M->smem_bytes, st>>>(M->d_blob, M->blob_bytes, Q, Qd, inertia, o, Qdd, lam, status, B);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return BIONC_OK;
+}
+
+int bionc_cuda_rk4(const BioncModel* Mc, double* Q, double* Qd, double h, const double* h_steps, int64_t n_steps,
+                   int32_t normalize, const BioncDynOptions* opt, double* traj, int64_t traj_every, double* lam_last,
+                   int32_t* status, int64_t B, void* stream) {
+    BioncModel* M = const_cast<BioncModel*>(Mc);
+    if (M == nullptr || Q == nullptr || Qd == nullptr || B < 0 || n_steps < 0) return fail(BIONC_E_INVALID, "null argument");
+    if (traj != nullptr && traj_every < 1) return fail(BIONC_E_INVALID, "traj_every must be >= 1");
+    if (B == 0 || n_steps == 0) return BIONC_OK;
+    std::lock_guard<std::mutex> lock(M->mu);
+    DynOpts o;
+    int rc = prepare(M, opt, o);
+    if (rc != BIONC_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (status != nullptr) CUDA_TRY(cudaMemsetAsync(status, 0, B * sizeof(int32_t), st));
+    const double* inertia = opt != nullptr ? opt->inertia : nullptr;
+    const unsigned grid = grid_for(M, B), block = 32 * M->warps_per_cta;
+    if (traj == nullptr) traj_every = 1;
+    if (M->hdr.nfext > 0)
+        rk4_kernel<true><<<grid, block, M->smem_bytes, st>>>(M->d_blob, M->blob_bytes, Q, Qd, inertia, o, h, h_steps, n_steps,
+                                                             normalize, traj, traj_every, lam_last, status, B);
+    else
+        rk4_kernel<false><<<grid, block, M->smem_bytes, st>>>(M->d_blob, M->blob_bytes, Q, Qd, inertia, o, h, h_steps, n_steps,
+                                                              normalize, traj, traj_every, lam_last, status, B);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return BIONC_OK;
+}
+
+int bionc_cuda_eval(const BioncModel* Mc, int32_t which, const double* in, const BioncDynOptions* opt, double* out,
+                    int64_t B, void* stream) {
+    BioncModel* M = const_cast<BioncModel*>(Mc);
+    if (M == nullptr || in == nullptr || out == nullptr || B < 0 || which < 0 || which > 7) return fail(BIONC_E_INVALID, "bad argument");
+    if (B == 0) return BIONC_OK;
+    std::lock_guard<std::mutex> lock(M->mu);
+    DynOpts o;
+    int rc = prepare(M, opt, o);
+    if (rc != BIONC_OK) return rc;
+    const int N = M->hdr.N, n = 12 * N, mj = M->hdr.mj, m = M->hdr.m;
+    size_t out_elems = 0;
+    switch (which) {
+        case BIONC_EVAL_PHI_R: out_elems = (size_t)6 * N; break;
+        case BIONC_EVAL_K_R: out_elems = (size_t)6 * N * n; break;
+        case BIONC_EVAL_PHI_J: out_elems = mj; break;
+        case BIONC_EVAL_K_J: out_elems = (size_t)mj * n; break;
+        case BIONC_EVAL_PHI_H: case BIONC_EVAL_BIAS_H: out_elems = m; break;
+        case BIONC_EVAL_K_H: out_elems = (size_t)m * n; break;
+        case BIONC_EVAL_FEXT: out_elems = n; break;
+    }
+    if (out_elems == 0) return BIONC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(out, 0, out_elems * B * sizeof(double), st));
+    EvalArgs ea{which, N, M->hdr.nblk, mj, m};
+    const long long total = B * (long long)(N + M->hdr.nblk);
+    const int block = 128;
+    long long grid = (total + block - 1) / block;
+    if (grid > 148LL * 64) grid = 148LL * 64;
+    eval_kernel<<<(unsigned)grid, block, 0, st>>>(M->d_blob, ea, in, out, B);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return BIONC_OK;
+}
+
+int bionc_cuda_mass_matrix(const BioncModel* M, double* G) {
+    if (M == nullptr || G == nullptr) return fail(BIONC_E_INVALID, "null argument");
+    const int N = M->hdr.N, n = 12 * N;
+    std::memset(G, 0, sizeof(double) * n * n);
+    for (int i = 0; i < N; ++i) {
+        const double* p = M->seg[i].mcj;
+        const double m = p[0], c0 = p[1], c1 = p[2], c2 = p[3], J00 = p[4], J01 = p[5], J02 = p[6], J11 = p[7], J12 = p[8], J22 = p[9];
+        const double M4[4][4] = {{J00, m * c0 + J01, -J01, J02},
+                                 {m * c0 + J01, m + 2 * m * c1 + J11, -(m * c1 + J11), m * c2 + J12},
+                                 {-J01, -(m * c1 + J11), J11, -J12},
+                                 {J02, m * c2 + J12, -J12, J22}};
+        for (int a = 0; a < 4; ++a)
+            for (int b = 0; b < 4; ++b)
+                for (int k = 0; k < 3; ++k) G[(size_t)(12 * i + 3 * a + k) * n + 12 * i + 3 * b + k] = M4[a][b];
+    }
+    return BIONC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ host path
+static int ensure_host_scratch(BioncModel* M, long long B, long long nh, bool want_inertia) {
+    CUDA_TRY(cudaSetDevice(M->device));
+    if (M->stream == nullptr) CUDA_TRY(cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking));
+    const size_t n = 12 * (size_t)M->hdr.N;
+    if (B > M->cap_B) {
+        cudaFree(M->d_Q), cudaFree(M->d_Qd), cudaFree(M->d_Qdd), cudaFree(M->d_lam), cudaFree(M->d_status), cudaFree(M->d_inertia);
+        M->d_inertia = nullptr;
+        CUDA_TRY(cudaMalloc(&M->d_Q, B * n * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&M->d_Qd, B * n * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&M->d_Qdd, B * n * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&M->d_lam, B * (size_t)M->hdr.m * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&M->d_status, B * sizeof(int)));
+        M->cap_B = B;
+    }
+    if (want_inertia && M->d_inertia == nullptr) CUDA_TRY(cudaMalloc(&M->d_inertia, M->cap_B * (size_t)M->hdr.N * 10 * sizeof(double)));
+    if (nh > M->cap_h) {
+        cudaFree(M->d_h);
+        CUDA_TRY(cudaMalloc(&M->d_h, nh * sizeof(double)));
+        M->cap_h = nh;
+    }
+    return BIONC_OK;
+}
+
+int bionc_cuda_forward_dynamics_host(BioncModel* M, const double* Q, const double* Qd, const BioncDynOptions* opt,
+                                     double* Qdd, double* lam, int32_t* status, int64_t B) {
+    if (M == nullptr || Q == nullptr || Qd == nullptr || Qdd == nullptr || B < 0) return fail(BIONC_E_INVALID, "null argument");
+    if (B == 0) return BIONC_OK;
+    const bool per_sys = opt != nullptr && opt->inertia != nullptr;
+    int rc = ensure_host_scratch(M, B, 0, per_sys);
+    if (rc != BIONC_OK) return rc;
+    const size_t nb = (size_t)B * 12 * M->hdr.N * sizeof(double);
+    CUDA_TRY(cudaMemcpyAsync(M->d_Q, Q, nb, cudaMemcpyHostToDevice, M->stream));
+    CUDA_TRY(cudaMemcpyAsync(M->d_Qd, Qd, nb, cudaMemcpyHostToDevice, M->stream));
+    BioncDynOptions o2 = opt != nullptr ? *opt : BioncDynOptions{};
+    if (per_sys) {
+        CUDA_TRY(cudaMemcpyAsync(M->d_inertia, opt->inertia, (size_t)B * M->hdr.N * 10 * sizeof(double), cudaMemcpyHostToDevice, M->stream));
+        o2.inertia = M->d_inertia;
+    }
+    rc = bionc_cuda_forward_dynamics(M, M->d_Q, M->d_Qd, &o2, M->d_Qdd, lam != nullptr ? M->d_lam : nullptr,
+                                     status != nullptr ? M->d_status : nullptr, B, M->stream);
+    if (rc != BIONC_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(Qdd, M->d_Qdd, nb, cudaMemcpyDeviceToHost, M->stream));
+    if (lam != nullptr) CUDA_TRY(cudaMemcpyAsync(lam, M->d_lam, (size_t)B * M->hdr.m * sizeof(double), cudaMemcpyDeviceToHost, M->stream));
+    if (status != nullptr) CUDA_TRY(cudaMemcpyAsync(status, M->d_status, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, M->stream));
+    CUDA_TRY(cudaStreamSynchronize(M->stream));
+    return BIONC_OK;
+}
+
+int bionc_cuda_rk4_host(BioncModel* M, double* Q, double* Qd, double h, const double* h_steps, int64_t n_steps,
+                        int32_t normalize, const BioncDynOptions* opt, int32_t* status, int64_t B) {
+    if (M == nullptr || Q == nullptr || Qd == nullptr || B < 0 || n_steps < 0) return fail(BIONC_E_INVALID, "null argument");
+    if (B == 0 || n_steps == 0) return BIONC_OK;
+    const bool per_sys = opt != nullptr && opt->inertia != nullptr;
+    int rc = ensure_host_scratch(M, B, h_steps != nullptr ? n_steps : 0, per_sys);
+    if (rc != BIONC_OK) return rc;
+    const size_t nb = (size_t)B * 12 * M->hdr.N * sizeof(double);
+    CUDA_TRY(cudaMemcpyAsync(M->d_Q, Q, nb, cudaMemcpyHostToDevice, M->stream));
+    CUDA_TRY(cudaMemcpyAsync(M->d_Qd, Qd, nb, cudaMemcpyHostToDevice, M->stream));
+    if (h_steps != nullptr) CUDA_TRY(cudaMemcpyAsync(M->d_h, h_steps, n_steps * sizeof(double), cudaMemcpyHostToDevice, M->stream));
+    BioncDynOptions o2 = opt != nullptr ? *opt : BioncDynOptions{};
+    if (per_sys) {
+        CUDA_TRY(cudaMemcpyAsync(M->d_inertia, opt->inertia, (size_t)B * M->hdr.N * 10 * sizeof(double), cudaMemcpyHostToDevice, M->stream));
+        o2.inertia = M->d_inertia;
+    }
+    rc = bionc_cuda_rk4(M, M->d_Q, M->d_Qd, h, h_steps != nullptr ? M->d_h : nullptr, n_steps, normalize, &o2, nullptr, 1,
+                        nullptr, status != nullptr ? M->d_status : nullptr, B, M->stream);
+    if (rc != BIONC_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(Q, M->d_Q, nb, cudaMemcpyDeviceToHost, M->stream));
+    CUDA_TRY(cudaMemcpyAsync(Qd, M->d_Qd, nb, cudaMemcpyDeviceToHost, M->stream));
+    if (status != nullptr) CUDA_TRY(cudaMemcpyAsync(status, M->d_status, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, M->stream));
+    CUDA_TRY(cudaStreamSynchronize(M->stream));
+    return BIONC_OK;
+}
+
+// FP64 roofline denominator: a DFMA-only kernel (8 independent accumulator chains per thread,
+// 2048 threads per SM resident) timed with CUDA events; MEASURED_PEAKS.json has no FP64 figure.
+int bionc_cuda_measure_fp64_peak(int device, int repeats, double* tflops_best, double* tflops_sustained) {
+    if (tflops_best == nullptr) return fail(BIONC_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(device));
+    int sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int block = 256, grid = sms * 8, iters = 1 << 14;
+    double* d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_out, (size_t)grid * block * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const double flops = 2.0 * 8.0 * (double)iters * (double)grid * block;
+    double best = 0.0, total_ms = 0.0;
+    if (repeats < 3) repeats = 3;
+    for (int r = 0; r < repeats + 2; ++r) {
+        CUDA_TRY(cudaEventRecord(e0));
+        dfma_peak_kernel<<<grid, block>>>(d_out, iters, 1.0000001, 1e-9);
+        g_launches++;
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (r >= 2) {  // two warm-up launches
+            const double tf = flops / (ms * 1e-3) / 1e12;
+            if (tf > best) best = tf;
+            total_ms += ms;
+        }
+    }
+    *tflops_best = best;
+    if (tflops_sustained != nullptr) *tflops_sustained = flops * repeats / (total_ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+    CUDA_TRY(cudaFree(d_out));
+    return BIONC_OK;
+}
+
+int64_t bionc_cuda_launch_count(void) { return g_launches.load(); }
+const char* bionc_cuda_last_error(void) { return g_last_error.c_str(); }
+const char* bionc_cuda_version(void) { return "bionc_cuda 0.1.0 (sm_100a, fp64)"; }
+
+}  // extern "C"

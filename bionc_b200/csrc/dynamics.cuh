@@ -1,0 +1,608 @@
+// Constrained forward dynamics of natural-coordinate models, one LANE per SEGMENT.
+//
+// System solved (reference bionc/bionc_numpy/biomechanical_model.py:404-426):
+//     [G K^T; K 0] [Qdd; lambda] = [f; -bias]        G = blockdiag(M4_i (x) I3)
+// The reference LU-factors the dense KKT matrix.  Here the same solution is obtained with a
+// fill-reducing block elimination of the Schur complement S = K G^-1 K^T:
+//   1. per segment (one lane, registers only): Sr_i = Kr_i G_i^-1 Kr_i^T (6x6) is factored LDL^T;
+//      rigid-body rows of different segments never couple, so this is the block-diagonal leading
+//      part of S under the ordering "all rigid rows first";
+//   2. per constraint row touching the segment: q' = A_i k^T with the projected inverse mass
+//      A_i = G_i^-1 - G_i^-1 Kr_i^T Sr_i^-1 Kr_i G_i^-1, and the segment's contribution
+//      k_a . q'_b to the joint-level Schur complement S' (mj x mj, shared memory);
+//   3. S' lambda_j = rhs' is factored LDL^T cooperatively by the lanes of the system, in place;
+//   4. back-substitution per segment: F = f - Kj^T lambda_j, a = G^-1 F,
+//      lambda_r = Sr^-1 (Kr a + bias_r), Qdd = a - G^-1 Kr^T lambda_r.
+// LDL^T (no square roots) instead of Cholesky because the reference's mass matrix is not positive
+// definite in general (SURVEY.md finding 1); a zero / non-finite pivot raises the status flag.
+//
+// Lane mapping: lane = sys_in_warp * N + segment, spw = 32 / N systems per warp, warps are fully
+// independent (only __syncwarp).  Shared memory per warp, all indexed [item][sys_in_warp] so that
+// lanes of different systems hit different banks and lanes of one system broadcast:
+//   Qs, Qds  : 12N          state of the current stage (cross-segment reads for two-segment joints)
+//   S0, S1   : mj(mj+1)/2   packed lower triangle; copy r is written only by the lane that has
+//                           role r (child/parent) in the block of the larger row -> no atomics
+//   r0, r1, dinv : mj
+//   knl      : rnl x 12 x 32 lanes   explicit Jacobian rows of non-LIN3 blocks (private per lane)
+#pragma once
+#include "model.cuh"
+
+namespace bionc {
+
+struct V3 {
+    double x, y, z;
+};
+__device__ __forceinline__ V3 mk(double x, double y, double z) { return V3{x, y, z}; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ V3 operator*(double s, V3 a) { return V3{s * a.x, s * a.y, s * a.z}; }
+__device__ __forceinline__ double dot(V3 a, V3 b) { return fma(a.x, b.x, fma(a.y, b.y, a.z * b.z)); }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) {
+    return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+// a + s * b
+__device__ __forceinline__ V3 axpy(double s, V3 b, V3 a) { return V3{fma(s, b.x, a.x), fma(s, b.y, a.y), fma(s, b.z, a.z)}; }
+__device__ __forceinline__ double comp(V3 a, int c) { return c == 0 ? a.x : (c == 1 ? a.y : a.z); }
+__device__ __forceinline__ V3 unit(int c, double s) { return V3{c == 0 ? s : 0.0, c == 1 ? s : 0.0, c == 2 ? s : 0.0}; }
+
+// A 12-vector as four 3-vectors on the slots (u, rp, rd, w).
+struct Q12 {
+    V3 s[4];
+};
+
+// index of W(t, s) in the packed upper triangle
+__device__ __forceinline__ constexpr int widx(int t, int s) {
+    return t <= s ? (t * 4 - t * (t - 1) / 2 + (s - t)) : (s * 4 - s * (s - 1) / 2 + (t - s));
+}
+
+// Per-lane view of one segment in one system.
+struct SegCtx {
+    double W[10];  // M4^-1
+    double fg[4];
+    V3 u, v, w;       // v = rp - rd
+    double L[15];     // unit lower factor of Sr, packed rows: (1,0) (2,0) (2,1) (3,0) ...
+    double dinv[6];
+};
+
+__device__ __forceinline__ constexpr int lidx(int r, int c) { return r * (r - 1) / 2 + c; }  // r > c
+
+// x = G^-1 k  (W (x) I3 applied to a 12-vector)
+__device__ __forceinline__ Q12 apply_W(const double (&W)[10], const Q12& k) {
+    Q12 q;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        V3 acc = W[widx(t, 0)] * k.s[0];
+#pragma unroll
+        for (int s = 1; s < 4; ++s) acc = axpy(W[widx(t, s)], k.s[s], acc);
+        q.s[t] = acc;
+    }
+    return q;
+}
+
+// Kr x for a 12-vector x (natural_segment.py:450-483 contracted): 6 numbers
+__device__ __forceinline__ void kr_apply(const SegCtx& c, const Q12& x, double (&out)[6]) {
+    const V3 xv = x.s[1] - x.s[2];
+    out[0] = 2.0 * dot(c.u, x.s[0]);
+    out[1] = dot(c.v, x.s[0]) + dot(c.u, xv);
+    out[2] = dot(c.w, x.s[0]) + dot(c.u, x.s[3]);
+    out[3] = 2.0 * dot(c.v, xv);
+    out[4] = dot(c.w, xv) + dot(c.v, x.s[3]);
+    out[5] = 2.0 * dot(c.w, x.s[3]);
+}
+
+// G^-1 Kr^T y for a 6-vector y
+__device__ __forceinline__ Q12 ginv_krt(const SegCtx& c, const double (&y)[6]) {
+    const V3 su = axpy(2.0 * y[0], c.u, axpy(y[1], c.v, y[2] * c.w));
+    const V3 p = axpy(y[1], c.u, axpy(2.0 * y[3], c.v, y[4] * c.w));  // rp slot; rd slot is -p
+    const V3 sw = axpy(y[2], c.u, axpy(y[4], c.v, (2.0 * y[5]) * c.w));
+    Q12 x;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const double wv = c.W[widx(t, 1)] - c.W[widx(t, 2)];
+        x.s[t] = axpy(c.W[widx(t, 0)], su, axpy(wv, p, c.W[widx(t, 3)] * sw));
+    }
+    return x;
+}
+
+// solve Sr y = rhs in place with the LDL^T factors held in registers
+__device__ __forceinline__ void sr_solve(const SegCtx& c, double (&y)[6]) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+#pragma unroll
+        for (int r = k + 1; r < 6; ++r) y[r] = fma(-c.L[lidx(r, k)], y[k], y[r]);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) y[k] *= c.dinv[k];
+#pragma unroll
+    for (int k = 5; k >= 0; --k)
+#pragma unroll
+        for (int r = k + 1; r < 6; ++r) y[k] = fma(-c.L[lidx(r, k)], y[r], y[k]);
+}
+
+// Build Sr = Kr G^-1 Kr^T from the Gram matrix of (u, v, w) and omega = E^T W E, E = [e_u, e_rp - e_rd, e_w],
+// and factor it.  Row (a,b) of Kr is e_a (x) b + e_b (x) a, so
+//   Sr[(a,b),(c,d)] = om_ac g_bd + om_ad g_bc + om_bc g_ad + om_bd g_ac.
+__device__ __forceinline__ void sr_factor(SegCtx& c, int& status) {
+    double g[3][3], om[3][3];
+    g[0][0] = dot(c.u, c.u);
+    g[0][1] = g[1][0] = dot(c.u, c.v);
+    g[0][2] = g[2][0] = dot(c.u, c.w);
+    g[1][1] = dot(c.v, c.v);
+    g[1][2] = g[2][1] = dot(c.v, c.w);
+    g[2][2] = dot(c.w, c.w);
+    om[0][0] = c.W[widx(0, 0)];
+    om[0][1] = om[1][0] = c.W[widx(0, 1)] - c.W[widx(0, 2)];
+    om[0][2] = om[2][0] = c.W[widx(0, 3)];
+    om[1][1] = c.W[widx(1, 1)] - 2.0 * c.W[widx(1, 2)] + c.W[widx(2, 2)];
+    om[1][2] = om[2][1] = c.W[widx(1, 3)] - c.W[widx(2, 3)];
+    om[2][2] = c.W[widx(3, 3)];
+    constexpr int pa[6] = {0, 0, 0, 1, 1, 2};
+    constexpr int pb[6] = {0, 1, 2, 1, 2, 2};
+    double A[6][6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int q = 0; q <= r; ++q) {
+            const int a = pa[r], b = pb[r], cc = pa[q], d = pb[q];
+            A[r][q] = fma(om[a][cc], g[b][d], fma(om[a][d], g[b][cc], fma(om[b][cc], g[a][d], om[b][d] * g[a][cc])));
+        }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const double piv = A[k][k];
+        if (!(fabs(piv) > 0.0) || !isfinite(piv)) status |= 1;
+        const double inv = 1.0 / piv;
+        c.dinv[k] = inv;
+        double col[6];
+#pragma unroll
+        for (int r = k + 1; r < 6; ++r) {
+            col[r] = A[r][k];
+            c.L[lidx(r, k)] = col[r] * inv;
+        }
+#pragma unroll
+        for (int r = k + 1; r < 6; ++r)
+#pragma unroll
+            for (int q = k + 1; q <= r; ++q) A[r][q] = fma(-c.L[lidx(r, k)], col[q], A[r][q]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp-level context
+// ---------------------------------------------------------------------------------------------
+struct WarpCtx {
+    const DevHeader* hdr;
+    const DevSeg* seg;
+    const DevBlk* blk;
+    const DevSide* side;
+    const DevFext* fext;
+    double* Qs;   // [12N][spw]
+    double* Qds;  // [12N][spw]
+    double* S0;   // [tri][spw]
+    double* S1;
+    double* r0;   // [mj][spw]
+    double* r1;
+    double* dinv;
+    double* knl;  // [rnl][12][32]
+    int spw, N, mj, tri;
+    int sys;   // system index inside the warp
+    int segi;  // this lane's segment
+    int lane;
+    bool has_seg;  // lane maps to a (system, segment) pair
+};
+
+__device__ __forceinline__ constexpr int tidx(int r, int c) { return r * (r + 1) / 2 + c; }  // r >= c
+
+// linear form over another segment's published state: sum_t a[t] * X[12 s + 3 t + :]
+__device__ __forceinline__ V3 lin_form(const WarpCtx& w, const double* X, int s, const double* a) {
+    V3 r = mk(0.0, 0.0, 0.0);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int o = (12 * s + 3 * t) * w.spw + w.sys;
+        r = axpy(a[t], mk(X[o], X[o + w.spw], X[o + 2 * w.spw]), r);
+    }
+    return r;
+}
+
+struct DynOpts {
+    int use_stab;
+    double alpha, beta;
+};
+
+// Explicit Jacobian row (restricted to this lane's segment) of a non-LIN3 block, plus -- on the
+// child side -- the row's right-hand-side term bias (+ alpha Phi + beta K Qdot when stabilised).
+// DOT : joints.py:203-208, :222-235, :252-282 ; joints_with_ground.py:155-162, :169-178
+// CLEN: joints.py:1300-1382        SOP: joints.py:657-748 (Jacobian blocks as coded: swapped)
+__device__ __forceinline__ void nonlin_row(const WarpCtx& w, const DevBlk& b, int role, const DynOpts& o, Q12& k,
+                                           double& bterm) {
+    const double* p = b.p;
+    bterm = 0.0;
+    if (b.type == DOT) {
+        const V3 Dc = lin_form(w, w.Qs, b.child, p + 4);
+        V3 Dp, Dpd = mk(0.0, 0.0, 0.0);
+        if (b.parent >= 0) {
+            Dp = lin_form(w, w.Qs, b.parent, p);
+        } else {
+            Dp = mk(p[0], p[1], p[2]);
+        }
+        if (role == CHILD) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) k.s[t] = p[4 + t] * Dp;
+            const V3 Dcd = lin_form(w, w.Qds, b.child, p + 4);
+            if (b.parent >= 0) {
+                Dpd = lin_form(w, w.Qds, b.parent, p);
+                bterm = 2.0 * dot(Dpd, Dcd);
+            }
+            if (o.use_stab) bterm += o.alpha * (dot(Dp, Dc) - p[8]) + o.beta * (dot(Dpd, Dc) + dot(Dp, Dcd));
+        } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) k.s[t] = p[t] * Dc;
+        }
+    } else if (b.type == CLEN) {
+        const V3 d = lin_form(w, w.Qs, b.parent, p) - lin_form(w, w.Qs, b.child, p + 4);
+        if (role == CHILD) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) k.s[t] = (-2.0 * p[4 + t]) * d;
+            const V3 dd = lin_form(w, w.Qds, b.parent, p) - lin_form(w, w.Qds, b.child, p + 4);
+            bterm = 2.0 * dot(dd, dd);
+            if (o.use_stab) bterm += o.alpha * (dot(d, d) - p[8]) + o.beta * (2.0 * dot(d, dd));
+        } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) k.s[t] = (2.0 * p[t]) * d;
+        }
+    } else {  // SOP
+        const V3 n = lin_form(w, w.Qs, b.child, p + 8);
+        if (role == CHILD) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) k.s[t] = p[t] * n;  // n^T N_P, stored in the child's columns
+            const V3 P = lin_form(w, w.Qs, b.parent, p), A = lin_form(w, w.Qs, b.child, p + 4);
+            const V3 Pd = lin_form(w, w.Qds, b.parent, p), Ad = lin_form(w, w.Qds, b.child, p + 4);
+            const V3 nd = lin_form(w, w.Qds, b.child, p + 8);
+            bterm = 2.0 * dot(Pd, nd) - 2.0 * dot(nd, Ad);
+            if (o.use_stab) {
+                // K Qdot with the blocks where the reference stores them:
+                // parent cols: -n^T N_A + (P-A)^T N_n applied to Qdot_parent; child cols: n^T N_P applied to Qdot_child
+                const V3 Apd = lin_form(w, w.Qds, b.parent, p + 4), npd = lin_form(w, w.Qds, b.parent, p + 8);
+                const V3 Pcd = lin_form(w, w.Qds, b.child, p);
+                const double kqd = -dot(n, Apd) + dot(P - A, npd) + dot(n, Pcd);
+                bterm += o.alpha * (dot(P - A, n) - p[12]) + o.beta * kqd;
+            }
+        } else {
+            const V3 PA = lin_form(w, w.Qs, b.parent, p) - lin_form(w, w.Qs, b.child, p + 4);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) k.s[t] = axpy(-p[4 + t], n, p[8 + t] * PA);  // stored in the parent's columns
+        }
+    }
+}
+
+// External forces on this lane's segment (external_force.py:143-180 and the four force classes).
+__device__ __forceinline__ Q12 external_forces(const WarpCtx& w, const DevSeg& sg, const SegCtx& c, V3 rp) {
+    Q12 f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) f.s[t] = mk(0.0, 0.0, 0.0);
+    for (int e = sg.fext_begin; e < sg.fext_end; ++e) {
+        const DevFext& fe = w.fext[e];
+        V3 tau = mk(fe.p[0], fe.p[1], fe.p[2]), F = mk(fe.p[3], fe.p[4], fe.p[5]);
+        const V3 pt = mk(fe.p[6], fe.p[7], fe.p[8]);
+        if (fe.kind == 3) {  // in local: rotate by [u v w] Tinv (external_force_in_local.py:85-91)
+            const double* T = fe.p + 9;
+            const V3 c0 = axpy(T[0], c.u, axpy(T[3], c.v, T[6] * c.w));
+            const V3 c1 = axpy(T[1], c.u, axpy(T[4], c.v, T[7] * c.w));
+            const V3 c2 = axpy(T[2], c.u, axpy(T[5], c.v, T[8] * c.w));
+            const V3 Fg = axpy(F.x, c0, axpy(F.y, c1, F.z * c2));
+            const V3 tg = axpy(tau.x, c0, axpy(tau.y, c1, tau.z * c2));
+            F = Fg;
+            tau = tg;
+        }
+        if (fe.kind == 1 || fe.kind == 3) {  // local application point (external_force_global_local_point.py:68-100)
+            // rp - P = -(pt0 u + pt1 (rp - rd) + pt2 w)
+            const V3 lever = mk(0.0, 0.0, 0.0) - axpy(pt.x, c.u, axpy(pt.y, c.v, pt.z * c.w));
+            tau = tau + cross(lever, F);
+        } else if (fe.kind == 2) {  // global application point (external_force_global.py:67-96)
+            tau = tau + cross(rp - pt, F);
+        }
+        // pseudo interpolation matrix (natural_coordinates.py:132-158): solve [w x u, u x v, -v x w] x = tau
+        const V3 b0 = cross(c.w, c.u), b1 = cross(c.u, c.v), b2 = cross(c.w, c.v);  // -v x w = w x v
+        const double det = dot(b0, cross(b1, b2));
+        const double idet = 1.0 / det;
+        const double x0 = dot(tau, cross(b1, b2)) * idet;
+        const double x1 = dot(b0, cross(tau, b2)) * idet;
+        const double x2 = dot(b0, cross(b1, tau)) * idet;
+        f.s[0] = axpy(x1, c.v, f.s[0]);
+        f.s[1] = f.s[1] + F - x2 * c.w;
+        f.s[2] = axpy(x2, c.w, f.s[2]);
+        f.s[3] = axpy(x0, c.u, f.s[3]);
+    }
+    return f;
+}
+
+// rigid-body right-hand side term: bias_r (+ alpha Phi_r + beta Kr Qdot)   (natural_segment.py:429-448, :508-545)
+__device__ __forceinline__ void rigid_bterm(const SegCtx& c, const DevSeg& sg, const Q12& Qd, const DynOpts& o,
+                                            double (&b)[6]) {
+    const V3 ud = Qd.s[0], vd = Qd.s[1] - Qd.s[2], wd = Qd.s[3];
+    b[0] = 2.0 * dot(ud, ud);
+    b[1] = 2.0 * dot(ud, vd);
+    b[2] = 2.0 * dot(ud, wd);
+    b[3] = 2.0 * dot(vd, vd);
+    b[4] = 2.0 * dot(vd, wd);
+    b[5] = 2.0 * dot(wd, wd);
+    if (o.use_stab) {
+        double kqd[6];
+        kr_apply(c, Qd, kqd);
+        const double phi[6] = {dot(c.u, c.u) - 1.0,         dot(c.u, c.v) - sg.phic[0], dot(c.u, c.w) - sg.phic[1],
+                               dot(c.v, c.v) - sg.phic[2], dot(c.v, c.w) - sg.phic[3], dot(c.w, c.w) - 1.0};
+#pragma unroll
+        for (int i = 0; i < 6; ++i) b[i] += o.alpha * phi[i] + o.beta * kqd[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One forward-dynamics evaluation for the whole warp.  Every lane passes its segment's Q, Qdot
+// (slots u, rp, rd, w) and receives Qddot; lambda (holonomic order) is written to lam_out if non-null.
+// All 32 lanes must call this (it contains __syncwarp); lanes without a segment pass has_seg=false.
+// ---------------------------------------------------------------------------------------------
+template <bool HAS_FEXT>
+__device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& c, const Q12& Q, const Q12& Qd,
+                                                      const DynOpts& o, Q12& Qdd, double* lam_out, int& status) {
+    const int spw = w.spw, sys = w.sys;
+    const DevSeg& sg = w.seg[w.segi];
+    const bool two_seg = w.N > 1 || w.mj > 0;
+
+    // ---- A. publish the stage state
+    if (w.has_seg && two_seg) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int ob = (12 * w.segi + 3 * t) * spw + sys;
+            w.Qs[ob] = Q.s[t].x, w.Qs[ob + spw] = Q.s[t].y, w.Qs[ob + 2 * spw] = Q.s[t].z;
+            w.Qds[ob] = Qd.s[t].x, w.Qds[ob + spw] = Qd.s[t].y, w.Qds[ob + 2 * spw] = Qd.s[t].z;
+        }
+    }
+    // ---- B. segment-local factorisation and free acceleration
+    c.u = Q.s[0], c.v = Q.s[1] - Q.s[2], c.w = Q.s[3];
+    sr_factor(c, status);
+    Q12 f;  // natural forces: gravity + external
+    if (HAS_FEXT) {
+        f = external_forces(w, sg, c, Q.s[1]);
+    } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) f.s[t] = mk(0.0, 0.0, 0.0);
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) f.s[t].z += c.fg[t];
+    double br[6];
+    rigid_bterm(c, sg, Qd, o, br);
+    Q12 abar;
+    {
+        const Q12 a0 = apply_W(c.W, f);
+        double z[6];
+        kr_apply(c, a0, z);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) z[i] += br[i];
+        sr_solve(c, z);
+        const Q12 corr = ginv_krt(c, z);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) abar.s[t] = a0.s[t] - corr.s[t];
+    }
+    if (w.mj == 0) {  // no joint rows at all (free bodies): abar is the answer
+        Qdd = abar;
+        if (lam_out != nullptr && w.has_seg) {
+            // lambda_r = Sr^-1 (Kr a0 + b) was z; recompute cheaply
+            const Q12 a0 = apply_W(c.W, f);
+            double z[6];
+            kr_apply(c, a0, z);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) z[i] += br[i];
+            sr_solve(c, z);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) lam_out[sg.rigid_row + i] = z[i];
+        }
+        return;
+    }
+
+    // ---- C. zero the joint-level system (cooperatively by the lanes of the system)
+    if (w.has_seg) {
+        for (int it = w.segi; it < w.tri; it += w.N) w.S0[it * spw + sys] = 0.0, w.S1[it * spw + sys] = 0.0;
+        for (int it = w.segi; it < w.mj; it += w.N) w.r0[it * spw + sys] = 0.0, w.r1[it * spw + sys] = 0.0;
+    }
+    __syncwarp();
+
+    // ---- D. pre-pass over the blocks touching this segment: right-hand side rhs' = Kj abar + b_j
+    //         (copy `role` of each row is written by exactly one lane) and explicit rows of non-LIN3 blocks
+    if (w.has_seg) {
+        for (int e = sg.side_begin; e < sg.side_end; ++e) {
+            const DevSide sd = w.side[e];
+            const DevBlk& b = w.blk[sd.blk];
+            double* rr = sd.role == CHILD ? w.r0 : w.r1;
+            if (b.type == LIN3) {
+                const double* a = b.p + (sd.role == CHILD ? 4 : 0);
+                const double sgn = sd.role == CHILD ? -1.0 : 1.0;
+                V3 r = mk(0.0, 0.0, 0.0);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) r = axpy(sgn * a[t], abar.s[t], r);
+                if (sd.role == CHILD && o.use_stab) {
+                    // Phi = c0 + N_p Q_p - N_c Q_c ; K Qdot = N_p Qdot_p - N_c Qdot_c
+                    V3 phi = mk(b.p[8], b.p[9], b.p[10]) - lin_form(w, w.Qs, b.child, b.p + 4);
+                    V3 kqd = mk(0.0, 0.0, 0.0) - lin_form(w, w.Qds, b.child, b.p + 4);
+                    if (b.parent >= 0) {
+                        phi = phi + lin_form(w, w.Qs, b.parent, b.p);
+                        kqd = kqd + lin_form(w, w.Qds, b.parent, b.p);
+                    }
+                    r = axpy(o.alpha, phi, axpy(o.beta, kqd, r));
+                }
+                rr[(b.jrow + 0) * spw + sys] = r.x;
+                rr[(b.jrow + 1) * spw + sys] = r.y;
+                rr[(b.jrow + 2) * spw + sys] = r.z;
+            } else {
+                Q12 k;
+                double bterm;
+                nonlin_row(w, b, sd.role, o, k, bterm);
+                double acc = bterm;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    acc += dot(k.s[t], abar.s[t]);
+                    double* dst = w.knl + (sd.nl_slot * 12 + 3 * t) * 32 + w.lane;
+                    dst[0] = k.s[t].x, dst[32] = k.s[t].y, dst[64] = k.s[t].z;
+                }
+                rr[b.jrow * spw + sys] = acc;
+            }
+        }
+    }
+
+    // ---- E. S' contributions of this segment: for every pair of rows (a >= b) touching it, k_a . q'_b
+    if (w.has_seg) {
+        for (int e = sg.side_begin; e < sg.side_end; ++e) {
+            const DevSide sd = w.side[e];
+            const DevBlk& b = w.blk[sd.blk];
+            const int nrow_b = b.type == LIN3 ? 3 : 1;
+            double beta4[4];  // LIN3: W (sgn alpha)
+            Q12 kb;           // non-LIN3: explicit row
+            if (b.type == LIN3) {
+                const double* a = b.p + (sd.role == CHILD ? 4 : 0);
+                const double sgn = sd.role == CHILD ? -1.0 : 1.0;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) acc = fma(c.W[widx(t, s)], a[s], acc);
+                    beta4[t] = sgn * acc;
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const double* src = w.knl + (sd.nl_slot * 12 + 3 * t) * 32 + w.lane;
+                    kb.s[t] = mk(src[0], src[32], src[64]);
+                }
+            }
+            for (int rb = 0; rb < nrow_b; ++rb) {
+                // q = G^-1 k_b^T, cvec = Kr q
+                Q12 q;
+                double y[6];
+                if (b.type == LIN3) {
+                    const double uc = comp(c.u, rb), vc = comp(c.v, rb), wc = comp(c.w, rb);
+                    const double bu = beta4[0], bv = beta4[1] - beta4[2], bw = beta4[3];
+                    y[0] = 2.0 * uc * bu;
+                    y[1] = fma(vc, bu, uc * bv);
+                    y[2] = fma(wc, bu, uc * bw);
+                    y[3] = 2.0 * vc * bv;
+                    y[4] = fma(wc, bv, vc * bw);
+                    y[5] = 2.0 * wc * bw;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) q.s[t] = unit(rb, beta4[t]);
+                } else {
+                    q = apply_W(c.W, kb);
+                    kr_apply(c, q, y);
+                }
+                sr_solve(c, y);
+                const Q12 corr = ginv_krt(c, y);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) q.s[t] = q.s[t] - corr.s[t];  // q' = A_i k_b^T
+                const int row_b = b.jrow + rb;
+                // inner loop over the blocks a at or after b in this segment's (jrow-sorted) list
+                for (int e2 = e; e2 < sg.side_end; ++e2) {
+                    const DevSide sa = w.side[e2];
+                    const DevBlk& a = w.blk[sa.blk];
+                    double* Sc = sa.role == CHILD ? w.S0 : w.S1;
+                    if (a.type == LIN3) {
+                        const double* al = a.p + (sa.role == CHILD ? 4 : 0);
+                        const double sgn = sa.role == CHILD ? -1.0 : 1.0;
+                        V3 r = mk(0.0, 0.0, 0.0);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) r = axpy(sgn * al[t], q.s[t], r);
+                        const int first = (e2 == e) ? rb : 0;  // same block: lower triangle only
+                        if (first <= 0) Sc[tidx(a.jrow + 0, row_b) * spw + sys] = r.x;
+                        if (first <= 1) Sc[tidx(a.jrow + 1, row_b) * spw + sys] = r.y;
+                        Sc[tidx(a.jrow + 2, row_b) * spw + sys] = r.z;
+                    } else {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const double* src = w.knl + (sa.nl_slot * 12 + 3 * t) * 32 + w.lane;
+                            acc += dot(mk(src[0], src[32], src[64]), q.s[t]);
+                        }
+                        Sc[tidx(a.jrow, row_b) * spw + sys] = acc;
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- F. combine the two copies, then LDL^T of S' in place (rows dealt round-robin to the lanes
+    //         of the system; column k is final before step k so one __syncwarp per pivot suffices)
+    if (w.has_seg) {
+        for (int it = w.segi; it < w.tri; it += w.N) w.S0[it * spw + sys] += w.S1[it * spw + sys];
+        for (int it = w.segi; it < w.mj; it += w.N) w.r0[it * spw + sys] += w.r1[it * spw + sys];
+    }
+    for (int k = 0; k < w.mj; ++k) {
+        __syncwarp();
+        if (w.has_seg) {
+            const double piv = w.S0[tidx(k, k) * spw + sys];
+            if (!(fabs(piv) > 0.0) || !isfinite(piv)) status |= 1;
+            const double inv = 1.0 / piv;
+            if (w.segi == 0) w.dinv[k * spw + sys] = inv;
+            for (int r = k + 1 + w.segi; r < w.mj; r += w.N) {
+                const double t = w.S0[tidx(r, k) * spw + sys] * inv;
+                for (int q = k + 1; q <= r; ++q)
+                    w.S0[tidx(r, q) * spw + sys] = fma(-t, w.S0[tidx(q, k) * spw + sys], w.S0[tidx(r, q) * spw + sys]);
+            }
+        }
+    }
+    __syncwarp();
+    // ---- G. triangular solves by the first lane of each system: L y = rhs ; lambda = L^-T D^-1 y
+    if (w.has_seg && w.segi == 0) {
+        for (int k = 0; k < w.mj; ++k) {
+            double x = w.r0[k * spw + sys];
+            for (int q = 0; q < k; ++q) x = fma(-w.S0[tidx(k, q) * spw + sys], w.r1[q * spw + sys], x);
+            w.r1[k * spw + sys] = x * w.dinv[k * spw + sys];  // y-hat = D^-1 y
+        }
+        for (int k = w.mj - 1; k >= 0; --k) {
+            double acc = 0.0;
+            for (int r = k + 1; r < w.mj; ++r) acc = fma(w.S0[tidx(r, k) * spw + sys], w.r0[r * spw + sys], acc);
+            w.r0[k * spw + sys] = w.r1[k * spw + sys] - w.dinv[k * spw + sys] * acc;  // lambda_j
+        }
+    }
+    __syncwarp();
+
+    // ---- H. back-substitution per segment
+    if (w.has_seg) {
+        for (int e = sg.side_begin; e < sg.side_end; ++e) {
+            const DevSide sd = w.side[e];
+            const DevBlk& b = w.blk[sd.blk];
+            if (b.type == LIN3) {
+                const double* a = b.p + (sd.role == CHILD ? 4 : 0);
+                const double sgn = sd.role == CHILD ? -1.0 : 1.0;
+                const V3 lam = mk(w.r0[(b.jrow + 0) * spw + sys], w.r0[(b.jrow + 1) * spw + sys],
+                                  w.r0[(b.jrow + 2) * spw + sys]);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) f.s[t] = axpy(-sgn * a[t], lam, f.s[t]);
+                if (lam_out != nullptr && sd.role == CHILD) {
+                    lam_out[b.row_h + 0] = lam.x, lam_out[b.row_h + 1] = lam.y, lam_out[b.row_h + 2] = lam.z;
+                }
+            } else {
+                const double lam = w.r0[b.jrow * spw + sys];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const double* src = w.knl + (sd.nl_slot * 12 + 3 * t) * 32 + w.lane;
+                    f.s[t] = axpy(-lam, mk(src[0], src[32], src[64]), f.s[t]);
+                }
+                if (lam_out != nullptr && sd.role == CHILD) lam_out[b.row_h] = lam;
+            }
+        }
+    }
+    {
+        const Q12 a = apply_W(c.W, f);
+        double z[6];
+        kr_apply(c, a, z);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) z[i] += br[i];
+        sr_solve(c, z);  // lambda_r
+        const Q12 corr = ginv_krt(c, z);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) Qdd.s[t] = a.s[t] - corr.s[t];
+        if (lam_out != nullptr && w.has_seg) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) lam_out[sg.rigid_row + i] = z[i];
+        }
+    }
+    // the published state / joint-level buffers are reused by the next evaluation
+    __syncwarp();
+}
+
+}  // namespace bionc

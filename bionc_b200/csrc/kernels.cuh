@@ -1,0 +1,401 @@
+// __global__ kernels: batched forward dynamics, fused RK4, component evaluators.
+#pragma once
+#include "dynamics.cuh"
+
+namespace bionc {
+
+constexpr int kMaxWarpsPerCta = 4;
+
+// ---- inverse of a symmetric 4x4 given by its packed upper triangle (LDL^T, no pivoting) ----------
+__device__ __forceinline__ void sym4_inverse(const double (&M)[10], double (&Wout)[10], int& status) {
+    double A[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) A[r][c] = M[widx(r, c)];
+    double dinv[4], L[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double piv = A[k][k];
+        if (!(fabs(piv) > 0.0) || !isfinite(piv)) status |= 1;
+        dinv[k] = 1.0 / piv;
+        double col[4];
+#pragma unroll
+        for (int r = k + 1; r < 4; ++r) {
+            col[r] = A[r][k];
+            L[r][k] = col[r] * dinv[k];
+        }
+#pragma unroll
+        for (int r = k + 1; r < 4; ++r)
+#pragma unroll
+            for (int c = k + 1; c <= r; ++c) A[r][c] = fma(-L[r][k], col[c], A[r][c]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // column j of the inverse, rows >= j are enough (symmetric)
+        double y[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) y[r] = (r == j) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int r = k + 1; r < 4; ++r) y[r] = fma(-L[r][k], y[k], y[r]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) y[k] *= dinv[k];
+#pragma unroll
+        for (int k = 3; k >= 0; --k)
+#pragma unroll
+            for (int r = k + 1; r < 4; ++r) y[k] = fma(-L[r][k], y[r], y[k]);
+#pragma unroll
+        for (int r = j; r < 4; ++r) Wout[widx(j, r)] = y[r];
+    }
+}
+
+// M4 from natural inertial parameters (natural_inertial_parameters.py:153-177) and gravity (natural_segment.py:562-572)
+__device__ __forceinline__ void inertia_to_constants(const double* ip, double (&W)[10], double (&fg)[4], int& status) {
+    const double m = ip[0], c0 = ip[1], c1 = ip[2], c2 = ip[3];
+    const double J00 = ip[4], J01 = ip[5], J02 = ip[6], J11 = ip[7], J12 = ip[8], J22 = ip[9];
+    double M[10];
+    M[widx(0, 0)] = J00;
+    M[widx(0, 1)] = m * c0 + J01;
+    M[widx(0, 2)] = -J01;
+    M[widx(0, 3)] = J02;
+    M[widx(1, 1)] = m + 2.0 * m * c1 + J11;
+    M[widx(1, 2)] = -(m * c1 + J11);
+    M[widx(1, 3)] = m * c2 + J12;
+    M[widx(2, 2)] = J11;
+    M[widx(2, 3)] = -J12;
+    M[widx(3, 3)] = J22;
+    sym4_inverse(M, W, status);
+    const double g = -9.81;
+    fg[0] = c0 * m * g;
+    fg[1] = (1.0 + c1) * m * g;
+    fg[2] = -c1 * m * g;
+    fg[3] = c2 * m * g;
+}
+
+// ---- per-CTA setup: copy the model blob to shared memory, carve the per-warp working sets ---------
+__device__ __forceinline__ void setup_warp(const unsigned char* __restrict__ blob, int blob_bytes, unsigned char* smem,
+                                           WarpCtx& w) {
+    {
+        const int4* src = reinterpret_cast<const int4*>(blob);
+        int4* dst = reinterpret_cast<int4*>(smem);
+        for (int i = threadIdx.x; i < blob_bytes / 16; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const DevHeader* h = reinterpret_cast<const DevHeader*>(smem);
+    w.hdr = h;
+    w.seg = reinterpret_cast<const DevSeg*>(smem + h->off_seg);
+    w.blk = reinterpret_cast<const DevBlk*>(smem + h->off_blk);
+    w.side = reinterpret_cast<const DevSide*>(smem + h->off_side);
+    w.fext = reinterpret_cast<const DevFext*>(smem + h->off_fext);
+    w.N = h->N, w.mj = h->mj, w.spw = h->spw, w.tri = h->mj * (h->mj + 1) / 2;
+    const int warp = threadIdx.x >> 5;
+    w.lane = threadIdx.x & 31;
+    double* base = reinterpret_cast<double*>(smem + blob_bytes) + (size_t)warp * warp_smem_doubles(w.N, w.mj, w.spw, h->rnl);
+    w.Qs = base;
+    w.Qds = w.Qs + 12 * w.N * w.spw;
+    w.S0 = w.Qds + 12 * w.N * w.spw;
+    w.S1 = w.S0 + w.tri * w.spw;
+    w.r0 = w.S1 + w.tri * w.spw;
+    w.r1 = w.r0 + w.mj * w.spw;
+    w.dinv = w.r1 + w.mj * w.spw;
+    w.knl = w.dinv + w.mj * w.spw;
+    w.sys = w.lane / w.N;
+    w.segi = w.lane - w.sys * w.N;
+    if (w.sys >= w.spw) w.sys = w.spw - 1, w.segi = 0, w.has_seg = false;
+    else w.has_seg = true;
+}
+
+__device__ __forceinline__ void load_q12(const double* __restrict__ p, Q12& q) {
+    const double2* p2 = reinterpret_cast<const double2*>(p);
+    const double2 a = p2[0], b = p2[1], c = p2[2], d = p2[3], e = p2[4], f = p2[5];
+    q.s[0] = mk(a.x, a.y, b.x);
+    q.s[1] = mk(b.y, c.x, c.y);
+    q.s[2] = mk(d.x, d.y, e.x);
+    q.s[3] = mk(e.y, f.x, f.y);
+}
+__device__ __forceinline__ void store_q12(double* __restrict__ p, const Q12& q) {
+    double2* p2 = reinterpret_cast<double2*>(p);
+    p2[0] = make_double2(q.s[0].x, q.s[0].y);
+    p2[1] = make_double2(q.s[0].z, q.s[1].x);
+    p2[2] = make_double2(q.s[1].y, q.s[1].z);
+    p2[3] = make_double2(q.s[2].x, q.s[2].y);
+    p2[4] = make_double2(q.s[2].z, q.s[3].x);
+    p2[5] = make_double2(q.s[3].y, q.s[3].z);
+}
+
+__device__ __forceinline__ void load_constants(const WarpCtx& w, const double* __restrict__ inertia, long long gsys,
+                                               SegCtx& c, int& status) {
+    if (inertia != nullptr) {
+        inertia_to_constants(inertia + ((size_t)gsys * w.N + w.segi) * 10, c.W, c.fg, status);
+    } else {
+        const DevSeg& sg = w.seg[w.segi];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) c.W[i] = sg.W[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c.fg[i] = sg.fg[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward_dynamics(Q, Qdot) -> Qddot, lambda       (biomechanical_model.py:351-429, batched)
+// ---------------------------------------------------------------------------------------------
+template <bool HAS_FEXT>
+__global__ void __launch_bounds__(32 * kMaxWarpsPerCta)
+    forward_dynamics_kernel(const unsigned char* __restrict__ blob, int blob_bytes, const double* __restrict__ Q,
+                            const double* __restrict__ Qd, const double* __restrict__ inertia, DynOpts o,
+                            double* __restrict__ Qdd, double* __restrict__ lam, int* __restrict__ status_out,
+                            long long B) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    WarpCtx w;
+    setup_warp(blob, blob_bytes, smem, w);
+    const int warps = blockDim.x >> 5;
+    long long gsys = ((long long)blockIdx.x * warps + (threadIdx.x >> 5)) * w.spw + w.sys;
+    const bool live = w.has_seg && gsys < B;
+    if (gsys >= B) gsys = B - 1;  // tail lanes recompute the last system, stores are masked
+    const int n = 12 * w.N;
+    int status = 0;
+    SegCtx c;
+    load_constants(w, inertia, gsys, c, status);
+    Q12 q, qd, qdd;
+    load_q12(Q + (size_t)gsys * n + 12 * w.segi, q);
+    load_q12(Qd + (size_t)gsys * n + 12 * w.segi, qd);
+    double* lam_sys = (lam != nullptr && live) ? lam + (size_t)gsys * w.hdr->m : nullptr;
+    eval_forward_dynamics<HAS_FEXT>(w, c, q, qd, o, qdd, lam_sys, status);
+    if (live) {
+        store_q12(Qdd + (size_t)gsys * n + 12 * w.segi, qdd);
+        if (status_out != nullptr && status != 0) atomicOr(status_out + gsys, status);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// RK4 with the forward-dynamics closure fused in (utils/ode_solver.py:8-53, :107-120).
+// The state stays in registers for all n_steps; HBM sees one read and one write of Q, Qdot per
+// launch (plus the optional trajectory snapshots).
+// ---------------------------------------------------------------------------------------------
+template <bool HAS_FEXT>
+__global__ void __launch_bounds__(32 * kMaxWarpsPerCta)
+    rk4_kernel(const unsigned char* __restrict__ blob, int blob_bytes, double* __restrict__ Q, double* __restrict__ Qd,
+               const double* __restrict__ inertia, DynOpts o, double h_const, const double* __restrict__ h_steps,
+               long long n_steps, int normalize, double* __restrict__ traj, long long traj_every,
+               double* __restrict__ lam_last, int* __restrict__ status_out, long long B) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    WarpCtx w;
+    setup_warp(blob, blob_bytes, smem, w);
+    const int warps = blockDim.x >> 5;
+    long long gsys = ((long long)blockIdx.x * warps + (threadIdx.x >> 5)) * w.spw + w.sys;
+    const bool live = w.has_seg && gsys < B;
+    if (gsys >= B) gsys = B - 1;
+    const int n = 12 * w.N;
+    int status = 0;
+    SegCtx c;
+    load_constants(w, inertia, gsys, c, status);
+    Q12 y0q, y0v;
+    load_q12(Q + (size_t)gsys * n + 12 * w.segi, y0q);
+    load_q12(Qd + (size_t)gsys * n + 12 * w.segi, y0v);
+
+    for (long long step = 0; step < n_steps; ++step) {
+        const double h = h_steps != nullptr ? h_steps[step] : h_const;
+        const double hh = h * 0.5;
+        Q12 a, accq, accv, sq, sv;
+        double* lam_sys = (lam_last != nullptr && live && step == n_steps - 1) ? lam_last + (size_t)gsys * w.hdr->m : nullptr;
+        // k1 = f(y0)
+        eval_forward_dynamics<HAS_FEXT>(w, c, y0q, y0v, o, a, lam_sys, status);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            accq.s[t] = y0v.s[t];
+            accv.s[t] = a.s[t];
+            sq.s[t] = axpy(hh, y0v.s[t], y0q.s[t]);
+            sv.s[t] = axpy(hh, a.s[t], y0v.s[t]);
+        }
+        // k2 = f(y0 + h/2 k1)
+        eval_forward_dynamics<HAS_FEXT>(w, c, sq, sv, o, a, nullptr, status);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            accq.s[t] = axpy(2.0, sv.s[t], accq.s[t]);
+            accv.s[t] = axpy(2.0, a.s[t], accv.s[t]);
+            sq.s[t] = axpy(hh, sv.s[t], y0q.s[t]);
+            sv.s[t] = axpy(hh, a.s[t], y0v.s[t]);
+        }
+        // k3 = f(y0 + h/2 k2)
+        eval_forward_dynamics<HAS_FEXT>(w, c, sq, sv, o, a, nullptr, status);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            accq.s[t] = axpy(2.0, sv.s[t], accq.s[t]);
+            accv.s[t] = axpy(2.0, a.s[t], accv.s[t]);
+            sq.s[t] = axpy(h, sv.s[t], y0q.s[t]);
+            sv.s[t] = axpy(h, a.s[t], y0v.s[t]);
+        }
+        // k4 = f(y0 + h k3)
+        eval_forward_dynamics<HAS_FEXT>(w, c, sq, sv, o, a, nullptr, status);
+        const double h6 = h / 6.0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            y0q.s[t] = axpy(h6, accq.s[t] + sv.s[t], y0q.s[t]);
+            y0v.s[t] = axpy(h6, accv.s[t] + a.s[t], y0v.s[t]);
+        }
+        if (normalize) {  // u <- u/|u|, w <- w/|w| of Q only (ode_solver.py:50-52)
+            y0q.s[0] = (1.0 / sqrt(dot(y0q.s[0], y0q.s[0]))) * y0q.s[0];
+            y0q.s[3] = (1.0 / sqrt(dot(y0q.s[3], y0q.s[3]))) * y0q.s[3];
+        }
+        if (traj != nullptr && ((step + 1) % traj_every) == 0 && live) {
+            double* dst = traj + (((size_t)((step + 1) / traj_every - 1) * B + gsys) * 2) * n;
+            store_q12(dst + 12 * w.segi, y0q);
+            store_q12(dst + n + 12 * w.segi, y0v);
+        }
+    }
+    if (live) {
+        double chk = 0.0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) chk += dot(y0q.s[t], y0q.s[t]) + dot(y0v.s[t], y0v.s[t]);
+        if (!isfinite(chk)) status |= 2;
+        store_q12(Q + (size_t)gsys * n + 12 * w.segi, y0q);
+        store_q12(Qd + (size_t)gsys * n + 12 * w.segi, y0v);
+        if (status_out != nullptr && status != 0) atomicOr(status_out + gsys, status);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Component evaluators: Phi_r, K_r, Phi_j, K_j, Phi_h, K_h, bias_h, f_ext with dense outputs.
+// One thread per (system, item), item = segment (rigid rows / forces) or constraint block.
+// Outputs are zero-filled by the host wrapper first; these kernels are output-bandwidth bound.
+// ---------------------------------------------------------------------------------------------
+struct EvalArgs {
+    int which;
+    int N, nblk, mj, m;
+};
+
+__device__ __forceinline__ V3 glin(const double* __restrict__ X, int s, const double* a) {
+    V3 r = mk(0.0, 0.0, 0.0);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) r = axpy(a[t], mk(X[12 * s + 3 * t], X[12 * s + 3 * t + 1], X[12 * s + 3 * t + 2]), r);
+    return r;
+}
+__device__ __forceinline__ void put_row(double* __restrict__ K, int ld, int row, int seg, const double* a, V3 d, double s) {
+    double* dst = K + (size_t)row * ld + 12 * seg;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        dst[3 * t] += s * a[t] * d.x;
+        dst[3 * t + 1] += s * a[t] * d.y;
+        dst[3 * t + 2] += s * a[t] * d.z;
+    }
+}
+
+__global__ void eval_kernel(const unsigned char* __restrict__ blob, EvalArgs ea, const double* __restrict__ in,
+                            double* __restrict__ out, long long B) {
+    const DevHeader* h = reinterpret_cast<const DevHeader*>(blob);
+    const DevSeg* seg = reinterpret_cast<const DevSeg*>(blob + h->off_seg);
+    const DevBlk* blk = reinterpret_cast<const DevBlk*>(blob + h->off_blk);
+    const DevFext* fext = reinterpret_cast<const DevFext*>(blob + h->off_fext);
+    const int n = 12 * ea.N;
+    const int nitem = ea.N + ea.nblk;
+    const long long total = B * nitem;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long sys = idx / nitem;
+        const int item = (int)(idx - sys * nitem);
+        const double* X = in + (size_t)sys * n;
+        const int which = ea.which;
+        if (item < ea.N) {  // ---------------- segment items
+            const int i = item;
+            const DevSeg& sg = seg[i];
+            const V3 u = mk(X[12 * i], X[12 * i + 1], X[12 * i + 2]);
+            const V3 rp = mk(X[12 * i + 3], X[12 * i + 4], X[12 * i + 5]);
+            const V3 rd = mk(X[12 * i + 6], X[12 * i + 7], X[12 * i + 8]);
+            const V3 w = mk(X[12 * i + 9], X[12 * i + 10], X[12 * i + 11]);
+            const V3 v = rp - rd;
+            if (which == 0 || which == 4) {  // Phi_r rows
+                double* o = (which == 0) ? out + (size_t)sys * 6 * ea.N + 6 * i : out + (size_t)sys * ea.m + sg.rigid_row;
+                o[0] = dot(u, u) - 1.0;
+                o[1] = dot(u, v) - sg.phic[0];
+                o[2] = dot(u, w) - sg.phic[1];
+                o[3] = dot(v, v) - sg.phic[2];
+                o[4] = dot(v, w) - sg.phic[3];
+                o[5] = dot(w, w) - 1.0;
+            } else if (which == 6) {  // rigid bias (input is Qdot)
+                double* o = out + (size_t)sys * ea.m + sg.rigid_row;
+                o[0] = 2.0 * dot(u, u), o[1] = 2.0 * dot(u, v), o[2] = 2.0 * dot(u, w);
+                o[3] = 2.0 * dot(v, v), o[4] = 2.0 * dot(v, w), o[5] = 2.0 * dot(w, w);
+            } else if (which == 1 || which == 5) {  // K_r rows
+                double* K = (which == 1) ? out + (size_t)sys * 6 * ea.N * n : out + (size_t)sys * ea.m * n;
+                const int r0 = (which == 1) ? 6 * i : sg.rigid_row;
+                const double eu[4] = {1, 0, 0, 0}, ev[4] = {0, 1, -1, 0}, ew[4] = {0, 0, 0, 1};
+                put_row(K, n, r0 + 0, i, eu, u, 2.0);
+                put_row(K, n, r0 + 1, i, eu, v, 1.0), put_row(K, n, r0 + 1, i, ev, u, 1.0);
+                put_row(K, n, r0 + 2, i, eu, w, 1.0), put_row(K, n, r0 + 2, i, ew, u, 1.0);
+                put_row(K, n, r0 + 3, i, ev, v, 2.0);
+                put_row(K, n, r0 + 4, i, ev, w, 1.0), put_row(K, n, r0 + 4, i, ew, v, 1.0);
+                put_row(K, n, r0 + 5, i, ew, w, 2.0);
+            } else if (which == 7) {  // natural external forces
+                double* o = out + (size_t)sys * n + 12 * i;
+                SegCtx c;
+                c.u = u, c.v = v, c.w = w;
+                WarpCtx wc;
+                wc.fext = fext;
+                const Q12 f = external_forces(wc, sg, c, rp);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) o[3 * t] = f.s[t].x, o[3 * t + 1] = f.s[t].y, o[3 * t + 2] = f.s[t].z;
+            }
+        } else {  // ---------------- constraint-block items
+            if (which == 0 || which == 1 || which == 7) continue;
+            const DevBlk& b = blk[item - ea.N];
+            const double* p = b.p;
+            const bool jorder = (which == 2 || which == 3);
+            const int row = jorder ? b.row_j : b.row_h;
+            const int nrows = jorder ? ea.mj : ea.m;
+            const bool want_phi = (which == 2 || which == 4), want_K = (which == 3 || which == 5), want_b = (which == 6);
+            double* o = out + (size_t)sys * nrows;
+            double* K = out + (size_t)sys * nrows * n;
+            const V3 ex = mk(1, 0, 0), ey = mk(0, 1, 0), ez = mk(0, 0, 1);
+            if (b.type == LIN3) {
+                if (want_phi) {
+                    V3 phi = mk(p[8], p[9], p[10]) - glin(X, b.child, p + 4);
+                    if (b.parent >= 0) phi = phi + glin(X, b.parent, p);
+                    o[row] = phi.x, o[row + 1] = phi.y, o[row + 2] = phi.z;
+                } else if (want_K) {
+                    put_row(K, n, row, b.child, p + 4, ex, -1.0), put_row(K, n, row + 1, b.child, p + 4, ey, -1.0);
+                    put_row(K, n, row + 2, b.child, p + 4, ez, -1.0);
+                    if (b.parent >= 0) {
+                        put_row(K, n, row, b.parent, p, ex, 1.0), put_row(K, n, row + 1, b.parent, p, ey, 1.0);
+                        put_row(K, n, row + 2, b.parent, p, ez, 1.0);
+                    }
+                }
+            } else if (b.type == DOT) {
+                const V3 Dc = glin(X, b.child, p + 4);
+                const V3 Dp = b.parent >= 0 ? glin(X, b.parent, p) : mk(p[0], p[1], p[2]);
+                if (want_phi) o[row] = dot(Dp, Dc) - p[8];
+                if (want_K) {
+                    put_row(K, n, row, b.child, p + 4, Dp, 1.0);
+                    if (b.parent >= 0) put_row(K, n, row, b.parent, p, Dc, 1.0);
+                }
+                if (want_b) o[row] = b.parent >= 0 ? 2.0 * dot(Dp, Dc) : 0.0;  // input is Qdot
+            } else if (b.type == CLEN) {
+                const V3 d = glin(X, b.parent, p) - glin(X, b.child, p + 4);
+                if (want_phi) o[row] = dot(d, d) - p[8];
+                if (want_K) put_row(K, n, row, b.parent, p, d, 2.0), put_row(K, n, row, b.child, p + 4, d, -2.0);
+                if (want_b) o[row] = 2.0 * dot(d, d);
+            } else {  // SOP
+                const V3 P = glin(X, b.parent, p), A = glin(X, b.child, p + 4), nn = glin(X, b.child, p + 8);
+                if (want_phi) o[row] = dot(P - A, nn) - p[12];
+                if (want_K) {
+                    put_row(K, n, row, b.parent, p + 4, nn, -1.0), put_row(K, n, row, b.parent, p + 8, P - A, 1.0);
+                    put_row(K, n, row, b.child, p, nn, 1.0);
+                }
+                if (want_b) o[row] = 2.0 * dot(P, nn) - 2.0 * dot(nn, A);
+            }
+        }
+    }
+}
+
+// FP64 peak probe: nothing but dependent-chain DFMAs, 8 chains per thread
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* __restrict__ out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b), x1 = fma(x1, a, b), x2 = fma(x2, a, b), x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b), x5 = fma(x5, a, b), x6 = fma(x6, a, b), x7 = fma(x7, a, b);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+}  // namespace bionc

@@ -1,0 +1,73 @@
+// Device-side model table ("blob") shared by every kernel.
+//
+// The host lowers a BioncModelDesc (include/bionc_cuda.h) to one contiguous blob:
+//   DevHeader | DevSeg[N] | DevBlk[nblk] | DevSide[nside] | DevFext[nfext]
+// which each CTA copies into shared memory once.  Everything a lane needs about "its" segment and
+// the constraint blocks touching it is found through DevSeg::side_begin/side_end.
+#pragma once
+#include <stdint.h>
+
+namespace bionc {
+
+constexpr int kMaxSegments = 32;  // one lane per segment, one system never straddles a warp
+constexpr int kBlkNParam = 16;
+constexpr int kFextNParam = 24;
+
+enum BlkType : int { LIN3 = 0, DOT = 1, CLEN = 2, SOP = 3 };
+enum Role : int { CHILD = 0, PARENT = 1 };
+
+struct DevHeader {
+    int N;        // segments
+    int nblk;     // constraint blocks
+    int nside;    // (block, segment) incidences
+    int mj;       // joint-constraint rows
+    int m;        // holonomic rows = mj + 6 N
+    int spw;      // systems per warp = 32 / N
+    int rnl;      // max number of non-LIN3 rows touching one segment (k rows kept in shared memory)
+    int nfext;    // external forces
+    int blob_bytes;
+    int off_seg, off_blk, off_side, off_fext;  // byte offsets inside the blob
+    int pad[3];
+};
+
+struct DevSeg {
+    double W[10];    // M4^{-1}, upper triangle row-major over (u, rp, rd, w): uu ur ud uw rr rd rw dd dw ww
+    double fg[4];    // gravity: natural force on slot s is fg[s] * e_z   (natural_segment.py:562-572)
+    double phic[4];  // L cos(gamma), cos(beta), L^2, L cos(alpha)         (natural_segment.py:441-446)
+    double mcj[10];  // mass, c(3), J00 J01 J02 J11 J12 J22 (for bionc_cuda_mass_matrix / documentation)
+    int side_begin, side_end;
+    int rigid_row;  // first holonomic row of the 6 rigid-body rows
+    int fext_begin, fext_end, pad0, pad1, pad2;
+};
+
+struct DevBlk {
+    double p[kBlkNParam];
+    int type, parent, child;
+    int jrow;   // first row inside the joint-level Schur system (holonomic order without rigid rows)
+    int row_h;  // first row, holonomic order (lambda / K / Phi / bias outputs)
+    int row_j;  // first row, joint-index order (joint_constraints*)
+    int pad0, pad1;
+};
+
+struct DevSide {
+    int blk;
+    int role;     // CHILD / PARENT
+    int nl_slot;  // row slot in the lane's non-LIN3 k storage, -1 for LIN3
+    int pad;
+};
+
+struct DevFext {
+    double p[kFextNParam];  // torque(3) force(3) point(3) Tinv(9, row-major)
+    int segment, kind, pad0, pad1;
+};
+
+// Per-warp shared-memory working set, in doubles (see dynamics.cuh for the layout).
+__host__ __device__ inline int warp_smem_doubles(int N, int mj, int spw, int rnl) {
+    const int tri = mj * (mj + 1) / 2;
+    return 2 * 12 * N * spw      // published Q, Qdot of the current stage
+           + 2 * tri * spw       // two exclusive-writer copies of the joint-level Schur matrix
+           + 3 * mj * spw        // rhs copy 0 / copy 1 (-> y-hat), dinv
+           + rnl * 12 * 32;      // k rows of non-LIN3 blocks, private per lane
+}
+
+}  // namespace bionc

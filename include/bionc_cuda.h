@@ -1,0 +1,145 @@
+/*
+ * bionc_cuda.h -- C ABI of the B200 (sm_100a, FP64) constrained forward-dynamics backend.
+ *
+ * The reference (Ipuch/bioNC) is pure Python and has no FFI of its own; the boundary this library
+ * sits behind is the backend-subpackage convention (bionc/bionc_numpy/__init__.py:1-27).  Each
+ * entry point below names the reference method it replaces.  All pointers in the "device" entry
+ * points are CUDA device pointers owned by the caller (PyTorch tensors on the Python side); the
+ * library allocates only the immutable model table.  The "_host" entry points take host pointers
+ * and do the host<->device copies themselves (the end-to-end path a non-PyTorch caller binds).
+ *
+ * Every function returns 0 on success or a negative BIONC_E_* code; no exception crosses the ABI.
+ * Arrays are FP64, C-contiguous, batch-major: Q, Qdot, Qddot (B, 12 N); lambda (B, m) in the
+ * holonomic row order of bionc/bionc_numpy/biomechanical_model.py:154-258.
+ */
+#ifndef BIONC_CUDA_H
+#define BIONC_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BIONC_OK 0
+#define BIONC_E_INVALID -1   /* bad argument / malformed model description */
+#define BIONC_E_CUDA -2      /* a CUDA runtime call failed (see bionc_cuda_last_error) */
+#define BIONC_E_TOO_LARGE -3 /* model does not fit the per-SM shared memory budget of the kernels */
+
+/* primitive constraint-block kinds (bionc_b200/bionc_cuda/model_table.py) */
+#define BIONC_BLK_LIN3 0
+#define BIONC_BLK_DOT 1
+#define BIONC_BLK_CLEN 2
+#define BIONC_BLK_SOP 3
+#define BIONC_BLK_NPARAM 16
+
+/* external-force kinds (bionc/bionc_numpy/external_force*.py) */
+#define BIONC_FEXT_GLOBAL_ON_PROXIMAL 0
+#define BIONC_FEXT_GLOBAL_LOCAL_POINT 1
+#define BIONC_FEXT_GLOBAL 2
+#define BIONC_FEXT_LOCAL 3
+#define BIONC_FEXT_NPARAM 24 /* torque(3) force(3) point(3) Tinv(9) pad(6) */
+
+/* per-system status bits written by forward_dynamics / rk4 */
+#define BIONC_STATUS_OK 0
+#define BIONC_STATUS_SINGULAR 1  /* zero or non-finite pivot (reference: numpy.linalg.LinAlgError) */
+#define BIONC_STATUS_NONFINITE 2 /* non-finite state or acceleration */
+
+/* which quantity bionc_cuda_eval computes */
+#define BIONC_EVAL_PHI_R 0  /* rigid_body_constraints(Q)                 -> (B, 6N)      biomechanical_model_segments.py:26-42 */
+#define BIONC_EVAL_K_R 1    /* rigid_body_constraints_jacobian(Q)        -> (B, 6N, 12N) biomechanical_model_segments.py:62-79 */
+#define BIONC_EVAL_PHI_J 2  /* joint_constraints(Q)                      -> (B, mj)      biomechanical_model_joints.py:13-41 */
+#define BIONC_EVAL_K_J 3    /* joint_constraints_jacobian(Q)             -> (B, mj, 12N) biomechanical_model_joints.py:43-77 */
+#define BIONC_EVAL_PHI_H 4  /* holonomic_constraints(Q)                  -> (B, m)       biomechanical_model.py:154-197 */
+#define BIONC_EVAL_K_H 5    /* holonomic_constraints_jacobian(Q)         -> (B, m, 12N)  biomechanical_model.py:199-258 */
+#define BIONC_EVAL_BIAS_H 6 /* holonomic_constraints_acceleration_bias(Qdot) -> (B, m)   biomechanical_model.py:260-317 */
+#define BIONC_EVAL_FEXT 7   /* ExternalForceSet.to_natural_external_forces(Q) -> (B, 12N) external_force.py:143-166 */
+
+/* Flat model description: the arrays of a compiled ModelTable (host pointers, copied at create). */
+typedef struct BioncModelDesc {
+    int32_t nb_segments;         /* N */
+    int32_t nb_blocks;           /* constraint blocks */
+    const double* seg_phi_const; /* (N, 4)  [L cos(gamma), cos(beta), L^2, L cos(alpha)]  natural_segment.py:441-446 */
+    const double* seg_mass;      /* (N)                                                                             */
+    const double* seg_com;       /* (N, 3)  natural centre of mass                                                  */
+    const double* seg_J;         /* (N, 9)  natural pseudo-inertia   natural_inertial_parameters.py:153-177         */
+    const int32_t* seg_rigid_row;/* (N)     first holonomic row of the segment's 6 rigid-body rows                  */
+    const int32_t* blk_type;     /* (nblk)  BIONC_BLK_*                                                              */
+    const int32_t* blk_parent;   /* (nblk)  -1 = ground                                                              */
+    const int32_t* blk_child;    /* (nblk)                                                                           */
+    const int32_t* blk_row_h;    /* (nblk)  first row, holonomic order                                               */
+    const int32_t* blk_row_j;    /* (nblk)  first row, joint-index order                                             */
+    const double* blk_param;     /* (nblk, BIONC_BLK_NPARAM)                                                         */
+} BioncModelDesc;
+
+/* External forces shared by every system of the batch (ExternalForceSet, external_force.py:13-180). */
+typedef struct BioncFextDesc {
+    int32_t nb_forces;
+    const int32_t* segment; /* (F) */
+    const int32_t* kind;    /* (F) BIONC_FEXT_* */
+    const double* param;    /* (F, BIONC_FEXT_NPARAM), torque first (external_force.py:84-85) */
+} BioncFextDesc;
+
+/* Options common to forward_dynamics and rk4. */
+typedef struct BioncDynOptions {
+    int32_t use_stabilization; /* Baumgarte, biomechanical_model.py:416-421 */
+    double alpha, beta;
+    const BioncFextDesc* fext; /* NULL = none (HOST pointers inside; uploaded per call, a few hundred bytes) */
+    /* optional per-system natural inertial parameters (device for the device entry points, host
+     * for the _host ones): (B, N, 10) = [mass, c0, c1, c2, J00, J01, J02, J11, J12, J22]; NULL = use
+     * the model's own (config 5: "perturbed inertial parameters") */
+    const double* inertia;
+} BioncDynOptions;
+
+typedef struct BioncModel BioncModel;
+
+/* replaces BiomechanicalModel construction / to_mx() (bionc_numpy/biomechanical_model.py:43-75) */
+int bionc_cuda_model_create(const BioncModelDesc* desc, int device, BioncModel** out);
+int bionc_cuda_model_destroy(BioncModel* model);
+/* counts of protocols/biomechanical_model.py:347-453 */
+int bionc_cuda_model_counts(const BioncModel* model, int32_t* nb_segments, int32_t* nb_joint_constraints,
+                            int32_t* nb_holonomic_constraints);
+
+/* replaces BiomechanicalModel.forward_dynamics (bionc_numpy/biomechanical_model.py:351-429), batched.
+ * lambda and status may be NULL. */
+int bionc_cuda_forward_dynamics(const BioncModel* model, const double* Q, const double* Qdot,
+                                const BioncDynOptions* opt, double* Qddot, double* lambda, int32_t* status,
+                                int64_t B, void* stream);
+
+/* replaces RK4 + the dynamics closure of forward_integration (utils/ode_solver.py:8-53, :107-120),
+ * all four stages fused, n_steps steps per launch, in place on Q / Qdot.
+ *   h_steps : device array of n_steps step sizes (h = t[i+1]-t[i], ode_solver.py:41) or NULL -> constant h
+ *   normalize: post-step renormalisation of u, w (model.normalized_coordinates, ode_solver.py:50-52)
+ *   traj / traj_every: if traj != NULL the state [Q; Qdot] is also written after every
+ *       traj_every-th step to traj[(step/traj_every - 1), b, 0:24N]  (n_steps / traj_every snapshots)
+ *   lambda_last: (B, m) multipliers of the first stage of the last step, or NULL */
+int bionc_cuda_rk4(const BioncModel* model, double* Q, double* Qdot, double h, const double* h_steps,
+                   int64_t n_steps, int32_t normalize, const BioncDynOptions* opt, double* traj,
+                   int64_t traj_every, double* lambda_last, int32_t* status, int64_t B, void* stream);
+
+/* component evaluators (the mass_matrix / *_constraints* / *_jacobian API); `in` is Q or Qdot */
+int bionc_cuda_eval(const BioncModel* model, int32_t which, const double* in, const BioncDynOptions* opt,
+                    double* out, int64_t B, void* stream);
+/* BiomechanicalModel.mass_matrix (protocols/biomechanical_model.py:455-466): host output (12N, 12N) */
+int bionc_cuda_mass_matrix(const BioncModel* model, double* G_host);
+
+/* host-buffer variants: H2D, kernel, D2H on an internal stream, synchronous on return */
+int bionc_cuda_forward_dynamics_host(BioncModel* model, const double* Q, const double* Qdot,
+                                     const BioncDynOptions* opt, double* Qddot, double* lambda, int32_t* status,
+                                     int64_t B);
+int bionc_cuda_rk4_host(BioncModel* model, double* Q, double* Qdot, double h, const double* h_steps,
+                        int64_t n_steps, int32_t normalize, const BioncDynOptions* opt, int32_t* status, int64_t B);
+
+/* FP64 roofline denominator: DFMA-only micro-benchmark timed with CUDA events (best single launch and
+ * the average over `repeats` back-to-back launches), in TFLOP/s */
+int bionc_cuda_measure_fp64_peak(int device, int repeats, double* tflops_best, double* tflops_sustained);
+
+/* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
+int64_t bionc_cuda_launch_count(void);
+const char* bionc_cuda_last_error(void);
+const char* bionc_cuda_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIONC_CUDA_H */

@@ -137,7 +137,12 @@ def integrate(model, Q, Qdot, t, normalize, fext=None):
     return np.array(finals), np.array(mids)
 
 
+ONLY = set(sys.argv[1:])
+
+
 def write_case(name, model, Q, Qdot, fext=None, traj=None, extra=None):
+    if ONLY and name not in ONLY:
+        return None
     t0 = time.time()
     table = ModelTable.from_numpy(model)
     table.save(os.path.join(OUT_MODELS, name + ".npz"))
@@ -260,8 +265,8 @@ FULL_BODY_SEGMENTS = [
     ("L_SHANK", "L_THIGH", (0.3531, 1.8364, np.pi / 2, np.pi / 2), (3.6, (0, -0.10, 0), (0.040, 0.020, 0.040)), None),
     ("L_FOOT", "L_SHANK", (0.1389, 1.7427, 1.4427, 2.8024), (0.9, (0.02, -0.03, 0), (0.0040, 0.0045, 0.0045)), None),
     ("THORAX", "PELVIS", (0.45, np.pi / 2, np.pi / 2, np.pi / 2), (25.0, (0, 0.20, 0), (0.60, 0.30, 0.60)), (0.0, 0.10, 0.0)),
-    ("R_ARM", "THORAX", (0.30, np.pi / 2, np.pi / 2, np.pi / 2), (2.1, (0, -0.13, 0), (0.020, 0.008, 0.020)), (0.0, -0.9, 0.20)),
-    ("R_FOREARM", "R_ARM", (0.27, np.pi / 2, np.pi / 2, np.pi / 2), (1.2, (0, -0.11, 0), (0.008, 0.003, 0.008)), None),
+    ("R_ARM", "THORAX", (0.30, np.pi / 2, np.pi / 2, np.pi / 2), (2.1, (0, -0.08, 0), (0.060, 0.012, 0.060)), (0.0, -0.9, 0.20)),
+    ("R_FOREARM", "R_ARM", (0.27, np.pi / 2, np.pi / 2, np.pi / 2), (1.2, (0, -0.04, 0), (0.030, 0.005, 0.030)), None),
 ]
 
 
