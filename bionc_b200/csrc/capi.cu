@@ -169,6 +169,8 @@ int build_blob(BioncModel* M, const BioncFextDesc* fx) {
 template <typename K>
 int ensure_smem(K kernel, size_t bytes) {
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    // as much shared memory as the SM has: residency is limited by the per-warp working sets
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return BIONC_OK;
 }
 
@@ -187,6 +189,10 @@ int prepare(BioncModel* M, const BioncDynOptions* opt, DynOpts& o) {
     }
     return BIONC_OK;
 }
+
+// the lean kernel instantiation covers models made of point-to-point (LIN3) blocks only, without
+// external forces or Baumgarte stabilisation; everything else takes the general one
+bool needs_general(const BioncModel* M, const DynOpts& o) { return M->hdr.rnl > 0 || M->hdr.nfext > 0 || o.use_stab != 0; }
 
 unsigned grid_for(const BioncModel* M, long long B) {
     const long long per_cta = (long long)M->warps_per_cta * M->hdr.spw;
@@ -308,7 +314,7 @@ int bionc_cuda_forward_dynamics(const BioncModel* Mc, const double* Q, const dou
     if (status != nullptr) CUDA_TRY(cudaMemsetAsync(status, 0, B * sizeof(int32_t), st));
     const double* inertia = opt != nullptr ? opt->inertia : nullptr;
     const unsigned grid = grid_for(M, B), block = 32 * M->warps_per_cta;
-    if (M->hdr.nfext > 0)
+    if (needs_general(M, o))
         forward_dynamics_kernel<true><<<grid, block, M->smem_bytes, st>>>(M->d_blob, M->blob_bytes, Q, Qd, inertia, o, Qdd, lam, status, B);
     else
         forward_dynamics_kernel<false><<<grid, block, M->smem_bytes, st>>>(M->d_blob, M->blob_bytes, Q, Qd, inertia, o, Qdd, lam, status, B);
@@ -333,7 +339,7 @@ int bionc_cuda_rk4(const BioncModel* Mc, double* Q, double* Qd, double h, const 
     const double* inertia = opt != nullptr ? opt->inertia : nullptr;
     const unsigned grid = grid_for(M, B), block = 32 * M->warps_per_cta;
     if (traj == nullptr) traj_every = 1;
-    if (M->hdr.nfext > 0)
+    if (needs_general(M, o))
         rk4_kernel<true><<<grid, block, M->smem_bytes, st>>>(M->d_blob, M->blob_bytes, Q, Qd, inertia, o, h, h_steps, n_steps,
                                                              normalize, traj, traj_every, lam_last, status, B);
     else

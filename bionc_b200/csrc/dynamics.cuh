@@ -313,9 +313,22 @@ __device__ __forceinline__ Q12 external_forces(const WarpCtx& w, const DevSeg& s
     return f;
 }
 
+// this lane's own segment, slot t, from the published stage state
+__device__ __forceinline__ V3 own3(const WarpCtx& w, const double* X, int t) {
+    const int o = (12 * w.segi + 3 * t) * w.spw + w.sys;
+    return mk(X[o], X[o + w.spw], X[o + 2 * w.spw]);
+}
+__device__ __forceinline__ void publish3(const WarpCtx& w, double* X, int t, V3 v) {
+    const int o = (12 * w.segi + 3 * t) * w.spw + w.sys;
+    X[o] = v.x, X[o + w.spw] = v.y, X[o + 2 * w.spw] = v.z;
+}
+
 // rigid-body right-hand side term: bias_r (+ alpha Phi_r + beta Kr Qdot)   (natural_segment.py:429-448, :508-545)
-__device__ __forceinline__ void rigid_bterm(const SegCtx& c, const DevSeg& sg, const Q12& Qd, const DynOpts& o,
+__device__ __forceinline__ void rigid_bterm(const WarpCtx& w, const SegCtx& c, const DevSeg& sg, const DynOpts& o,
                                             double (&b)[6]) {
+    Q12 Qd;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) Qd.s[t] = own3(w, w.Qds, t);
     const V3 ud = Qd.s[0], vd = Qd.s[1] - Qd.s[2], wd = Qd.s[3];
     b[0] = 2.0 * dot(ud, ud);
     b[1] = 2.0 * dot(ud, vd);
@@ -333,33 +346,75 @@ __device__ __forceinline__ void rigid_bterm(const SegCtx& c, const DevSeg& sg, c
     }
 }
 
+// three right-hand sides at once (the three rows of a LIN3 block): 3-way instruction-level parallelism
+__device__ __forceinline__ void sr_solve3(const SegCtx& c, double (&y)[6][3]) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+#pragma unroll
+        for (int r = k + 1; r < 6; ++r)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) y[r][j] = fma(-c.L[lidx(r, k)], y[k][j], y[r][j]);
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) y[k][j] *= c.dinv[k];
+#pragma unroll
+    for (int k = 5; k >= 0; --k)
+#pragma unroll
+        for (int r = k + 1; r < 6; ++r)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) y[k][j] = fma(-c.L[lidx(r, k)], y[r][j], y[k][j]);
+}
+
+// signed coefficient vector of a LIN3 block restricted to one side: rows are  as (x) e_c
+__device__ __forceinline__ void lin3_coefs(const DevBlk& b, int role, double (&as)[4]) {
+    const double* a = b.p + (role == CHILD ? 4 : 0);
+    const double sgn = role == CHILD ? -1.0 : 1.0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) as[t] = sgn * a[t];
+}
+// beta = W as, and its (u, v, w) reduction b3 = E^T beta with E = [e_u, e_rp - e_rd, e_w]
+__device__ __forceinline__ void lin3_beta(const SegCtx& c, const double (&as)[4], double (&beta)[4], double (&b3)[3]) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        double acc = 0.0;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) acc = fma(c.W[widx(t, s)], as[s], acc);
+        beta[t] = acc;
+    }
+    b3[0] = beta[0], b3[1] = beta[1] - beta[2], b3[2] = beta[3];
+}
+
 // ---------------------------------------------------------------------------------------------
-// One forward-dynamics evaluation for the whole warp.  Every lane passes its segment's Q, Qdot
-// (slots u, rp, rd, w) and receives Qddot; lambda (holonomic order) is written to lam_out if non-null.
-// All 32 lanes must call this (it contains __syncwarp); lanes without a segment pass has_seg=false.
+// One forward-dynamics evaluation for the whole warp.
+// Precondition: every lane has published its segment's stage state (Q, Qdot) in w.Qs / w.Qds.
+// Every lane receives Qddot of its segment; lambda (holonomic order) goes to lam_out if non-null.
+// All 32 lanes must call this (it contains __syncwarp); lanes without a segment have has_seg=false.
+//
+// GENERAL=false is the lean instantiation for models whose joints are all point-to-point (LIN3:
+// spherical / ground spherical / weld halves), without external forces or stabilisation -- the
+// lower-limb and full-body trees.  GENERAL=true handles everything.
+//
+// For two LIN3 block sides a, b on one segment (rows as_a (x) e_c', as_b (x) e_c) the contribution to
+// the joint-level Schur complement has the closed form
+//     S'_ab = (as_a . W as_b) I3 - B M_ab B^T,   M_ab = Gamma(a3)^T Sr^-1 Gamma(b3),   B = [u v w]
+// with Gamma(b3) the 6x3 matrix [[2bu,0,0],[bv,bu,0],[bw,0,bu],[0,2bv,0],[0,bw,bv],[0,0,2bw]]
+// (Kr G^-1 (as_b (x) e_c)^T = Gamma(b3) B[c,:]^T), so the three rows of a block share one
+// three-right-hand-side solve Z_b = Sr^-1 Gamma(b3).
 // ---------------------------------------------------------------------------------------------
-template <bool HAS_FEXT>
-__device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& c, const Q12& Q, const Q12& Qd,
-                                                      const DynOpts& o, Q12& Qdd, double* lam_out, int& status) {
+template <bool GENERAL>
+__device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& c, const DynOpts& o, Q12& Qdd,
+                                                      double* lam_out, int& status) {
     const int spw = w.spw, sys = w.sys;
     const DevSeg& sg = w.seg[w.segi];
-    const bool two_seg = w.N > 1 || w.mj > 0;
 
-    // ---- A. publish the stage state
-    if (w.has_seg && two_seg) {
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const int ob = (12 * w.segi + 3 * t) * spw + sys;
-            w.Qs[ob] = Q.s[t].x, w.Qs[ob + spw] = Q.s[t].y, w.Qs[ob + 2 * spw] = Q.s[t].z;
-            w.Qds[ob] = Qd.s[t].x, w.Qds[ob + spw] = Qd.s[t].y, w.Qds[ob + 2 * spw] = Qd.s[t].z;
-        }
-    }
-    // ---- B. segment-local factorisation and free acceleration
-    c.u = Q.s[0], c.v = Q.s[1] - Q.s[2], c.w = Q.s[3];
+    // ---- B. segment-local factorisation
+    const V3 rp = own3(w, w.Qs, 1);
+    c.u = own3(w, w.Qs, 0), c.v = rp - own3(w, w.Qs, 2), c.w = own3(w, w.Qs, 3);
     sr_factor(c, status);
     Q12 f;  // natural forces: gravity + external
-    if (HAS_FEXT) {
-        f = external_forces(w, sg, c, Q.s[1]);
+    if (GENERAL && sg.fext_end > sg.fext_begin) {
+        f = external_forces(w, sg, c, rp);
     } else {
 #pragma unroll
         for (int t = 0; t < 4; ++t) f.s[t] = mk(0.0, 0.0, 0.0);
@@ -367,238 +422,259 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
 #pragma unroll
     for (int t = 0; t < 4; ++t) f.s[t].z += c.fg[t];
     double br[6];
-    rigid_bterm(c, sg, Qd, o, br);
-    Q12 abar;
-    {
-        const Q12 a0 = apply_W(c.W, f);
+    DynOpts oo = o;
+    if (!GENERAL) oo.use_stab = 0;
+    rigid_bterm(w, c, sg, oo, br);
+
+    // Two passes over the same segment solve  x = A_i f + (particular part):
+    //   pass 0 with f = applied forces gives the free acceleration abar that feeds the joint-level system,
+    //   pass 1 with f - Kj^T lambda_j gives Qddot and lambda_r.
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        Q12 x;
         double z[6];
-        kr_apply(c, a0, z);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) z[i] += br[i];
-        sr_solve(c, z);
-        const Q12 corr = ginv_krt(c, z);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) abar.s[t] = a0.s[t] - corr.s[t];
-    }
-    if (w.mj == 0) {  // no joint rows at all (free bodies): abar is the answer
-        Qdd = abar;
-        if (lam_out != nullptr && w.has_seg) {
-            // lambda_r = Sr^-1 (Kr a0 + b) was z; recompute cheaply
-            const Q12 a0 = apply_W(c.W, f);
-            double z[6];
-            kr_apply(c, a0, z);
+        {
+            const Q12 a = apply_W(c.W, f);
+            kr_apply(c, a, z);
 #pragma unroll
             for (int i = 0; i < 6; ++i) z[i] += br[i];
             sr_solve(c, z);
+            const Q12 corr = ginv_krt(c, z);
 #pragma unroll
-            for (int i = 0; i < 6; ++i) lam_out[sg.rigid_row + i] = z[i];
+            for (int t = 0; t < 4; ++t) x.s[t] = a.s[t] - corr.s[t];
         }
-        return;
-    }
-
-    // ---- C. zero the joint-level system (cooperatively by the lanes of the system)
-    if (w.has_seg) {
-        for (int it = w.segi; it < w.tri; it += w.N) w.S0[it * spw + sys] = 0.0, w.S1[it * spw + sys] = 0.0;
-        for (int it = w.segi; it < w.mj; it += w.N) w.r0[it * spw + sys] = 0.0, w.r1[it * spw + sys] = 0.0;
-    }
-    __syncwarp();
-
-    // ---- D. pre-pass over the blocks touching this segment: right-hand side rhs' = Kj abar + b_j
-    //         (copy `role` of each row is written by exactly one lane) and explicit rows of non-LIN3 blocks
-    if (w.has_seg) {
-        for (int e = sg.side_begin; e < sg.side_end; ++e) {
-            const DevSide sd = w.side[e];
-            const DevBlk& b = w.blk[sd.blk];
-            double* rr = sd.role == CHILD ? w.r0 : w.r1;
-            if (b.type == LIN3) {
-                const double* a = b.p + (sd.role == CHILD ? 4 : 0);
-                const double sgn = sd.role == CHILD ? -1.0 : 1.0;
-                V3 r = mk(0.0, 0.0, 0.0);
+        if (pass == 1 || w.mj == 0) {
+            Qdd = x;
+            if (lam_out != nullptr && w.has_seg) {
 #pragma unroll
-                for (int t = 0; t < 4; ++t) r = axpy(sgn * a[t], abar.s[t], r);
-                if (sd.role == CHILD && o.use_stab) {
-                    // Phi = c0 + N_p Q_p - N_c Q_c ; K Qdot = N_p Qdot_p - N_c Qdot_c
-                    V3 phi = mk(b.p[8], b.p[9], b.p[10]) - lin_form(w, w.Qs, b.child, b.p + 4);
-                    V3 kqd = mk(0.0, 0.0, 0.0) - lin_form(w, w.Qds, b.child, b.p + 4);
-                    if (b.parent >= 0) {
-                        phi = phi + lin_form(w, w.Qs, b.parent, b.p);
-                        kqd = kqd + lin_form(w, w.Qds, b.parent, b.p);
+                for (int i = 0; i < 6; ++i) lam_out[sg.rigid_row + i] = z[i];  // lambda_r
+            }
+            break;
+        }
+
+        // ---- C. zero the joint-level system (cooperatively by the lanes of the system)
+        if (w.has_seg) {
+            for (int it = w.segi; it < w.tri; it += w.N) w.S0[it * spw + sys] = 0.0, w.S1[it * spw + sys] = 0.0;
+            for (int it = w.segi; it < w.mj; it += w.N) w.r0[it * spw + sys] = 0.0, w.r1[it * spw + sys] = 0.0;
+        }
+        __syncwarp();
+
+        // ---- D. right-hand side rhs' = Kj abar + b_j (copy `role` of each row is written by exactly one
+        //         lane) and the explicit rows of non-LIN3 blocks
+        if (w.has_seg) {
+            for (int e = sg.side_begin; e < sg.side_end; ++e) {
+                const DevSide sd = w.side[e];
+                const DevBlk& b = w.blk[sd.blk];
+                double* rr = sd.role == CHILD ? w.r0 : w.r1;
+                if (!GENERAL || b.type == LIN3) {
+                    double as[4];
+                    lin3_coefs(b, sd.role, as);
+                    V3 r = mk(0.0, 0.0, 0.0);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) r = axpy(as[t], x.s[t], r);
+                    if (GENERAL && sd.role == CHILD && o.use_stab) {
+                        // Phi = c0 + N_p Q_p - N_c Q_c ; K Qdot = N_p Qdot_p - N_c Qdot_c
+                        V3 phi = mk(b.p[8], b.p[9], b.p[10]) - lin_form(w, w.Qs, b.child, b.p + 4);
+                        V3 kqd = mk(0.0, 0.0, 0.0) - lin_form(w, w.Qds, b.child, b.p + 4);
+                        if (b.parent >= 0) {
+                            phi = phi + lin_form(w, w.Qs, b.parent, b.p);
+                            kqd = kqd + lin_form(w, w.Qds, b.parent, b.p);
+                        }
+                        r = axpy(o.alpha, phi, axpy(o.beta, kqd, r));
                     }
-                    r = axpy(o.alpha, phi, axpy(o.beta, kqd, r));
-                }
-                rr[(b.jrow + 0) * spw + sys] = r.x;
-                rr[(b.jrow + 1) * spw + sys] = r.y;
-                rr[(b.jrow + 2) * spw + sys] = r.z;
-            } else {
-                Q12 k;
-                double bterm;
-                nonlin_row(w, b, sd.role, o, k, bterm);
-                double acc = bterm;
+                    rr[(b.jrow + 0) * spw + sys] = r.x;
+                    rr[(b.jrow + 1) * spw + sys] = r.y;
+                    rr[(b.jrow + 2) * spw + sys] = r.z;
+                } else {
+                    Q12 k;
+                    double bterm;
+                    nonlin_row(w, b, sd.role, o, k, bterm);
+                    double acc = bterm;
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    acc += dot(k.s[t], abar.s[t]);
-                    double* dst = w.knl + (sd.nl_slot * 12 + 3 * t) * 32 + w.lane;
-                    dst[0] = k.s[t].x, dst[32] = k.s[t].y, dst[64] = k.s[t].z;
+                    for (int t = 0; t < 4; ++t) {
+                        acc += dot(k.s[t], x.s[t]);
+                        double* dst = w.knl + (sd.nl_slot * 12 + 3 * t) * 32 + w.lane;
+                        dst[0] = k.s[t].x, dst[32] = k.s[t].y, dst[64] = k.s[t].z;
+                    }
+                    rr[b.jrow * spw + sys] = acc;
                 }
-                rr[b.jrow * spw + sys] = acc;
             }
         }
-    }
 
-    // ---- E. S' contributions of this segment: for every pair of rows (a >= b) touching it, k_a . q'_b
-    if (w.has_seg) {
-        for (int e = sg.side_begin; e < sg.side_end; ++e) {
-            const DevSide sd = w.side[e];
-            const DevBlk& b = w.blk[sd.blk];
-            const int nrow_b = b.type == LIN3 ? 3 : 1;
-            double beta4[4];  // LIN3: W (sgn alpha)
-            Q12 kb;           // non-LIN3: explicit row
-            if (b.type == LIN3) {
-                const double* a = b.p + (sd.role == CHILD ? 4 : 0);
-                const double sgn = sd.role == CHILD ? -1.0 : 1.0;
+        // ---- E1. LIN3 x LIN3 pairs on this segment: S'_ab = gamma I3 - B M_ab B^T
+        if (w.has_seg) {
+            for (int e = sg.side_begin; e < sg.side_end; ++e) {
+                const DevSide sd = w.side[e];
+                const DevBlk& b = w.blk[sd.blk];
+                if (GENERAL && b.type != LIN3) continue;
+                double asb[4], betab[4], b3[3];
+                lin3_coefs(b, sd.role, asb);
+                lin3_beta(c, asb, betab, b3);
+                double Z[6][3];  // Sr^-1 Gamma(b3)
+                Z[0][0] = 2.0 * b3[0], Z[0][1] = 0.0, Z[0][2] = 0.0;
+                Z[1][0] = b3[1], Z[1][1] = b3[0], Z[1][2] = 0.0;
+                Z[2][0] = b3[2], Z[2][1] = 0.0, Z[2][2] = b3[0];
+                Z[3][0] = 0.0, Z[3][1] = 2.0 * b3[1], Z[3][2] = 0.0;
+                Z[4][0] = 0.0, Z[4][1] = b3[2], Z[4][2] = b3[1];
+                Z[5][0] = 0.0, Z[5][1] = 0.0, Z[5][2] = 2.0 * b3[2];
+                sr_solve3(c, Z);
+                for (int e2 = e; e2 < sg.side_end; ++e2) {
+                    const DevSide sa = w.side[e2];
+                    const DevBlk& a = w.blk[sa.blk];
+                    if (GENERAL && a.type != LIN3) continue;
+                    double asa[4], betaa[4], a3[3];
+                    lin3_coefs(a, sa.role, asa);
+                    lin3_beta(c, asa, betaa, a3);
+                    double gamma = 0.0;
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    double acc = 0.0;
+                    for (int t = 0; t < 4; ++t) gamma = fma(asa[t], betab[t], gamma);
+                    // M = Gamma(a3)^T Z (3x3), P = B M (columns), block = gamma I - P B^T
+                    V3 Pc[3];
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) acc = fma(c.W[widx(t, s)], a[s], acc);
-                    beta4[t] = sgn * acc;
+                    for (int j = 0; j < 3; ++j) {
+                        const double m0 = fma(2.0 * a3[0], Z[0][j], fma(a3[1], Z[1][j], a3[2] * Z[2][j]));
+                        const double m1 = fma(a3[0], Z[1][j], fma(2.0 * a3[1], Z[3][j], a3[2] * Z[4][j]));
+                        const double m2 = fma(a3[0], Z[2][j], fma(a3[1], Z[4][j], (2.0 * a3[2]) * Z[5][j]));
+                        Pc[j] = axpy(m0, c.u, axpy(m1, c.v, m2 * c.w));
+                    }
+                    // entry (row c' of a, row cc of b) = gamma delta - sum_j Pc[j][c'] * B[cc][j],  B[cc] = (u_cc, v_cc, w_cc)
+                    double* Sc = sa.role == CHILD ? w.S0 : w.S1;
+                    const bool same = (e2 == e);
+                    const V3 col0 = mk(0, 0, 0) - axpy(c.u.x, Pc[0], axpy(c.v.x, Pc[1], c.w.x * Pc[2]));  // cc = 0
+                    const V3 col1 = mk(0, 0, 0) - axpy(c.u.y, Pc[0], axpy(c.v.y, Pc[1], c.w.y * Pc[2]));  // cc = 1
+                    const V3 col2 = mk(0, 0, 0) - axpy(c.u.z, Pc[0], axpy(c.v.z, Pc[1], c.w.z * Pc[2]));  // cc = 2
+                    const int ra = a.jrow, rb = b.jrow;
+                    Sc[tidx(ra + 0, rb + 0) * spw + sys] = col0.x + gamma;
+                    Sc[tidx(ra + 1, rb + 0) * spw + sys] = col0.y;
+                    Sc[tidx(ra + 2, rb + 0) * spw + sys] = col0.z;
+                    if (!same) Sc[tidx(ra + 0, rb + 1) * spw + sys] = col1.x;
+                    Sc[tidx(ra + 1, rb + 1) * spw + sys] = col1.y + gamma;
+                    Sc[tidx(ra + 2, rb + 1) * spw + sys] = col1.z;
+                    if (!same) Sc[tidx(ra + 0, rb + 2) * spw + sys] = col2.x;
+                    if (!same) Sc[tidx(ra + 1, rb + 2) * spw + sys] = col2.y;
+                    Sc[tidx(ra + 2, rb + 2) * spw + sys] = col2.z + gamma;
                 }
-            } else {
+            }
+        }
+
+        // ---- E2. pairs with at least one non-LIN3 row: explicit q' = A_i k_b^T of the non-LIN3 row b
+        if (GENERAL && w.has_seg) {
+            for (int e = sg.side_begin; e < sg.side_end; ++e) {
+                const DevSide sd = w.side[e];
+                const DevBlk& b = w.blk[sd.blk];
+                if (b.type == LIN3) continue;
+                Q12 kb, q;
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     const double* src = w.knl + (sd.nl_slot * 12 + 3 * t) * 32 + w.lane;
                     kb.s[t] = mk(src[0], src[32], src[64]);
                 }
-            }
-            for (int rb = 0; rb < nrow_b; ++rb) {
-                // q = G^-1 k_b^T, cvec = Kr q
-                Q12 q;
-                double y[6];
-                if (b.type == LIN3) {
-                    const double uc = comp(c.u, rb), vc = comp(c.v, rb), wc = comp(c.w, rb);
-                    const double bu = beta4[0], bv = beta4[1] - beta4[2], bw = beta4[3];
-                    y[0] = 2.0 * uc * bu;
-                    y[1] = fma(vc, bu, uc * bv);
-                    y[2] = fma(wc, bu, uc * bw);
-                    y[3] = 2.0 * vc * bv;
-                    y[4] = fma(wc, bv, vc * bw);
-                    y[5] = 2.0 * wc * bw;
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) q.s[t] = unit(rb, beta4[t]);
-                } else {
+                {
+                    double y[6];
                     q = apply_W(c.W, kb);
                     kr_apply(c, q, y);
-                }
-                sr_solve(c, y);
-                const Q12 corr = ginv_krt(c, y);
+                    sr_solve(c, y);
+                    const Q12 corr = ginv_krt(c, y);
 #pragma unroll
-                for (int t = 0; t < 4; ++t) q.s[t] = q.s[t] - corr.s[t];  // q' = A_i k_b^T
-                const int row_b = b.jrow + rb;
-                // inner loop over the blocks a at or after b in this segment's (jrow-sorted) list
-                for (int e2 = e; e2 < sg.side_end; ++e2) {
+                    for (int t = 0; t < 4; ++t) q.s[t] = q.s[t] - corr.s[t];
+                }
+                for (int e2 = sg.side_begin; e2 < sg.side_end; ++e2) {
                     const DevSide sa = w.side[e2];
                     const DevBlk& a = w.blk[sa.blk];
-                    double* Sc = sa.role == CHILD ? w.S0 : w.S1;
+                    // the copy is chosen by this lane's role in the block holding the larger row
                     if (a.type == LIN3) {
-                        const double* al = a.p + (sa.role == CHILD ? 4 : 0);
-                        const double sgn = sa.role == CHILD ? -1.0 : 1.0;
+                        double asa[4];
+                        lin3_coefs(a, sa.role, asa);
                         V3 r = mk(0.0, 0.0, 0.0);
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) r = axpy(sgn * al[t], q.s[t], r);
-                        const int first = (e2 == e) ? rb : 0;  // same block: lower triangle only
-                        if (first <= 0) Sc[tidx(a.jrow + 0, row_b) * spw + sys] = r.x;
-                        if (first <= 1) Sc[tidx(a.jrow + 1, row_b) * spw + sys] = r.y;
-                        Sc[tidx(a.jrow + 2, row_b) * spw + sys] = r.z;
-                    } else {
+                        for (int t = 0; t < 4; ++t) r = axpy(asa[t], q.s[t], r);
+                        if (a.jrow > b.jrow) {
+                            double* Sc = sa.role == CHILD ? w.S0 : w.S1;
+                            Sc[tidx(a.jrow + 0, b.jrow) * spw + sys] = r.x;
+                            Sc[tidx(a.jrow + 1, b.jrow) * spw + sys] = r.y;
+                            Sc[tidx(a.jrow + 2, b.jrow) * spw + sys] = r.z;
+                        } else {
+                            double* Sc = sd.role == CHILD ? w.S0 : w.S1;
+                            Sc[tidx(b.jrow, a.jrow + 0) * spw + sys] = r.x;
+                            Sc[tidx(b.jrow, a.jrow + 1) * spw + sys] = r.y;
+                            Sc[tidx(b.jrow, a.jrow + 2) * spw + sys] = r.z;
+                        }
+                    } else if (e2 >= e) {
                         double acc = 0.0;
 #pragma unroll
                         for (int t = 0; t < 4; ++t) {
                             const double* src = w.knl + (sa.nl_slot * 12 + 3 * t) * 32 + w.lane;
                             acc += dot(mk(src[0], src[32], src[64]), q.s[t]);
                         }
-                        Sc[tidx(a.jrow, row_b) * spw + sys] = acc;
+                        double* Sc = sa.role == CHILD ? w.S0 : w.S1;
+                        Sc[tidx(a.jrow, b.jrow) * spw + sys] = acc;
                     }
                 }
             }
         }
-    }
-    __syncwarp();
-
-    // ---- F. combine the two copies, then LDL^T of S' in place (rows dealt round-robin to the lanes
-    //         of the system; column k is final before step k so one __syncwarp per pivot suffices)
-    if (w.has_seg) {
-        for (int it = w.segi; it < w.tri; it += w.N) w.S0[it * spw + sys] += w.S1[it * spw + sys];
-        for (int it = w.segi; it < w.mj; it += w.N) w.r0[it * spw + sys] += w.r1[it * spw + sys];
-    }
-    for (int k = 0; k < w.mj; ++k) {
         __syncwarp();
-        if (w.has_seg) {
-            const double piv = w.S0[tidx(k, k) * spw + sys];
-            if (!(fabs(piv) > 0.0) || !isfinite(piv)) status |= 1;
-            const double inv = 1.0 / piv;
-            if (w.segi == 0) w.dinv[k * spw + sys] = inv;
-            for (int r = k + 1 + w.segi; r < w.mj; r += w.N) {
-                const double t = w.S0[tidx(r, k) * spw + sys] * inv;
-                for (int q = k + 1; q <= r; ++q)
-                    w.S0[tidx(r, q) * spw + sys] = fma(-t, w.S0[tidx(q, k) * spw + sys], w.S0[tidx(r, q) * spw + sys]);
-            }
-        }
-    }
-    __syncwarp();
-    // ---- G. triangular solves by the first lane of each system: L y = rhs ; lambda = L^-T D^-1 y
-    if (w.has_seg && w.segi == 0) {
-        for (int k = 0; k < w.mj; ++k) {
-            double x = w.r0[k * spw + sys];
-            for (int q = 0; q < k; ++q) x = fma(-w.S0[tidx(k, q) * spw + sys], w.r1[q * spw + sys], x);
-            w.r1[k * spw + sys] = x * w.dinv[k * spw + sys];  // y-hat = D^-1 y
-        }
-        for (int k = w.mj - 1; k >= 0; --k) {
-            double acc = 0.0;
-            for (int r = k + 1; r < w.mj; ++r) acc = fma(w.S0[tidx(r, k) * spw + sys], w.r0[r * spw + sys], acc);
-            w.r0[k * spw + sys] = w.r1[k * spw + sys] - w.dinv[k * spw + sys] * acc;  // lambda_j
-        }
-    }
-    __syncwarp();
 
-    // ---- H. back-substitution per segment
-    if (w.has_seg) {
-        for (int e = sg.side_begin; e < sg.side_end; ++e) {
-            const DevSide sd = w.side[e];
-            const DevBlk& b = w.blk[sd.blk];
-            if (b.type == LIN3) {
-                const double* a = b.p + (sd.role == CHILD ? 4 : 0);
-                const double sgn = sd.role == CHILD ? -1.0 : 1.0;
-                const V3 lam = mk(w.r0[(b.jrow + 0) * spw + sys], w.r0[(b.jrow + 1) * spw + sys],
-                                  w.r0[(b.jrow + 2) * spw + sys]);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) f.s[t] = axpy(-sgn * a[t], lam, f.s[t]);
-                if (lam_out != nullptr && sd.role == CHILD) {
-                    lam_out[b.row_h + 0] = lam.x, lam_out[b.row_h + 1] = lam.y, lam_out[b.row_h + 2] = lam.z;
+        // ---- F. combine the two copies, then LDL^T of S' in place (rows dealt round-robin to the lanes
+        //         of the system; column k is final before step k so one __syncwarp per pivot suffices)
+        if (w.has_seg) {
+            for (int it = w.segi; it < w.tri; it += w.N) w.S0[it * spw + sys] += w.S1[it * spw + sys];
+            for (int it = w.segi; it < w.mj; it += w.N) w.r0[it * spw + sys] += w.r1[it * spw + sys];
+        }
+        for (int k = 0; k < w.mj; ++k) {
+            __syncwarp();
+            if (w.has_seg) {
+                const double piv = w.S0[tidx(k, k) * spw + sys];
+                if (!(fabs(piv) > 0.0) || !isfinite(piv)) status |= 1;
+                const double inv = 1.0 / piv;
+                if (w.segi == 0) w.dinv[k * spw + sys] = inv;
+                for (int r = k + 1 + w.segi; r < w.mj; r += w.N) {
+                    const double t = w.S0[tidx(r, k) * spw + sys] * inv;
+                    for (int q = k + 1; q <= r; ++q)
+                        w.S0[tidx(r, q) * spw + sys] = fma(-t, w.S0[tidx(q, k) * spw + sys], w.S0[tidx(r, q) * spw + sys]);
                 }
-            } else {
-                const double lam = w.r0[b.jrow * spw + sys];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const double* src = w.knl + (sd.nl_slot * 12 + 3 * t) * 32 + w.lane;
-                    f.s[t] = axpy(-lam, mk(src[0], src[32], src[64]), f.s[t]);
-                }
-                if (lam_out != nullptr && sd.role == CHILD) lam_out[b.row_h] = lam;
             }
         }
-    }
-    {
-        const Q12 a = apply_W(c.W, f);
-        double z[6];
-        kr_apply(c, a, z);
+        __syncwarp();
+        // ---- G. triangular solves by the first lane of each system: L y = rhs ; lambda = L^-T D^-1 y
+        if (w.has_seg && w.segi == 0) {
+            for (int k = 0; k < w.mj; ++k) {
+                double xx = w.r0[k * spw + sys];
+                for (int q = 0; q < k; ++q) xx = fma(-w.S0[tidx(k, q) * spw + sys], w.r1[q * spw + sys], xx);
+                w.r1[k * spw + sys] = xx * w.dinv[k * spw + sys];  // y-hat = D^-1 y
+            }
+            for (int k = w.mj - 1; k >= 0; --k) {
+                double acc = 0.0;
+                for (int r = k + 1; r < w.mj; ++r) acc = fma(w.S0[tidx(r, k) * spw + sys], w.r0[r * spw + sys], acc);
+                w.r0[k * spw + sys] = w.r1[k * spw + sys] - w.dinv[k * spw + sys] * acc;  // lambda_j
+            }
+        }
+        __syncwarp();
+
+        // ---- H. f <- f - Kj^T lambda_j for the second pass
+        if (w.has_seg) {
+            for (int e = sg.side_begin; e < sg.side_end; ++e) {
+                const DevSide sd = w.side[e];
+                const DevBlk& b = w.blk[sd.blk];
+                if (!GENERAL || b.type == LIN3) {
+                    double as[4];
+                    lin3_coefs(b, sd.role, as);
+                    const V3 lam = mk(w.r0[(b.jrow + 0) * spw + sys], w.r0[(b.jrow + 1) * spw + sys],
+                                      w.r0[(b.jrow + 2) * spw + sys]);
 #pragma unroll
-        for (int i = 0; i < 6; ++i) z[i] += br[i];
-        sr_solve(c, z);  // lambda_r
-        const Q12 corr = ginv_krt(c, z);
+                    for (int t = 0; t < 4; ++t) f.s[t] = axpy(-as[t], lam, f.s[t]);
+                    if (lam_out != nullptr && sd.role == CHILD) {
+                        lam_out[b.row_h + 0] = lam.x, lam_out[b.row_h + 1] = lam.y, lam_out[b.row_h + 2] = lam.z;
+                    }
+                } else {
+                    const double lam = w.r0[b.jrow * spw + sys];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) Qdd.s[t] = a.s[t] - corr.s[t];
-        if (lam_out != nullptr && w.has_seg) {
-#pragma unroll
-            for (int i = 0; i < 6; ++i) lam_out[sg.rigid_row + i] = z[i];
+                    for (int t = 0; t < 4; ++t) {
+                        const double* src = w.knl + (sd.nl_slot * 12 + 3 * t) * 32 + w.lane;
+                        f.s[t] = axpy(-lam, mk(src[0], src[32], src[64]), f.s[t]);
+                    }
+                    if (lam_out != nullptr && sd.role == CHILD) lam_out[b.row_h] = lam;
+                }
+            }
         }
     }
     // the published state / joint-level buffers are reused by the next evaluation

@@ -140,8 +140,8 @@ __device__ __forceinline__ void load_constants(const WarpCtx& w, const double* _
 // ---------------------------------------------------------------------------------------------
 // forward_dynamics(Q, Qdot) -> Qddot, lambda       (biomechanical_model.py:351-429, batched)
 // ---------------------------------------------------------------------------------------------
-template <bool HAS_FEXT>
-__global__ void __launch_bounds__(32 * kMaxWarpsPerCta)
+template <bool GENERAL>
+__global__ void __launch_bounds__(32 * kMaxWarpsPerCta, 3)
     forward_dynamics_kernel(const unsigned char* __restrict__ blob, int blob_bytes, const double* __restrict__ Q,
                             const double* __restrict__ Qd, const double* __restrict__ inertia, DynOpts o,
                             double* __restrict__ Qdd, double* __restrict__ lam, int* __restrict__ status_out,
@@ -157,11 +157,19 @@ __global__ void __launch_bounds__(32 * kMaxWarpsPerCta)
     int status = 0;
     SegCtx c;
     load_constants(w, inertia, gsys, c, status);
-    Q12 q, qd, qdd;
-    load_q12(Q + (size_t)gsys * n + 12 * w.segi, q);
-    load_q12(Qd + (size_t)gsys * n + 12 * w.segi, qd);
+    {
+        Q12 q, qd;
+        load_q12(Q + (size_t)gsys * n + 12 * w.segi, q);
+        load_q12(Qd + (size_t)gsys * n + 12 * w.segi, qd);
+        if (w.has_seg) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) publish3(w, w.Qs, t, q.s[t]), publish3(w, w.Qds, t, qd.s[t]);
+        }
+    }
+    __syncwarp();
+    Q12 qdd;
     double* lam_sys = (lam != nullptr && live) ? lam + (size_t)gsys * w.hdr->m : nullptr;
-    eval_forward_dynamics<HAS_FEXT>(w, c, q, qd, o, qdd, lam_sys, status);
+    eval_forward_dynamics<GENERAL>(w, c, o, qdd, lam_sys, status);
     if (live) {
         store_q12(Qdd + (size_t)gsys * n + 12 * w.segi, qdd);
         if (status_out != nullptr && status != 0) atomicOr(status_out + gsys, status);
@@ -170,11 +178,13 @@ __global__ void __launch_bounds__(32 * kMaxWarpsPerCta)
 
 // ---------------------------------------------------------------------------------------------
 // RK4 with the forward-dynamics closure fused in (utils/ode_solver.py:8-53, :107-120).
-// The state stays in registers for all n_steps; HBM sees one read and one write of Q, Qdot per
-// launch (plus the optional trajectory snapshots).
+// The state of a system stays on chip for all n_steps: HBM sees one read and one write of Q, Qdot
+// per launch (plus the optional trajectory snapshots).  The stage state lives in shared memory
+// (it has to be published there anyway for the two-segment joints); y0 and the k-accumulator are
+// per-lane values that the compiler keeps in registers or spills to L1-resident local memory.
 // ---------------------------------------------------------------------------------------------
-template <bool HAS_FEXT>
-__global__ void __launch_bounds__(32 * kMaxWarpsPerCta)
+template <bool GENERAL>
+__global__ void __launch_bounds__(32 * kMaxWarpsPerCta, 3)
     rk4_kernel(const unsigned char* __restrict__ blob, int blob_bytes, double* __restrict__ Q, double* __restrict__ Qd,
                const double* __restrict__ inertia, DynOpts o, double h_const, const double* __restrict__ h_steps,
                long long n_steps, int normalize, double* __restrict__ traj, long long traj_every,
@@ -194,45 +204,42 @@ __global__ void __launch_bounds__(32 * kMaxWarpsPerCta)
     load_q12(Q + (size_t)gsys * n + 12 * w.segi, y0q);
     load_q12(Qd + (size_t)gsys * n + 12 * w.segi, y0v);
 
+#pragma unroll 1
     for (long long step = 0; step < n_steps; ++step) {
         const double h = h_steps != nullptr ? h_steps[step] : h_const;
-        const double hh = h * 0.5;
-        Q12 a, accq, accv, sq, sv;
-        double* lam_sys = (lam_last != nullptr && live && step == n_steps - 1) ? lam_last + (size_t)gsys * w.hdr->m : nullptr;
-        // k1 = f(y0)
-        eval_forward_dynamics<HAS_FEXT>(w, c, y0q, y0v, o, a, lam_sys, status);
+        Q12 accq, accv;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-            accq.s[t] = y0v.s[t];
-            accv.s[t] = a.s[t];
-            sq.s[t] = axpy(hh, y0v.s[t], y0q.s[t]);
-            sv.s[t] = axpy(hh, a.s[t], y0v.s[t]);
+            accq.s[t] = mk(0.0, 0.0, 0.0), accv.s[t] = mk(0.0, 0.0, 0.0);
+            if (w.has_seg) publish3(w, w.Qs, t, y0q.s[t]), publish3(w, w.Qds, t, y0v.s[t]);
         }
-        // k2 = f(y0 + h/2 k1)
-        eval_forward_dynamics<HAS_FEXT>(w, c, sq, sv, o, a, nullptr, status);
+        __syncwarp();
+#pragma unroll 1
+        for (int stage = 0; stage < 4; ++stage) {
+            // k_stage = f(stage state): (stage velocity, Qddot)
+            Q12 a;
+            double* lam_sys = (lam_last != nullptr && live && stage == 0 && step == n_steps - 1)
+                                  ? lam_last + (size_t)gsys * w.hdr->m : nullptr;
+            eval_forward_dynamics<GENERAL>(w, c, o, a, lam_sys, status);
+            const double wt = (stage == 0 || stage == 3) ? 1.0 : 2.0;
+            const double cn = (stage == 2) ? h : 0.5 * h;  // next stage is y0 + cn * k_stage
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            accq.s[t] = axpy(2.0, sv.s[t], accq.s[t]);
-            accv.s[t] = axpy(2.0, a.s[t], accv.s[t]);
-            sq.s[t] = axpy(hh, sv.s[t], y0q.s[t]);
-            sv.s[t] = axpy(hh, a.s[t], y0v.s[t]);
+            for (int t = 0; t < 4; ++t) {
+                const V3 sv = own3(w, w.Qds, t);
+                accq.s[t] = axpy(wt, sv, accq.s[t]);
+                accv.s[t] = axpy(wt, a.s[t], accv.s[t]);
+                if (stage < 3 && w.has_seg) {
+                    publish3(w, w.Qs, t, axpy(cn, sv, y0q.s[t]));
+                    publish3(w, w.Qds, t, axpy(cn, a.s[t], y0v.s[t]));
+                }
+            }
+            __syncwarp();
         }
-        // k3 = f(y0 + h/2 k2)
-        eval_forward_dynamics<HAS_FEXT>(w, c, sq, sv, o, a, nullptr, status);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            accq.s[t] = axpy(2.0, sv.s[t], accq.s[t]);
-            accv.s[t] = axpy(2.0, a.s[t], accv.s[t]);
-            sq.s[t] = axpy(h, sv.s[t], y0q.s[t]);
-            sv.s[t] = axpy(h, a.s[t], y0v.s[t]);
-        }
-        // k4 = f(y0 + h k3)
-        eval_forward_dynamics<HAS_FEXT>(w, c, sq, sv, o, a, nullptr, status);
         const double h6 = h / 6.0;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-            y0q.s[t] = axpy(h6, accq.s[t] + sv.s[t], y0q.s[t]);
-            y0v.s[t] = axpy(h6, accv.s[t] + a.s[t], y0v.s[t]);
+            y0q.s[t] = axpy(h6, accq.s[t], y0q.s[t]);
+            y0v.s[t] = axpy(h6, accv.s[t], y0v.s[t]);
         }
         if (normalize) {  // u <- u/|u|, w <- w/|w| of Q only (ode_solver.py:50-52)
             y0q.s[0] = (1.0 / sqrt(dot(y0q.s[0], y0q.s[0]))) * y0q.s[0];
