@@ -268,17 +268,19 @@ def run_gpu_arm(args):
     barrier()
 
     # ---- reduce over ranks: slowest rank defines the job time
-    t = torch.tensor([total_ms, e2e_s, float(np.mean(kernel_ms)), float(bad)], dtype=torch.float64, device=dev)
+    from bionc_b200.utils.sharding import gather_states, max_over_ranks
+
+    t = max_over_ranks([total_ms, e2e_s, float(np.mean(kernel_ms)), float(bad)], device=dev)
     if distributed:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        # the only collective of the workload: a final gather (of per-rank checksums; --gather-states gathers the states)
-        chk = torch.stack([Q.sum(), Qd.sum()])
-        allchk = [torch.zeros_like(chk) for _ in range(world)]
-        dist.all_gather(allchk, chk)
+        # the only collective of the workload: a final gather (of per-rank checksums by default;
+        # --gather-states gathers the full states, 768 MB per rank at the default batch)
+        chk = torch.stack([Q.sum(), Qd.sum()])[None]
+        allchk = gather_states(chk, world)
+        assert allchk.shape == (world, 2) and bool(torch.isfinite(allchk).all())
         if args.gather_states:
-            out = torch.empty((world * B, n), dtype=torch.float64, device=dev)
-            dist.all_gather_into_tensor(out, Q)
-    total_ms, e2e_s, kernel_ms_mean, bad = (float(x) for x in t.tolist())
+            full = gather_states(Q, world * B)
+            assert full.shape == (world * B, n)
+    total_ms, e2e_s, kernel_ms_mean, bad = t
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
