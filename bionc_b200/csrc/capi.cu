@@ -141,7 +141,7 @@ int build_blob(BioncModel* M, const BioncFextDesc* fx) {
     // shared-memory budget: as many warps per CTA (<= 4) as fit
     int dev_smem = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, M->device));
-    const size_t per_warp = (size_t)warp_smem_doubles(h.N, h.mj, h.spw, h.rnl) * sizeof(double);
+    const size_t per_warp = (size_t)warp_smem_doubles(h.nb, h.spw, h.rnl) * sizeof(double);
     int warps = kMaxWarpsPerCta;
     while (warps > 1 && h.blob_bytes + warps * per_warp > (size_t)dev_smem) warps >>= 1;
     if (h.blob_bytes + warps * per_warp > (size_t)dev_smem)
@@ -212,23 +212,31 @@ int bionc_cuda_model_create(const BioncModelDesc* d, int device, BioncModel** ou
     M->device = device;
     M->seg.resize(N);
     M->blk.resize(nblk);
+    // Internal row order of the joint-level Schur system: LIN3 blocks first (each is one whole 3x3 block
+    // row), then the single rows of the other block kinds, padded with unit rows to a multiple of 3.
     int mj = 0;
-    for (int b = 0; b < nblk; ++b) {
-        DevBlk& B = M->blk[b];
-        std::memset(&B, 0, sizeof(B));
-        B.type = d->blk_type[b], B.parent = d->blk_parent[b], B.child = d->blk_child[b];
-        if (B.type < 0 || B.type > 3 || B.child < 0 || B.child >= N || B.parent < -1 || B.parent >= N || B.parent == B.child) {
-            delete M;
-            return fail(BIONC_E_INVALID, "malformed constraint block");
+    for (int pass = 0; pass < 2; ++pass)
+        for (int b = 0; b < nblk; ++b) {
+            DevBlk& B = M->blk[b];
+            if (pass == 0) {
+                std::memset(&B, 0, sizeof(B));
+                B.type = d->blk_type[b], B.parent = d->blk_parent[b], B.child = d->blk_child[b];
+                if (B.type < 0 || B.type > 3 || B.child < 0 || B.child >= N || B.parent < -1 || B.parent >= N || B.parent == B.child) {
+                    delete M;
+                    return fail(BIONC_E_INVALID, "malformed constraint block");
+                }
+                if (B.parent < 0 && (B.type == CLEN || B.type == SOP)) {
+                    delete M;
+                    return fail(BIONC_E_INVALID, "constant-length / sphere-on-plane blocks need two segments");
+                }
+                B.row_h = d->blk_row_h[b], B.row_j = d->blk_row_j[b];
+                std::memcpy(B.p, d->blk_param + (size_t)b * kBlkNParam, kBlkNParam * sizeof(double));
+            }
+            if ((pass == 0) == (B.type == LIN3)) {
+                B.jrow = mj;
+                mj += (B.type == LIN3) ? 3 : 1;
+            }
         }
-        if (B.parent < 0 && (B.type == CLEN || B.type == SOP)) {
-            delete M;
-            return fail(BIONC_E_INVALID, "constant-length / sphere-on-plane blocks need two segments");
-        }
-        B.row_h = d->blk_row_h[b], B.row_j = d->blk_row_j[b], B.jrow = mj;
-        std::memcpy(B.p, d->blk_param + (size_t)b * kBlkNParam, kBlkNParam * sizeof(double));
-        mj += (B.type == LIN3) ? 3 : 1;
-    }
     int rnl = 0;
     for (int i = 0; i < N; ++i) {
         DevSeg& S = M->seg[i];
@@ -277,7 +285,7 @@ int bionc_cuda_model_create(const BioncModelDesc* d, int device, BioncModel** ou
         if (nl > rnl) rnl = nl;
     }
     M->hdr.N = N, M->hdr.nblk = nblk, M->hdr.nside = (int)M->side.size();
-    M->hdr.mj = mj, M->hdr.m = mj + 6 * N, M->hdr.spw = 32 / N, M->hdr.rnl = rnl;
+    M->hdr.mj = mj, M->hdr.nb = (mj + 2) / 3, M->hdr.m = mj + 6 * N, M->hdr.spw = 32 / N, M->hdr.rnl = rnl;
     *out = M;
     return BIONC_OK;
 }

@@ -165,7 +165,15 @@ __device__ __forceinline__ void sr_factor(SegCtx& c, int& status) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// warp-level context
+// warp-level context.  All shared-memory pointers are pre-offset for this lane, so that the hot
+// code addresses them with compile-time multiples of a stride:
+//   Qo/Qdo     own segment's stage state, slot element k at Qo[k * 32]          ([12][32 lanes])
+//   Qsys/Qdsys the system's first lane; segment s, element k at Qsys[s + k * 32]
+//   S0/S1      joint-level Schur matrix as 3x3 blocks: block pair p = I(I+1)/2 + J (I >= J),
+//              element e = 3 r + c at S0[(9 p + e) * spw]                       ([9 nbp][spw])
+//   r0/r1      right-hand side / y-hat, row j at r0[j * spw]                    ([3 nb][spw])
+//   dinv       inverse diagonal blocks, 6 unique entries of block K at dinv[(6 K + i) * spw]
+//   knl        explicit rows of non-LIN3 blocks, slot q element i at knl[(12 q + i) * 32]
 // ---------------------------------------------------------------------------------------------
 struct WarpCtx {
     const DevHeader* hdr;
@@ -173,31 +181,23 @@ struct WarpCtx {
     const DevBlk* blk;
     const DevSide* side;
     const DevFext* fext;
-    double* Qs;   // [12N][spw]
-    double* Qds;  // [12N][spw]
-    double* S0;   // [tri][spw]
-    double* S1;
-    double* r0;   // [mj][spw]
-    double* r1;
-    double* dinv;
-    double* knl;  // [rnl][12][32]
-    int spw, N, mj, tri;
+    double *Qo, *Qdo, *Qsys, *Qdsys;
+    double *S0, *S1, *r0, *r1, *dinv, *knl;
+    int spw, N, mj, nb;
     int sys;   // system index inside the warp
     int segi;  // this lane's segment
     int lane;
     bool has_seg;  // lane maps to a (system, segment) pair
 };
 
-__device__ __forceinline__ constexpr int tidx(int r, int c) { return r * (r + 1) / 2 + c; }  // r >= c
+__device__ __forceinline__ constexpr int bpair(int I, int J) { return I * (I + 1) / 2 + J; }  // I >= J
 
-// linear form over another segment's published state: sum_t a[t] * X[12 s + 3 t + :]
-__device__ __forceinline__ V3 lin_form(const WarpCtx& w, const double* X, int s, const double* a) {
+// linear form over a segment's published state: sum_t a[t] * X[segment s, slot t]
+__device__ __forceinline__ V3 lin_form(const WarpCtx& w, const double* Xsys, int s, const double* a) {
     V3 r = mk(0.0, 0.0, 0.0);
+    const double* X = Xsys + s;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        const int o = (12 * s + 3 * t) * w.spw + w.sys;
-        r = axpy(a[t], mk(X[o], X[o + w.spw], X[o + 2 * w.spw]), r);
-    }
+    for (int t = 0; t < 4; ++t) r = axpy(a[t], mk(X[(3 * t) * 32], X[(3 * t + 1) * 32], X[(3 * t + 2) * 32]), r);
     return r;
 }
 
@@ -215,19 +215,19 @@ __device__ __forceinline__ void nonlin_row(const WarpCtx& w, const DevBlk& b, in
     const double* p = b.p;
     bterm = 0.0;
     if (b.type == DOT) {
-        const V3 Dc = lin_form(w, w.Qs, b.child, p + 4);
+        const V3 Dc = lin_form(w, w.Qsys, b.child, p + 4);
         V3 Dp, Dpd = mk(0.0, 0.0, 0.0);
         if (b.parent >= 0) {
-            Dp = lin_form(w, w.Qs, b.parent, p);
+            Dp = lin_form(w, w.Qsys, b.parent, p);
         } else {
             Dp = mk(p[0], p[1], p[2]);
         }
         if (role == CHILD) {
 #pragma unroll
             for (int t = 0; t < 4; ++t) k.s[t] = p[4 + t] * Dp;
-            const V3 Dcd = lin_form(w, w.Qds, b.child, p + 4);
+            const V3 Dcd = lin_form(w, w.Qdsys, b.child, p + 4);
             if (b.parent >= 0) {
-                Dpd = lin_form(w, w.Qds, b.parent, p);
+                Dpd = lin_form(w, w.Qdsys, b.parent, p);
                 bterm = 2.0 * dot(Dpd, Dcd);
             }
             if (o.use_stab) bterm += o.alpha * (dot(Dp, Dc) - p[8]) + o.beta * (dot(Dpd, Dc) + dot(Dp, Dcd));
@@ -236,11 +236,11 @@ __device__ __forceinline__ void nonlin_row(const WarpCtx& w, const DevBlk& b, in
             for (int t = 0; t < 4; ++t) k.s[t] = p[t] * Dc;
         }
     } else if (b.type == CLEN) {
-        const V3 d = lin_form(w, w.Qs, b.parent, p) - lin_form(w, w.Qs, b.child, p + 4);
+        const V3 d = lin_form(w, w.Qsys, b.parent, p) - lin_form(w, w.Qsys, b.child, p + 4);
         if (role == CHILD) {
 #pragma unroll
             for (int t = 0; t < 4; ++t) k.s[t] = (-2.0 * p[4 + t]) * d;
-            const V3 dd = lin_form(w, w.Qds, b.parent, p) - lin_form(w, w.Qds, b.child, p + 4);
+            const V3 dd = lin_form(w, w.Qdsys, b.parent, p) - lin_form(w, w.Qdsys, b.child, p + 4);
             bterm = 2.0 * dot(dd, dd);
             if (o.use_stab) bterm += o.alpha * (dot(d, d) - p[8]) + o.beta * (2.0 * dot(d, dd));
         } else {
@@ -248,24 +248,24 @@ __device__ __forceinline__ void nonlin_row(const WarpCtx& w, const DevBlk& b, in
             for (int t = 0; t < 4; ++t) k.s[t] = (2.0 * p[t]) * d;
         }
     } else {  // SOP
-        const V3 n = lin_form(w, w.Qs, b.child, p + 8);
+        const V3 n = lin_form(w, w.Qsys, b.child, p + 8);
         if (role == CHILD) {
 #pragma unroll
             for (int t = 0; t < 4; ++t) k.s[t] = p[t] * n;  // n^T N_P, stored in the child's columns
-            const V3 P = lin_form(w, w.Qs, b.parent, p), A = lin_form(w, w.Qs, b.child, p + 4);
-            const V3 Pd = lin_form(w, w.Qds, b.parent, p), Ad = lin_form(w, w.Qds, b.child, p + 4);
-            const V3 nd = lin_form(w, w.Qds, b.child, p + 8);
+            const V3 P = lin_form(w, w.Qsys, b.parent, p), A = lin_form(w, w.Qsys, b.child, p + 4);
+            const V3 Pd = lin_form(w, w.Qdsys, b.parent, p), Ad = lin_form(w, w.Qdsys, b.child, p + 4);
+            const V3 nd = lin_form(w, w.Qdsys, b.child, p + 8);
             bterm = 2.0 * dot(Pd, nd) - 2.0 * dot(nd, Ad);
             if (o.use_stab) {
                 // K Qdot with the blocks where the reference stores them:
                 // parent cols: -n^T N_A + (P-A)^T N_n applied to Qdot_parent; child cols: n^T N_P applied to Qdot_child
-                const V3 Apd = lin_form(w, w.Qds, b.parent, p + 4), npd = lin_form(w, w.Qds, b.parent, p + 8);
-                const V3 Pcd = lin_form(w, w.Qds, b.child, p);
+                const V3 Apd = lin_form(w, w.Qdsys, b.parent, p + 4), npd = lin_form(w, w.Qdsys, b.parent, p + 8);
+                const V3 Pcd = lin_form(w, w.Qdsys, b.child, p);
                 const double kqd = -dot(n, Apd) + dot(P - A, npd) + dot(n, Pcd);
                 bterm += o.alpha * (dot(P - A, n) - p[12]) + o.beta * kqd;
             }
         } else {
-            const V3 PA = lin_form(w, w.Qs, b.parent, p) - lin_form(w, w.Qs, b.child, p + 4);
+            const V3 PA = lin_form(w, w.Qsys, b.parent, p) - lin_form(w, w.Qsys, b.child, p + 4);
 #pragma unroll
             for (int t = 0; t < 4; ++t) k.s[t] = axpy(-p[4 + t], n, p[8 + t] * PA);  // stored in the parent's columns
         }
@@ -313,14 +313,12 @@ __device__ __forceinline__ Q12 external_forces(const WarpCtx& w, const DevSeg& s
     return f;
 }
 
-// this lane's own segment, slot t, from the published stage state
-__device__ __forceinline__ V3 own3(const WarpCtx& w, const double* X, int t) {
-    const int o = (12 * w.segi + 3 * t) * w.spw + w.sys;
-    return mk(X[o], X[o + w.spw], X[o + 2 * w.spw]);
+// this lane's own segment, slot t, from / to the published stage state (Xo = w.Qo or w.Qdo)
+__device__ __forceinline__ V3 own3(const double* Xo, int t) {
+    return mk(Xo[(3 * t) * 32], Xo[(3 * t + 1) * 32], Xo[(3 * t + 2) * 32]);
 }
-__device__ __forceinline__ void publish3(const WarpCtx& w, double* X, int t, V3 v) {
-    const int o = (12 * w.segi + 3 * t) * w.spw + w.sys;
-    X[o] = v.x, X[o + w.spw] = v.y, X[o + 2 * w.spw] = v.z;
+__device__ __forceinline__ void publish3(double* Xo, int t, V3 v) {
+    Xo[(3 * t) * 32] = v.x, Xo[(3 * t + 1) * 32] = v.y, Xo[(3 * t + 2) * 32] = v.z;
 }
 
 // rigid-body right-hand side term: bias_r (+ alpha Phi_r + beta Kr Qdot)   (natural_segment.py:429-448, :508-545)
@@ -328,7 +326,7 @@ __device__ __forceinline__ void rigid_bterm(const WarpCtx& w, const SegCtx& c, c
                                             double (&b)[6]) {
     Q12 Qd;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) Qd.s[t] = own3(w, w.Qds, t);
+    for (int t = 0; t < 4; ++t) Qd.s[t] = own3(w.Qdo, t);
     const V3 ud = Qd.s[0], vd = Qd.s[1] - Qd.s[2], wd = Qd.s[3];
     b[0] = 2.0 * dot(ud, ud);
     b[1] = 2.0 * dot(ud, vd);
@@ -402,15 +400,42 @@ __device__ __forceinline__ void lin3_beta(const SegCtx& c, const double (&as)[4]
 // (Kr G^-1 (as_b (x) e_c)^T = Gamma(b3) B[c,:]^T), so the three rows of a block share one
 // three-right-hand-side solve Z_b = Sr^-1 Gamma(b3).
 // ---------------------------------------------------------------------------------------------
+// 3x3 helpers for the blocked joint-level factorisation (blocks are stored row-major, element e = 3 r + c)
+__device__ __forceinline__ void load9(const double* p, int spw, double (&A)[9]) {
+#pragma unroll
+    for (int e = 0; e < 9; ++e) A[e] = p[e * spw];
+}
+// inverse of a symmetric 3x3 given by its lower triangle (adjugate); di = [i00 i10 i11 i20 i21 i22]
+__device__ __forceinline__ void sym3_inverse(double a00, double a10, double a11, double a20, double a21, double a22,
+                                             double (&di)[6], int& status) {
+    const double c00 = a11 * a22 - a21 * a21;
+    const double c10 = a20 * a21 - a10 * a22;
+    const double c20 = a10 * a21 - a20 * a11;
+    const double det = fma(a00, c00, fma(a10, c10, a20 * c20));
+    if (!(fabs(det) > 0.0) || !isfinite(det)) status |= 1;
+    const double id = 1.0 / det;
+    di[0] = c00 * id;
+    di[1] = c10 * id;
+    di[2] = (a00 * a22 - a20 * a20) * id;
+    di[3] = c20 * id;
+    di[4] = (a10 * a20 - a00 * a21) * id;
+    di[5] = (a00 * a11 - a10 * a10) * id;
+}
+// y = Dinv x for the symmetric 3x3 Dinv stored as 6 entries
+__device__ __forceinline__ V3 sym3_apply(const double (&di)[6], V3 x) {
+    return mk(fma(di[0], x.x, fma(di[1], x.y, di[3] * x.z)), fma(di[1], x.x, fma(di[2], x.y, di[4] * x.z)),
+              fma(di[3], x.x, fma(di[4], x.y, di[5] * x.z)));
+}
+
 template <bool GENERAL>
 __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& c, const DynOpts& o, Q12& Qdd,
                                                       double* lam_out, int& status) {
-    const int spw = w.spw, sys = w.sys;
+    const int spw = w.spw;
     const DevSeg& sg = w.seg[w.segi];
 
     // ---- B. segment-local factorisation
-    const V3 rp = own3(w, w.Qs, 1);
-    c.u = own3(w, w.Qs, 0), c.v = rp - own3(w, w.Qs, 2), c.w = own3(w, w.Qs, 3);
+    const V3 rp = own3(w.Qo, 1);
+    c.u = own3(w.Qo, 0), c.v = rp - own3(w.Qo, 2), c.w = own3(w.Qo, 3);
     sr_factor(c, status);
     Q12 f;  // natural forces: gravity + external
     if (GENERAL && sg.fext_end > sg.fext_begin) {
@@ -451,13 +476,18 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
             }
             break;
         }
+        const int nb = w.nb, nbp9 = 9 * (nb * (nb + 1) / 2), mjp = 3 * nb;
 
-        // ---- C. zero the joint-level system (cooperatively by the lanes of the system)
+        // ---- C. zero the joint-level system (cooperatively by the lanes of the system); padding rows
+        //         (the system is padded to whole 3x3 blocks) get a unit diagonal
         if (w.has_seg) {
-            for (int it = w.segi; it < w.tri; it += w.N) w.S0[it * spw + sys] = 0.0, w.S1[it * spw + sys] = 0.0;
-            for (int it = w.segi; it < w.mj; it += w.N) w.r0[it * spw + sys] = 0.0, w.r1[it * spw + sys] = 0.0;
+            for (int it = w.segi; it < nbp9; it += w.N) w.S0[it * spw] = 0.0, w.S1[it * spw] = 0.0;
+            for (int it = w.segi; it < mjp; it += w.N) w.r0[it * spw] = 0.0, w.r1[it * spw] = 0.0;
         }
         __syncwarp();
+        if (w.has_seg && w.segi == 0) {
+            for (int r = w.mj; r < mjp; ++r) w.S0[(9 * bpair(nb - 1, nb - 1) + 4 * (r - 3 * (nb - 1))) * spw] = 1.0;
+        }
 
         // ---- D. right-hand side rhs' = Kj abar + b_j (copy `role` of each row is written by exactly one
         //         lane) and the explicit rows of non-LIN3 blocks
@@ -465,7 +495,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
             for (int e = sg.side_begin; e < sg.side_end; ++e) {
                 const DevSide sd = w.side[e];
                 const DevBlk& b = w.blk[sd.blk];
-                double* rr = sd.role == CHILD ? w.r0 : w.r1;
+                double* rr = (sd.role == CHILD ? w.r0 : w.r1) + b.jrow * spw;
                 if (!GENERAL || b.type == LIN3) {
                     double as[4];
                     lin3_coefs(b, sd.role, as);
@@ -474,17 +504,15 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                     for (int t = 0; t < 4; ++t) r = axpy(as[t], x.s[t], r);
                     if (GENERAL && sd.role == CHILD && o.use_stab) {
                         // Phi = c0 + N_p Q_p - N_c Q_c ; K Qdot = N_p Qdot_p - N_c Qdot_c
-                        V3 phi = mk(b.p[8], b.p[9], b.p[10]) - lin_form(w, w.Qs, b.child, b.p + 4);
-                        V3 kqd = mk(0.0, 0.0, 0.0) - lin_form(w, w.Qds, b.child, b.p + 4);
+                        V3 phi = mk(b.p[8], b.p[9], b.p[10]) - lin_form(w, w.Qsys, b.child, b.p + 4);
+                        V3 kqd = mk(0.0, 0.0, 0.0) - lin_form(w, w.Qdsys, b.child, b.p + 4);
                         if (b.parent >= 0) {
-                            phi = phi + lin_form(w, w.Qs, b.parent, b.p);
-                            kqd = kqd + lin_form(w, w.Qds, b.parent, b.p);
+                            phi = phi + lin_form(w, w.Qsys, b.parent, b.p);
+                            kqd = kqd + lin_form(w, w.Qdsys, b.parent, b.p);
                         }
                         r = axpy(o.alpha, phi, axpy(o.beta, kqd, r));
                     }
-                    rr[(b.jrow + 0) * spw + sys] = r.x;
-                    rr[(b.jrow + 1) * spw + sys] = r.y;
-                    rr[(b.jrow + 2) * spw + sys] = r.z;
+                    rr[0] = r.x, rr[spw] = r.y, rr[2 * spw] = r.z;
                 } else {
                     Q12 k;
                     double bterm;
@@ -493,15 +521,15 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
                         acc += dot(k.s[t], x.s[t]);
-                        double* dst = w.knl + (sd.nl_slot * 12 + 3 * t) * 32 + w.lane;
+                        double* dst = w.knl + (sd.nl_slot * 12 + 3 * t) * 32;
                         dst[0] = k.s[t].x, dst[32] = k.s[t].y, dst[64] = k.s[t].z;
                     }
-                    rr[b.jrow * spw + sys] = acc;
+                    rr[0] = acc;
                 }
             }
         }
 
-        // ---- E1. LIN3 x LIN3 pairs on this segment: S'_ab = gamma I3 - B M_ab B^T
+        // ---- E1. LIN3 x LIN3 pairs on this segment: S'_ab = gamma I3 - B M_ab B^T, one 3x3 block each
         if (w.has_seg) {
             for (int e = sg.side_begin; e < sg.side_end; ++e) {
                 const DevSide sd = w.side[e];
@@ -518,6 +546,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                 Z[4][0] = 0.0, Z[4][1] = b3[2], Z[4][2] = b3[1];
                 Z[5][0] = 0.0, Z[5][1] = 0.0, Z[5][2] = 2.0 * b3[2];
                 sr_solve3(c, Z);
+                const int Jb = b.jrow / 3;
                 for (int e2 = e; e2 < sg.side_end; ++e2) {
                     const DevSide sa = w.side[e2];
                     const DevBlk& a = w.blk[sa.blk];
@@ -537,22 +566,14 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                         const double m2 = fma(a3[0], Z[2][j], fma(a3[1], Z[4][j], (2.0 * a3[2]) * Z[5][j]));
                         Pc[j] = axpy(m0, c.u, axpy(m1, c.v, m2 * c.w));
                     }
-                    // entry (row c' of a, row cc of b) = gamma delta - sum_j Pc[j][c'] * B[cc][j],  B[cc] = (u_cc, v_cc, w_cc)
-                    double* Sc = sa.role == CHILD ? w.S0 : w.S1;
-                    const bool same = (e2 == e);
-                    const V3 col0 = mk(0, 0, 0) - axpy(c.u.x, Pc[0], axpy(c.v.x, Pc[1], c.w.x * Pc[2]));  // cc = 0
-                    const V3 col1 = mk(0, 0, 0) - axpy(c.u.y, Pc[0], axpy(c.v.y, Pc[1], c.w.y * Pc[2]));  // cc = 1
-                    const V3 col2 = mk(0, 0, 0) - axpy(c.u.z, Pc[0], axpy(c.v.z, Pc[1], c.w.z * Pc[2]));  // cc = 2
-                    const int ra = a.jrow, rb = b.jrow;
-                    Sc[tidx(ra + 0, rb + 0) * spw + sys] = col0.x + gamma;
-                    Sc[tidx(ra + 1, rb + 0) * spw + sys] = col0.y;
-                    Sc[tidx(ra + 2, rb + 0) * spw + sys] = col0.z;
-                    if (!same) Sc[tidx(ra + 0, rb + 1) * spw + sys] = col1.x;
-                    Sc[tidx(ra + 1, rb + 1) * spw + sys] = col1.y + gamma;
-                    Sc[tidx(ra + 2, rb + 1) * spw + sys] = col1.z;
-                    if (!same) Sc[tidx(ra + 0, rb + 2) * spw + sys] = col2.x;
-                    if (!same) Sc[tidx(ra + 1, rb + 2) * spw + sys] = col2.y;
-                    Sc[tidx(ra + 2, rb + 2) * spw + sys] = col2.z + gamma;
+                    // element (row r of a, row cc of b) = gamma delta - sum_j Pc[j][r] * B[cc][j],  B[cc] = (u_cc, v_cc, w_cc)
+                    const V3 col0 = mk(0, 0, 0) - axpy(c.u.x, Pc[0], axpy(c.v.x, Pc[1], c.w.x * Pc[2]));
+                    const V3 col1 = mk(0, 0, 0) - axpy(c.u.y, Pc[0], axpy(c.v.y, Pc[1], c.w.y * Pc[2]));
+                    const V3 col2 = mk(0, 0, 0) - axpy(c.u.z, Pc[0], axpy(c.v.z, Pc[1], c.w.z * Pc[2]));
+                    double* Sc = (sa.role == CHILD ? w.S0 : w.S1) + 9 * bpair(a.jrow / 3, Jb) * spw;
+                    Sc[0 * spw] = col0.x + gamma, Sc[1 * spw] = col1.x, Sc[2 * spw] = col2.x;
+                    Sc[3 * spw] = col0.y, Sc[4 * spw] = col1.y + gamma, Sc[5 * spw] = col2.y;
+                    Sc[6 * spw] = col0.z, Sc[7 * spw] = col1.z, Sc[8 * spw] = col2.z + gamma;
                 }
             }
         }
@@ -566,7 +587,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                 Q12 kb, q;
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
-                    const double* src = w.knl + (sd.nl_slot * 12 + 3 * t) * 32 + w.lane;
+                    const double* src = w.knl + (sd.nl_slot * 12 + 3 * t) * 32;
                     kb.s[t] = mk(src[0], src[32], src[64]);
                 }
                 {
@@ -578,6 +599,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
 #pragma unroll
                     for (int t = 0; t < 4; ++t) q.s[t] = q.s[t] - corr.s[t];
                 }
+                const int Ib = b.jrow / 3, rb = b.jrow - 3 * Ib;
                 for (int e2 = sg.side_begin; e2 < sg.side_end; ++e2) {
                     const DevSide sa = w.side[e2];
                     const DevBlk& a = w.blk[sa.blk];
@@ -588,64 +610,112 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                         V3 r = mk(0.0, 0.0, 0.0);
 #pragma unroll
                         for (int t = 0; t < 4; ++t) r = axpy(asa[t], q.s[t], r);
-                        if (a.jrow > b.jrow) {
-                            double* Sc = sa.role == CHILD ? w.S0 : w.S1;
-                            Sc[tidx(a.jrow + 0, b.jrow) * spw + sys] = r.x;
-                            Sc[tidx(a.jrow + 1, b.jrow) * spw + sys] = r.y;
-                            Sc[tidx(a.jrow + 2, b.jrow) * spw + sys] = r.z;
-                        } else {
-                            double* Sc = sd.role == CHILD ? w.S0 : w.S1;
-                            Sc[tidx(b.jrow, a.jrow + 0) * spw + sys] = r.x;
-                            Sc[tidx(b.jrow, a.jrow + 1) * spw + sys] = r.y;
-                            Sc[tidx(b.jrow, a.jrow + 2) * spw + sys] = r.z;
+                        const int Ia = a.jrow / 3;  // LIN3 blocks are whole 3x3 block rows, never Ib
+                        if (Ia > Ib) {  // rows of a, column rb
+                            double* Sc = (sa.role == CHILD ? w.S0 : w.S1) + (9 * bpair(Ia, Ib) + rb) * spw;
+                            Sc[0] = r.x, Sc[3 * spw] = r.y, Sc[6 * spw] = r.z;
+                        } else {  // row rb, columns of a
+                            double* Sc = (sd.role == CHILD ? w.S0 : w.S1) + (9 * bpair(Ib, Ia) + 3 * rb) * spw;
+                            Sc[0] = r.x, Sc[spw] = r.y, Sc[2 * spw] = r.z;
                         }
-                    } else if (e2 >= e) {
+                    } else if (e2 >= e) {  // a.jrow >= b.jrow
                         double acc = 0.0;
 #pragma unroll
                         for (int t = 0; t < 4; ++t) {
-                            const double* src = w.knl + (sa.nl_slot * 12 + 3 * t) * 32 + w.lane;
+                            const double* src = w.knl + (sa.nl_slot * 12 + 3 * t) * 32;
                             acc += dot(mk(src[0], src[32], src[64]), q.s[t]);
                         }
-                        double* Sc = sa.role == CHILD ? w.S0 : w.S1;
-                        Sc[tidx(a.jrow, b.jrow) * spw + sys] = acc;
+                        const int Ia = a.jrow / 3, ra = a.jrow - 3 * Ia;
+                        double* Sc = (sa.role == CHILD ? w.S0 : w.S1) + 9 * bpair(Ia, Ib) * spw;
+                        Sc[(3 * ra + rb) * spw] = acc;
+                        if (Ia == Ib && ra != rb) Sc[(3 * rb + ra) * spw] = acc;  // keep diagonal blocks symmetric
                     }
                 }
             }
         }
         __syncwarp();
 
-        // ---- F. combine the two copies, then LDL^T of S' in place (rows dealt round-robin to the lanes
-        //         of the system; column k is final before step k so one __syncwarp per pivot suffices)
+        // ---- F. combine the two copies, then blocked LDL^T of S' in place with 3x3 pivots: block rows are
+        //         dealt round-robin to the lanes of the system, every block operation runs in registers.
+        //         Block column K is final before step K, so one __syncwarp per pivot block suffices;
+        //         S_IK is kept unscaled (L_IK = S_IK D_K^-1 is applied through y-hat in the solves).
         if (w.has_seg) {
-            for (int it = w.segi; it < w.tri; it += w.N) w.S0[it * spw + sys] += w.S1[it * spw + sys];
-            for (int it = w.segi; it < w.mj; it += w.N) w.r0[it * spw + sys] += w.r1[it * spw + sys];
+            for (int it = w.segi; it < nbp9; it += w.N) w.S0[it * spw] += w.S1[it * spw];
+            for (int it = w.segi; it < mjp; it += w.N) w.r0[it * spw] += w.r1[it * spw];
         }
-        for (int k = 0; k < w.mj; ++k) {
+#pragma unroll 1
+        for (int K = 0; K < nb; ++K) {
             __syncwarp();
             if (w.has_seg) {
-                const double piv = w.S0[tidx(k, k) * spw + sys];
-                if (!(fabs(piv) > 0.0) || !isfinite(piv)) status |= 1;
-                const double inv = 1.0 / piv;
-                if (w.segi == 0) w.dinv[k * spw + sys] = inv;
-                for (int r = k + 1 + w.segi; r < w.mj; r += w.N) {
-                    const double t = w.S0[tidx(r, k) * spw + sys] * inv;
-                    for (int q = k + 1; q <= r; ++q)
-                        w.S0[tidx(r, q) * spw + sys] = fma(-t, w.S0[tidx(q, k) * spw + sys], w.S0[tidx(r, q) * spw + sys]);
+                const double* D = w.S0 + 9 * bpair(K, K) * spw;
+                double di[6];
+                sym3_inverse(D[0], D[3 * spw], D[4 * spw], D[6 * spw], D[7 * spw], D[8 * spw], di, status);
+                if (w.segi == 0) {
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) w.dinv[(6 * K + i) * spw] = di[i];
+                }
+#pragma unroll 1
+                for (int I = K + 1 + w.segi; I < nb; I += w.N) {
+                    double A[9], T[9];
+                    load9(w.S0 + 9 * bpair(I, K) * spw, spw, A);
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {  // T = A Dinv
+                        const V3 t = sym3_apply(di, mk(A[3 * r], A[3 * r + 1], A[3 * r + 2]));
+                        T[3 * r] = t.x, T[3 * r + 1] = t.y, T[3 * r + 2] = t.z;
+                    }
+#pragma unroll 1
+                    for (int J = K + 1; J <= I; ++J) {
+                        double Bj[9];
+                        load9(w.S0 + 9 * bpair(J, K) * spw, spw, Bj);
+                        double* Sij = w.S0 + 9 * bpair(I, J) * spw;
+#pragma unroll
+                        for (int r = 0; r < 3; ++r)
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) {
+                                const double upd = fma(T[3 * r], Bj[3 * q], fma(T[3 * r + 1], Bj[3 * q + 1], T[3 * r + 2] * Bj[3 * q + 2]));
+                                Sij[(3 * r + q) * spw] -= upd;
+                            }
+                    }
                 }
             }
         }
         __syncwarp();
-        // ---- G. triangular solves by the first lane of each system: L y = rhs ; lambda = L^-T D^-1 y
+        // ---- G. block triangular solves by the first lane of each system: L y = rhs ; lambda = L^-T D^-1 y
         if (w.has_seg && w.segi == 0) {
-            for (int k = 0; k < w.mj; ++k) {
-                double xx = w.r0[k * spw + sys];
-                for (int q = 0; q < k; ++q) xx = fma(-w.S0[tidx(k, q) * spw + sys], w.r1[q * spw + sys], xx);
-                w.r1[k * spw + sys] = xx * w.dinv[k * spw + sys];  // y-hat = D^-1 y
+#pragma unroll 1
+            for (int K = 0; K < nb; ++K) {
+                double di[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) di[i] = w.dinv[(6 * K + i) * spw];
+                const V3 yh = sym3_apply(di, mk(w.r0[(3 * K) * spw], w.r0[(3 * K + 1) * spw], w.r0[(3 * K + 2) * spw]));
+                w.r1[(3 * K) * spw] = yh.x, w.r1[(3 * K + 1) * spw] = yh.y, w.r1[(3 * K + 2) * spw] = yh.z;  // y-hat = D^-1 y
+#pragma unroll 1
+                for (int I = K + 1; I < nb; ++I) {
+                    double A[9];
+                    load9(w.S0 + 9 * bpair(I, K) * spw, spw, A);
+                    double* ri = w.r0 + 3 * I * spw;
+                    ri[0] -= fma(A[0], yh.x, fma(A[1], yh.y, A[2] * yh.z));
+                    ri[spw] -= fma(A[3], yh.x, fma(A[4], yh.y, A[5] * yh.z));
+                    ri[2 * spw] -= fma(A[6], yh.x, fma(A[7], yh.y, A[8] * yh.z));
+                }
             }
-            for (int k = w.mj - 1; k >= 0; --k) {
-                double acc = 0.0;
-                for (int r = k + 1; r < w.mj; ++r) acc = fma(w.S0[tidx(r, k) * spw + sys], w.r0[r * spw + sys], acc);
-                w.r0[k * spw + sys] = w.r1[k * spw + sys] - w.dinv[k * spw + sys] * acc;  // lambda_j
+#pragma unroll 1
+            for (int K = nb - 1; K >= 0; --K) {
+                V3 acc = mk(0.0, 0.0, 0.0);
+#pragma unroll 1
+                for (int I = K + 1; I < nb; ++I) {  // acc += S_IK^T lambda_I
+                    double A[9];
+                    load9(w.S0 + 9 * bpair(I, K) * spw, spw, A);
+                    const V3 li = mk(w.r0[(3 * I) * spw], w.r0[(3 * I + 1) * spw], w.r0[(3 * I + 2) * spw]);
+                    acc = axpy(li.x, mk(A[0], A[1], A[2]), axpy(li.y, mk(A[3], A[4], A[5]), axpy(li.z, mk(A[6], A[7], A[8]), acc)));
+                }
+                double di[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) di[i] = w.dinv[(6 * K + i) * spw];
+                const V3 corr = sym3_apply(di, acc);
+                w.r0[(3 * K) * spw] = w.r1[(3 * K) * spw] - corr.x;
+                w.r0[(3 * K + 1) * spw] = w.r1[(3 * K + 1) * spw] - corr.y;
+                w.r0[(3 * K + 2) * spw] = w.r1[(3 * K + 2) * spw] - corr.z;  // lambda_j
             }
         }
         __syncwarp();
@@ -655,21 +725,21 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
             for (int e = sg.side_begin; e < sg.side_end; ++e) {
                 const DevSide sd = w.side[e];
                 const DevBlk& b = w.blk[sd.blk];
+                const double* lj = w.r0 + b.jrow * spw;
                 if (!GENERAL || b.type == LIN3) {
                     double as[4];
                     lin3_coefs(b, sd.role, as);
-                    const V3 lam = mk(w.r0[(b.jrow + 0) * spw + sys], w.r0[(b.jrow + 1) * spw + sys],
-                                      w.r0[(b.jrow + 2) * spw + sys]);
+                    const V3 lam = mk(lj[0], lj[spw], lj[2 * spw]);
 #pragma unroll
                     for (int t = 0; t < 4; ++t) f.s[t] = axpy(-as[t], lam, f.s[t]);
                     if (lam_out != nullptr && sd.role == CHILD) {
                         lam_out[b.row_h + 0] = lam.x, lam_out[b.row_h + 1] = lam.y, lam_out[b.row_h + 2] = lam.z;
                     }
                 } else {
-                    const double lam = w.r0[b.jrow * spw + sys];
+                    const double lam = lj[0];
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
-                        const double* src = w.knl + (sd.nl_slot * 12 + 3 * t) * 32 + w.lane;
+                        const double* src = w.knl + (sd.nl_slot * 12 + 3 * t) * 32;
                         f.s[t] = axpy(-lam, mk(src[0], src[32], src[64]), f.s[t]);
                     }
                     if (lam_out != nullptr && sd.role == CHILD) lam_out[b.row_h] = lam;

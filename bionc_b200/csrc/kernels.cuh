@@ -88,22 +88,26 @@ __device__ __forceinline__ void setup_warp(const unsigned char* __restrict__ blo
     w.blk = reinterpret_cast<const DevBlk*>(smem + h->off_blk);
     w.side = reinterpret_cast<const DevSide*>(smem + h->off_side);
     w.fext = reinterpret_cast<const DevFext*>(smem + h->off_fext);
-    w.N = h->N, w.mj = h->mj, w.spw = h->spw, w.tri = h->mj * (h->mj + 1) / 2;
+    w.N = h->N, w.mj = h->mj, w.nb = h->nb, w.spw = h->spw;
     const int warp = threadIdx.x >> 5;
     w.lane = threadIdx.x & 31;
-    double* base = reinterpret_cast<double*>(smem + blob_bytes) + (size_t)warp * warp_smem_doubles(w.N, w.mj, w.spw, h->rnl);
-    w.Qs = base;
-    w.Qds = w.Qs + 12 * w.N * w.spw;
-    w.S0 = w.Qds + 12 * w.N * w.spw;
-    w.S1 = w.S0 + w.tri * w.spw;
-    w.r0 = w.S1 + w.tri * w.spw;
-    w.r1 = w.r0 + w.mj * w.spw;
-    w.dinv = w.r1 + w.mj * w.spw;
-    w.knl = w.dinv + w.mj * w.spw;
     w.sys = w.lane / w.N;
     w.segi = w.lane - w.sys * w.N;
     if (w.sys >= w.spw) w.sys = w.spw - 1, w.segi = 0, w.has_seg = false;
     else w.has_seg = true;
+    const int nbp9 = 9 * (w.nb * (w.nb + 1) / 2);
+    double* base = reinterpret_cast<double*>(smem + blob_bytes) + (size_t)warp * warp_smem_doubles(w.nb, w.spw, h->rnl);
+    double* Qs = base;
+    double* Qds = Qs + 12 * 32;
+    const int own_lane = w.sys * w.N + w.segi;  // == lane for lanes that own a segment
+    w.Qo = Qs + own_lane, w.Qdo = Qds + own_lane;
+    w.Qsys = Qs + w.sys * w.N, w.Qdsys = Qds + w.sys * w.N;
+    w.S0 = Qds + 12 * 32 + w.sys;
+    w.S1 = w.S0 + nbp9 * w.spw;
+    w.r0 = w.S1 + nbp9 * w.spw;
+    w.r1 = w.r0 + 3 * w.nb * w.spw;
+    w.dinv = w.r1 + 3 * w.nb * w.spw;
+    w.knl = (w.dinv - w.sys) + 6 * w.nb * w.spw + w.lane;
 }
 
 __device__ __forceinline__ void load_q12(const double* __restrict__ p, Q12& q) {
@@ -163,7 +167,7 @@ __global__ void __launch_bounds__(32 * kMaxWarpsPerCta, 3)
         load_q12(Qd + (size_t)gsys * n + 12 * w.segi, qd);
         if (w.has_seg) {
 #pragma unroll
-            for (int t = 0; t < 4; ++t) publish3(w, w.Qs, t, q.s[t]), publish3(w, w.Qds, t, qd.s[t]);
+            for (int t = 0; t < 4; ++t) publish3(w.Qo, t, q.s[t]), publish3(w.Qdo, t, qd.s[t]);
         }
     }
     __syncwarp();
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(32 * kMaxWarpsPerCta, 3)
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             accq.s[t] = mk(0.0, 0.0, 0.0), accv.s[t] = mk(0.0, 0.0, 0.0);
-            if (w.has_seg) publish3(w, w.Qs, t, y0q.s[t]), publish3(w, w.Qds, t, y0v.s[t]);
+            if (w.has_seg) publish3(w.Qo, t, y0q.s[t]), publish3(w.Qdo, t, y0v.s[t]);
         }
         __syncwarp();
 #pragma unroll 1
@@ -225,12 +229,12 @@ __global__ void __launch_bounds__(32 * kMaxWarpsPerCta, 3)
             const double cn = (stage == 2) ? h : 0.5 * h;  // next stage is y0 + cn * k_stage
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                const V3 sv = own3(w, w.Qds, t);
+                const V3 sv = own3(w.Qdo, t);
                 accq.s[t] = axpy(wt, sv, accq.s[t]);
                 accv.s[t] = axpy(wt, a.s[t], accv.s[t]);
                 if (stage < 3 && w.has_seg) {
-                    publish3(w, w.Qs, t, axpy(cn, sv, y0q.s[t]));
-                    publish3(w, w.Qds, t, axpy(cn, a.s[t], y0v.s[t]));
+                    publish3(w.Qo, t, axpy(cn, sv, y0q.s[t]));
+                    publish3(w.Qdo, t, axpy(cn, a.s[t], y0v.s[t]));
                 }
             }
             __syncwarp();

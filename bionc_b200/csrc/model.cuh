@@ -21,13 +21,14 @@ struct DevHeader {
     int nblk;     // constraint blocks
     int nside;    // (block, segment) incidences
     int mj;       // joint-constraint rows
+    int nb;       // 3x3 blocks of the joint-level Schur system (mj padded up to a multiple of 3)
     int m;        // holonomic rows = mj + 6 N
     int spw;      // systems per warp = 32 / N
     int rnl;      // max number of non-LIN3 rows touching one segment (k rows kept in shared memory)
     int nfext;    // external forces
     int blob_bytes;
     int off_seg, off_blk, off_side, off_fext;  // byte offsets inside the blob
-    int pad[3];
+    int pad[2];
 };
 
 struct DevSeg {
@@ -62,12 +63,13 @@ struct DevFext {
 };
 
 // Per-warp shared-memory working set, in doubles (see dynamics.cuh for the layout).
-__host__ __device__ inline int warp_smem_doubles(int N, int mj, int spw, int rnl) {
-    const int tri = mj * (mj + 1) / 2;
-    return 2 * 12 * N * spw      // published Q, Qdot of the current stage
-           + 2 * tri * spw       // two exclusive-writer copies of the joint-level Schur matrix
-           + 3 * mj * spw        // rhs copy 0 / copy 1 (-> y-hat), dinv
-           + rnl * 12 * 32;      // k rows of non-LIN3 blocks, private per lane
+__host__ __device__ inline int warp_smem_doubles(int nb, int spw, int rnl) {
+    const int nbp = nb * (nb + 1) / 2;
+    return 2 * 12 * 32            // published Q, Qdot of the current stage, [12][32 lanes] each
+           + 2 * 9 * nbp * spw    // two exclusive-writer copies of the blocked joint-level Schur matrix
+           + 2 * 3 * nb * spw     // rhs copy 0 / copy 1 (-> y-hat)
+           + 6 * nb * spw         // inverse pivot blocks
+           + rnl * 12 * 32;       // k rows of non-LIN3 blocks, private per lane
 }
 
 }  // namespace bionc
