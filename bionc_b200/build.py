@@ -39,7 +39,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = [nvcc_path(), *NVCC_FLAGS] + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    extra = os.environ.get("BIONC_NVCC_EXTRA", "").split()
+    cmd = [nvcc_path(), *NVCC_FLAGS, *extra] + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)

@@ -74,6 +74,7 @@ struct BioncModel {
     std::vector<DevSeg> seg;
     std::vector<DevBlk> blk;
     std::vector<DevSide> side;
+    std::vector<int> sym;  // symbolic factorisation tables (see DevHeader::off_sym)
     // device blob for the current external-force set (rebuilt when the set changes)
     std::vector<unsigned char> fext_key;
     unsigned char* d_blob = nullptr;
@@ -91,6 +92,131 @@ struct BioncModel {
 };
 
 namespace {
+
+// ---------------------------------------------------------------------------------------------
+// Symbolic analysis of the joint-level Schur complement S' (host, once per model).
+//
+// The rows of S' are grouped into 3-row "nodes": every LIN3 block is one node, the single rows of the
+// other block kinds are packed three to a node (padded with unit rows).  Two nodes are coupled when
+// a segment is touched by both.  The nodes are renumbered with a greedy minimum-degree ordering, the
+// fill pattern of the block LDL^T is computed, and the kernel receives
+//   slot_tab / slot2_tab : storage slot of block (I, J), I >= J (-1 outside the pattern); the second
+//                          copy exists for blocks that can receive contributions from two segments
+//   zero list            : slots the assembly does not fully overwrite (pure fill, nodes with single rows)
+//   combine list         : (slot, slot2) pairs to add after the assembly
+//   unit list            : diagonal elements of padding rows
+//   column lists         : for every pivot node K the nodes I > K with a block (I, K)
+// Sets DevBlk::jrow and the header counts; returns mj (number of real joint rows).
+// ---------------------------------------------------------------------------------------------
+int symbolic_analysis(BioncModel* M, int N) {
+    const int nblk = (int)M->blk.size();
+    // nodes in natural order: LIN3 blocks first, then singles three at a time
+    std::vector<std::vector<int>> node_blocks;  // blocks of every node, in row order
+    std::vector<char> mixed;                    // node holds single rows
+    for (int b = 0; b < nblk; ++b)
+        if (M->blk[b].type == LIN3) node_blocks.push_back({b}), mixed.push_back(0);
+    int mj = 3 * (int)node_blocks.size();
+    {
+        std::vector<int> cur;
+        for (int b = 0; b < nblk; ++b)
+            if (M->blk[b].type != LIN3) {
+                cur.push_back(b), ++mj;
+                if (cur.size() == 3) node_blocks.push_back(cur), mixed.push_back(1), cur.clear();
+            }
+        if (!cur.empty()) node_blocks.push_back(cur), mixed.push_back(1);
+    }
+    const int nb = (int)node_blocks.size();
+    // contributions: number of segments shared by two nodes
+    std::vector<int> contrib(nb * nb, 0);
+    for (int sgm = 0; sgm < N; ++sgm) {
+        std::vector<int> touched;
+        for (int I = 0; I < nb; ++I)
+            for (int b : node_blocks[I])
+                if (M->blk[b].child == sgm || M->blk[b].parent == sgm) {
+                    touched.push_back(I);
+                    break;
+                }
+        for (int I : touched)
+            for (int J : touched) contrib[I * nb + J] += 1;
+    }
+    // greedy minimum-degree ordering on the node graph (with fill), ties broken by index
+    std::vector<char> adj(nb * nb, 0), gone(nb, 0);
+    for (int I = 0; I < nb; ++I)
+        for (int J = 0; J < nb; ++J) adj[I * nb + J] = (I != J && contrib[I * nb + J] > 0);
+    std::vector<int> order;
+    for (int step = 0; step < nb; ++step) {
+        int best = -1, best_deg = 1 << 30;
+        for (int I = 0; I < nb; ++I) {
+            if (gone[I]) continue;
+            int deg = 0;
+            for (int J = 0; J < nb; ++J) deg += (!gone[J] && adj[I * nb + J]);
+            if (deg < best_deg) best_deg = deg, best = I;
+        }
+        order.push_back(best), gone[best] = 1;
+        for (int I = 0; I < nb; ++I)
+            for (int J = 0; J < nb; ++J)
+                if (I != J && !gone[I] && !gone[J] && adj[I * nb + best] && adj[J * nb + best]) adj[I * nb + J] = 1;
+    }
+    std::vector<int> newidx(nb);
+    for (int k = 0; k < nb; ++k) newidx[order[k]] = k;
+    // renumbered structures
+    std::vector<int> contrib2(nb * nb, 0);
+    std::vector<char> mixed2(nb, 0), pat(nb * nb, 0);
+    for (int I = 0; I < nb; ++I) {
+        mixed2[newidx[I]] = mixed[I];
+        for (int J = 0; J < nb; ++J) contrib2[newidx[I] * nb + newidx[J]] = contrib[I * nb + J];
+    }
+    for (int I = 0; I < nb; ++I) {
+        int r = 0;
+        for (int b : node_blocks[I]) {
+            M->blk[b].jrow = 3 * newidx[I] + r;
+            r += (M->blk[b].type == LIN3) ? 3 : 1;
+        }
+    }
+    for (int I = 0; I < nb; ++I)
+        for (int J = 0; J <= I; ++J) pat[I * nb + J] = (I == J) || contrib2[I * nb + J] > 0;
+    for (int K = 0; K < nb; ++K)  // symbolic elimination: fill
+        for (int I = K + 1; I < nb; ++I)
+            if (pat[I * nb + K])
+                for (int J = K + 1; J <= I; ++J)
+                    if (pat[J * nb + K]) pat[I * nb + J] = 1;
+    std::vector<int> slot_tab(nb * nb, -1), slot2_tab(nb * nb, -1), zero, comb, unit, colptr(nb + 1, 0), colrow;
+    int nslot = 0, nslot2 = 0;
+    for (int I = 0; I < nb; ++I)
+        for (int J = 0; J <= I; ++J)
+            if (pat[I * nb + J]) {
+                const int s = nslot++;
+                slot_tab[I * nb + J] = s;
+                const bool any_mixed = mixed2[I] || mixed2[J];
+                const int c = contrib2[I * nb + J];
+                int s2 = -1;
+                if (c >= 2 || (any_mixed && c >= 1)) s2 = nslot2++, slot2_tab[I * nb + J] = s2;
+                if (c == 0 || any_mixed) {  // not fully overwritten by the assembly
+                    zero.push_back(s);
+                    if (s2 >= 0) zero.push_back(-(s2 + 1));  // negative: second copy
+                }
+                if (s2 >= 0) comb.push_back(s), comb.push_back(s2);
+            }
+    // padding rows sit at the end of the node that received the last single rows
+    for (int I = 0; I < nb; ++I)
+        if (mixed[I]) {
+            int rows = (int)node_blocks[I].size();
+            for (int r = rows; r < 3; ++r) unit.push_back(9 * slot_tab[newidx[I] * nb + newidx[I]] + 4 * r);
+        }
+    for (int K = 0; K < nb; ++K) {
+        for (int I = K + 1; I < nb; ++I)
+            if (pat[I * nb + K]) colrow.push_back(I);
+        colptr[K + 1] = (int)colrow.size();
+    }
+    M->sym.clear();
+    auto append = [&](const std::vector<int>& v) { M->sym.insert(M->sym.end(), v.begin(), v.end()); };
+    append(slot_tab), append(slot2_tab), append(zero), append(comb), append(unit), append(colptr), append(colrow);
+    M->hdr.nb = nb, M->hdr.nslot = nslot, M->hdr.nslot2 = nslot2;
+    M->hdr.nzero = (int)zero.size(), M->hdr.ncomb = (int)comb.size() / 2, M->hdr.nunit = (int)unit.size();
+    M->hdr.ncol = (int)colrow.size();
+    return mj;
+}
+
 
 int build_blob(BioncModel* M, const BioncFextDesc* fx) {
     // key = raw bytes of the force description
@@ -130,22 +256,32 @@ int build_blob(BioncModel* M, const BioncFextDesc* fx) {
     h.off_blk = align16(h.off_seg + (int)(seg.size() * sizeof(DevSeg)));
     h.off_side = align16(h.off_blk + (int)(M->blk.size() * sizeof(DevBlk)));
     h.off_fext = align16(h.off_side + (int)(M->side.size() * sizeof(DevSide)));
-    h.blob_bytes = align16(h.off_fext + (int)(fext.size() * sizeof(DevFext)));
+    h.off_sym = align16(h.off_fext + (int)(fext.size() * sizeof(DevFext)));
+    h.blob_bytes = align16(h.off_sym + (int)(M->sym.size() * sizeof(int)));
     std::vector<unsigned char> blob(h.blob_bytes, 0);
     std::memcpy(blob.data(), &h, sizeof(h));
     std::memcpy(blob.data() + h.off_seg, seg.data(), seg.size() * sizeof(DevSeg));
     if (!M->blk.empty()) std::memcpy(blob.data() + h.off_blk, M->blk.data(), M->blk.size() * sizeof(DevBlk));
     if (!M->side.empty()) std::memcpy(blob.data() + h.off_side, M->side.data(), M->side.size() * sizeof(DevSide));
     if (!fext.empty()) std::memcpy(blob.data() + h.off_fext, fext.data(), fext.size() * sizeof(DevFext));
+    if (!M->sym.empty()) std::memcpy(blob.data() + h.off_sym, M->sym.data(), M->sym.size() * sizeof(int));
 
-    // shared-memory budget: as many warps per CTA (<= 4) as fit
-    int dev_smem = 0;
+    // shared-memory budget: pick the CTA size (1..4 warps) that keeps the most warps resident per SM
+    // (every CTA carries its own copy of the blob; 168 registers/thread cap residency at 12 warps)
+    int dev_smem = 0, sm_smem = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, M->device));
-    const size_t per_warp = (size_t)warp_smem_doubles(h.nb, h.spw, h.rnl) * sizeof(double);
-    int warps = kMaxWarpsPerCta;
-    while (warps > 1 && h.blob_bytes + warps * per_warp > (size_t)dev_smem) warps >>= 1;
-    if (h.blob_bytes + warps * per_warp > (size_t)dev_smem)
-        return fail(BIONC_E_TOO_LARGE, "model needs more shared memory per warp than one SM has");
+    CUDA_TRY(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, M->device));
+    const size_t per_warp = (size_t)warp_smem_doubles(h.nb, h.nslot, h.nslot2, h.spw, h.rnl) * sizeof(double);
+    int warps = 0, best_resident = 0;
+    for (int wcta = kMaxWarpsPerCta; wcta >= 1; --wcta) {
+        const size_t cta = h.blob_bytes + wcta * per_warp;
+        if (cta > (size_t)dev_smem) continue;
+        int ctas = (int)((size_t)sm_smem / (cta + 1024));  // 1 KB reserved per CTA by the driver
+        int resident = ctas * wcta;
+        if (resident > 12) resident = 12;
+        if (resident > best_resident) best_resident = resident, warps = wcta;
+    }
+    if (warps == 0) return fail(BIONC_E_TOO_LARGE, "model needs more shared memory per warp than one SM has");
 
     CUDA_TRY(cudaSetDevice(M->device));
     if (M->d_blob != nullptr && M->blob_bytes < h.blob_bytes) {
@@ -212,31 +348,22 @@ int bionc_cuda_model_create(const BioncModelDesc* d, int device, BioncModel** ou
     M->device = device;
     M->seg.resize(N);
     M->blk.resize(nblk);
-    // Internal row order of the joint-level Schur system: LIN3 blocks first (each is one whole 3x3 block
-    // row), then the single rows of the other block kinds, padded with unit rows to a multiple of 3.
-    int mj = 0;
-    for (int pass = 0; pass < 2; ++pass)
-        for (int b = 0; b < nblk; ++b) {
-            DevBlk& B = M->blk[b];
-            if (pass == 0) {
-                std::memset(&B, 0, sizeof(B));
-                B.type = d->blk_type[b], B.parent = d->blk_parent[b], B.child = d->blk_child[b];
-                if (B.type < 0 || B.type > 3 || B.child < 0 || B.child >= N || B.parent < -1 || B.parent >= N || B.parent == B.child) {
-                    delete M;
-                    return fail(BIONC_E_INVALID, "malformed constraint block");
-                }
-                if (B.parent < 0 && (B.type == CLEN || B.type == SOP)) {
-                    delete M;
-                    return fail(BIONC_E_INVALID, "constant-length / sphere-on-plane blocks need two segments");
-                }
-                B.row_h = d->blk_row_h[b], B.row_j = d->blk_row_j[b];
-                std::memcpy(B.p, d->blk_param + (size_t)b * kBlkNParam, kBlkNParam * sizeof(double));
-            }
-            if ((pass == 0) == (B.type == LIN3)) {
-                B.jrow = mj;
-                mj += (B.type == LIN3) ? 3 : 1;
-            }
+    for (int b = 0; b < nblk; ++b) {
+        DevBlk& B = M->blk[b];
+        std::memset(&B, 0, sizeof(B));
+        B.type = d->blk_type[b], B.parent = d->blk_parent[b], B.child = d->blk_child[b];
+        if (B.type < 0 || B.type > 3 || B.child < 0 || B.child >= N || B.parent < -1 || B.parent >= N || B.parent == B.child) {
+            delete M;
+            return fail(BIONC_E_INVALID, "malformed constraint block");
         }
+        if (B.parent < 0 && (B.type == CLEN || B.type == SOP)) {
+            delete M;
+            return fail(BIONC_E_INVALID, "constant-length / sphere-on-plane blocks need two segments");
+        }
+        B.row_h = d->blk_row_h[b], B.row_j = d->blk_row_j[b];
+        std::memcpy(B.p, d->blk_param + (size_t)b * kBlkNParam, kBlkNParam * sizeof(double));
+    }
+    const int mj = symbolic_analysis(M, N);
     int rnl = 0;
     for (int i = 0; i < N; ++i) {
         DevSeg& S = M->seg[i];
@@ -285,7 +412,7 @@ int bionc_cuda_model_create(const BioncModelDesc* d, int device, BioncModel** ou
         if (nl > rnl) rnl = nl;
     }
     M->hdr.N = N, M->hdr.nblk = nblk, M->hdr.nside = (int)M->side.size();
-    M->hdr.mj = mj, M->hdr.nb = (mj + 2) / 3, M->hdr.m = mj + 6 * N, M->hdr.spw = 32 / N, M->hdr.rnl = rnl;
+    M->hdr.mj = mj, M->hdr.m = mj + 6 * N, M->hdr.spw = 32 / N, M->hdr.rnl = rnl;
     *out = M;
     return BIONC_OK;
 }

@@ -169,8 +169,10 @@ __device__ __forceinline__ void sr_factor(SegCtx& c, int& status) {
 // code addresses them with compile-time multiples of a stride:
 //   Qo/Qdo     own segment's stage state, slot element k at Qo[k * 32]          ([12][32 lanes])
 //   Qsys/Qdsys the system's first lane; segment s, element k at Qsys[s + k * 32]
-//   S0/S1      joint-level Schur matrix as 3x3 blocks: block pair p = I(I+1)/2 + J (I >= J),
-//              element e = 3 r + c at S0[(9 p + e) * spw]                       ([9 nbp][spw])
+//   S0/S1      joint-level Schur matrix as 3x3 blocks: the block (I, J), I >= J, lives in storage slot
+//              p = slot_tab[I nb + J] (structural non-zeros + fill only), element e = 3 r + c at
+//              S0[(9 p + e) * spw]; S1 holds the second exclusive-writer copy of the blocks that can
+//              receive contributions from two segments (slot2_tab)           ([9 nslot][spw])
 //   r0/r1      right-hand side / y-hat, row j at r0[j * spw]                    ([3 nb][spw])
 //   dinv       inverse diagonal blocks, 6 unique entries of block K at dinv[(6 K + i) * spw]
 //   knl        explicit rows of non-LIN3 blocks, slot q element i at knl[(12 q + i) * 32]
@@ -183,6 +185,8 @@ struct WarpCtx {
     const DevFext* fext;
     double *Qo, *Qdo, *Qsys, *Qdsys;
     double *S0, *S1, *r0, *r1, *dinv, *knl;
+    // symbolic factorisation tables (host, capi.cu symbolic_analysis)
+    const int *slot_tab, *slot2_tab, *zero_list, *comb_list, *unit_list, *colptr, *colrow;
     int spw, N, mj, nb;
     int sys;   // system index inside the warp
     int segi;  // this lane's segment
@@ -190,7 +194,6 @@ struct WarpCtx {
     bool has_seg;  // lane maps to a (system, segment) pair
 };
 
-__device__ __forceinline__ constexpr int bpair(int I, int J) { return I * (I + 1) / 2 + J; }  // I >= J
 
 // linear form over a segment's published state: sum_t a[t] * X[segment s, slot t]
 __device__ __forceinline__ V3 lin_form(const WarpCtx& w, const double* Xsys, int s, const double* a) {
@@ -476,17 +479,22 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
             }
             break;
         }
-        const int nb = w.nb, nbp9 = 9 * (nb * (nb + 1) / 2), mjp = 3 * nb;
+        const int nb = w.nb, mjp = 3 * nb;
+        const DevHeader* hd = w.hdr;
 
-        // ---- C. zero the joint-level system (cooperatively by the lanes of the system); padding rows
-        //         (the system is padded to whole 3x3 blocks) get a unit diagonal
+        // ---- C. zero what the assembly does not overwrite: the right-hand sides, pure fill blocks and
+        //         the blocks of nodes made of single rows; padding rows get a unit diagonal
         if (w.has_seg) {
-            for (int it = w.segi; it < nbp9; it += w.N) w.S0[it * spw] = 0.0, w.S1[it * spw] = 0.0;
             for (int it = w.segi; it < mjp; it += w.N) w.r0[it * spw] = 0.0, w.r1[it * spw] = 0.0;
+            for (int it = w.segi; it < 9 * hd->nzero; it += w.N) {
+                const int z = w.zero_list[it / 9], e = it - 9 * (it / 9);
+                double* dst = z >= 0 ? w.S0 + (9 * z + e) * spw : w.S1 + (9 * (-z - 1) + e) * spw;
+                *dst = 0.0;
+            }
         }
         __syncwarp();
         if (w.has_seg && w.segi == 0) {
-            for (int r = w.mj; r < mjp; ++r) w.S0[(9 * bpair(nb - 1, nb - 1) + 4 * (r - 3 * (nb - 1))) * spw] = 1.0;
+            for (int it = 0; it < hd->nunit; ++it) w.S0[w.unit_list[it] * spw] = 1.0;
         }
 
         // ---- D. right-hand side rhs' = Kj abar + b_j (copy `role` of each row is written by exactly one
@@ -570,10 +578,20 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                     const V3 col0 = mk(0, 0, 0) - axpy(c.u.x, Pc[0], axpy(c.v.x, Pc[1], c.w.x * Pc[2]));
                     const V3 col1 = mk(0, 0, 0) - axpy(c.u.y, Pc[0], axpy(c.v.y, Pc[1], c.w.y * Pc[2]));
                     const V3 col2 = mk(0, 0, 0) - axpy(c.u.z, Pc[0], axpy(c.v.z, Pc[1], c.w.z * Pc[2]));
-                    double* Sc = (sa.role == CHILD ? w.S0 : w.S1) + 9 * bpair(a.jrow / 3, Jb) * spw;
-                    Sc[0 * spw] = col0.x + gamma, Sc[1 * spw] = col1.x, Sc[2 * spw] = col2.x;
-                    Sc[3 * spw] = col0.y, Sc[4 * spw] = col1.y + gamma, Sc[5 * spw] = col2.y;
-                    Sc[6 * spw] = col0.z, Sc[7 * spw] = col1.z, Sc[8 * spw] = col2.z + gamma;
+                    const int Ia = a.jrow / 3;
+                    if (Ia >= Jb) {  // block (Ia, Jb): rows of a, columns of b
+                        const int s2 = w.slot2_tab[Ia * nb + Jb];
+                        double* Sc = (sa.role == PARENT && s2 >= 0) ? w.S1 + 9 * s2 * spw : w.S0 + 9 * w.slot_tab[Ia * nb + Jb] * spw;
+                        Sc[0 * spw] = col0.x + gamma, Sc[1 * spw] = col1.x, Sc[2 * spw] = col2.x;
+                        Sc[3 * spw] = col0.y, Sc[4 * spw] = col1.y + gamma, Sc[5 * spw] = col2.y;
+                        Sc[6 * spw] = col0.z, Sc[7 * spw] = col1.z, Sc[8 * spw] = col2.z + gamma;
+                    } else {  // block (Jb, Ia): transposed; the copy follows this lane's role in the larger node b
+                        const int s2 = w.slot2_tab[Jb * nb + Ia];
+                        double* Sc = (sd.role == PARENT && s2 >= 0) ? w.S1 + 9 * s2 * spw : w.S0 + 9 * w.slot_tab[Jb * nb + Ia] * spw;
+                        Sc[0 * spw] = col0.x + gamma, Sc[1 * spw] = col0.y, Sc[2 * spw] = col0.z;
+                        Sc[3 * spw] = col1.x, Sc[4 * spw] = col1.y + gamma, Sc[5 * spw] = col1.z;
+                        Sc[6 * spw] = col2.x, Sc[7 * spw] = col2.y, Sc[8 * spw] = col2.z + gamma;
+                    }
                 }
             }
         }
@@ -610,15 +628,17 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                         V3 r = mk(0.0, 0.0, 0.0);
 #pragma unroll
                         for (int t = 0; t < 4; ++t) r = axpy(asa[t], q.s[t], r);
-                        const int Ia = a.jrow / 3;  // LIN3 blocks are whole 3x3 block rows, never Ib
+                        const int Ia = a.jrow / 3;  // LIN3 blocks are whole nodes, never Ib
                         if (Ia > Ib) {  // rows of a, column rb
-                            double* Sc = (sa.role == CHILD ? w.S0 : w.S1) + (9 * bpair(Ia, Ib) + rb) * spw;
+                            const int s2 = w.slot2_tab[Ia * nb + Ib];
+                            double* Sc = ((sa.role == PARENT && s2 >= 0) ? w.S1 + 9 * s2 * spw : w.S0 + 9 * w.slot_tab[Ia * nb + Ib] * spw) + rb * spw;
                             Sc[0] = r.x, Sc[3 * spw] = r.y, Sc[6 * spw] = r.z;
                         } else {  // row rb, columns of a
-                            double* Sc = (sd.role == CHILD ? w.S0 : w.S1) + (9 * bpair(Ib, Ia) + 3 * rb) * spw;
+                            const int s2 = w.slot2_tab[Ib * nb + Ia];
+                            double* Sc = ((sd.role == PARENT && s2 >= 0) ? w.S1 + 9 * s2 * spw : w.S0 + 9 * w.slot_tab[Ib * nb + Ia] * spw) + 3 * rb * spw;
                             Sc[0] = r.x, Sc[spw] = r.y, Sc[2 * spw] = r.z;
                         }
-                    } else if (e2 >= e) {  // a.jrow >= b.jrow
+                    } else if (e2 >= e) {  // every pair of single rows once
                         double acc = 0.0;
 #pragma unroll
                         for (int t = 0; t < 4; ++t) {
@@ -626,48 +646,61 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                             acc += dot(mk(src[0], src[32], src[64]), q.s[t]);
                         }
                         const int Ia = a.jrow / 3, ra = a.jrow - 3 * Ia;
-                        double* Sc = (sa.role == CHILD ? w.S0 : w.S1) + 9 * bpair(Ia, Ib) * spw;
-                        Sc[(3 * ra + rb) * spw] = acc;
-                        if (Ia == Ib && ra != rb) Sc[(3 * rb + ra) * spw] = acc;  // keep diagonal blocks symmetric
+                        // the larger ROW decides the block orientation and whose role picks the copy
+                        const bool a_larger = a.jrow >= b.jrow;
+                        const int Ihi = a_larger ? Ia : Ib, Ilo = a_larger ? Ib : Ia;
+                        const int rhi = a_larger ? ra : rb, rlo = a_larger ? rb : ra;
+                        const int role = a_larger ? sa.role : sd.role;
+                        const int s2 = w.slot2_tab[Ihi * nb + Ilo];
+                        double* Sc = (role == PARENT && s2 >= 0) ? w.S1 + 9 * s2 * spw : w.S0 + 9 * w.slot_tab[Ihi * nb + Ilo] * spw;
+                        Sc[(3 * rhi + rlo) * spw] = acc;
+                        if (Ihi == Ilo && rhi != rlo) Sc[(3 * rlo + rhi) * spw] = acc;  // keep diagonal blocks symmetric
                     }
                 }
             }
         }
         __syncwarp();
 
-        // ---- F. combine the two copies, then blocked LDL^T of S' in place with 3x3 pivots: block rows are
-        //         dealt round-robin to the lanes of the system, every block operation runs in registers.
-        //         Block column K is final before step K, so one __syncwarp per pivot block suffices;
-        //         S_IK is kept unscaled (L_IK = S_IK D_K^-1 is applied through y-hat in the solves).
+        // ---- F. combine the second copies, then sparse blocked LDL^T of S' in place with 3x3 pivots along the
+        //         host-computed pattern: for pivot node K the block rows I of its column list are dealt
+        //         round-robin to the lanes of the system, every block operation runs in registers.
+        //         Block column K is final before step K, so one __syncwarp per pivot suffices; S_IK is
+        //         kept unscaled (L_IK = S_IK D_K^-1 is applied through y-hat in the solves).
         if (w.has_seg) {
-            for (int it = w.segi; it < nbp9; it += w.N) w.S0[it * spw] += w.S1[it * spw];
+            for (int it = w.segi; it < 9 * hd->ncomb; it += w.N) {
+                const int cpair = it / 9, e = it - 9 * cpair;
+                w.S0[(9 * w.comb_list[2 * cpair] + e) * spw] += w.S1[(9 * w.comb_list[2 * cpair + 1] + e) * spw];
+            }
             for (int it = w.segi; it < mjp; it += w.N) w.r0[it * spw] += w.r1[it * spw];
         }
 #pragma unroll 1
         for (int K = 0; K < nb; ++K) {
             __syncwarp();
             if (w.has_seg) {
-                const double* D = w.S0 + 9 * bpair(K, K) * spw;
+                const double* D = w.S0 + 9 * w.slot_tab[K * nb + K] * spw;
                 double di[6];
                 sym3_inverse(D[0], D[3 * spw], D[4 * spw], D[6 * spw], D[7 * spw], D[8 * spw], di, status);
                 if (w.segi == 0) {
 #pragma unroll
                     for (int i = 0; i < 6; ++i) w.dinv[(6 * K + i) * spw] = di[i];
                 }
+                const int c0 = w.colptr[K], c1 = w.colptr[K + 1];
 #pragma unroll 1
-                for (int I = K + 1 + w.segi; I < nb; I += w.N) {
+                for (int ci = c0 + w.segi; ci < c1; ci += w.N) {
+                    const int I = w.colrow[ci];
                     double A[9], T[9];
-                    load9(w.S0 + 9 * bpair(I, K) * spw, spw, A);
+                    load9(w.S0 + 9 * w.slot_tab[I * nb + K] * spw, spw, A);
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {  // T = A Dinv
                         const V3 t = sym3_apply(di, mk(A[3 * r], A[3 * r + 1], A[3 * r + 2]));
                         T[3 * r] = t.x, T[3 * r + 1] = t.y, T[3 * r + 2] = t.z;
                     }
 #pragma unroll 1
-                    for (int J = K + 1; J <= I; ++J) {
+                    for (int cj = c0; cj <= ci; ++cj) {  // every J <= I of the same column: (I, J) is in the pattern
+                        const int J = w.colrow[cj];
                         double Bj[9];
-                        load9(w.S0 + 9 * bpair(J, K) * spw, spw, Bj);
-                        double* Sij = w.S0 + 9 * bpair(I, J) * spw;
+                        load9(w.S0 + 9 * w.slot_tab[J * nb + K] * spw, spw, Bj);
+                        double* Sij = w.S0 + 9 * w.slot_tab[I * nb + J] * spw;
 #pragma unroll
                         for (int r = 0; r < 3; ++r)
 #pragma unroll
@@ -690,9 +723,10 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                 const V3 yh = sym3_apply(di, mk(w.r0[(3 * K) * spw], w.r0[(3 * K + 1) * spw], w.r0[(3 * K + 2) * spw]));
                 w.r1[(3 * K) * spw] = yh.x, w.r1[(3 * K + 1) * spw] = yh.y, w.r1[(3 * K + 2) * spw] = yh.z;  // y-hat = D^-1 y
 #pragma unroll 1
-                for (int I = K + 1; I < nb; ++I) {
+                for (int ci = w.colptr[K]; ci < w.colptr[K + 1]; ++ci) {
+                    const int I = w.colrow[ci];
                     double A[9];
-                    load9(w.S0 + 9 * bpair(I, K) * spw, spw, A);
+                    load9(w.S0 + 9 * w.slot_tab[I * nb + K] * spw, spw, A);
                     double* ri = w.r0 + 3 * I * spw;
                     ri[0] -= fma(A[0], yh.x, fma(A[1], yh.y, A[2] * yh.z));
                     ri[spw] -= fma(A[3], yh.x, fma(A[4], yh.y, A[5] * yh.z));
@@ -703,9 +737,10 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
             for (int K = nb - 1; K >= 0; --K) {
                 V3 acc = mk(0.0, 0.0, 0.0);
 #pragma unroll 1
-                for (int I = K + 1; I < nb; ++I) {  // acc += S_IK^T lambda_I
+                for (int ci = w.colptr[K]; ci < w.colptr[K + 1]; ++ci) {  // acc += S_IK^T lambda_I
+                    const int I = w.colrow[ci];
                     double A[9];
-                    load9(w.S0 + 9 * bpair(I, K) * spw, spw, A);
+                    load9(w.S0 + 9 * w.slot_tab[I * nb + K] * spw, spw, A);
                     const V3 li = mk(w.r0[(3 * I) * spw], w.r0[(3 * I + 1) * spw], w.r0[(3 * I + 2) * spw]);
                     acc = axpy(li.x, mk(A[0], A[1], A[2]), axpy(li.y, mk(A[3], A[4], A[5]), axpy(li.z, mk(A[6], A[7], A[8]), acc)));
                 }

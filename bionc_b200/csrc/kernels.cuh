@@ -5,6 +5,9 @@
 namespace bionc {
 
 constexpr int kMaxWarpsPerCta = 4;
+#ifndef BIONC_MIN_CTAS
+#define BIONC_MIN_CTAS 3  // CTAs per SM the register allocation is sized for (168 registers/thread)
+#endif
 
 // ---- inverse of a symmetric 4x4 given by its packed upper triangle (LDL^T, no pivoting) ----------
 __device__ __forceinline__ void sym4_inverse(const double (&M)[10], double (&Wout)[10], int& status) {
@@ -95,19 +98,27 @@ __device__ __forceinline__ void setup_warp(const unsigned char* __restrict__ blo
     w.segi = w.lane - w.sys * w.N;
     if (w.sys >= w.spw) w.sys = w.spw - 1, w.segi = 0, w.has_seg = false;
     else w.has_seg = true;
-    const int nbp9 = 9 * (w.nb * (w.nb + 1) / 2);
-    double* base = reinterpret_cast<double*>(smem + blob_bytes) + (size_t)warp * warp_smem_doubles(w.nb, w.spw, h->rnl);
+    double* base = reinterpret_cast<double*>(smem + blob_bytes) +
+                   (size_t)warp * warp_smem_doubles(w.nb, h->nslot, h->nslot2, w.spw, h->rnl);
     double* Qs = base;
     double* Qds = Qs + 12 * 32;
     const int own_lane = w.sys * w.N + w.segi;  // == lane for lanes that own a segment
     w.Qo = Qs + own_lane, w.Qdo = Qds + own_lane;
     w.Qsys = Qs + w.sys * w.N, w.Qdsys = Qds + w.sys * w.N;
     w.S0 = Qds + 12 * 32 + w.sys;
-    w.S1 = w.S0 + nbp9 * w.spw;
-    w.r0 = w.S1 + nbp9 * w.spw;
+    w.S1 = w.S0 + 9 * h->nslot * w.spw;
+    w.r0 = w.S1 + 9 * h->nslot2 * w.spw;
     w.r1 = w.r0 + 3 * w.nb * w.spw;
     w.dinv = w.r1 + 3 * w.nb * w.spw;
     w.knl = (w.dinv - w.sys) + 6 * w.nb * w.spw + w.lane;
+    const int* sym = reinterpret_cast<const int*>(smem + h->off_sym);
+    w.slot_tab = sym;
+    w.slot2_tab = w.slot_tab + w.nb * w.nb;
+    w.zero_list = w.slot2_tab + w.nb * w.nb;
+    w.comb_list = w.zero_list + h->nzero;
+    w.unit_list = w.comb_list + 2 * h->ncomb;
+    w.colptr = w.unit_list + h->nunit;
+    w.colrow = w.colptr + w.nb + 1;
 }
 
 __device__ __forceinline__ void load_q12(const double* __restrict__ p, Q12& q) {
@@ -145,7 +156,7 @@ __device__ __forceinline__ void load_constants(const WarpCtx& w, const double* _
 // forward_dynamics(Q, Qdot) -> Qddot, lambda       (biomechanical_model.py:351-429, batched)
 // ---------------------------------------------------------------------------------------------
 template <bool GENERAL>
-__global__ void __launch_bounds__(32 * kMaxWarpsPerCta, 3)
+__global__ void __launch_bounds__(32 * kMaxWarpsPerCta, BIONC_MIN_CTAS)
     forward_dynamics_kernel(const unsigned char* __restrict__ blob, int blob_bytes, const double* __restrict__ Q,
                             const double* __restrict__ Qd, const double* __restrict__ inertia, DynOpts o,
                             double* __restrict__ Qdd, double* __restrict__ lam, int* __restrict__ status_out,
@@ -188,7 +199,7 @@ __global__ void __launch_bounds__(32 * kMaxWarpsPerCta, 3)
 // per-lane values that the compiler keeps in registers or spills to L1-resident local memory.
 // ---------------------------------------------------------------------------------------------
 template <bool GENERAL>
-__global__ void __launch_bounds__(32 * kMaxWarpsPerCta, 3)
+__global__ void __launch_bounds__(32 * kMaxWarpsPerCta, BIONC_MIN_CTAS)
     rk4_kernel(const unsigned char* __restrict__ blob, int blob_bytes, double* __restrict__ Q, double* __restrict__ Qd,
                const double* __restrict__ inertia, DynOpts o, double h_const, const double* __restrict__ h_steps,
                long long n_steps, int normalize, double* __restrict__ traj, long long traj_every,

@@ -21,14 +21,23 @@ struct DevHeader {
     int nblk;     // constraint blocks
     int nside;    // (block, segment) incidences
     int mj;       // joint-constraint rows
-    int nb;       // 3x3 blocks of the joint-level Schur system (mj padded up to a multiple of 3)
+    int nb;       // 3x3 block rows ("nodes") of the joint-level Schur system (mj padded up to a multiple of 3)
     int m;        // holonomic rows = mj + 6 N
     int spw;      // systems per warp = 32 / N
     int rnl;      // max number of non-LIN3 rows touching one segment (k rows kept in shared memory)
     int nfext;    // external forces
     int blob_bytes;
     int off_seg, off_blk, off_side, off_fext;  // byte offsets inside the blob
-    int pad[2];
+    // symbolic factorisation of the joint-level Schur complement (computed on the host, see capi.cu)
+    int nslot;    // stored 3x3 blocks of the lower triangle: structural non-zeros + fill
+    int nslot2;   // blocks that can receive contributions from two segments (second, exclusive-writer copy)
+    int nzero;    // entries of the zero list (slots that are not fully overwritten by the assembly)
+    int ncomb;    // entries of the combine list (slot, slot2) pairs
+    int nunit;    // entries of the unit list: diagonal elements of padding rows
+    int ncol;     // total length of the column lists
+    int off_sym;  // byte offset of the symbolic tables (ints): slot_tab[nb*nb] slot2_tab[nb*nb] zero[nzero]
+                  // comb[2*ncomb] unit[nunit] colptr[nb+1] colrow[ncol]
+    int pad[3];
 };
 
 struct DevSeg {
@@ -63,13 +72,12 @@ struct DevFext {
 };
 
 // Per-warp shared-memory working set, in doubles (see dynamics.cuh for the layout).
-__host__ __device__ inline int warp_smem_doubles(int nb, int spw, int rnl) {
-    const int nbp = nb * (nb + 1) / 2;
-    return 2 * 12 * 32            // published Q, Qdot of the current stage, [12][32 lanes] each
-           + 2 * 9 * nbp * spw    // two exclusive-writer copies of the blocked joint-level Schur matrix
-           + 2 * 3 * nb * spw     // rhs copy 0 / copy 1 (-> y-hat)
-           + 6 * nb * spw         // inverse pivot blocks
-           + rnl * 12 * 32;       // k rows of non-LIN3 blocks, private per lane
+__host__ __device__ inline int warp_smem_doubles(int nb, int nslot, int nslot2, int spw, int rnl) {
+    return 2 * 12 * 32                 // published Q, Qdot of the current stage, [12][32 lanes] each
+           + 9 * (nslot + nslot2) * spw  // stored 3x3 blocks of the joint-level Schur matrix (+ second copies)
+           + 2 * 3 * nb * spw          // rhs copy 0 / copy 1 (-> y-hat)
+           + 6 * nb * spw              // inverse pivot blocks
+           + rnl * 12 * 32;            // k rows of non-LIN3 blocks, private per lane
 }
 
 }  // namespace bionc
