@@ -29,6 +29,10 @@
 
 namespace bionc {
 
+// A pivot (or 3x3 pivot determinant) this small relative to the diagonal scale raises the SMALL_PIVOT status
+// bit: the unpivoted LDL^T may have lost accuracy (the reference's LU with partial pivoting would not).
+constexpr double kSmallPivot = 1e-11;
+
 struct V3 {
     double x, y, z;
 };
@@ -145,10 +149,14 @@ __device__ __forceinline__ void sr_factor(SegCtx& c, int& status) {
             const int a = pa[r], b = pb[r], cc = pa[q], d = pb[q];
             A[r][q] = fma(om[a][cc], g[b][d], fma(om[a][d], g[b][cc], fma(om[b][cc], g[a][d], om[b][d] * g[a][cc])));
         }
+    double dmax = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) dmax = fmax(dmax, fabs(A[k][k]));
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
         const double piv = A[k][k];
         if (!(fabs(piv) > 0.0) || !isfinite(piv)) status |= 1;
+        else if (fabs(piv) < kSmallPivot * dmax) status |= 4;
         const double inv = 1.0 / piv;
         c.dinv[k] = inv;
         double col[6];
@@ -415,7 +423,9 @@ __device__ __forceinline__ void sym3_inverse(double a00, double a10, double a11,
     const double c10 = a20 * a21 - a10 * a22;
     const double c20 = a10 * a21 - a20 * a11;
     const double det = fma(a00, c00, fma(a10, c10, a20 * c20));
+    const double dmax = fmax(fabs(a00), fmax(fabs(a11), fabs(a22)));
     if (!(fabs(det) > 0.0) || !isfinite(det)) status |= 1;
+    else if (fabs(det) < kSmallPivot * dmax * dmax * dmax) status |= 4;
     const double id = 1.0 / det;
     di[0] = c00 * id;
     di[1] = c10 * id;

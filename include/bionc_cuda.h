@@ -44,6 +44,8 @@ extern "C" {
 #define BIONC_STATUS_OK 0
 #define BIONC_STATUS_SINGULAR 1  /* zero or non-finite pivot (reference: numpy.linalg.LinAlgError) */
 #define BIONC_STATUS_NONFINITE 2 /* non-finite state or acceleration */
+#define BIONC_STATUS_SMALL_PIVOT 4 /* a pivot below 1e-11 of the diagonal scale: (near-)singular constraints, the
+                                      unpivoted LDL^T result may be inaccurate (e.g. redundant constraints) */
 
 /* which quantity bionc_cuda_eval computes */
 #define BIONC_EVAL_PHI_R 0  /* rigid_body_constraints(Q)                 -> (B, 6N)      biomechanical_model_segments.py:26-42 */

@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--steps-per-launch", type=int, default=10)
     ap.add_argument("--launches", type=int, default=5)
     ap.add_argument("--out", default=os.path.join(REPO, "gpurun_out", "config_sweep.json"))
+    ap.add_argument("--only", default=None, help="substring of the model name to restrict the sweep to")
     args = ap.parse_args()
     B, S = args.batch, args.steps_per_launch
     lib = _lib.load()
@@ -48,6 +49,8 @@ def main():
         ("config5 full body (10 segments), per-system inertial parameters", "full_body", "tree", 0.01, None, True),
     ]
     for label, name, kind, h, fx, per_sys in configs:
+        if args.only is not None and args.only not in name:
+            continue
         model = BiomechanicalModel.load(os.path.join(GOLD, "models", name + ".npz"))
         cs = case(name)
         pool = min(B, 1 << 15)

@@ -221,6 +221,19 @@ def test_error_conventions():
     assert (status & 1).all()
 
 
+def test_redundant_constraints_are_flagged():
+    """GroundJoint.Weld + rigid-body row 4 are linearly dependent: the reference silently returns rounding noise
+    (|lambda| ~ 1e16); the kernel raises the SMALL_PIVOT status bit instead."""
+    case = load_case("tj_ground_weld")
+    model = _model("tj_ground_weld")
+    _, _, status = model.forward_dynamics(case["Q"], case["Qdot"], return_status=True)
+    assert (status & 4).all()
+    for name in ("lower_limb", "knee_feikes", "pendulum_root", "full_body"):
+        c = load_case(name)
+        _, _, st_ok = _model(name).forward_dynamics(c["Q"], c["Qdot"], return_status=True)
+        assert not st_ok.any(), name
+
+
 def test_python_level_RK4_with_cuda_model_in_the_closure():
     """The reference's closure pattern (ode_solver.py:107-120) must still work, stage by stage."""
     from bionc_b200.utils import RK4
@@ -264,3 +277,32 @@ def test_host_buffer_entry_points():
     Qf, Qdf = model.rk4(case["Q"][:2], case["Qdot"][:2], h=0.001, n_steps=50)
     np.testing.assert_array_equal(Q, Qf)
     np.testing.assert_array_equal(Qd, Qdf)
+
+
+def test_rk4_lambdas_trajectory_and_inplace():
+    case = load_case("lower_limb")
+    model = _model("lower_limb")
+    Q, Qd = case["Q"], case["Qdot"]
+    # multipliers of the first stage of the last step == forward_dynamics at the state before that step
+    Q9, Qd9 = model.rk4(Q, Qd, h=0.01, n_steps=9)
+    Q10, Qd10, lam = model.rk4(Q, Qd, h=0.01, n_steps=10, return_lambdas=True)
+    _, lam_ref = model.forward_dynamics(Q9, Qd9)
+    np.testing.assert_array_equal(lam, lam_ref)
+    # trajectory snapshots: every 5th step of 10 == two chained 5-step runs
+    _, _, traj = model.rk4(Q, Qd, h=0.01, n_steps=10, save_every=5)
+    assert traj.shape == (2, Q.shape[0], 2 * model.nb_Q)
+    Q5, Qd5 = model.rk4(Q, Qd, h=0.01, n_steps=5)
+    np.testing.assert_array_equal(traj[0], np.concatenate([Q5, Qd5], axis=1))
+    np.testing.assert_array_equal(traj[1], np.concatenate([Q10, Qd10], axis=1))
+    # in place on CUDA tensors
+    Qt, Qdt = torch.from_numpy(Q).cuda(), torch.from_numpy(Qd).cuda()
+    out_q, out_qd = model.rk4(Qt, Qdt, h=0.01, n_steps=10, inplace=True)
+    assert out_q.data_ptr() == Qt.data_ptr()
+    np.testing.assert_array_equal(Qt.cpu().numpy(), Q10)
+    # a time grid with unequal steps (h_i = t[i+1] - t[i], ode_solver.py:41)
+    t = np.array([0.0, 0.01, 0.015, 0.03])
+    Qa, Qda = model.rk4(Q, Qd, t=t)
+    Qb, Qdb = Q, Qd
+    for h in np.diff(t):
+        Qb, Qdb = model.rk4(Qb, Qdb, h=float(h), n_steps=1)
+    np.testing.assert_array_equal(Qa, Qb)

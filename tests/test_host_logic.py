@@ -139,12 +139,44 @@ for fn, name in (("pendulum.nmod", "pendulum_root"), ("pendulum_with_force.nmod"
     ref = ModelTable.load(%r + "/models/" + name + ".npz")
     for k in ModelTable._ARRAYS:
         assert np.array_equal(getattr(t, k), getattr(ref, k)), (name, k)
+# a model with a ground segment (protocols/biomechanical_model.py:283-311): indices shift, the ground is skipped
+import importlib.util, os
+spec = importlib.util.spec_from_file_location("nlp", %r + "/examples/forward_dynamics/n_link_pendulum.py")
+mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+from bionc.bionc_numpy import NaturalCoordinates, NaturalVelocities
+sys.path.insert(0, %r)
+from bionc_oracle import OracleModel
+gm = mod.build_n_link_pendulum(nb_segments=4)
+gm.remove_joint(name="hinge_0"); gm.remove_joint(name="hinge_1"); gm.set_ground_segment(name="pendulum_0")
+gt = ModelTable.from_numpy(gm)
+assert gt.nb_segments == 3 and gt.segment_names == ["pendulum_1", "pendulum_2", "pendulum_3"], gt.segment_names
+assert gt.nb_holonomic_constraints == gm.nb_holonomic_constraints == 28
+Qg = np.linspace(0.1, 0.9, 36); Qdg = np.linspace(0, 0.02, 36)
+ref_K = gm.holonomic_constraints_jacobian(NaturalCoordinates(Qg))
+om = OracleModel(gt)
+assert np.allclose(om.holonomic_constraints_jacobian(Qg), ref_K, rtol=0, atol=1e-14)
+print("ground ok")
+# a reference ExternalForceSet lowers to the same arrays as the mirror's own construction API
+from bionc.bionc_numpy import ExternalForceSet as RefSet
+from bionc_b200.bionc_cuda import ExternalForceSet as CudaSet
+rs = RefSet.empty_from_nb_segment(2)
+rs.add_in_global_local_point(segment_index=0, external_force=np.arange(6.0), point_in_local=np.array([0.1, 0.2, 0.3]))
+rs.add_in_global(segment_index=1, external_force=np.arange(6.0) + 1, point_in_global=np.array([1.0, 2.0, 3.0]))
+rs.add_in_local(segment_index=1, external_force=np.arange(6.0) + 2, point_in_local=np.array([0, 0.5, 0]), transformation_matrix=np.diag([1.0, 2.0, 4.0]))
+cs = CudaSet.empty_from_nb_segment(2)
+cs.add_in_global_local_point(0, np.arange(6.0), point_in_local=[0.1, 0.2, 0.3])
+cs.add_in_global(1, np.arange(6.0) + 1, point_in_global=[1, 2, 3])
+cs.add_in_local(1, np.arange(6.0) + 2, point_in_local=[0, 0.5, 0], transformation_matrix=np.diag([1.0, 2.0, 4.0]))
+for a, b in zip(CudaSet.from_reference(rs).to_arrays(), cs.to_arrays()):
+    assert np.array_equal(a, b)
+print("fext ok")
 # error conventions at compile time: a model without inertia (lower_limb.nc as shipped) raises ValueError
 try:
     ModelTable.from_numpy(BiomechanicalModel.load(%r + "/examples/models/lower_limb.nc"))
 except ValueError as e:
     print("ValueError ok")
 print("tables ok")
-''' % (os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "stubs"), REFERENCE, os.path.join(GOLDEN, "..", ".."), REFERENCE, GOLDEN, REFERENCE)
+''' % (os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "stubs"), REFERENCE, os.path.join(GOLDEN, "..", ".."), REFERENCE, GOLDEN, REFERENCE, os.path.join(GOLDEN, "..", "..", "oracle"), REFERENCE)
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(os.path.dirname(GOLDEN)))
-    assert "tables ok" in res.stdout and "ValueError ok" in res.stdout, res.stdout + res.stderr
+    for token in ("tables ok", "ValueError ok", "ground ok", "fext ok"):
+        assert token in res.stdout, res.stdout + res.stderr
