@@ -278,7 +278,7 @@ int build_blob(BioncModel* M, const BioncFextDesc* fx) {
         if (cta > (size_t)dev_smem) continue;
         int ctas = (int)((size_t)sm_smem / (cta + 1024));  // 1 KB reserved per CTA by the driver
         int resident = ctas * wcta;
-        if (resident > 12) resident = 12;
+        if (resident > 4 * BIONC_MIN_CTAS) resident = 4 * BIONC_MIN_CTAS;
         if (resident > best_resident) best_resident = resident, warps = wcta;
     }
     if (warps == 0) return fail(BIONC_E_TOO_LARGE, "model needs more shared memory per warp than one SM has");
