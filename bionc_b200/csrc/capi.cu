@@ -190,7 +190,7 @@ int symbolic_analysis(BioncModel* M, int N) {
                 const bool any_mixed = mixed2[I] || mixed2[J];
                 const int c = contrib2[I * nb + J];
                 int s2 = -1;
-                if (c >= 2 || (any_mixed && c >= 1)) s2 = nslot2++, slot2_tab[I * nb + J] = s2;
+                if (c >= 2) s2 = nslot2++, slot2_tab[I * nb + J] = s2;  // one contributing segment = one writer lane
                 if (c == 0 || any_mixed) {  // not fully overwritten by the assembly
                     zero.push_back(s);
                     if (s2 >= 0) zero.push_back(-(s2 + 1));  // negative: second copy

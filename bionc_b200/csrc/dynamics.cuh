@@ -23,7 +23,7 @@
 //   S0, S1   : mj(mj+1)/2   packed lower triangle; copy r is written only by the lane that has
 //                           role r (child/parent) in the block of the larger row -> no atomics
 //   r0, r1, dinv : mj
-//   knl      : rnl x 12 x 32 lanes   explicit Jacobian rows of non-LIN3 blocks (private per lane)
+//   knl      : rnl x 6 x 32 lanes    state-dependent vectors of the non-LIN3 rows (private per lane)
 #pragma once
 #include "model.cuh"
 
@@ -183,7 +183,7 @@ __device__ __forceinline__ void sr_factor(SegCtx& c, int& status) {
 //              receive contributions from two segments (slot2_tab)           ([9 nslot][spw])
 //   r0/r1      right-hand side / y-hat, row j at r0[j * spw]                    ([3 nb][spw])
 //   dinv       inverse diagonal blocks, 6 unique entries of block K at dinv[(6 K + i) * spw]
-//   knl        explicit rows of non-LIN3 blocks, slot q element i at knl[(12 q + i) * 32]
+//   knl        state-dependent vectors (d1, d2) of non-LIN3 rows, slot q element i at knl[(6 q + i) * 32]
 // ---------------------------------------------------------------------------------------------
 struct WarpCtx {
     const DevHeader* hdr;
@@ -217,14 +217,43 @@ struct DynOpts {
     double alpha, beta;
 };
 
-// Explicit Jacobian row (restricted to this lane's segment) of a non-LIN3 block, plus -- on the
-// child side -- the row's right-hand-side term bias (+ alpha Phi + beta K Qdot when stabilised).
+// Jacobian row (restricted to this lane's segment) of a non-LIN3 block.  Every such row has the form
+//     k = a1 (x) d1  [+ a2 (x) d2]
+// with constant 4-coefficient vectors a (block parameters) and state-dependent 3-vectors d.  nonlin_row
+// evaluates d1, d2 (these 6 doubles are what is kept in shared memory per row and lane) and -- on the
+// child side -- the row's right-hand-side term bias (+ alpha Phi + beta K Qdot when stabilised);
+// nonlin_k rebuilds the 12-vector from them.
 // DOT : joints.py:203-208, :222-235, :252-282 ; joints_with_ground.py:155-162, :169-178
 // CLEN: joints.py:1300-1382        SOP: joints.py:657-748 (Jacobian blocks as coded: swapped)
-__device__ __forceinline__ void nonlin_row(const WarpCtx& w, const DevBlk& b, int role, const DynOpts& o, Q12& k,
+__device__ __forceinline__ Q12 nonlin_k(const DevBlk& b, int role, V3 d1, V3 d2) {
+    const double* p = b.p;
+    Q12 k;
+    if (b.type == DOT) {
+        const double* a = role == CHILD ? p + 4 : p;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) k.s[t] = a[t] * d1;
+    } else if (b.type == CLEN) {
+        const double* a = role == CHILD ? p + 4 : p;
+        const double sg = role == CHILD ? -2.0 : 2.0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) k.s[t] = (sg * a[t]) * d1;
+    } else {  // SOP
+        if (role == CHILD) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) k.s[t] = p[t] * d1;  // n^T N_P, stored in the child's columns
+        } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) k.s[t] = axpy(-p[4 + t], d1, p[8 + t] * d2);  // stored in the parent's columns
+        }
+    }
+    return k;
+}
+
+__device__ __forceinline__ void nonlin_row(const WarpCtx& w, const DevBlk& b, int role, const DynOpts& o, V3& d1, V3& d2,
                                            double& bterm) {
     const double* p = b.p;
     bterm = 0.0;
+    d2 = mk(0.0, 0.0, 0.0);
     if (b.type == DOT) {
         const V3 Dc = lin_form(w, w.Qsys, b.child, p + 4);
         V3 Dp, Dpd = mk(0.0, 0.0, 0.0);
@@ -234,8 +263,7 @@ __device__ __forceinline__ void nonlin_row(const WarpCtx& w, const DevBlk& b, in
             Dp = mk(p[0], p[1], p[2]);
         }
         if (role == CHILD) {
-#pragma unroll
-            for (int t = 0; t < 4; ++t) k.s[t] = p[4 + t] * Dp;
+            d1 = Dp;
             const V3 Dcd = lin_form(w, w.Qdsys, b.child, p + 4);
             if (b.parent >= 0) {
                 Dpd = lin_form(w, w.Qdsys, b.parent, p);
@@ -243,26 +271,20 @@ __device__ __forceinline__ void nonlin_row(const WarpCtx& w, const DevBlk& b, in
             }
             if (o.use_stab) bterm += o.alpha * (dot(Dp, Dc) - p[8]) + o.beta * (dot(Dpd, Dc) + dot(Dp, Dcd));
         } else {
-#pragma unroll
-            for (int t = 0; t < 4; ++t) k.s[t] = p[t] * Dc;
+            d1 = Dc;
         }
     } else if (b.type == CLEN) {
         const V3 d = lin_form(w, w.Qsys, b.parent, p) - lin_form(w, w.Qsys, b.child, p + 4);
+        d1 = d;
         if (role == CHILD) {
-#pragma unroll
-            for (int t = 0; t < 4; ++t) k.s[t] = (-2.0 * p[4 + t]) * d;
             const V3 dd = lin_form(w, w.Qdsys, b.parent, p) - lin_form(w, w.Qdsys, b.child, p + 4);
             bterm = 2.0 * dot(dd, dd);
             if (o.use_stab) bterm += o.alpha * (dot(d, d) - p[8]) + o.beta * (2.0 * dot(d, dd));
-        } else {
-#pragma unroll
-            for (int t = 0; t < 4; ++t) k.s[t] = (2.0 * p[t]) * d;
         }
     } else {  // SOP
         const V3 n = lin_form(w, w.Qsys, b.child, p + 8);
+        d1 = n;
         if (role == CHILD) {
-#pragma unroll
-            for (int t = 0; t < 4; ++t) k.s[t] = p[t] * n;  // n^T N_P, stored in the child's columns
             const V3 P = lin_form(w, w.Qsys, b.parent, p), A = lin_form(w, w.Qsys, b.child, p + 4);
             const V3 Pd = lin_form(w, w.Qdsys, b.parent, p), Ad = lin_form(w, w.Qdsys, b.child, p + 4);
             const V3 nd = lin_form(w, w.Qdsys, b.child, p + 8);
@@ -276,11 +298,15 @@ __device__ __forceinline__ void nonlin_row(const WarpCtx& w, const DevBlk& b, in
                 bterm += o.alpha * (dot(P - A, n) - p[12]) + o.beta * kqd;
             }
         } else {
-            const V3 PA = lin_form(w, w.Qsys, b.parent, p) - lin_form(w, w.Qsys, b.child, p + 4);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) k.s[t] = axpy(-p[4 + t], n, p[8 + t] * PA);  // stored in the parent's columns
+            d2 = lin_form(w, w.Qsys, b.parent, p) - lin_form(w, w.Qsys, b.child, p + 4);
         }
     }
+}
+
+// the stored (d1, d2) of non-LIN3 row slot q of this lane
+__device__ __forceinline__ Q12 load_nonlin_k(const WarpCtx& w, const DevBlk& b, int role, int q) {
+    const double* src = w.knl + (6 * q) * 32;
+    return nonlin_k(b, role, mk(src[0], src[32], src[64]), mk(src[96], src[128], src[160]));
 }
 
 // External forces on this lane's segment (external_force.py:143-180 and the four force classes).
@@ -532,16 +558,15 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                     }
                     rr[0] = r.x, rr[spw] = r.y, rr[2 * spw] = r.z;
                 } else {
-                    Q12 k;
+                    V3 d1, d2;
                     double bterm;
-                    nonlin_row(w, b, sd.role, o, k, bterm);
+                    nonlin_row(w, b, sd.role, o, d1, d2, bterm);
+                    const Q12 k = nonlin_k(b, sd.role, d1, d2);
                     double acc = bterm;
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        acc += dot(k.s[t], x.s[t]);
-                        double* dst = w.knl + (sd.nl_slot * 12 + 3 * t) * 32;
-                        dst[0] = k.s[t].x, dst[32] = k.s[t].y, dst[64] = k.s[t].z;
-                    }
+                    for (int t = 0; t < 4; ++t) acc += dot(k.s[t], x.s[t]);
+                    double* dst = w.knl + (6 * sd.nl_slot) * 32;
+                    dst[0] = d1.x, dst[32] = d1.y, dst[64] = d1.z, dst[96] = d2.x, dst[128] = d2.y, dst[160] = d2.z;
                     rr[0] = acc;
                 }
             }
@@ -612,12 +637,8 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                 const DevSide sd = w.side[e];
                 const DevBlk& b = w.blk[sd.blk];
                 if (b.type == LIN3) continue;
-                Q12 kb, q;
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const double* src = w.knl + (sd.nl_slot * 12 + 3 * t) * 32;
-                    kb.s[t] = mk(src[0], src[32], src[64]);
-                }
+                const Q12 kb = load_nonlin_k(w, b, sd.role, sd.nl_slot);
+                Q12 q;
                 {
                     double y[6];
                     q = apply_W(c.W, kb);
@@ -649,12 +670,10 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                             Sc[0] = r.x, Sc[spw] = r.y, Sc[2 * spw] = r.z;
                         }
                     } else if (e2 >= e) {  // every pair of single rows once
+                        const Q12 ka = load_nonlin_k(w, a, sa.role, sa.nl_slot);
                         double acc = 0.0;
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            const double* src = w.knl + (sa.nl_slot * 12 + 3 * t) * 32;
-                            acc += dot(mk(src[0], src[32], src[64]), q.s[t]);
-                        }
+                        for (int t = 0; t < 4; ++t) acc += dot(ka.s[t], q.s[t]);
                         const int Ia = a.jrow / 3, ra = a.jrow - 3 * Ia;
                         // the larger ROW decides the block orientation and whose role picks the copy
                         const bool a_larger = a.jrow >= b.jrow;
@@ -782,11 +801,9 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                     }
                 } else {
                     const double lam = lj[0];
+                    const Q12 k = load_nonlin_k(w, b, sd.role, sd.nl_slot);
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const double* src = w.knl + (sd.nl_slot * 12 + 3 * t) * 32;
-                        f.s[t] = axpy(-lam, mk(src[0], src[32], src[64]), f.s[t]);
-                    }
+                    for (int t = 0; t < 4; ++t) f.s[t] = axpy(-lam, k.s[t], f.s[t]);
                     if (lam_out != nullptr && sd.role == CHILD) lam_out[b.row_h] = lam;
                 }
             }

@@ -77,7 +77,7 @@ __host__ __device__ inline int warp_smem_doubles(int nb, int nslot, int nslot2, 
            + 9 * (nslot + nslot2) * spw  // stored 3x3 blocks of the joint-level Schur matrix (+ second copies)
            + 2 * 3 * nb * spw          // rhs copy 0 / copy 1 (-> y-hat)
            + 6 * nb * spw              // inverse pivot blocks
-           + rnl * 12 * 32;            // k rows of non-LIN3 blocks, private per lane
+           + rnl * 6 * 32;             // (d1, d2) of the non-LIN3 rows, private per lane
 }
 
 }  // namespace bionc
