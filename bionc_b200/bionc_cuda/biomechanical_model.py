@@ -289,6 +289,30 @@ class BiomechanicalModel:
         A[:, :n, n:] = K.transpose(1, 2)
         return b.out(A)
 
+    # ------------------------------------------------------------------ energies (post-processing, torch on the device)
+    def kinetic_energy(self, Qdot):
+        """biomechanical_model.py:98-113: ``1/2 Qdot^T G Qdot`` -> float / (B,)"""
+        b = _Batch(Qdot, self.nb_Q, self.device, "Qdot")
+        G = torch.from_numpy(self.mass_matrix).to(self.device)
+        E = 0.5 * ((b.t @ G) * b.t).sum(dim=1)
+        return float(E[0].item()) if (b.single and not b.torch_in) else b.out(E)
+
+    def potential_energy(self, Q):
+        """biomechanical_model.py:115-133: ``sum_i m_i (N_com,i Q_i)[z]`` exactly as the reference codes it
+        (``natural_segment.py:775-789``, no factor g) -> float / (B,)"""
+        b = _Batch(Q, self.nb_Q, self.device, "Q")
+        t = self.table
+        coef = np.zeros(self.nb_Q)
+        for i in range(self.nb_segments):
+            c, m = t.seg_com[i], t.seg_mass[i]
+            coef[12 * i + 2], coef[12 * i + 5], coef[12 * i + 8], coef[12 * i + 11] = m * c[0], m * (1 + c[1]), -m * c[1], m * c[2]
+        E = b.t @ torch.from_numpy(coef).to(self.device)
+        return float(E[0].item()) if (b.single and not b.torch_in) else b.out(E)
+
+    def lagrangian(self, Q, Qdot):
+        """biomechanical_model.py:135-152"""
+        return self.kinetic_energy(Qdot) - self.potential_energy(Q)
+
     # ------------------------------------------------------------------ dynamics
     def forward_dynamics(
         self,

@@ -98,6 +98,22 @@ class OracleModel:
     def gravity_forces(self):
         return self._fg.copy()
 
+    # ----------------------------------------------------------------- energies
+    def kinetic_energy(self, Qdot):
+        """biomechanical_model.py:98-113: 1/2 Qdot^T G Qdot."""
+        Qdot = np.asarray(Qdot, float).reshape(-1)
+        return 0.5 * Qdot @ self._G @ Qdot
+
+    def potential_energy(self, Q):
+        """biomechanical_model.py:115-133 summing natural_segment.py:775-789: sum_i m_i (N_com,i Q_i)[z]
+        (as coded: no factor g)."""
+        Q = np.asarray(Q, float).reshape(-1)
+        E = 0.0
+        for i in range(self.nb_segments):
+            c = self.seg_com[i]
+            E += self.seg_mass[i] * (np.kron(np.array([[c[0], 1 + c[1], -c[1], c[2]]]), np.eye(3)) @ Q[12 * i : 12 * i + 12])[2]
+        return E
+
     # ----------------------------------------------------------------- rigid body (per segment)
     @staticmethod
     def _uvw(Qi):

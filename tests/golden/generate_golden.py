@@ -102,7 +102,7 @@ def fext_to_arrays(fext: ExternalForceSet | None):
 # ----------------------------------------------------------------------------- reference evaluation
 def evaluate(model, Q, Qdot, fext=None, stab=(0.7, 1.3)):
     """Reference outputs for a batch of states, one system at a time (the reference has no batch axis)."""
-    out = {k: [] for k in "phi_r phi_j K_j phi_h K_h bias fext Qddot lam Qddot_stab lam_stab".split()}
+    out = {k: [] for k in "phi_r phi_j K_j phi_h K_h bias fext Qddot lam Qddot_stab lam_stab kinetic potential".split()}
     for q, qd in zip(Q, Qdot):
         Qn, Qdn = NaturalCoordinates(q), NaturalVelocities(qd)
         out["phi_r"].append(np.asarray(model.rigid_body_constraints(Qn)).reshape(-1))
@@ -111,6 +111,8 @@ def evaluate(model, Q, Qdot, fext=None, stab=(0.7, 1.3)):
         out["phi_h"].append(np.asarray(model.holonomic_constraints(Qn)).reshape(-1))
         out["K_h"].append(np.asarray(model.holonomic_constraints_jacobian(Qn)))
         out["bias"].append(np.asarray(model.holonomic_constraints_acceleration_bias(Qdn)).reshape(-1))
+        out["kinetic"].append(float(np.asarray(model.kinetic_energy(Qdn)).reshape(-1)[0]))
+        out["potential"].append(float(np.asarray(model.potential_energy(Qn)).reshape(-1)[0]))
         fe = model.external_force_set() if fext is None else fext
         out["fext"].append(np.asarray(fe.to_natural_external_forces(Qn)).reshape(-1))
         qdd, lam = model.forward_dynamics(Qn, Qdn, external_forces=fext)

@@ -71,6 +71,9 @@ def test_component_api_matches_reference(name):
     np.testing.assert_allclose(model.holonomic_constraints(Q), case["ref_phi_h"], **tol)
     np.testing.assert_allclose(model.holonomic_constraints_jacobian(Q), case["ref_K_h"], **tol)
     np.testing.assert_allclose(model.holonomic_constraints_acceleration_bias(Qd), case["ref_bias"], **tol)
+    np.testing.assert_allclose(model.kinetic_energy(Qd), case["ref_kinetic"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(model.potential_energy(Q), case["ref_potential"], rtol=1e-12, atol=1e-12)
+    assert isinstance(model.kinetic_energy(Qd[0]), float)
     fext = _fext(model, case)
     if fext is not None:
         np.testing.assert_allclose(model.natural_external_forces(Q, fext), case["ref_fext"], rtol=1e-11, atol=1e-11)

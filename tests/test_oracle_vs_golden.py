@@ -28,6 +28,8 @@ def test_oracle_components_match_reference(name):
         np.testing.assert_allclose(om.holonomic_constraints_jacobian(Q), case["ref_K_h"][s], **tol)
         np.testing.assert_allclose(om.holonomic_constraints_acceleration_bias(Qd), case["ref_bias"][s], **tol)
         np.testing.assert_allclose(om.natural_external_forces(Q, fext), case["ref_fext"][s], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(om.kinetic_energy(Qd), case["ref_kinetic"][s], rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(om.potential_energy(Q), case["ref_potential"][s], rtol=1e-13, atol=1e-13)
 
 
 @pytest.mark.parametrize("name", CASES)
