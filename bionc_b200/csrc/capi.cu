@@ -86,6 +86,7 @@ struct BioncModel {
     std::mutex mu;
     // host-path scratch
     cudaStream_t stream = nullptr;
+    cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};  // chunk pipeline of the host-buffer entry points
     double *d_Q = nullptr, *d_Qd = nullptr, *d_Qdd = nullptr, *d_lam = nullptr, *d_inertia = nullptr, *d_h = nullptr;
     int* d_status = nullptr;
     long long cap_B = 0, cap_h = 0;
@@ -424,6 +425,8 @@ int bionc_cuda_model_destroy(BioncModel* M) {
     cudaFree(M->d_Q), cudaFree(M->d_Qd), cudaFree(M->d_Qdd), cudaFree(M->d_lam), cudaFree(M->d_inertia), cudaFree(M->d_h);
     cudaFree(M->d_status);
     if (M->stream != nullptr) cudaStreamDestroy(M->stream);
+    for (auto& ps : M->pipe)
+        if (ps != nullptr) cudaStreamDestroy(ps);
     delete M;
     return BIONC_OK;
 }
@@ -541,6 +544,8 @@ int bionc_cuda_mass_matrix(const BioncModel* M, double* G) {
 static int ensure_host_scratch(BioncModel* M, long long B, long long nh, bool want_inertia) {
     CUDA_TRY(cudaSetDevice(M->device));
     if (M->stream == nullptr) CUDA_TRY(cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking));
+    for (auto& ps : M->pipe)
+        if (ps == nullptr) CUDA_TRY(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
     const size_t n = 12 * (size_t)M->hdr.N;
     if (B > M->cap_B) {
         cudaFree(M->d_Q), cudaFree(M->d_Qd), cudaFree(M->d_Qdd), cudaFree(M->d_lam), cudaFree(M->d_status), cudaFree(M->d_inertia);
@@ -561,6 +566,18 @@ static int ensure_host_scratch(BioncModel* M, long long B, long long nh, bool wa
     return BIONC_OK;
 }
 
+// Chunking of the host-buffer entry points: the batch is cut into up to 8 chunks that go round-robin
+// through three streams, so the H2D copy of chunk i+1 and the D2H copy of chunk i-1 overlap the kernel
+// of chunk i (PCIe is full duplex); chunks are multiples of 4096 systems.
+static int64_t host_chunk(int64_t B) {
+    const int64_t min_chunk = 65536;
+    int64_t n = (B + min_chunk - 1) / min_chunk;
+    if (n > 8) n = 8;
+    if (n < 1) n = 1;
+    int64_t c = (B + n - 1) / n;
+    return (c + 4095) / 4096 * 4096;
+}
+
 int bionc_cuda_forward_dynamics_host(BioncModel* M, const double* Q, const double* Qd, const BioncDynOptions* opt,
                                      double* Qdd, double* lam, int32_t* status, int64_t B) {
     if (M == nullptr || Q == nullptr || Qd == nullptr || Qdd == nullptr || B < 0) return fail(BIONC_E_INVALID, "null argument");
@@ -568,21 +585,29 @@ int bionc_cuda_forward_dynamics_host(BioncModel* M, const double* Q, const doubl
     const bool per_sys = opt != nullptr && opt->inertia != nullptr;
     int rc = ensure_host_scratch(M, B, 0, per_sys);
     if (rc != BIONC_OK) return rc;
-    const size_t nb = (size_t)B * 12 * M->hdr.N * sizeof(double);
-    CUDA_TRY(cudaMemcpyAsync(M->d_Q, Q, nb, cudaMemcpyHostToDevice, M->stream));
-    CUDA_TRY(cudaMemcpyAsync(M->d_Qd, Qd, nb, cudaMemcpyHostToDevice, M->stream));
-    BioncDynOptions o2 = opt != nullptr ? *opt : BioncDynOptions{};
-    if (per_sys) {
-        CUDA_TRY(cudaMemcpyAsync(M->d_inertia, opt->inertia, (size_t)B * M->hdr.N * 10 * sizeof(double), cudaMemcpyHostToDevice, M->stream));
-        o2.inertia = M->d_inertia;
+    const size_t n = 12 * (size_t)M->hdr.N, m = (size_t)M->hdr.m;
+    const int64_t chunk = host_chunk(B);
+    int k = 0;
+    for (int64_t lo = 0; lo < B; lo += chunk, ++k) {
+        const int64_t b = (B - lo < chunk) ? B - lo : chunk;
+        cudaStream_t st = M->pipe[k % 3];
+        const size_t nb = (size_t)b * n * sizeof(double);
+        CUDA_TRY(cudaMemcpyAsync(M->d_Q + lo * n, Q + lo * n, nb, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(M->d_Qd + lo * n, Qd + lo * n, nb, cudaMemcpyHostToDevice, st));
+        BioncDynOptions o2 = opt != nullptr ? *opt : BioncDynOptions{};
+        if (per_sys) {
+            const size_t ni = (size_t)M->hdr.N * 10;
+            CUDA_TRY(cudaMemcpyAsync(M->d_inertia + lo * ni, opt->inertia + lo * ni, (size_t)b * ni * sizeof(double), cudaMemcpyHostToDevice, st));
+            o2.inertia = M->d_inertia + lo * ni;
+        }
+        rc = bionc_cuda_forward_dynamics(M, M->d_Q + lo * n, M->d_Qd + lo * n, &o2, M->d_Qdd + lo * n,
+                                         lam != nullptr ? M->d_lam + lo * m : nullptr, status != nullptr ? M->d_status + lo : nullptr, b, st);
+        if (rc != BIONC_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(Qdd + lo * n, M->d_Qdd + lo * n, nb, cudaMemcpyDeviceToHost, st));
+        if (lam != nullptr) CUDA_TRY(cudaMemcpyAsync(lam + lo * m, M->d_lam + lo * m, (size_t)b * m * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (status != nullptr) CUDA_TRY(cudaMemcpyAsync(status + lo, M->d_status + lo, (size_t)b * sizeof(int), cudaMemcpyDeviceToHost, st));
     }
-    rc = bionc_cuda_forward_dynamics(M, M->d_Q, M->d_Qd, &o2, M->d_Qdd, lam != nullptr ? M->d_lam : nullptr,
-                                     status != nullptr ? M->d_status : nullptr, B, M->stream);
-    if (rc != BIONC_OK) return rc;
-    CUDA_TRY(cudaMemcpyAsync(Qdd, M->d_Qdd, nb, cudaMemcpyDeviceToHost, M->stream));
-    if (lam != nullptr) CUDA_TRY(cudaMemcpyAsync(lam, M->d_lam, (size_t)B * M->hdr.m * sizeof(double), cudaMemcpyDeviceToHost, M->stream));
-    if (status != nullptr) CUDA_TRY(cudaMemcpyAsync(status, M->d_status, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, M->stream));
-    CUDA_TRY(cudaStreamSynchronize(M->stream));
+    for (auto& ps : M->pipe) CUDA_TRY(cudaStreamSynchronize(ps));
     return BIONC_OK;
 }
 
@@ -593,22 +618,33 @@ int bionc_cuda_rk4_host(BioncModel* M, double* Q, double* Qd, double h, const do
     const bool per_sys = opt != nullptr && opt->inertia != nullptr;
     int rc = ensure_host_scratch(M, B, h_steps != nullptr ? n_steps : 0, per_sys);
     if (rc != BIONC_OK) return rc;
-    const size_t nb = (size_t)B * 12 * M->hdr.N * sizeof(double);
-    CUDA_TRY(cudaMemcpyAsync(M->d_Q, Q, nb, cudaMemcpyHostToDevice, M->stream));
-    CUDA_TRY(cudaMemcpyAsync(M->d_Qd, Qd, nb, cudaMemcpyHostToDevice, M->stream));
-    if (h_steps != nullptr) CUDA_TRY(cudaMemcpyAsync(M->d_h, h_steps, n_steps * sizeof(double), cudaMemcpyHostToDevice, M->stream));
-    BioncDynOptions o2 = opt != nullptr ? *opt : BioncDynOptions{};
-    if (per_sys) {
-        CUDA_TRY(cudaMemcpyAsync(M->d_inertia, opt->inertia, (size_t)B * M->hdr.N * 10 * sizeof(double), cudaMemcpyHostToDevice, M->stream));
-        o2.inertia = M->d_inertia;
+    const size_t n = 12 * (size_t)M->hdr.N;
+    if (h_steps != nullptr) {
+        CUDA_TRY(cudaMemcpyAsync(M->d_h, h_steps, n_steps * sizeof(double), cudaMemcpyHostToDevice, M->stream));
+        CUDA_TRY(cudaStreamSynchronize(M->stream));
     }
-    rc = bionc_cuda_rk4(M, M->d_Q, M->d_Qd, h, h_steps != nullptr ? M->d_h : nullptr, n_steps, normalize, &o2, nullptr, 1,
-                        nullptr, status != nullptr ? M->d_status : nullptr, B, M->stream);
-    if (rc != BIONC_OK) return rc;
-    CUDA_TRY(cudaMemcpyAsync(Q, M->d_Q, nb, cudaMemcpyDeviceToHost, M->stream));
-    CUDA_TRY(cudaMemcpyAsync(Qd, M->d_Qd, nb, cudaMemcpyDeviceToHost, M->stream));
-    if (status != nullptr) CUDA_TRY(cudaMemcpyAsync(status, M->d_status, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, M->stream));
-    CUDA_TRY(cudaStreamSynchronize(M->stream));
+    const int64_t chunk = host_chunk(B);
+    int k = 0;
+    for (int64_t lo = 0; lo < B; lo += chunk, ++k) {
+        const int64_t b = (B - lo < chunk) ? B - lo : chunk;
+        cudaStream_t st = M->pipe[k % 3];
+        const size_t nb = (size_t)b * n * sizeof(double);
+        CUDA_TRY(cudaMemcpyAsync(M->d_Q + lo * n, Q + lo * n, nb, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(M->d_Qd + lo * n, Qd + lo * n, nb, cudaMemcpyHostToDevice, st));
+        BioncDynOptions o2 = opt != nullptr ? *opt : BioncDynOptions{};
+        if (per_sys) {
+            const size_t ni = (size_t)M->hdr.N * 10;
+            CUDA_TRY(cudaMemcpyAsync(M->d_inertia + lo * ni, opt->inertia + lo * ni, (size_t)b * ni * sizeof(double), cudaMemcpyHostToDevice, st));
+            o2.inertia = M->d_inertia + lo * ni;
+        }
+        rc = bionc_cuda_rk4(M, M->d_Q + lo * n, M->d_Qd + lo * n, h, h_steps != nullptr ? M->d_h : nullptr, n_steps, normalize,
+                            &o2, nullptr, 1, nullptr, status != nullptr ? M->d_status + lo : nullptr, b, st);
+        if (rc != BIONC_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(Q + lo * n, M->d_Q + lo * n, nb, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(Qd + lo * n, M->d_Qd + lo * n, nb, cudaMemcpyDeviceToHost, st));
+        if (status != nullptr) CUDA_TRY(cudaMemcpyAsync(status + lo, M->d_status + lo, (size_t)b * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
+    for (auto& ps : M->pipe) CUDA_TRY(cudaStreamSynchronize(ps));
     return BIONC_OK;
 }
 

@@ -270,8 +270,22 @@ def test_forward_integration_mirror():
 
 
 def test_host_buffer_entry_points():
+    from bionc_b200.utils import states as st
+
     case = load_case("lower_limb")
     model = _model("lower_limb")
+    # a batch large enough to be cut into several pipelined chunks (ragged last chunk)
+    Qb, Qdb = st.tree_states(model.table, 4096, seed=21)
+    Qb, Qdb = np.tile(Qb, (49, 1))[:200_001], np.tile(Qdb, (49, 1))[:200_001]
+    qdd_h, lam_h, status_h = model.forward_dynamics_host(Qb, Qdb)
+    qdd_d, lam_d = model.forward_dynamics(Qb, Qdb)
+    np.testing.assert_array_equal(qdd_h, qdd_d)
+    np.testing.assert_array_equal(lam_h, lam_d)
+    Qh, Qdh = np.ascontiguousarray(Qb).copy(), np.ascontiguousarray(Qdb).copy()
+    model.rk4_host(Qh, Qdh, h=0.001, n_steps=3)
+    Qr, Qdr = model.rk4(Qb, Qdb, h=0.001, n_steps=3)
+    np.testing.assert_array_equal(Qh, Qr)
+    np.testing.assert_array_equal(Qdh, Qdr)
     qdd, lam, status = model.forward_dynamics_host(case["Q"], case["Qdot"])
     assert rel_err(qdd, case["ref_Qddot"]) < TOL_EVAL and not status.any()
     Q = np.ascontiguousarray(case["Q"][:2]).copy()
