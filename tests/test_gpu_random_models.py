@@ -1,0 +1,167 @@
+"""Randomised topology test: model tables are generated directly (trees with every block kind, ground
+joints, loop closures, up to 14 segments) and the CUDA path is compared with the CPU oracle.  The oracle
+is pinned against the reference per block kind (tests/test_oracle_vs_golden.py); this test stresses what
+the goldens cannot enumerate -- the host-side symbolic analysis (ordering, fill pattern, slot tables,
+second copies) and the lane mapping for arbitrary segment counts."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from helpers import rel_err  # noqa: E402
+
+from bionc_b200.bionc_cuda.model_table import BLK_CLEN, BLK_DOT, BLK_LIN3, BLK_NPARAM, BLK_ROWS, BLK_SOP, ModelTable  # noqa: E402
+from bionc_b200.utils import states as st  # noqa: E402
+
+
+def _point(rng):
+    b = rng.uniform(-1.2, 0.2)
+    return np.array([rng.uniform(-0.3, 0.3), 1.0 + b, -b, rng.uniform(-0.3, 0.3)])  # natural point (a, 1+b, -b, c)
+
+
+def _direction(rng):
+    d = rng.normal(size=3)
+    d /= np.linalg.norm(d)
+    return np.array([d[0], d[1], -d[1], d[2]])
+
+
+def random_table(seed: int, N: int, loops: int = 0) -> ModelTable:
+    rng = np.random.default_rng(seed)
+    geom = np.column_stack([rng.uniform(0.2, 0.6, N), *(np.pi / 2 + rng.uniform(-0.3, 0.3, (3, N)))])
+    phic = np.column_stack([geom[:, 0] * np.cos(geom[:, 3]), np.cos(geom[:, 2]), geom[:, 0] ** 2, geom[:, 0] * np.cos(geom[:, 1])])
+    mass = rng.uniform(1.0, 10.0, N)
+    com = np.column_stack([rng.uniform(-0.1, 0.1, N), rng.uniform(-0.8, -0.2, N), rng.uniform(-0.1, 0.1, N)])
+    J = np.zeros((N, 3, 3))
+    for i in range(N):
+        A = rng.normal(size=(3, 3)) * 0.3
+        J[i] = mass[i] * np.outer(com[i], com[i]) + A @ A.T + 0.05 * np.eye(3)  # J - m c c^T > 0  =>  M4 > 0
+    joints = []  # (parent, child, [blocks]) in creation order; blocks = (type, params)
+
+    def hinge_like(p, c, ndot):
+        a_p = np.array([0, 0, 1.0, 0]) if p >= 0 else np.zeros(4)
+        blocks = [(BLK_LIN3, np.concatenate([a_p, [0, 1.0, 0, 0], np.zeros(3)]))]
+        for _ in range(ndot):
+            if p >= 0:
+                ap = _direction(rng)
+            else:
+                ax = np.zeros(4)
+                ax[rng.integers(0, 3)] = 1.0
+                ap = ax
+            blocks.append((BLK_DOT, np.concatenate([ap, _direction(rng), [np.cos(rng.uniform(0.5, 2.5))]])))
+        return blocks
+
+    for c in range(N):
+        if c == 0:
+            kind = rng.choice(["free", "gsph", "ghinge"])
+            p = -1
+        else:
+            p = int(rng.integers(0, c))
+            kind = rng.choice(["sph", "sph", "hinge", "univ", "clen", "sop", "free"])
+        if kind == "free":
+            continue
+        if kind == "gsph":
+            blocks = [(BLK_LIN3, np.concatenate([np.zeros(4), [0, 1.0, 0, 0], rng.normal(size=3) * 0.1]))]
+        elif kind == "ghinge":
+            blocks = hinge_like(-1, c, 2)
+        elif kind == "sph":
+            blocks = [(BLK_LIN3, np.concatenate([_point(rng), _point(rng), np.zeros(3)]))]
+        elif kind == "hinge":
+            blocks = hinge_like(p, c, 2)
+        elif kind == "univ":
+            blocks = hinge_like(p, c, 1)
+        elif kind == "clen":
+            blocks = [(BLK_CLEN, np.concatenate([_point(rng), _point(rng), [rng.uniform(0.1, 0.5) ** 2]]))]
+        else:
+            blocks = [(BLK_SOP, np.concatenate([_point(rng), _point(rng), _direction(rng), [0.02]]))]
+        joints.append((p, c, blocks))
+    for _ in range(loops):  # loop closures: extra constraints between arbitrary segment pairs
+        p, c = sorted(rng.choice(N, size=2, replace=False))
+        if rng.random() < 0.5:
+            joints.append((int(p), int(c), [(BLK_CLEN, np.concatenate([_point(rng), _point(rng), [0.09]]))]))
+        else:
+            joints.append((int(p), int(c), [(BLK_SOP, np.concatenate([_point(rng), _point(rng), _direction(rng), [0.01]]))]))
+    # bookkeeping: joint-index order = creation order; holonomic order = per child segment, then its rigid rows
+    row_j, jstart = 0, []
+    for _, _, blocks in joints:
+        jstart.append(row_j)
+        row_j += sum(BLK_ROWS[t] for t, _ in blocks)
+    btype, bpar, bchi, bjoint, browh, browj, bparam = [], [], [], [], [], [], []
+    seg_rigid_row = np.zeros(N, dtype=np.int32)
+    row_h = 0
+    for i in range(N):
+        for jid, (p, c, blocks) in enumerate(joints):
+            if c != i:
+                continue
+            r = 0
+            for t, par in blocks:
+                btype.append(t), bpar.append(p), bchi.append(c), bjoint.append(jid)
+                browh.append(row_h + r), browj.append(jstart[jid] + r)
+                q = np.zeros(BLK_NPARAM)
+                q[: par.size] = par
+                bparam.append(q)
+                r += BLK_ROWS[t]
+            row_h += r
+        seg_rigid_row[i] = row_h
+        row_h += 6
+    return ModelTable(
+        segment_names=[f"s{i}" for i in range(N)], seg_phi_const=phic, seg_geometry=geom, seg_mass=mass, seg_com=com, seg_J=J,
+        seg_rigid_row=seg_rigid_row, joint_names=[f"j{k}" for k in range(len(joints))], joint_kinds=["random"] * len(joints),
+        blk_type=np.array(btype, dtype=np.int32), blk_parent=np.array(bpar, dtype=np.int32), blk_child=np.array(bchi, dtype=np.int32),
+        blk_joint=np.array(bjoint, dtype=np.int32), blk_row_h=np.array(browh, dtype=np.int32), blk_row_j=np.array(browj, dtype=np.int32),
+        blk_param=np.array(bparam, dtype=np.float64).reshape(len(btype), BLK_NPARAM),
+    ).validate()
+
+
+def random_states(table: ModelTable, B: int, seed: int):
+    """Rigid (Phi_r = 0) segments at random poses with random velocities; joint constraints are NOT satisfied,
+    which the dynamics equations do not require."""
+    rng = np.random.default_rng(seed)
+    N = table.nb_segments
+    Q, Qd = np.zeros((B, 12 * N)), np.zeros((B, 12 * N))
+    for i in range(N):
+        R = st.rotation_from_rotvec(rng.normal(0, 1.0, (B, 3)))
+        Qi, Qdi = st._place(R, st.nominal_frame(table.seg_phi_const[i]), rng.normal(0, 0.5, (B, 3)), rng.normal(0, 1.0, (B, 3)), rng.normal(0, 0.5, (B, 3)))
+        Q[:, 12 * i : 12 * i + 12], Qd[:, 12 * i : 12 * i + 12] = Qi, Qdi
+    return Q, Qd
+
+
+CASES = [(seed, N, loops) for seed, (N, loops) in enumerate(
+    [(1, 0), (2, 0), (2, 2), (3, 0), (3, 1), (4, 0), (4, 2), (5, 1), (6, 0), (7, 2), (8, 0), (9, 3), (10, 1), (11, 0), (12, 2), (14, 3), (16, 0), (5, 4), (3, 3), (6, 5)])]
+
+
+@pytest.mark.parametrize("seed,N,loops", CASES)
+def test_random_model_matches_oracle(seed, N, loops):
+    from bionc_oracle import OracleModel
+
+    from bionc_b200.bionc_cuda import BiomechanicalModel, ExternalForceSet
+
+    table = random_table(1000 + seed, N, loops)
+    model = BiomechanicalModel.from_table(table)
+    om = OracleModel(table)
+    B = 7
+    Q, Qd = random_states(table, B, seed)
+    fext = ExternalForceSet.empty_from_nb_segment(N)
+    rng = np.random.default_rng(seed)
+    fext.add_in_global_local_point(int(rng.integers(0, N)), rng.normal(size=6), point_in_local=rng.normal(size=3) * 0.2)
+    fl = [(s, k, p) for s, forces in enumerate(fext.external_forces) for k, p in forces]
+    stab = dict(alpha=0.3, beta=0.7)
+    for kw_gpu, kw_cpu in (({}, {}), (dict(external_forces=fext, stabilization=stab), dict(fext=fl, stabilization=stab))):
+        qdd, lam, status = model.forward_dynamics(Q, Qd, return_status=True, **kw_gpu)
+        assert not (status & 3).any()
+        for s in range(B):
+            A = om.augmented_mass_matrix(Q[s])
+            cond = np.linalg.cond(A)
+            rq, rl = om.forward_dynamics(Q[s], Qd[s], **kw_cpu)
+            tol = 1e-10 * max(1.0, cond / 1e5)  # 1e-10 up to cond 1e5, then proportional to the conditioning
+            assert rel_err(qdd[s], rq) < tol, (seed, N, loops, s, cond)
+            assert rel_err(lam[s], rl) < tol, (seed, N, loops, s, cond)
+    # component API on the same random model
+    np.testing.assert_allclose(model.holonomic_constraints_jacobian(Q[0]), om.holonomic_constraints_jacobian(Q[0]), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(model.joint_constraints(Q[0]), om.joint_constraints(Q[0]), rtol=1e-12, atol=1e-12)
+    # a short fused integration against the oracle's RK4
+    t = np.linspace(0, 0.02, 11)
+    Qf, Qdf = model.rk4(Q[:2], Qd[:2], t=t, normalize=True)
+    for s in range(2):
+        rq, rqd = om.rk4(Q[s], Qd[s], t, normalize=True)
+        assert rel_err(np.concatenate([Qf[s], Qdf[s]]), np.concatenate([rq, rqd])) < 1e-8
