@@ -7,8 +7,20 @@ numpy pieces -- the model table and the force set -- stay importable in light-we
 
 from .model_table import ModelTable, UnsupportedModelError  # noqa: F401
 from .external_force import ExternalForceSet  # noqa: F401
+from .natural_types import (  # noqa: F401
+    NaturalAccelerations,
+    NaturalCoordinates,
+    NaturalVelocities,
+    SegmentNaturalAccelerations,
+    SegmentNaturalCoordinates,
+    SegmentNaturalVelocities,
+)
 
-__all__ = ["BiomechanicalModel", "BioncCudaError", "ExternalForceSet", "ModelTable", "UnsupportedModelError"]
+__all__ = [
+    "BiomechanicalModel", "BioncCudaError", "ExternalForceSet", "ModelTable", "UnsupportedModelError",
+    "NaturalCoordinates", "NaturalVelocities", "NaturalAccelerations",
+    "SegmentNaturalCoordinates", "SegmentNaturalVelocities", "SegmentNaturalAccelerations",
+]
 
 
 def __getattr__(name):

@@ -97,6 +97,33 @@ def m4_from_natural_parameters(mass, com, J) -> np.ndarray:
     return M4
 
 
+def natural_inertial_parameters_from_cartesian(mass, center_of_mass, inertia, length, alpha, beta, gamma):
+    """Cartesian inertial parameters given in the segment coordinate system (``Buv`` convention) ->
+    natural ``(c_nat, J)``, exactly as the reference codes it
+    (``NaturalSegment.with_cartesian_inertial_parameters``, natural_segment.py:223-264, and
+    ``NaturalInertialParameters.compute_natural_center_of_mass`` / ``compute_pseudo_inertia_matrix``,
+    natural_inertial_parameters.py:298-352):
+
+    * the matrix handed over is the TRANSPOSE of ``transformation_matrix.py:7-33``'s ``Buv``;
+    * the middle block is ``I + m (c.c) E - (c.c) 11^T`` -- ``np.dot(c.T, c)`` is the scalar ``c.c``, the
+      ``m c c^T`` outer product of the textbook formula is never formed.
+    """
+    c = np.asarray(center_of_mass, dtype=np.float64).reshape(3)
+    I = np.asarray(inertia, dtype=np.float64).reshape(3, 3)
+    ca, cb, cg, sg = np.cos(alpha), np.cos(beta), np.cos(gamma), np.sin(gamma)
+    Buv = np.array(
+        [
+            [1, length * cg, cb],
+            [0, length * sg, (ca - cb * cg) / sg],
+            [0, 0, np.sqrt(1 - cb**2 - ((ca - cb * cg) / sg) ** 2)],
+        ]
+    )
+    Binv = np.linalg.inv(Buv.T)
+    cc = float(c @ c)
+    middle = I + mass * cc * np.eye(3) - cc
+    return Binv @ c, Binv @ (middle @ Binv.T)
+
+
 def gravity_from_natural_parameters(mass, com) -> np.ndarray:
     """``m N_com^T (0, 0, -9.81)`` (natural_segment.py:562-572).  Broadcasts over leading axes."""
     mass = np.asarray(mass, dtype=np.float64)

@@ -224,6 +224,15 @@ def test_error_conventions():
     assert (status & 1).all()
 
 
+def test_literal_free_box_xdot():
+    # reference tests/test_forward_dynamics.py:95-136: single free box at Q = Qdot = linspace(0, 11, 12)
+    expected = np.array([-1.97372982e-16, -1.0, -2.0, 1.77635684e-15, -1.59872116e-15, -9.81, -3.0, -3.0, -1.281e01, -9.0, -1.0e01, -1.1e01])
+    model = _model("free_box")
+    qdd, lam = model.forward_dynamics(np.linspace(0, 11, 12), np.linspace(0, 11, 12))
+    np.testing.assert_almost_equal(qdd[:, 0], expected, decimal=6)
+    assert lam.shape == (6, 1)
+
+
 def test_redundant_constraints_are_flagged():
     """GroundJoint.Weld + rigid-body row 4 are linearly dependent: the reference silently returns rounding noise
     (|lambda| ~ 1e16); the kernel raises the SMALL_PIVOT status bit instead."""

@@ -39,6 +39,28 @@ def test_holonomic_row_order_of_the_knee():
     assert [BLK_ROWS[int(x)] for x in t.blk_type] == [3, 1, 1, 1, 1, 1]
 
 
+def test_cartesian_to_natural_inertia_matches_reference_models():
+    """The as-coded conversion (natural_inertial_parameters.py:298-352) against values the reference itself
+    produced for the golden models (orthogonal box, skewed bbox of tests/test_joints.py, lower-limb segments)."""
+    from bionc_b200.bionc_cuda.model_table import natural_inertial_parameters_from_cartesian as conv
+
+    t = ModelTable.load(model_path("tj_revolute"))
+    c, J = conv(1.0, [0, 0, 0], np.eye(3), 1.0, np.pi / 2, np.pi / 2, np.pi / 2)
+    np.testing.assert_allclose(c, t.seg_com[0], atol=1e-14)
+    np.testing.assert_allclose(np.triu(J), np.triu(t.seg_J[0]), atol=1e-14)
+    c, J = conv(1.1, [0.1, 0.11, 0.111], np.diag([1.1, 1.2, 1.3]), 1.5, np.pi / 1.9, np.pi / 2.3, np.pi / 2.1)
+    np.testing.assert_allclose(c, t.seg_com[1], atol=1e-14)
+    np.testing.assert_allclose(np.triu(J), np.triu(t.seg_J[1]), atol=1e-13)
+    ll = ModelTable.load(model_path("lower_limb"))
+    inertia = [(10.65, (0, -0.05, 0), (0.10, 0.11, 0.09)), (9.2, (0, -0.17, 0), (0.13, 0.05, 0.13)),
+               (3.6, (0, -0.10, 0), (0.040, 0.020, 0.040)), (0.9, (0.02, -0.03, 0), (0.0040, 0.0045, 0.0045))]
+    for i, (m, com, I) in enumerate(inertia):
+        L, al, be, ga = ll.seg_geometry[i]
+        c, J = conv(m, com, np.diag(I), L, al, be, ga)
+        np.testing.assert_allclose(c, ll.seg_com[i], atol=1e-13)
+        np.testing.assert_allclose(np.triu(J), np.triu(ll.seg_J[i]), atol=1e-13)
+
+
 def test_m4_matches_reference_formula():
     rng = np.random.default_rng(0)
     m, c, J = 2.0, rng.normal(size=3), rng.normal(size=(3, 3))
@@ -100,6 +122,26 @@ def test_generic_rk4_mirror_matches_reference_known_answer():
     # batch axis: two identical systems evolve identically
     yb = RK4(t, lambda t, y: y + t, np.array([[1.0], [1.0]]))
     assert yb.shape == (2, 1, 10) and np.allclose(yb[0, 0], expected, rtol=1e-5) and np.array_equal(yb[0], yb[1])
+
+
+def test_natural_types_mirror_the_reference_layout():
+    from bionc_b200.bionc_cuda import NaturalCoordinates, NaturalVelocities, SegmentNaturalCoordinates, SegmentNaturalVelocities
+
+    # reference natural_coordinates.py:51-69: slots u, rp, rd, w and v = rp - rd
+    Q0 = SegmentNaturalCoordinates.from_components(u=[1, 2, 3.05], rp=[1.1, 1, 3.1], rd=[1.2, 2, 4.1], w=[1.3, 2, 5.1])
+    np.testing.assert_array_equal(Q0.u, [1, 2, 3.05])
+    np.testing.assert_allclose(Q0.v, [-0.1, -1.0, -1.0])
+    Q1 = SegmentNaturalCoordinates.from_components([1.4, 2.1, 3.2], [1.5, 1.1, 3.2], [1.6, 2.2, 4.2], [1.7, 2, 5.3])
+    Q = NaturalCoordinates.from_qi((Q0, Q1))
+    assert Q.shape == (24, 1) and Q.nb_qi() == 2  # one system is a column, like the reference
+    np.testing.assert_array_equal(Q.vector(1).w, [1.7, 2, 5.3])
+    np.testing.assert_array_equal(Q.to_array(), np.concatenate([np.asarray(Q0), np.asarray(Q1)]))
+    Qd = NaturalVelocities.from_qdoti((SegmentNaturalVelocities.from_components(udot=[0, 0, 0], rpdot=[1, 0, 0], rddot=[0, 1, 0], wdot=[0, 0, 0]),))
+    np.testing.assert_array_equal(Qd.vector(0).v, [1, -1, 0])
+    Qb = NaturalCoordinates(np.arange(48.0).reshape(2, 24))  # batch of two systems
+    assert Qb.nb_qi() == 2 and Qb.vector(1).rp.shape == (2, 3)
+    with pytest.raises(ValueError):
+        NaturalCoordinates(np.zeros(13))
 
 
 def test_external_force_set_lowering_matches_the_oracle_kinds():

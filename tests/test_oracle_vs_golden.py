@@ -140,6 +140,14 @@ def test_literal_n_link_linspace_state():
     np.testing.assert_almost_equal(qdd[:3], case["ref_Qddot_linspace"][:3], decimal=6)
 
 
+def test_literal_free_box_xdot():
+    # reference tests/test_forward_dynamics.py:95-136: single free box at Q = Qdot = linspace(0, 11, 12)
+    expected = np.array([-1.97372982e-16, -1.0, -2.0, 1.77635684e-15, -1.59872116e-15, -9.81, -3.0, -3.0, -1.281e01, -9.0, -1.0e01, -1.1e01])
+    om = OracleModel(model_path("free_box"))
+    qdd, _ = om.forward_dynamics(np.linspace(0, 11, 12), np.linspace(0, 11, 12))
+    np.testing.assert_almost_equal(qdd, expected, decimal=6)
+
+
 def test_literal_ode_solver():
     # reference tests/test_ode_solver.py:6-53: y' = y + t on linspace(0, 1, 10), with and without normalize_idx
     expected = [1.0, 1.12392674, 1.27547487, 1.45789044, 1.67480095, 1.9302602, 2.22879841, 2.57547816, 2.97595701, 3.43655736]
