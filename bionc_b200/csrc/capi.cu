@@ -406,7 +406,12 @@ int bionc_cuda_model_create(const BioncModelDesc* d, int device, BioncModel** ou
             if (B.child != i && B.parent != i) continue;
             DevSide sd{};
             sd.blk = b, sd.role = (B.child == i) ? CHILD : PARENT;
-            sd.nl_slot = (B.type == LIN3) ? -1 : nl++;
+            if (B.type == LIN3) {
+                sd.nl_slot = -1;
+            } else {
+                sd.nl_slot = nl;
+                nl += (B.type == SOP && sd.role == PARENT) ? 6 : 3;  // d1 (and d2 for the two-term row kind)
+            }
             M->side.push_back(sd);
         }
         S.side_end = (int)M->side.size();

@@ -23,7 +23,7 @@
 //   S0, S1   : mj(mj+1)/2   packed lower triangle; copy r is written only by the lane that has
 //                           role r (child/parent) in the block of the larger row -> no atomics
 //   r0, r1, dinv : mj
-//   knl      : rnl x 6 x 32 lanes    state-dependent vectors of the non-LIN3 rows (private per lane)
+//   knl      : rnl x 32 lanes        state-dependent vectors of the non-LIN3 rows (3 or 6 doubles per row, private per lane)
 #pragma once
 #include "model.cuh"
 
@@ -183,7 +183,8 @@ __device__ __forceinline__ void sr_factor(SegCtx& c, int& status) {
 //              receive contributions from two segments (slot2_tab)           ([9 nslot][spw])
 //   r0/r1      right-hand side / y-hat, row j at r0[j * spw]                    ([3 nb][spw])
 //   dinv       inverse diagonal blocks, 6 unique entries of block K at dinv[(6 K + i) * spw]
-//   knl        state-dependent vectors (d1, d2) of non-LIN3 rows, slot q element i at knl[(6 q + i) * 32]
+//   knl        state-dependent vectors of the non-LIN3 rows (d1; d2 too for sphere-on-plane parent sides),
+//              double offset q element i at knl[(q + i) * 32]
 // ---------------------------------------------------------------------------------------------
 struct WarpCtx {
     const DevHeader* hdr;
@@ -303,10 +304,14 @@ __device__ __forceinline__ void nonlin_row(const WarpCtx& w, const DevBlk& b, in
     }
 }
 
-// the stored (d1, d2) of non-LIN3 row slot q of this lane
+// the stored state-dependent vectors of a non-LIN3 row of this lane: d1 at offset q (in doubles), d2 behind
+// it for the only two-term row kind (sphere-on-plane, parent side)
+__device__ __forceinline__ bool nonlin_two_terms(const DevBlk& b, int role) { return b.type == SOP && role == PARENT; }
 __device__ __forceinline__ Q12 load_nonlin_k(const WarpCtx& w, const DevBlk& b, int role, int q) {
-    const double* src = w.knl + (6 * q) * 32;
-    return nonlin_k(b, role, mk(src[0], src[32], src[64]), mk(src[96], src[128], src[160]));
+    const double* src = w.knl + q * 32;
+    const V3 d1 = mk(src[0], src[32], src[64]);
+    const V3 d2 = nonlin_two_terms(b, role) ? mk(src[96], src[128], src[160]) : mk(0.0, 0.0, 0.0);
+    return nonlin_k(b, role, d1, d2);
 }
 
 // External forces on this lane's segment (external_force.py:143-180 and the four force classes).
@@ -565,8 +570,9 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                     double acc = bterm;
 #pragma unroll
                     for (int t = 0; t < 4; ++t) acc += dot(k.s[t], x.s[t]);
-                    double* dst = w.knl + (6 * sd.nl_slot) * 32;
-                    dst[0] = d1.x, dst[32] = d1.y, dst[64] = d1.z, dst[96] = d2.x, dst[128] = d2.y, dst[160] = d2.z;
+                    double* dst = w.knl + sd.nl_slot * 32;
+                    dst[0] = d1.x, dst[32] = d1.y, dst[64] = d1.z;
+                    if (nonlin_two_terms(b, sd.role)) dst[96] = d2.x, dst[128] = d2.y, dst[160] = d2.z;
                     rr[0] = acc;
                 }
             }

@@ -24,7 +24,7 @@ struct DevHeader {
     int nb;       // 3x3 block rows ("nodes") of the joint-level Schur system (mj padded up to a multiple of 3)
     int m;        // holonomic rows = mj + 6 N
     int spw;      // systems per warp = 32 / N
-    int rnl;      // max number of non-LIN3 rows touching one segment (k rows kept in shared memory)
+    int rnl;      // doubles of shared memory per lane for the d-vectors of the non-LIN3 rows touching a segment
     int nfext;    // external forces
     int blob_bytes;
     int off_seg, off_blk, off_side, off_fext;  // byte offsets inside the blob
@@ -62,7 +62,7 @@ struct DevBlk {
 struct DevSide {
     int blk;
     int role;     // CHILD / PARENT
-    int nl_slot;  // row slot in the lane's non-LIN3 k storage, -1 for LIN3
+    int nl_slot;  // offset (in doubles) of the row's d-vectors in the lane's storage, -1 for LIN3
     int pad;
 };
 
@@ -77,7 +77,7 @@ __host__ __device__ inline int warp_smem_doubles(int nb, int nslot, int nslot2, 
            + 9 * (nslot + nslot2) * spw  // stored 3x3 blocks of the joint-level Schur matrix (+ second copies)
            + 2 * 3 * nb * spw          // rhs copy 0 / copy 1 (-> y-hat)
            + 6 * nb * spw              // inverse pivot blocks
-           + rnl * 6 * 32;             // (d1, d2) of the non-LIN3 rows, private per lane
+           + rnl * 32;                 // d-vectors of the non-LIN3 rows (rnl doubles per lane), private per lane
 }
 
 }  // namespace bionc
