@@ -184,7 +184,7 @@ def run_gpu_arm(args):
     cpu_baseline = None
     if not distributed and not args.no_cpu_baseline:
         cores = host_cores()
-        nsys, nsteps = 8, 500  # ~10-20 s of CPU work per core at a few hundred system-steps/s/core
+        nsys, nsteps = 8, 1000  # ~10-25 s of CPU work per core at a few hundred system-steps/s/core
         rate, wall = cpu_rate(nsys, nsteps, cores)
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"{cores} cores x {nsys} systems x {nsteps} RK4 steps, same model/h/normalize ({wall:.1f} s wall)"}

@@ -21,7 +21,7 @@ __device__ __forceinline__ void sym4_inverse(const double (&M)[10], double (&Wou
     for (int k = 0; k < 4; ++k) {
         const double piv = A[k][k];
         if (!(fabs(piv) > 0.0) || !isfinite(piv)) status |= 1;
-        dinv[k] = 1.0 / piv;
+        dinv[k] = fast_rcp(piv);
         double col[4];
 #pragma unroll
         for (int r = k + 1; r < 4; ++r) {
@@ -257,8 +257,8 @@ __global__ void __launch_bounds__(32 * kMaxWarpsPerCta, BIONC_MIN_CTAS)
             y0v.s[t] = axpy(h6, accv.s[t], y0v.s[t]);
         }
         if (normalize) {  // u <- u/|u|, w <- w/|w| of Q only (ode_solver.py:50-52)
-            y0q.s[0] = (1.0 / sqrt(dot(y0q.s[0], y0q.s[0]))) * y0q.s[0];
-            y0q.s[3] = (1.0 / sqrt(dot(y0q.s[3], y0q.s[3]))) * y0q.s[3];
+            y0q.s[0] = fast_rsqrt(dot(y0q.s[0], y0q.s[0])) * y0q.s[0];
+            y0q.s[3] = fast_rsqrt(dot(y0q.s[3], y0q.s[3])) * y0q.s[3];
         }
         if (traj != nullptr && ((step + 1) % traj_every) == 0 && live) {
             double* dst = traj + (((size_t)((step + 1) / traj_every - 1) * B + gsys) * 2) * n;
