@@ -80,9 +80,7 @@ struct BioncModel {
     unsigned char* d_blob = nullptr;
     int blob_bytes = 0;
     bool blob_valid = false;
-    int warps_per_cta = 4;
     size_t smem_bytes = 0;
-    bool attr_set = false;
     std::mutex mu;
     // host-path scratch
     cudaStream_t stream = nullptr;
@@ -267,22 +265,16 @@ int build_blob(BioncModel* M, const BioncFextDesc* fx) {
     if (!fext.empty()) std::memcpy(blob.data() + h.off_fext, fext.data(), fext.size() * sizeof(DevFext));
     if (!M->sym.empty()) std::memcpy(blob.data() + h.off_sym, M->sym.data(), M->sym.size() * sizeof(int));
 
-    // shared-memory budget: pick the CTA size (1..4 warps) that keeps the most warps resident per SM
-    // (every CTA carries its own copy of the blob; 168 registers/thread cap residency at 12 warps)
-    int dev_smem = 0, sm_smem = 0;
+    // shared-memory budget of one CTA (32 systems, one warp per segment)
+    int dev_smem = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, M->device));
-    CUDA_TRY(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, M->device));
-    const size_t per_warp = (size_t)warp_smem_doubles(h.nb, h.nslot, h.nslot2, h.spw, h.rnl) * sizeof(double);
-    int warps = 0, best_resident = 0;
-    for (int wcta = kMaxWarpsPerCta; wcta >= 1; --wcta) {
-        const size_t cta = h.blob_bytes + wcta * per_warp;
-        if (cta > (size_t)dev_smem) continue;
-        int ctas = (int)((size_t)sm_smem / (cta + 1024));  // 1 KB reserved per CTA by the driver
-        int resident = ctas * wcta;
-        if (resident > 4 * BIONC_MIN_CTAS) resident = 4 * BIONC_MIN_CTAS;
-        if (resident > best_resident) best_resident = resident, warps = wcta;
+    // 32 systems per CTA (every lane busy); large models whose working set does not fit run 16 per CTA
+    size_t cta_bytes = 0;
+    for (h.spw = 32; h.spw >= 16; h.spw >>= 1) {
+        cta_bytes = h.blob_bytes + (size_t)cta_smem_doubles(h.spw, h.N, h.nb, h.nslot, h.nslot2, h.rnl) * sizeof(double);
+        if (cta_bytes <= (size_t)dev_smem) break;
     }
-    if (warps == 0) return fail(BIONC_E_TOO_LARGE, "model needs more shared memory per warp than one SM has");
+    if (h.spw < 16) return fail(BIONC_E_TOO_LARGE, "model needs more shared memory per CTA than one SM has");
 
     CUDA_TRY(cudaSetDevice(M->device));
     if (M->d_blob != nullptr && M->blob_bytes < h.blob_bytes) {
@@ -295,19 +287,44 @@ int build_blob(BioncModel* M, const BioncFextDesc* fx) {
     CUDA_TRY(cudaMemcpy(M->d_blob, blob.data(), h.blob_bytes, cudaMemcpyHostToDevice));
     M->blob_bytes = h.blob_bytes;
     M->hdr = h;
-    M->warps_per_cta = warps;
-    M->smem_bytes = h.blob_bytes + warps * per_warp;
+    M->smem_bytes = cta_bytes;
     M->fext_key.swap(key);
     M->blob_valid = true;
-    M->attr_set = false;
     return BIONC_OK;
 }
 
-template <typename K>
-int ensure_smem(K kernel, size_t bytes) {
+// kernel instantiations by CTA-size class (threads = 32 x segments) and path (lean / general)
+struct KernelSet {
+    const void* fd;
+    const void* rk4;
+};
+#define BIONC_PICK(T, S)                                                                                          \
+    (general ? KernelSet{(const void*)forward_dynamics_kernel<true, T, S>, (const void*)rk4_kernel<true, T, S>}    \
+             : KernelSet{(const void*)forward_dynamics_kernel<false, T, S>, (const void*)rk4_kernel<false, T, S>})
+KernelSet pick_kernels(bool general, int threads, int spc) {
+    if (spc == 32) {
+        if (threads <= 128) return BIONC_PICK(128, 32);
+        if (threads <= 256) return BIONC_PICK(256, 32);
+        if (threads <= 384) return BIONC_PICK(384, 32);
+        if (threads <= 512) return BIONC_PICK(512, 32);
+        return BIONC_PICK(1024, 32);
+    }
+    // 16 systems per CTA: only models with many segments / joint rows get here
+    if (threads <= 256) return BIONC_PICK(256, 16);
+    if (threads <= 512) return BIONC_PICK(512, 16);
+    return BIONC_PICK(1024, 16);
+}
+
+int ensure_smem(const void* kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::vector<std::pair<const void*, size_t>> done;
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto& d : done)
+        if (d.first == kernel && d.second >= bytes) return BIONC_OK;
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    // as much shared memory as the SM has: residency is limited by the per-warp working sets
+    // as much shared memory as the SM has: residency is limited by the per-CTA working sets
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    done.emplace_back(kernel, bytes);
     return BIONC_OK;
 }
 
@@ -315,26 +332,14 @@ int prepare(BioncModel* M, const BioncDynOptions* opt, DynOpts& o) {
     o.use_stab = (opt != nullptr && opt->use_stabilization) ? 1 : 0;
     o.alpha = opt != nullptr ? opt->alpha : 0.0;
     o.beta = opt != nullptr ? opt->beta : 0.0;
-    int rc = build_blob(M, opt != nullptr ? opt->fext : nullptr);
-    if (rc != BIONC_OK) return rc;
-    if (!M->attr_set) {
-        if ((rc = ensure_smem(forward_dynamics_kernel<false>, M->smem_bytes)) != BIONC_OK) return rc;
-        if ((rc = ensure_smem(forward_dynamics_kernel<true>, M->smem_bytes)) != BIONC_OK) return rc;
-        if ((rc = ensure_smem(rk4_kernel<false>, M->smem_bytes)) != BIONC_OK) return rc;
-        if ((rc = ensure_smem(rk4_kernel<true>, M->smem_bytes)) != BIONC_OK) return rc;
-        M->attr_set = true;
-    }
-    return BIONC_OK;
+    return build_blob(M, opt != nullptr ? opt->fext : nullptr);
 }
 
 // the lean kernel instantiation covers models made of point-to-point (LIN3) blocks only, without
 // external forces or Baumgarte stabilisation; everything else takes the general one
 bool needs_general(const BioncModel* M, const DynOpts& o) { return M->hdr.rnl > 0 || M->hdr.nfext > 0 || o.use_stab != 0; }
 
-unsigned grid_for(const BioncModel* M, long long B) {
-    const long long per_cta = (long long)M->warps_per_cta * M->hdr.spw;
-    return (unsigned)((B + per_cta - 1) / per_cta);
-}
+unsigned grid_for(const BioncModel* M, long long B) { return (unsigned)((B + M->hdr.spw - 1) / M->hdr.spw); }
 
 }  // namespace
 
@@ -343,7 +348,7 @@ extern "C" {
 int bionc_cuda_model_create(const BioncModelDesc* d, int device, BioncModel** out) {
     if (d == nullptr || out == nullptr) return fail(BIONC_E_INVALID, "null argument");
     const int N = d->nb_segments, nblk = d->nb_blocks;
-    if (N < 1 || N > kMaxSegments) return fail(BIONC_E_INVALID, "nb_segments must be in [1, 32] (one lane per segment)");
+    if (N < 1 || N > kMaxSegments) return fail(BIONC_E_INVALID, "nb_segments must be in [1, 32] (one warp per segment, 1024 threads per CTA)");
     if (nblk < 0) return fail(BIONC_E_INVALID, "nb_blocks < 0");
     auto M = new BioncModel();
     M->device = device;
@@ -418,7 +423,7 @@ int bionc_cuda_model_create(const BioncModelDesc* d, int device, BioncModel** ou
         if (nl > rnl) rnl = nl;
     }
     M->hdr.N = N, M->hdr.nblk = nblk, M->hdr.nside = (int)M->side.size();
-    M->hdr.mj = mj, M->hdr.m = mj + 6 * N, M->hdr.spw = 32 / N, M->hdr.rnl = rnl;
+    M->hdr.mj = mj, M->hdr.m = mj + 6 * N, M->hdr.spw = 32, M->hdr.rnl = rnl;  // spw is settled in build_blob
     *out = M;
     return BIONC_OK;
 }
@@ -456,11 +461,14 @@ int bionc_cuda_forward_dynamics(const BioncModel* Mc, const double* Q, const dou
     cudaStream_t st = (cudaStream_t)stream;
     if (status != nullptr) CUDA_TRY(cudaMemsetAsync(status, 0, B * sizeof(int32_t), st));
     const double* inertia = opt != nullptr ? opt->inertia : nullptr;
-    const unsigned grid = grid_for(M, B), block = 32 * M->warps_per_cta;
-    if (needs_general(M, o))
-        forward_dynamics_kernel<true><<<grid, block, M->smem_bytes, st>>>(M->d_blob, M->blob_bytes, Q, Qd, inertia, o, Qdd, lam, status, B);
-    else
-        forward_dynamics_kernel<false><<<grid, block, M->smem_bytes, st>>>(M->d_blob, M->blob_bytes, Q, Qd, inertia, o, Qdd, lam, status, B);
+    const unsigned grid = grid_for(M, B), block = 32 * M->hdr.N;
+    const KernelSet ks = pick_kernels(needs_general(M, o), (int)block, M->hdr.spw);
+    if ((rc = ensure_smem(ks.fd, M->smem_bytes)) != BIONC_OK) return rc;
+    const unsigned char* blob = M->d_blob;
+    int blob_bytes = M->blob_bytes;
+    long long Bll = B;
+    void* args[] = {&blob, &blob_bytes, &Q, &Qd, &inertia, &o, &Qdd, &lam, &status, &Bll};
+    CUDA_TRY(cudaLaunchKernel(ks.fd, dim3(grid), dim3(block), args, M->smem_bytes, st));
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return BIONC_OK;
@@ -480,14 +488,16 @@ int bionc_cuda_rk4(const BioncModel* Mc, double* Q, double* Qd, double h, const 
     cudaStream_t st = (cudaStream_t)stream;
     if (status != nullptr) CUDA_TRY(cudaMemsetAsync(status, 0, B * sizeof(int32_t), st));
     const double* inertia = opt != nullptr ? opt->inertia : nullptr;
-    const unsigned grid = grid_for(M, B), block = 32 * M->warps_per_cta;
+    const unsigned grid = grid_for(M, B), block = 32 * M->hdr.N;
     if (traj == nullptr) traj_every = 1;
-    if (needs_general(M, o))
-        rk4_kernel<true><<<grid, block, M->smem_bytes, st>>>(M->d_blob, M->blob_bytes, Q, Qd, inertia, o, h, h_steps, n_steps,
-                                                             normalize, traj, traj_every, lam_last, status, B);
-    else
-        rk4_kernel<false><<<grid, block, M->smem_bytes, st>>>(M->d_blob, M->blob_bytes, Q, Qd, inertia, o, h, h_steps, n_steps,
-                                                              normalize, traj, traj_every, lam_last, status, B);
+    const KernelSet ks = pick_kernels(needs_general(M, o), (int)block, M->hdr.spw);
+    if ((rc = ensure_smem(ks.rk4, M->smem_bytes)) != BIONC_OK) return rc;
+    const unsigned char* blob = M->d_blob;
+    int blob_bytes = M->blob_bytes;
+    long long Bll = B, nsteps = n_steps, tevery = traj_every;
+    int norm = normalize;
+    void* args[] = {&blob, &blob_bytes, &Q, &Qd, &inertia, &o, &h, &h_steps, &nsteps, &norm, &traj, &tevery, &lam_last, &status, &Bll};
+    CUDA_TRY(cudaLaunchKernel(ks.rk4, dim3(grid), dim3(block), args, M->smem_bytes, st));
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return BIONC_OK;

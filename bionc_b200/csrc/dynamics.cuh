@@ -16,14 +16,16 @@
 // LDL^T (no square roots) instead of Cholesky because the reference's mass matrix is not positive
 // definite in general (SURVEY.md finding 1); a zero / non-finite pivot raises the status flag.
 //
-// Lane mapping: lane = sys_in_warp * N + segment, spw = 32 / N systems per warp, warps are fully
-// independent (only __syncwarp).  Shared memory per warp, all indexed [item][sys_in_warp] so that
-// lanes of different systems hit different banks and lanes of one system broadcast:
-//   Qs, Qds  : 12N          state of the current stage (cross-segment reads for two-segment joints)
-//   S0, S1   : mj(mj+1)/2   packed lower triangle; copy r is written only by the lane that has
-//                           role r (child/parent) in the block of the larger row -> no atomics
-//   r0, r1, dinv : mj
-//   knl      : rnl x 32 lanes        state-dependent vectors of the non-LIN3 rows (3 or 6 doubles per row, private per lane)
+// Thread mapping: one CTA integrates 32 systems; WARP = SEGMENT, LANE = SYSTEM.  All lanes of a warp walk
+// the same constraint-block lists (no divergence between segments), every shared-memory array is indexed
+// [item][32 lanes] (conflict-free, immediate offsets) and the N warps of a CTA meet at block barriers
+// (__syncthreads) between the phases; warps of lightly coupled segments simply wait there while the
+// other resident CTAs use the issue slots.  Shared memory per CTA:
+//   Qs, Qds  : N x 12 x 32   stage state (own segment at compile-time offsets, other segments at + 12*32*s)
+//   S0, S1   : 9 nslot x 32, 9 nslot2 x 32   stored 3x3 blocks of the joint-level Schur matrix; a block that
+//              two segments contribute to has a second copy written by the PARENT-role warp -> no atomics
+//   r0, r1, dinv : 3 nb, 3 nb, 6 nb (x 32)
+//   knl      : N x rnl x 32   state-dependent vectors of the non-LIN3 rows (3 or 6 doubles per row and segment)
 #pragma once
 #include "model.cuh"
 
@@ -195,8 +197,8 @@ __device__ __forceinline__ void sr_factor(SegCtx& c, int& status) {
 // ---------------------------------------------------------------------------------------------
 // warp-level context.  All shared-memory pointers are pre-offset for this lane, so that the hot
 // code addresses them with compile-time multiples of a stride:
-//   Qo/Qdo     own segment's stage state, slot element k at Qo[k * 32]          ([12][32 lanes])
-//   Qsys/Qdsys the system's first lane; segment s, element k at Qsys[s + k * 32]
+//   Qo/Qdo     own segment's stage state, slot element k at Qo[k * 32]          ([N][12][32 lanes])
+//   Qsys/Qdsys segment 0 of this lane's system; segment s, element k at Qsys[(12 s + k) * 32]
 //   S0/S1      joint-level Schur matrix as 3x3 blocks: the block (I, J), I >= J, lives in storage slot
 //              p = slot_tab[I nb + J] (structural non-zeros + fill only), element e = 3 r + c at
 //              S0[(9 p + e) * spw]; S1 holds the second exclusive-writer copy of the blocks that can
@@ -216,20 +218,19 @@ struct WarpCtx {
     double *S0, *S1, *r0, *r1, *dinv, *knl;
     // symbolic factorisation tables (host, capi.cu symbolic_analysis)
     const int *slot_tab, *slot2_tab, *zero_list, *comb_list, *unit_list, *colptr, *colrow;
-    int spw, N, mj, nb;
-    int sys;   // system index inside the warp
-    int segi;  // this lane's segment
-    int lane;
-    bool has_seg;  // lane maps to a (system, segment) pair
+    int N, mj, nb;
+    int segi;  // this warp's segment
+    int lane;  // this lane's system inside the CTA
 };
 
 
 // linear form over a segment's published state: sum_t a[t] * X[segment s, slot t]
+template <int S>
 __device__ __forceinline__ V3 lin_form(const WarpCtx& w, const double* Xsys, int s, const double* a) {
     V3 r = mk(0.0, 0.0, 0.0);
-    const double* X = Xsys + s;
+    const double* X = Xsys + 12 * S * s;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) r = axpy(a[t], mk(X[(3 * t) * 32], X[(3 * t + 1) * 32], X[(3 * t + 2) * 32]), r);
+    for (int t = 0; t < 4; ++t) r = axpy(a[t], mk(X[(3 * t) * S], X[(3 * t + 1) * S], X[(3 * t + 2) * S]), r);
     return r;
 }
 
@@ -270,24 +271,25 @@ __device__ __forceinline__ Q12 nonlin_k(const DevBlk& b, int role, V3 d1, V3 d2)
     return k;
 }
 
+template <int S>
 __device__ __forceinline__ void nonlin_row(const WarpCtx& w, const DevBlk& b, int role, const DynOpts& o, V3& d1, V3& d2,
                                            double& bterm) {
     const double* p = b.p;
     bterm = 0.0;
     d2 = mk(0.0, 0.0, 0.0);
     if (b.type == DOT) {
-        const V3 Dc = lin_form(w, w.Qsys, b.child, p + 4);
+        const V3 Dc = lin_form<S>(w, w.Qsys, b.child, p + 4);
         V3 Dp, Dpd = mk(0.0, 0.0, 0.0);
         if (b.parent >= 0) {
-            Dp = lin_form(w, w.Qsys, b.parent, p);
+            Dp = lin_form<S>(w, w.Qsys, b.parent, p);
         } else {
             Dp = mk(p[0], p[1], p[2]);
         }
         if (role == CHILD) {
             d1 = Dp;
-            const V3 Dcd = lin_form(w, w.Qdsys, b.child, p + 4);
+            const V3 Dcd = lin_form<S>(w, w.Qdsys, b.child, p + 4);
             if (b.parent >= 0) {
-                Dpd = lin_form(w, w.Qdsys, b.parent, p);
+                Dpd = lin_form<S>(w, w.Qdsys, b.parent, p);
                 bterm = 2.0 * dot(Dpd, Dcd);
             }
             if (o.use_stab) bterm += o.alpha * (dot(Dp, Dc) - p[8]) + o.beta * (dot(Dpd, Dc) + dot(Dp, Dcd));
@@ -295,31 +297,31 @@ __device__ __forceinline__ void nonlin_row(const WarpCtx& w, const DevBlk& b, in
             d1 = Dc;
         }
     } else if (b.type == CLEN) {
-        const V3 d = lin_form(w, w.Qsys, b.parent, p) - lin_form(w, w.Qsys, b.child, p + 4);
+        const V3 d = lin_form<S>(w, w.Qsys, b.parent, p) - lin_form<S>(w, w.Qsys, b.child, p + 4);
         d1 = d;
         if (role == CHILD) {
-            const V3 dd = lin_form(w, w.Qdsys, b.parent, p) - lin_form(w, w.Qdsys, b.child, p + 4);
+            const V3 dd = lin_form<S>(w, w.Qdsys, b.parent, p) - lin_form<S>(w, w.Qdsys, b.child, p + 4);
             bterm = 2.0 * dot(dd, dd);
             if (o.use_stab) bterm += o.alpha * (dot(d, d) - p[8]) + o.beta * (2.0 * dot(d, dd));
         }
     } else {  // SOP
-        const V3 n = lin_form(w, w.Qsys, b.child, p + 8);
+        const V3 n = lin_form<S>(w, w.Qsys, b.child, p + 8);
         d1 = n;
         if (role == CHILD) {
-            const V3 P = lin_form(w, w.Qsys, b.parent, p), A = lin_form(w, w.Qsys, b.child, p + 4);
-            const V3 Pd = lin_form(w, w.Qdsys, b.parent, p), Ad = lin_form(w, w.Qdsys, b.child, p + 4);
-            const V3 nd = lin_form(w, w.Qdsys, b.child, p + 8);
+            const V3 P = lin_form<S>(w, w.Qsys, b.parent, p), A = lin_form<S>(w, w.Qsys, b.child, p + 4);
+            const V3 Pd = lin_form<S>(w, w.Qdsys, b.parent, p), Ad = lin_form<S>(w, w.Qdsys, b.child, p + 4);
+            const V3 nd = lin_form<S>(w, w.Qdsys, b.child, p + 8);
             bterm = 2.0 * dot(Pd, nd) - 2.0 * dot(nd, Ad);
             if (o.use_stab) {
                 // K Qdot with the blocks where the reference stores them:
                 // parent cols: -n^T N_A + (P-A)^T N_n applied to Qdot_parent; child cols: n^T N_P applied to Qdot_child
-                const V3 Apd = lin_form(w, w.Qdsys, b.parent, p + 4), npd = lin_form(w, w.Qdsys, b.parent, p + 8);
-                const V3 Pcd = lin_form(w, w.Qdsys, b.child, p);
+                const V3 Apd = lin_form<S>(w, w.Qdsys, b.parent, p + 4), npd = lin_form<S>(w, w.Qdsys, b.parent, p + 8);
+                const V3 Pcd = lin_form<S>(w, w.Qdsys, b.child, p);
                 const double kqd = -dot(n, Apd) + dot(P - A, npd) + dot(n, Pcd);
                 bterm += o.alpha * (dot(P - A, n) - p[12]) + o.beta * kqd;
             }
         } else {
-            d2 = lin_form(w, w.Qsys, b.parent, p) - lin_form(w, w.Qsys, b.child, p + 4);
+            d2 = lin_form<S>(w, w.Qsys, b.parent, p) - lin_form<S>(w, w.Qsys, b.child, p + 4);
         }
     }
 }
@@ -327,10 +329,11 @@ __device__ __forceinline__ void nonlin_row(const WarpCtx& w, const DevBlk& b, in
 // the stored state-dependent vectors of a non-LIN3 row of this lane: d1 at offset q (in doubles), d2 behind
 // it for the only two-term row kind (sphere-on-plane, parent side)
 __device__ __forceinline__ bool nonlin_two_terms(const DevBlk& b, int role) { return b.type == SOP && role == PARENT; }
+template <int S>
 __device__ __forceinline__ Q12 load_nonlin_k(const WarpCtx& w, const DevBlk& b, int role, int q) {
-    const double* src = w.knl + q * 32;
-    const V3 d1 = mk(src[0], src[32], src[64]);
-    const V3 d2 = nonlin_two_terms(b, role) ? mk(src[96], src[128], src[160]) : mk(0.0, 0.0, 0.0);
+    const double* src = w.knl + q * S;
+    const V3 d1 = mk(src[0], src[S], src[2 * S]);
+    const V3 d2 = nonlin_two_terms(b, role) ? mk(src[3 * S], src[4 * S], src[5 * S]) : mk(0.0, 0.0, 0.0);
     return nonlin_k(b, role, d1, d2);
 }
 
@@ -376,19 +379,22 @@ __device__ __forceinline__ Q12 external_forces(const WarpCtx& w, const DevSeg& s
 }
 
 // this lane's own segment, slot t, from / to the published stage state (Xo = w.Qo or w.Qdo)
+template <int S>
 __device__ __forceinline__ V3 own3(const double* Xo, int t) {
-    return mk(Xo[(3 * t) * 32], Xo[(3 * t + 1) * 32], Xo[(3 * t + 2) * 32]);
+    return mk(Xo[(3 * t) * S], Xo[(3 * t + 1) * S], Xo[(3 * t + 2) * S]);
 }
+template <int S>
 __device__ __forceinline__ void publish3(double* Xo, int t, V3 v) {
-    Xo[(3 * t) * 32] = v.x, Xo[(3 * t + 1) * 32] = v.y, Xo[(3 * t + 2) * 32] = v.z;
+    Xo[(3 * t) * S] = v.x, Xo[(3 * t + 1) * S] = v.y, Xo[(3 * t + 2) * S] = v.z;
 }
 
 // rigid-body right-hand side term: bias_r (+ alpha Phi_r + beta Kr Qdot)   (natural_segment.py:429-448, :508-545)
+template <int S>
 __device__ __forceinline__ void rigid_bterm(const WarpCtx& w, const SegCtx& c, const DevSeg& sg, const DynOpts& o,
                                             double (&b)[6]) {
     Q12 Qd;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) Qd.s[t] = own3(w.Qdo, t);
+    for (int t = 0; t < 4; ++t) Qd.s[t] = own3<S>(w.Qdo, t);
     const V3 ud = Qd.s[0], vd = Qd.s[1] - Qd.s[2], wd = Qd.s[3];
     b[0] = 2.0 * dot(ud, ud);
     b[1] = 2.0 * dot(ud, vd);
@@ -449,7 +455,7 @@ __device__ __forceinline__ void lin3_beta(const SegCtx& c, const double (&as)[4]
 // One forward-dynamics evaluation for the whole warp.
 // Precondition: every lane has published its segment's stage state (Q, Qdot) in w.Qs / w.Qds.
 // Every lane receives Qddot of its segment; lambda (holonomic order) goes to lam_out if non-null.
-// All 32 lanes must call this (it contains __syncwarp); lanes without a segment have has_seg=false.
+// Every thread of the CTA must call this (it contains __syncthreads).
 //
 // GENERAL=false is the lean instantiation for models whose joints are all point-to-point (LIN3:
 // spherical / ground spherical / weld halves), without external forces or stabilisation -- the
@@ -463,7 +469,8 @@ __device__ __forceinline__ void lin3_beta(const SegCtx& c, const double (&as)[4]
 // three-right-hand-side solve Z_b = Sr^-1 Gamma(b3).
 // ---------------------------------------------------------------------------------------------
 // 3x3 helpers for the blocked joint-level factorisation (blocks are stored row-major, element e = 3 r + c)
-__device__ __forceinline__ void load9(const double* p, int spw, double (&A)[9]) {
+template <int spw>
+__device__ __forceinline__ void load9(const double* p, double (&A)[9]) {
 #pragma unroll
     for (int e = 0; e < 9; ++e) A[e] = p[e * spw];
 }
@@ -491,15 +498,15 @@ __device__ __forceinline__ V3 sym3_apply(const double (&di)[6], V3 x) {
               fma(di[3], x.x, fma(di[4], x.y, di[5] * x.z)));
 }
 
-template <bool GENERAL>
+template <bool GENERAL, int S>
 __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& c, const DynOpts& o, Q12& Qdd,
                                                       double* lam_out, int& status) {
-    const int spw = w.spw;
+    constexpr int spw = S;
     const DevSeg& sg = w.seg[w.segi];
 
     // ---- B. segment-local factorisation
-    const V3 rp = own3(w.Qo, 1);
-    c.u = own3(w.Qo, 0), c.v = rp - own3(w.Qo, 2), c.w = own3(w.Qo, 3);
+    const V3 rp = own3<S>(w.Qo, 1);
+    c.u = own3<S>(w.Qo, 0), c.v = rp - own3<S>(w.Qo, 2), c.w = own3<S>(w.Qo, 3);
     sr_factor(c, status);
     Q12 f;  // natural forces: gravity + external
     if (GENERAL && sg.fext_end > sg.fext_begin) {
@@ -513,7 +520,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
     double br[6];
     DynOpts oo = o;
     if (!GENERAL) oo.use_stab = 0;
-    rigid_bterm(w, c, sg, oo, br);
+    rigid_bterm<S>(w, c, sg, oo, br);
 
     // Two passes over the same segment solve  x = A_i f + (particular part):
     //   pass 0 with f = applied forces gives the free acceleration abar that feeds the joint-level system,
@@ -534,7 +541,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
         }
         if (pass == 1 || w.mj == 0) {
             Qdd = x;
-            if (lam_out != nullptr && w.has_seg) {
+            if (lam_out != nullptr) {
 #pragma unroll
                 for (int i = 0; i < 6; ++i) lam_out[sg.rigid_row + i] = z[i];  // lambda_r
             }
@@ -545,7 +552,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
 
         // ---- C. zero what the assembly does not overwrite: the right-hand sides, pure fill blocks and
         //         the blocks of nodes made of single rows; padding rows get a unit diagonal
-        if (w.has_seg) {
+        {
             for (int it = w.segi; it < mjp; it += w.N) w.r0[it * spw] = 0.0, w.r1[it * spw] = 0.0;
             for (int it = w.segi; it < 9 * hd->nzero; it += w.N) {
                 const int z = w.zero_list[it / 9], e = it - 9 * (it / 9);
@@ -553,14 +560,14 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                 *dst = 0.0;
             }
         }
-        __syncwarp();
-        if (w.has_seg && w.segi == 0) {
+        __syncthreads();
+        if (w.segi == 0) {
             for (int it = 0; it < hd->nunit; ++it) w.S0[w.unit_list[it] * spw] = 1.0;
         }
 
         // ---- D. right-hand side rhs' = Kj abar + b_j (copy `role` of each row is written by exactly one
         //         lane) and the explicit rows of non-LIN3 blocks
-        if (w.has_seg) {
+        {
             for (int e = sg.side_begin; e < sg.side_end; ++e) {
                 const DevSide sd = w.side[e];
                 const DevBlk& b = w.blk[sd.blk];
@@ -573,11 +580,11 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                     for (int t = 0; t < 4; ++t) r = axpy(as[t], x.s[t], r);
                     if (GENERAL && sd.role == CHILD && o.use_stab) {
                         // Phi = c0 + N_p Q_p - N_c Q_c ; K Qdot = N_p Qdot_p - N_c Qdot_c
-                        V3 phi = mk(b.p[8], b.p[9], b.p[10]) - lin_form(w, w.Qsys, b.child, b.p + 4);
-                        V3 kqd = mk(0.0, 0.0, 0.0) - lin_form(w, w.Qdsys, b.child, b.p + 4);
+                        V3 phi = mk(b.p[8], b.p[9], b.p[10]) - lin_form<S>(w, w.Qsys, b.child, b.p + 4);
+                        V3 kqd = mk(0.0, 0.0, 0.0) - lin_form<S>(w, w.Qdsys, b.child, b.p + 4);
                         if (b.parent >= 0) {
-                            phi = phi + lin_form(w, w.Qsys, b.parent, b.p);
-                            kqd = kqd + lin_form(w, w.Qdsys, b.parent, b.p);
+                            phi = phi + lin_form<S>(w, w.Qsys, b.parent, b.p);
+                            kqd = kqd + lin_form<S>(w, w.Qdsys, b.parent, b.p);
                         }
                         r = axpy(o.alpha, phi, axpy(o.beta, kqd, r));
                     }
@@ -585,21 +592,21 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                 } else {
                     V3 d1, d2;
                     double bterm;
-                    nonlin_row(w, b, sd.role, o, d1, d2, bterm);
+                    nonlin_row<S>(w, b, sd.role, o, d1, d2, bterm);
                     const Q12 k = nonlin_k(b, sd.role, d1, d2);
                     double acc = bterm;
 #pragma unroll
                     for (int t = 0; t < 4; ++t) acc += dot(k.s[t], x.s[t]);
-                    double* dst = w.knl + sd.nl_slot * 32;
-                    dst[0] = d1.x, dst[32] = d1.y, dst[64] = d1.z;
-                    if (nonlin_two_terms(b, sd.role)) dst[96] = d2.x, dst[128] = d2.y, dst[160] = d2.z;
+                    double* dst = w.knl + sd.nl_slot * S;
+                    dst[0] = d1.x, dst[S] = d1.y, dst[2 * S] = d1.z;
+                    if (nonlin_two_terms(b, sd.role)) dst[3 * S] = d2.x, dst[4 * S] = d2.y, dst[5 * S] = d2.z;
                     rr[0] = acc;
                 }
             }
         }
 
         // ---- E1. LIN3 x LIN3 pairs on this segment: S'_ab = gamma I3 - B M_ab B^T, one 3x3 block each
-        if (w.has_seg) {
+        {
             for (int e = sg.side_begin; e < sg.side_end; ++e) {
                 const DevSide sd = w.side[e];
                 const DevBlk& b = w.blk[sd.blk];
@@ -658,12 +665,12 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
         }
 
         // ---- E2. pairs with at least one non-LIN3 row: explicit q' = A_i k_b^T of the non-LIN3 row b
-        if (GENERAL && w.has_seg) {
+        if (GENERAL) {
             for (int e = sg.side_begin; e < sg.side_end; ++e) {
                 const DevSide sd = w.side[e];
                 const DevBlk& b = w.blk[sd.blk];
                 if (b.type == LIN3) continue;
-                const Q12 kb = load_nonlin_k(w, b, sd.role, sd.nl_slot);
+                const Q12 kb = load_nonlin_k<S>(w, b, sd.role, sd.nl_slot);
                 Q12 q;
                 {
                     double y[6];
@@ -696,7 +703,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                             Sc[0] = r.x, Sc[spw] = r.y, Sc[2 * spw] = r.z;
                         }
                     } else if (e2 >= e) {  // every pair of single rows once
-                        const Q12 ka = load_nonlin_k(w, a, sa.role, sa.nl_slot);
+                        const Q12 ka = load_nonlin_k<S>(w, a, sa.role, sa.nl_slot);
                         double acc = 0.0;
 #pragma unroll
                         for (int t = 0; t < 4; ++t) acc += dot(ka.s[t], q.s[t]);
@@ -714,14 +721,14 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                 }
             }
         }
-        __syncwarp();
+        __syncthreads();
 
         // ---- F. combine the second copies, then sparse blocked LDL^T of S' in place with 3x3 pivots along the
         //         host-computed pattern: for pivot node K the block rows I of its column list are dealt
         //         round-robin to the lanes of the system, every block operation runs in registers.
         //         Block column K is final before step K, so one __syncwarp per pivot suffices; S_IK is
         //         kept unscaled (L_IK = S_IK D_K^-1 is applied through y-hat in the solves).
-        if (w.has_seg) {
+        {
             for (int it = w.segi; it < 9 * hd->ncomb; it += w.N) {
                 const int cpair = it / 9, e = it - 9 * cpair;
                 w.S0[(9 * w.comb_list[2 * cpair] + e) * spw] += w.S1[(9 * w.comb_list[2 * cpair + 1] + e) * spw];
@@ -730,8 +737,8 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
         }
 #pragma unroll 1
         for (int K = 0; K < nb; ++K) {
-            __syncwarp();
-            if (w.has_seg) {
+            __syncthreads();
+            {
                 const double* D = w.S0 + 9 * w.slot_tab[K * nb + K] * spw;
                 double di[6];
                 sym3_inverse(D[0], D[3 * spw], D[4 * spw], D[6 * spw], D[7 * spw], D[8 * spw], di, status);
@@ -744,7 +751,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                 for (int ci = c0 + w.segi; ci < c1; ci += w.N) {
                     const int I = w.colrow[ci];
                     double A[9], T[9];
-                    load9(w.S0 + 9 * w.slot_tab[I * nb + K] * spw, spw, A);
+                    load9<S>(w.S0 + 9 * w.slot_tab[I * nb + K] * spw, A);
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {  // T = A Dinv
                         const V3 t = sym3_apply(di, mk(A[3 * r], A[3 * r + 1], A[3 * r + 2]));
@@ -754,7 +761,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                     for (int cj = c0; cj <= ci; ++cj) {  // every J <= I of the same column: (I, J) is in the pattern
                         const int J = w.colrow[cj];
                         double Bj[9];
-                        load9(w.S0 + 9 * w.slot_tab[J * nb + K] * spw, spw, Bj);
+                        load9<S>(w.S0 + 9 * w.slot_tab[J * nb + K] * spw, Bj);
                         double* Sij = w.S0 + 9 * w.slot_tab[I * nb + J] * spw;
 #pragma unroll
                         for (int r = 0; r < 3; ++r)
@@ -767,9 +774,9 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                 }
             }
         }
-        __syncwarp();
+        __syncthreads();
         // ---- G. block triangular solves by the first lane of each system: L y = rhs ; lambda = L^-T D^-1 y
-        if (w.has_seg && w.segi == 0) {
+        if (w.segi == 0) {
 #pragma unroll 1
             for (int K = 0; K < nb; ++K) {
                 double di[6];
@@ -781,7 +788,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                 for (int ci = w.colptr[K]; ci < w.colptr[K + 1]; ++ci) {
                     const int I = w.colrow[ci];
                     double A[9];
-                    load9(w.S0 + 9 * w.slot_tab[I * nb + K] * spw, spw, A);
+                    load9<S>(w.S0 + 9 * w.slot_tab[I * nb + K] * spw, A);
                     double* ri = w.r0 + 3 * I * spw;
                     ri[0] -= fma(A[0], yh.x, fma(A[1], yh.y, A[2] * yh.z));
                     ri[spw] -= fma(A[3], yh.x, fma(A[4], yh.y, A[5] * yh.z));
@@ -795,7 +802,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                 for (int ci = w.colptr[K]; ci < w.colptr[K + 1]; ++ci) {  // acc += S_IK^T lambda_I
                     const int I = w.colrow[ci];
                     double A[9];
-                    load9(w.S0 + 9 * w.slot_tab[I * nb + K] * spw, spw, A);
+                    load9<S>(w.S0 + 9 * w.slot_tab[I * nb + K] * spw, A);
                     const V3 li = mk(w.r0[(3 * I) * spw], w.r0[(3 * I + 1) * spw], w.r0[(3 * I + 2) * spw]);
                     acc = axpy(li.x, mk(A[0], A[1], A[2]), axpy(li.y, mk(A[3], A[4], A[5]), axpy(li.z, mk(A[6], A[7], A[8]), acc)));
                 }
@@ -808,10 +815,10 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                 w.r0[(3 * K + 2) * spw] = w.r1[(3 * K + 2) * spw] - corr.z;  // lambda_j
             }
         }
-        __syncwarp();
+        __syncthreads();
 
         // ---- H. f <- f - Kj^T lambda_j for the second pass
-        if (w.has_seg) {
+        {
             for (int e = sg.side_begin; e < sg.side_end; ++e) {
                 const DevSide sd = w.side[e];
                 const DevBlk& b = w.blk[sd.blk];
@@ -827,7 +834,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                     }
                 } else {
                     const double lam = lj[0];
-                    const Q12 k = load_nonlin_k(w, b, sd.role, sd.nl_slot);
+                    const Q12 k = load_nonlin_k<S>(w, b, sd.role, sd.nl_slot);
 #pragma unroll
                     for (int t = 0; t < 4; ++t) f.s[t] = axpy(-lam, k.s[t], f.s[t]);
                     if (lam_out != nullptr && sd.role == CHILD) lam_out[b.row_h] = lam;
@@ -836,7 +843,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
         }
     }
     // the published state / joint-level buffers are reused by the next evaluation
-    __syncwarp();
+    __syncthreads();
 }
 
 }  // namespace bionc

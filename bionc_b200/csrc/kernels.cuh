@@ -4,10 +4,13 @@
 
 namespace bionc {
 
-constexpr int kMaxWarpsPerCta = 4;
-#ifndef BIONC_MIN_CTAS
-#define BIONC_MIN_CTAS 3  // CTAs per SM the register allocation is sized for (168 registers/thread)
-#endif
+// Kernels are instantiated per CTA-size class (threads = 32 x segments): the register budget follows from
+// __launch_bounds__(MAXT, kMinCtas<MAXT>): 128 threads x 3 CTAs -> 168 registers, 256 x 2 -> 128, 384 x 1 -> 168,
+// 512 x 1 -> 128, 1024 x 1 -> 64.
+template <int MAXT>
+struct MinCtas {
+    static constexpr int value = MAXT <= 128 ? 3 : (MAXT <= 256 ? 2 : 1);
+};
 
 // ---- inverse of a symmetric 4x4 given by its packed upper triangle (LDL^T, no pivoting) ----------
 __device__ __forceinline__ void sym4_inverse(const double (&M)[10], double (&Wout)[10], int& status) {
@@ -76,9 +79,10 @@ __device__ __forceinline__ void inertia_to_constants(const double* ip, double (&
     fg[3] = c2 * m * g;
 }
 
-// ---- per-CTA setup: copy the model blob to shared memory, carve the per-warp working sets ---------
-__device__ __forceinline__ void setup_warp(const unsigned char* __restrict__ blob, int blob_bytes, unsigned char* smem,
-                                           WarpCtx& w) {
+// ---- per-CTA setup: copy the model blob to shared memory, carve the working set ----------------------
+template <int S>
+__device__ __forceinline__ void setup_cta(const unsigned char* __restrict__ blob, int blob_bytes, unsigned char* smem,
+                                          WarpCtx& w) {
     {
         const int4* src = reinterpret_cast<const int4*>(blob);
         int4* dst = reinterpret_cast<int4*>(smem);
@@ -91,26 +95,20 @@ __device__ __forceinline__ void setup_warp(const unsigned char* __restrict__ blo
     w.blk = reinterpret_cast<const DevBlk*>(smem + h->off_blk);
     w.side = reinterpret_cast<const DevSide*>(smem + h->off_side);
     w.fext = reinterpret_cast<const DevFext*>(smem + h->off_fext);
-    w.N = h->N, w.mj = h->mj, w.nb = h->nb, w.spw = h->spw;
-    const int warp = threadIdx.x >> 5;
-    w.lane = threadIdx.x & 31;
-    w.sys = w.lane / w.N;
-    w.segi = w.lane - w.sys * w.N;
-    if (w.sys >= w.spw) w.sys = w.spw - 1, w.segi = 0, w.has_seg = false;
-    else w.has_seg = true;
-    double* base = reinterpret_cast<double*>(smem + blob_bytes) +
-                   (size_t)warp * warp_smem_doubles(w.nb, h->nslot, h->nslot2, w.spw, h->rnl);
+    w.N = h->N, w.mj = h->mj, w.nb = h->nb;
+    w.segi = threadIdx.x >> 5;       // warp = segment
+    w.lane = threadIdx.x & (S - 1);  // lane = system; with S < 32 systems per CTA the upper lanes mirror the lower ones
+    double* base = reinterpret_cast<double*>(smem + blob_bytes);
     double* Qs = base;
-    double* Qds = Qs + 12 * 32;
-    const int own_lane = w.sys * w.N + w.segi;  // == lane for lanes that own a segment
-    w.Qo = Qs + own_lane, w.Qdo = Qds + own_lane;
-    w.Qsys = Qs + w.sys * w.N, w.Qdsys = Qds + w.sys * w.N;
-    w.S0 = Qds + 12 * 32 + w.sys;
-    w.S1 = w.S0 + 9 * h->nslot * w.spw;
-    w.r0 = w.S1 + 9 * h->nslot2 * w.spw;
-    w.r1 = w.r0 + 3 * w.nb * w.spw;
-    w.dinv = w.r1 + 3 * w.nb * w.spw;
-    w.knl = (w.dinv - w.sys) + 6 * w.nb * w.spw + w.lane;
+    double* Qds = Qs + 12 * S * w.N;
+    w.Qsys = Qs + w.lane, w.Qdsys = Qds + w.lane;
+    w.Qo = w.Qsys + 12 * S * w.segi, w.Qdo = w.Qdsys + 12 * S * w.segi;
+    w.S0 = Qds + 12 * S * w.N + w.lane;
+    w.S1 = w.S0 + 9 * S * h->nslot;
+    w.r0 = w.S1 + 9 * S * h->nslot2;
+    w.r1 = w.r0 + 3 * S * w.nb;
+    w.dinv = w.r1 + 3 * S * w.nb;
+    w.knl = w.dinv + 6 * S * w.nb + S * h->rnl * w.segi;
     const int* sym = reinterpret_cast<const int*>(smem + h->off_sym);
     w.slot_tab = sym;
     w.slot2_tab = w.slot_tab + w.nb * w.nb;
@@ -155,18 +153,17 @@ __device__ __forceinline__ void load_constants(const WarpCtx& w, const double* _
 // ---------------------------------------------------------------------------------------------
 // forward_dynamics(Q, Qdot) -> Qddot, lambda       (biomechanical_model.py:351-429, batched)
 // ---------------------------------------------------------------------------------------------
-template <bool GENERAL>
-__global__ void __launch_bounds__(32 * kMaxWarpsPerCta, BIONC_MIN_CTAS)
+template <bool GENERAL, int MAXT, int S>
+__global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
     forward_dynamics_kernel(const unsigned char* __restrict__ blob, int blob_bytes, const double* __restrict__ Q,
                             const double* __restrict__ Qd, const double* __restrict__ inertia, DynOpts o,
                             double* __restrict__ Qdd, double* __restrict__ lam, int* __restrict__ status_out,
                             long long B) {
     extern __shared__ __align__(16) unsigned char smem[];
     WarpCtx w;
-    setup_warp(blob, blob_bytes, smem, w);
-    const int warps = blockDim.x >> 5;
-    long long gsys = ((long long)blockIdx.x * warps + (threadIdx.x >> 5)) * w.spw + w.sys;
-    const bool live = w.has_seg && gsys < B;
+    setup_cta<S>(blob, blob_bytes, smem, w);
+    long long gsys = (long long)blockIdx.x * S + w.lane;
+    const bool live = (int)(threadIdx.x & 31) < S && gsys < B;
     if (gsys >= B) gsys = B - 1;  // tail lanes recompute the last system, stores are masked
     const int n = 12 * w.N;
     int status = 0;
@@ -176,15 +173,13 @@ __global__ void __launch_bounds__(32 * kMaxWarpsPerCta, BIONC_MIN_CTAS)
         Q12 q, qd;
         load_q12(Q + (size_t)gsys * n + 12 * w.segi, q);
         load_q12(Qd + (size_t)gsys * n + 12 * w.segi, qd);
-        if (w.has_seg) {
 #pragma unroll
-            for (int t = 0; t < 4; ++t) publish3(w.Qo, t, q.s[t]), publish3(w.Qdo, t, qd.s[t]);
-        }
+        for (int t = 0; t < 4; ++t) publish3<S>(w.Qo, t, q.s[t]), publish3<S>(w.Qdo, t, qd.s[t]);
     }
-    __syncwarp();
+    __syncthreads();
     Q12 qdd;
     double* lam_sys = (lam != nullptr && live) ? lam + (size_t)gsys * w.hdr->m : nullptr;
-    eval_forward_dynamics<GENERAL>(w, c, o, qdd, lam_sys, status);
+    eval_forward_dynamics<GENERAL, S>(w, c, o, qdd, lam_sys, status);
     if (live) {
         store_q12(Qdd + (size_t)gsys * n + 12 * w.segi, qdd);
         if (status_out != nullptr && status != 0) atomicOr(status_out + gsys, status);
@@ -196,20 +191,19 @@ __global__ void __launch_bounds__(32 * kMaxWarpsPerCta, BIONC_MIN_CTAS)
 // The state of a system stays on chip for all n_steps: HBM sees one read and one write of Q, Qdot
 // per launch (plus the optional trajectory snapshots).  The stage state lives in shared memory
 // (it has to be published there anyway for the two-segment joints); y0 and the k-accumulator are
-// per-lane values that the compiler keeps in registers or spills to L1-resident local memory.
+// per-thread values that the compiler keeps in registers or spills to L1/L2-resident local memory.
 // ---------------------------------------------------------------------------------------------
-template <bool GENERAL>
-__global__ void __launch_bounds__(32 * kMaxWarpsPerCta, BIONC_MIN_CTAS)
+template <bool GENERAL, int MAXT, int S>
+__global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
     rk4_kernel(const unsigned char* __restrict__ blob, int blob_bytes, double* __restrict__ Q, double* __restrict__ Qd,
                const double* __restrict__ inertia, DynOpts o, double h_const, const double* __restrict__ h_steps,
                long long n_steps, int normalize, double* __restrict__ traj, long long traj_every,
                double* __restrict__ lam_last, int* __restrict__ status_out, long long B) {
     extern __shared__ __align__(16) unsigned char smem[];
     WarpCtx w;
-    setup_warp(blob, blob_bytes, smem, w);
-    const int warps = blockDim.x >> 5;
-    long long gsys = ((long long)blockIdx.x * warps + (threadIdx.x >> 5)) * w.spw + w.sys;
-    const bool live = w.has_seg && gsys < B;
+    setup_cta<S>(blob, blob_bytes, smem, w);
+    long long gsys = (long long)blockIdx.x * S + w.lane;
+    const bool live = (int)(threadIdx.x & 31) < S && gsys < B;
     if (gsys >= B) gsys = B - 1;
     const int n = 12 * w.N;
     int status = 0;
@@ -226,29 +220,29 @@ __global__ void __launch_bounds__(32 * kMaxWarpsPerCta, BIONC_MIN_CTAS)
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             accq.s[t] = mk(0.0, 0.0, 0.0), accv.s[t] = mk(0.0, 0.0, 0.0);
-            if (w.has_seg) publish3(w.Qo, t, y0q.s[t]), publish3(w.Qdo, t, y0v.s[t]);
+            publish3<S>(w.Qo, t, y0q.s[t]), publish3<S>(w.Qdo, t, y0v.s[t]);
         }
-        __syncwarp();
+        __syncthreads();
 #pragma unroll 1
         for (int stage = 0; stage < 4; ++stage) {
             // k_stage = f(stage state): (stage velocity, Qddot)
             Q12 a;
             double* lam_sys = (lam_last != nullptr && live && stage == 0 && step == n_steps - 1)
                                   ? lam_last + (size_t)gsys * w.hdr->m : nullptr;
-            eval_forward_dynamics<GENERAL>(w, c, o, a, lam_sys, status);
+            eval_forward_dynamics<GENERAL, S>(w, c, o, a, lam_sys, status);
             const double wt = (stage == 0 || stage == 3) ? 1.0 : 2.0;
             const double cn = (stage == 2) ? h : 0.5 * h;  // next stage is y0 + cn * k_stage
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                const V3 sv = own3(w.Qdo, t);
+                const V3 sv = own3<S>(w.Qdo, t);
                 accq.s[t] = axpy(wt, sv, accq.s[t]);
                 accv.s[t] = axpy(wt, a.s[t], accv.s[t]);
-                if (stage < 3 && w.has_seg) {
-                    publish3(w.Qo, t, axpy(cn, sv, y0q.s[t]));
-                    publish3(w.Qdo, t, axpy(cn, a.s[t], y0v.s[t]));
+                if (stage < 3) {
+                    publish3<S>(w.Qo, t, axpy(cn, sv, y0q.s[t]));
+                    publish3<S>(w.Qdo, t, axpy(cn, a.s[t], y0v.s[t]));
                 }
             }
-            __syncwarp();
+            __syncthreads();
         }
         const double h6 = h / 6.0;
 #pragma unroll

@@ -9,7 +9,7 @@
 
 namespace bionc {
 
-constexpr int kMaxSegments = 32;  // one lane per segment, one system never straddles a warp
+constexpr int kMaxSegments = 32;  // one warp per segment, at most 1024 threads per CTA
 constexpr int kBlkNParam = 16;
 constexpr int kFextNParam = 24;
 
@@ -23,7 +23,7 @@ struct DevHeader {
     int mj;       // joint-constraint rows
     int nb;       // 3x3 block rows ("nodes") of the joint-level Schur system (mj padded up to a multiple of 3)
     int m;        // holonomic rows = mj + 6 N
-    int spw;      // systems per warp = 32 / N
+    int spw;      // systems per CTA: 32 (one lane per system), or 16 when the working set of 32 does not fit
     int rnl;      // doubles of shared memory per lane for the d-vectors of the non-LIN3 rows touching a segment
     int nfext;    // external forces
     int blob_bytes;
@@ -71,13 +71,13 @@ struct DevFext {
     int segment, kind, pad0, pad1;
 };
 
-// Per-warp shared-memory working set, in doubles (see dynamics.cuh for the layout).
-__host__ __device__ inline int warp_smem_doubles(int nb, int nslot, int nslot2, int spw, int rnl) {
-    return 2 * 12 * 32                 // published Q, Qdot of the current stage, [12][32 lanes] each
-           + 9 * (nslot + nslot2) * spw  // stored 3x3 blocks of the joint-level Schur matrix (+ second copies)
-           + 2 * 3 * nb * spw          // rhs copy 0 / copy 1 (-> y-hat)
-           + 6 * nb * spw              // inverse pivot blocks
-           + rnl * 32;                 // d-vectors of the non-LIN3 rows (rnl doubles per lane), private per lane
+// Shared-memory working set of one CTA (spc systems, one warp per segment), in doubles (layout: dynamics.cuh).
+__host__ __device__ inline int cta_smem_doubles(int spc, int N, int nb, int nslot, int nslot2, int rnl) {
+    return spc * (2 * 12 * N              // published Q, Qdot of the current stage
+                 + 9 * (nslot + nslot2)  // stored 3x3 blocks of the joint-level Schur matrix (+ second copies)
+                 + 2 * 3 * nb            // rhs copy 0 / copy 1 (-> y-hat)
+                 + 6 * nb                // inverse pivot blocks
+                 + rnl * N);             // d-vectors of the non-LIN3 rows (rnl doubles per segment)
 }
 
 }  // namespace bionc
