@@ -1,6 +1,7 @@
 // C ABI (include/bionc_cuda.h): model lowering to the device blob, launch logic, host-buffer path.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -207,9 +208,27 @@ int symbolic_analysis(BioncModel* M, int N) {
             if (pat[I * nb + K]) colrow.push_back(I);
         colptr[K + 1] = (int)colrow.size();
     }
+    // elimination tree levels: parent(K) = first row of column K; a pivot sits one level above its deepest child.
+    // Pivots of one level touch disjoint columns, so the kernel needs one barrier per level, not per pivot.
+    std::vector<int> level(nb, 0), lvlptr, lvlpiv;
+    for (int K = 0; K < nb; ++K)
+        if (colptr[K + 1] > colptr[K]) {
+            const int parent = colrow[colptr[K]];
+            if (level[parent] < level[K] + 1) level[parent] = level[K] + 1;
+        }
+    int nlevel = 0;
+    for (int K = 0; K < nb; ++K) nlevel = std::max(nlevel, level[K] + 1);
+    for (int L = 0; L < nlevel; ++L) {
+        lvlptr.push_back((int)lvlpiv.size());
+        for (int K = 0; K < nb; ++K)
+            if (level[K] == L) lvlpiv.push_back(K);
+    }
+    lvlptr.push_back((int)lvlpiv.size());
     M->sym.clear();
     auto append = [&](const std::vector<int>& v) { M->sym.insert(M->sym.end(), v.begin(), v.end()); };
     append(slot_tab), append(slot2_tab), append(zero), append(comb), append(unit), append(colptr), append(colrow);
+    append(lvlptr), append(lvlpiv);
+    M->hdr.nlevel = nlevel;
     M->hdr.nb = nb, M->hdr.nslot = nslot, M->hdr.nslot2 = nslot2;
     M->hdr.nzero = (int)zero.size(), M->hdr.ncomb = (int)comb.size() / 2, M->hdr.nunit = (int)unit.size();
     M->hdr.ncol = (int)colrow.size();

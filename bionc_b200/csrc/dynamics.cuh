@@ -215,9 +215,9 @@ struct WarpCtx {
     const DevSide* side;
     const DevFext* fext;
     double *Qo, *Qdo, *Qsys, *Qdsys;
-    double *S0, *S1, *r0, *r1, *dinv, *knl;
+    double *S0, *S1, *r0, *r1, *lamv, *dinv, *knl;
     // symbolic factorisation tables (host, capi.cu symbolic_analysis)
-    const int *slot_tab, *slot2_tab, *zero_list, *comb_list, *unit_list, *colptr, *colrow;
+    const int *slot_tab, *slot2_tab, *zero_list, *comb_list, *unit_list, *colptr, *colrow, *lvlptr, *lvlpiv;
     int N, mj, nb;
     int segi;  // this warp's segment
     int lane;  // this lane's system inside the CTA
@@ -550,19 +550,20 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
         const int nb = w.nb, mjp = 3 * nb;
         const DevHeader* hd = w.hdr;
 
-        // ---- C. zero what the assembly does not overwrite: the right-hand sides, pure fill blocks and
-        //         the blocks of nodes made of single rows; padding rows get a unit diagonal
-        {
-            for (int it = w.segi; it < mjp; it += w.N) w.r0[it * spw] = 0.0, w.r1[it * spw] = 0.0;
+        // ---- C. zero what the assembly does not overwrite (pure fill blocks, blocks of nodes made of single
+        //         rows); padding rows get a unit diagonal and a zero right-hand side.  Lean models have
+        //         neither, so this phase and its barrier vanish for them.
+        if (hd->nzero > 0 || hd->nunit > 0) {
             for (int it = w.segi; it < 9 * hd->nzero; it += w.N) {
                 const int z = w.zero_list[it / 9], e = it - 9 * (it / 9);
                 double* dst = z >= 0 ? w.S0 + (9 * z + e) * spw : w.S1 + (9 * (-z - 1) + e) * spw;
                 *dst = 0.0;
             }
-        }
-        __syncthreads();
-        if (w.segi == 0) {
-            for (int it = 0; it < hd->nunit; ++it) w.S0[w.unit_list[it] * spw] = 1.0;
+            __syncthreads();
+            if (w.segi == 0) {
+                for (int it = 0; it < hd->nunit; ++it) w.S0[w.unit_list[it] * spw] = 1.0;
+                for (int r = w.mj; r < mjp; ++r) w.r0[r * spw] = 0.0, w.r1[r * spw] = 0.0;
+            }
         }
 
         // ---- D. right-hand side rhs' = Kj abar + b_j (copy `role` of each row is written by exactly one
@@ -589,6 +590,10 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                         r = axpy(o.alpha, phi, axpy(o.beta, kqd, r));
                     }
                     rr[0] = r.x, rr[spw] = r.y, rr[2 * spw] = r.z;
+                    if (b.parent < 0) {  // no parent lane: the child also settles the second copy
+                        double* r1p = w.r1 + b.jrow * spw;
+                        r1p[0] = 0.0, r1p[spw] = 0.0, r1p[2 * spw] = 0.0;
+                    }
                 } else {
                     V3 d1, d2;
                     double bterm;
@@ -601,6 +606,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                     dst[0] = d1.x, dst[S] = d1.y, dst[2 * S] = d1.z;
                     if (nonlin_two_terms(b, sd.role)) dst[3 * S] = d2.x, dst[4 * S] = d2.y, dst[5 * S] = d2.z;
                     rr[0] = acc;
+                    if (b.parent < 0) w.r1[b.jrow * spw] = 0.0;
                 }
             }
         }
@@ -724,34 +730,44 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
         __syncthreads();
 
         // ---- F. combine the second copies, then sparse blocked LDL^T of S' in place with 3x3 pivots along the
-        //         host-computed pattern: for pivot node K the block rows I of its column list are dealt
-        //         round-robin to the lanes of the system, every block operation runs in registers.
-        //         Block column K is final before step K, so one __syncwarp per pivot suffices; S_IK is
-        //         kept unscaled (L_IK = S_IK D_K^-1 is applied through y-hat in the solves).
-        {
-            for (int it = w.segi; it < 9 * hd->ncomb; it += w.N) {
-                const int cpair = it / 9, e = it - 9 * cpair;
-                w.S0[(9 * w.comb_list[2 * cpair] + e) * spw] += w.S1[(9 * w.comb_list[2 * cpair + 1] + e) * spw];
-            }
-            for (int it = w.segi; it < mjp; it += w.N) w.r0[it * spw] += w.r1[it * spw];
+        //         host-computed pattern, level by level of the elimination tree (pivots of one level are
+        //         independent: one barrier per level).  A block row I is always handled by warp I mod N, so
+        //         concurrent pivots never write the same block.  The forward substitution is fused in
+        //         (r_I -= S_IK D_K^-1 r_K); S_IK is kept unscaled (L_IK = S_IK D_K^-1 acts through y-hat).
+        for (int it = w.segi; it < 9 * hd->ncomb; it += w.N) {
+            const int cpair = it / 9, e = it - 9 * cpair;
+            w.S0[(9 * w.comb_list[2 * cpair] + e) * spw] += w.S1[(9 * w.comb_list[2 * cpair + 1] + e) * spw];
         }
+        for (int it = w.segi; it < mjp; it += w.N) w.r0[it * spw] += w.r1[it * spw];
 #pragma unroll 1
-        for (int K = 0; K < nb; ++K) {
+        for (int lv = 0; lv < hd->nlevel; ++lv) {
             __syncthreads();
-            {
+#pragma unroll 1
+            for (int pi = w.lvlptr[lv]; pi < w.lvlptr[lv + 1]; ++pi) {
+                const int K = w.lvlpiv[pi];
+                const int c0 = w.colptr[K], c1 = w.colptr[K + 1];
+                bool mine = (w.segi == 0);
+                for (int ci = c0; ci < c1; ++ci) mine = mine || (w.colrow[ci] % w.N == w.segi);
+                if (!mine) continue;
                 const double* D = w.S0 + 9 * w.slot_tab[K * nb + K] * spw;
                 double di[6];
                 sym3_inverse(D[0], D[3 * spw], D[4 * spw], D[6 * spw], D[7 * spw], D[8 * spw], di, status);
+                const V3 yh = sym3_apply(di, mk(w.r0[(3 * K) * spw], w.r0[(3 * K + 1) * spw], w.r0[(3 * K + 2) * spw]));
                 if (w.segi == 0) {
 #pragma unroll
                     for (int i = 0; i < 6; ++i) w.dinv[(6 * K + i) * spw] = di[i];
+                    w.r1[(3 * K) * spw] = yh.x, w.r1[(3 * K + 1) * spw] = yh.y, w.r1[(3 * K + 2) * spw] = yh.z;  // y-hat = D^-1 y
                 }
-                const int c0 = w.colptr[K], c1 = w.colptr[K + 1];
 #pragma unroll 1
-                for (int ci = c0 + w.segi; ci < c1; ci += w.N) {
+                for (int ci = c0; ci < c1; ++ci) {
                     const int I = w.colrow[ci];
+                    if (I % w.N != w.segi) continue;
                     double A[9], T[9];
                     load9<S>(w.S0 + 9 * w.slot_tab[I * nb + K] * spw, A);
+                    double* ri = w.r0 + 3 * I * spw;  // fused forward substitution
+                    ri[0] -= fma(A[0], yh.x, fma(A[1], yh.y, A[2] * yh.z));
+                    ri[spw] -= fma(A[3], yh.x, fma(A[4], yh.y, A[5] * yh.z));
+                    ri[2 * spw] -= fma(A[6], yh.x, fma(A[7], yh.y, A[8] * yh.z));
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {  // T = A Dinv
                         const V3 t = sym3_apply(di, mk(A[3 * r], A[3 * r + 1], A[3 * r + 2]));
@@ -775,44 +791,26 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
             }
         }
         __syncthreads();
-        // ---- G. block triangular solves by the first lane of each system: L y = rhs ; lambda = L^-T D^-1 y
+        // ---- G. backward substitution by the first warp: lambda_K = y-hat_K - D_K^-1 sum_I S_IK^T lambda_I
         if (w.segi == 0) {
 #pragma unroll 1
-            for (int K = 0; K < nb; ++K) {
-                double di[6];
-#pragma unroll
-                for (int i = 0; i < 6; ++i) di[i] = w.dinv[(6 * K + i) * spw];
-                const V3 yh = sym3_apply(di, mk(w.r0[(3 * K) * spw], w.r0[(3 * K + 1) * spw], w.r0[(3 * K + 2) * spw]));
-                w.r1[(3 * K) * spw] = yh.x, w.r1[(3 * K + 1) * spw] = yh.y, w.r1[(3 * K + 2) * spw] = yh.z;  // y-hat = D^-1 y
+            for (int K = nb - 1; K >= 0; --K) {
+                V3 acc = mk(0.0, 0.0, 0.0);
 #pragma unroll 1
                 for (int ci = w.colptr[K]; ci < w.colptr[K + 1]; ++ci) {
                     const int I = w.colrow[ci];
                     double A[9];
                     load9<S>(w.S0 + 9 * w.slot_tab[I * nb + K] * spw, A);
-                    double* ri = w.r0 + 3 * I * spw;
-                    ri[0] -= fma(A[0], yh.x, fma(A[1], yh.y, A[2] * yh.z));
-                    ri[spw] -= fma(A[3], yh.x, fma(A[4], yh.y, A[5] * yh.z));
-                    ri[2 * spw] -= fma(A[6], yh.x, fma(A[7], yh.y, A[8] * yh.z));
-                }
-            }
-#pragma unroll 1
-            for (int K = nb - 1; K >= 0; --K) {
-                V3 acc = mk(0.0, 0.0, 0.0);
-#pragma unroll 1
-                for (int ci = w.colptr[K]; ci < w.colptr[K + 1]; ++ci) {  // acc += S_IK^T lambda_I
-                    const int I = w.colrow[ci];
-                    double A[9];
-                    load9<S>(w.S0 + 9 * w.slot_tab[I * nb + K] * spw, A);
-                    const V3 li = mk(w.r0[(3 * I) * spw], w.r0[(3 * I + 1) * spw], w.r0[(3 * I + 2) * spw]);
+                    const V3 li = mk(w.lamv[(3 * I) * spw], w.lamv[(3 * I + 1) * spw], w.lamv[(3 * I + 2) * spw]);
                     acc = axpy(li.x, mk(A[0], A[1], A[2]), axpy(li.y, mk(A[3], A[4], A[5]), axpy(li.z, mk(A[6], A[7], A[8]), acc)));
                 }
                 double di[6];
 #pragma unroll
                 for (int i = 0; i < 6; ++i) di[i] = w.dinv[(6 * K + i) * spw];
                 const V3 corr = sym3_apply(di, acc);
-                w.r0[(3 * K) * spw] = w.r1[(3 * K) * spw] - corr.x;
-                w.r0[(3 * K + 1) * spw] = w.r1[(3 * K + 1) * spw] - corr.y;
-                w.r0[(3 * K + 2) * spw] = w.r1[(3 * K + 2) * spw] - corr.z;  // lambda_j
+                w.lamv[(3 * K) * spw] = w.r1[(3 * K) * spw] - corr.x;
+                w.lamv[(3 * K + 1) * spw] = w.r1[(3 * K + 1) * spw] - corr.y;
+                w.lamv[(3 * K + 2) * spw] = w.r1[(3 * K + 2) * spw] - corr.z;
             }
         }
         __syncthreads();
@@ -822,7 +820,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
             for (int e = sg.side_begin; e < sg.side_end; ++e) {
                 const DevSide sd = w.side[e];
                 const DevBlk& b = w.blk[sd.blk];
-                const double* lj = w.r0 + b.jrow * spw;
+                const double* lj = w.lamv + b.jrow * spw;
                 if (!GENERAL || b.type == LIN3) {
                     double as[4];
                     lin3_coefs(b, sd.role, as);
@@ -842,8 +840,8 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
             }
         }
     }
-    // the published state / joint-level buffers are reused by the next evaluation
-    __syncthreads();
+    // No barrier here: lambda_j lives in its own array, so the next evaluation may start assembling while
+    // slower warps still read it; the barriers inside the next evaluation order everything else.
 }
 
 }  // namespace bionc

@@ -5,11 +5,14 @@
 namespace bionc {
 
 // Kernels are instantiated per CTA-size class (threads = 32 x segments): the register budget follows from
-// __launch_bounds__(MAXT, kMinCtas<MAXT>): 128 threads x 3 CTAs -> 168 registers, 256 x 2 -> 128, 384 x 1 -> 168,
+// __launch_bounds__(MAXT, MinCtas<MAXT>): 128 threads x 4 CTAs -> 128 registers, 256 x 2 -> 128, 384 x 1 -> 168,
 // 512 x 1 -> 128, 1024 x 1 -> 64.
+#ifndef BIONC_MIN_CTAS_128
+#define BIONC_MIN_CTAS_128 4  // 128 registers/thread: barrier waits want resident CTAs more than registers
+#endif
 template <int MAXT>
 struct MinCtas {
-    static constexpr int value = MAXT <= 128 ? 3 : (MAXT <= 256 ? 2 : 1);
+    static constexpr int value = MAXT <= 128 ? BIONC_MIN_CTAS_128 : (MAXT <= 256 ? 2 : 1);
 };
 
 // ---- inverse of a symmetric 4x4 given by its packed upper triangle (LDL^T, no pivoting) ----------
@@ -107,7 +110,8 @@ __device__ __forceinline__ void setup_cta(const unsigned char* __restrict__ blob
     w.S1 = w.S0 + 9 * S * h->nslot;
     w.r0 = w.S1 + 9 * S * h->nslot2;
     w.r1 = w.r0 + 3 * S * w.nb;
-    w.dinv = w.r1 + 3 * S * w.nb;
+    w.lamv = w.r1 + 3 * S * w.nb;
+    w.dinv = w.lamv + 3 * S * w.nb;
     w.knl = w.dinv + 6 * S * w.nb + S * h->rnl * w.segi;
     const int* sym = reinterpret_cast<const int*>(smem + h->off_sym);
     w.slot_tab = sym;
@@ -117,6 +121,8 @@ __device__ __forceinline__ void setup_cta(const unsigned char* __restrict__ blob
     w.unit_list = w.comb_list + 2 * h->ncomb;
     w.colptr = w.unit_list + h->nunit;
     w.colrow = w.colptr + w.nb + 1;
+    w.lvlptr = w.colrow + h->ncol;
+    w.lvlpiv = w.lvlptr + h->nlevel + 1;
 }
 
 __device__ __forceinline__ void load_q12(const double* __restrict__ p, Q12& q) {
@@ -222,7 +228,7 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
             accq.s[t] = mk(0.0, 0.0, 0.0), accv.s[t] = mk(0.0, 0.0, 0.0);
             publish3<S>(w.Qo, t, y0q.s[t]), publish3<S>(w.Qdo, t, y0v.s[t]);
         }
-        __syncthreads();
+        if (GENERAL) __syncthreads();  // only the general path reads other segments' published state
 #pragma unroll 1
         for (int stage = 0; stage < 4; ++stage) {
             // k_stage = f(stage state): (stage velocity, Qddot)
@@ -242,7 +248,7 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
                     publish3<S>(w.Qdo, t, axpy(cn, a.s[t], y0v.s[t]));
                 }
             }
-            __syncthreads();
+            if (GENERAL) __syncthreads();
         }
         const double h6 = h / 6.0;
 #pragma unroll

@@ -36,8 +36,9 @@ struct DevHeader {
     int nunit;    // entries of the unit list: diagonal elements of padding rows
     int ncol;     // total length of the column lists
     int off_sym;  // byte offset of the symbolic tables (ints): slot_tab[nb*nb] slot2_tab[nb*nb] zero[nzero]
-                  // comb[2*ncomb] unit[nunit] colptr[nb+1] colrow[ncol]
-    int pad[3];
+                  // comb[2*ncomb] unit[nunit] colptr[nb+1] colrow[ncol] lvlptr[nlevel+1] lvlpiv[nb]
+    int nlevel;   // levels of the elimination tree: pivots of one level are mutually independent
+    int pad[2];
 };
 
 struct DevSeg {
@@ -75,7 +76,7 @@ struct DevFext {
 __host__ __device__ inline int cta_smem_doubles(int spc, int N, int nb, int nslot, int nslot2, int rnl) {
     return spc * (2 * 12 * N              // published Q, Qdot of the current stage
                  + 9 * (nslot + nslot2)  // stored 3x3 blocks of the joint-level Schur matrix (+ second copies)
-                 + 2 * 3 * nb            // rhs copy 0 / copy 1 (-> y-hat)
+                 + 3 * 3 * nb            // rhs copy 0 / copy 1 (-> y-hat), lambda_j
                  + 6 * nb                // inverse pivot blocks
                  + rnl * N);             // d-vectors of the non-LIN3 rows (rnl doubles per segment)
 }
