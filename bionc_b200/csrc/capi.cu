@@ -287,13 +287,24 @@ int build_blob(BioncModel* M, const BioncFextDesc* fx) {
     // shared-memory budget of one CTA (32 systems, one warp per segment)
     int dev_smem = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, M->device));
-    // 32 systems per CTA (every lane busy); large models whose working set does not fit run 16 per CTA
+    // Systems per CTA: 32 (every lane busy) or 16 (upper half-warps idle).  Pick what keeps more systems
+    // resident per SM: large per-system working sets (many joint rows) can fit three 16-system CTAs where
+    // only one 32-system CTA fits.
+    int sm_smem = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, M->device));
     size_t cta_bytes = 0;
-    for (h.spw = 32; h.spw >= 16; h.spw >>= 1) {
-        cta_bytes = h.blob_bytes + (size_t)cta_smem_doubles(h.spw, h.N, h.nb, h.nslot, h.nslot2, h.rnl) * sizeof(double);
-        if (cta_bytes <= (size_t)dev_smem) break;
+    int best_spc = 0, best_resident = 0;
+    for (int spc = 32; spc >= 16; spc >>= 1) {
+        const size_t bytes = h.blob_bytes + (size_t)cta_smem_doubles(spc, h.N, h.nb, h.nslot, h.nslot2, h.rnl) * sizeof(double);
+        if (bytes > (size_t)dev_smem) continue;
+        int ctas = (int)((size_t)sm_smem / (bytes + 1024));  // 1 KB per CTA is reserved by the driver
+        const int by_threads = 2048 / (32 * h.N);
+        if (ctas > by_threads) ctas = by_threads;
+        if (ctas > 32) ctas = 32;
+        if (ctas * spc > best_resident) best_resident = ctas * spc, best_spc = spc, cta_bytes = bytes;
     }
-    if (h.spw < 16) return fail(BIONC_E_TOO_LARGE, "model needs more shared memory per CTA than one SM has");
+    if (best_spc == 0) return fail(BIONC_E_TOO_LARGE, "model needs more shared memory per CTA than one SM has");
+    h.spw = best_spc;
 
     CUDA_TRY(cudaSetDevice(M->device));
     if (M->d_blob != nullptr && M->blob_bytes < h.blob_bytes) {
@@ -322,15 +333,18 @@ struct KernelSet {
              : KernelSet{(const void*)forward_dynamics_kernel<false, T, S>, (const void*)rk4_kernel<false, T, S>})
 KernelSet pick_kernels(bool general, int threads, int spc) {
     if (spc == 32) {
+        if (threads <= 32) return BIONC_PICK(32, 32);
+        if (threads <= 64) return BIONC_PICK(64, 32);
         if (threads <= 128) return BIONC_PICK(128, 32);
         if (threads <= 256) return BIONC_PICK(256, 32);
         if (threads <= 384) return BIONC_PICK(384, 32);
         if (threads <= 512) return BIONC_PICK(512, 32);
         return BIONC_PICK(1024, 32);
     }
-    // 16 systems per CTA: only models with many segments / joint rows get here
+    // 16 systems per CTA (upper half-warps mirror the lower ones): models whose working set for 32 systems
+    // would leave fewer systems resident per SM
+    if (threads <= 128) return BIONC_PICK(128, 16);
     if (threads <= 256) return BIONC_PICK(256, 16);
-    if (threads <= 512) return BIONC_PICK(512, 16);
     return BIONC_PICK(1024, 16);
 }
 

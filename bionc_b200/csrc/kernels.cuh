@@ -4,15 +4,13 @@
 
 namespace bionc {
 
-// Kernels are instantiated per CTA-size class (threads = 32 x segments): the register budget follows from
-// __launch_bounds__(MAXT, MinCtas<MAXT>): 128 threads x 4 CTAs -> 128 registers, 256 x 2 -> 128, 384 x 1 -> 168,
-// 512 x 1 -> 128, 1024 x 1 -> 64.
-#ifndef BIONC_MIN_CTAS_128
-#define BIONC_MIN_CTAS_128 4  // 128 registers/thread: barrier waits want resident CTAs more than registers
-#endif
+// Kernels are instantiated per CTA-size class (threads = 32 x segments); the register budget follows from
+// __launch_bounds__(MAXT, MinCtas<MAXT>): up to 64 threads -> 255 registers (shared memory limits residency
+// long before registers do), 128 threads x 4 CTAs -> 128 registers (barrier waits want resident CTAs more
+// than registers), 256 x 2 -> 128, 384 x 1 -> 168, 512 x 1 -> 128, 1024 x 1 -> 64.
 template <int MAXT>
 struct MinCtas {
-    static constexpr int value = MAXT <= 128 ? BIONC_MIN_CTAS_128 : (MAXT <= 256 ? 2 : 1);
+    static constexpr int value = MAXT <= 32 ? 8 : (MAXT <= 64 ? 4 : (MAXT <= 128 ? 4 : (MAXT <= 256 ? 2 : 1)));
 };
 
 // ---- inverse of a symmetric 4x4 given by its packed upper triangle (LDL^T, no pivoting) ----------
