@@ -517,10 +517,8 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
     }
 #pragma unroll
     for (int t = 0; t < 4; ++t) f.s[t].z += c.fg[t];
-    double br[6];
     DynOpts oo = o;
     if (!GENERAL) oo.use_stab = 0;
-    rigid_bterm<S>(w, c, sg, oo, br);
 
     // Two passes over the same segment solve  x = A_i f + (particular part):
     //   pass 0 with f = applied forces gives the free acceleration abar that feeds the joint-level system,
@@ -532,6 +530,8 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
         {
             const Q12 a = apply_W(c.W, f);
             kr_apply(c, a, z);
+            double br[6];  // recomputed in both passes rather than kept alive across the joint-level phases
+            rigid_bterm<S>(w, c, sg, oo, br);
 #pragma unroll
             for (int i = 0; i < 6; ++i) z[i] += br[i];
             sr_solve(c, z);
@@ -815,7 +815,12 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
         }
         __syncthreads();
 
-        // ---- H. f <- f - Kj^T lambda_j for the second pass
+        // ---- H. f <- f - Kj^T lambda_j for the second pass.  Without external forces f is just gravity: it is
+        //         rebuilt here instead of being kept alive (24 registers) across the joint-level phases.
+        if (!GENERAL) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) f.s[t] = mk(0.0, 0.0, c.fg[t]);
+        }
         {
             for (int e = sg.side_begin; e < sg.side_end; ++e) {
                 const DevSide sd = w.side[e];
