@@ -474,6 +474,20 @@ __device__ __forceinline__ void load9(const double* p, double (&A)[9]) {
 #pragma unroll
     for (int e = 0; e < 9; ++e) A[e] = p[e * spw];
 }
+// Effective block (I, J) of the joint-level matrix: storage slot plus, where two segments contribute, the
+// second exclusive-writer copy.  The copies are never merged in memory: every reader adds them, every
+// update goes to the first copy.
+template <int spw>
+__device__ __forceinline__ void load_block(const WarpCtx& w, int idx, double (&A)[9]) {
+    load9<spw>(w.S0 + 9 * w.slot_tab[idx] * spw, A);
+    const int s2 = w.slot2_tab[idx];
+    if (s2 >= 0) {
+        const double* p2 = w.S1 + 9 * s2 * spw;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) A[e] += p2[e * spw];
+    }
+}
+
 // inverse of a symmetric 3x3 given by its lower triangle (adjugate); di = [i00 i10 i11 i20 i21 i22]
 __device__ __forceinline__ void sym3_inverse(double a00, double a10, double a11, double a20, double a21, double a22,
                                              double (&di)[6], int& status) {
@@ -729,16 +743,11 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
         }
         __syncthreads();
 
-        // ---- F. combine the second copies, then sparse blocked LDL^T of S' in place with 3x3 pivots along the
-        //         host-computed pattern, level by level of the elimination tree (pivots of one level are
-        //         independent: one barrier per level).  A block row I is always handled by warp I mod N, so
-        //         concurrent pivots never write the same block.  The forward substitution is fused in
+        // ---- F. sparse blocked LDL^T of S' in place with 3x3 pivots along the host-computed pattern, level by
+        //         level of the elimination tree (pivots of one level are independent: one barrier per level,
+        //         the first one also closes the assembly).  A block row I is always handled by warp I mod N,
+        //         so concurrent pivots never write the same block.  The forward substitution is fused in
         //         (r_I -= S_IK D_K^-1 r_K); S_IK is kept unscaled (L_IK = S_IK D_K^-1 acts through y-hat).
-        for (int it = w.segi; it < 9 * hd->ncomb; it += w.N) {
-            const int cpair = it / 9, e = it - 9 * cpair;
-            w.S0[(9 * w.comb_list[2 * cpair] + e) * spw] += w.S1[(9 * w.comb_list[2 * cpair + 1] + e) * spw];
-        }
-        for (int it = w.segi; it < mjp; it += w.N) w.r0[it * spw] += w.r1[it * spw];
 #pragma unroll 1
         for (int lv = 0; lv < hd->nlevel; ++lv) {
             __syncthreads();
@@ -749,21 +758,22 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                 bool mine = (w.segi == 0);
                 for (int ci = c0; ci < c1; ++ci) mine = mine || (w.colrow[ci] % w.N == w.segi);
                 if (!mine) continue;
-                const double* D = w.S0 + 9 * w.slot_tab[K * nb + K] * spw;
-                double di[6];
-                sym3_inverse(D[0], D[3 * spw], D[4 * spw], D[6 * spw], D[7 * spw], D[8 * spw], di, status);
-                const V3 yh = sym3_apply(di, mk(w.r0[(3 * K) * spw], w.r0[(3 * K + 1) * spw], w.r0[(3 * K + 2) * spw]));
+                double D[9], di[6];
+                load_block<S>(w, K * nb + K, D);
+                sym3_inverse(D[0], D[3], D[4], D[6], D[7], D[8], di, status);
+                const V3 yh = sym3_apply(di, mk(w.r0[(3 * K) * spw] + w.r1[(3 * K) * spw], w.r0[(3 * K + 1) * spw] + w.r1[(3 * K + 1) * spw],
+                                                w.r0[(3 * K + 2) * spw] + w.r1[(3 * K + 2) * spw]));
                 if (w.segi == 0) {
 #pragma unroll
                     for (int i = 0; i < 6; ++i) w.dinv[(6 * K + i) * spw] = di[i];
-                    w.r1[(3 * K) * spw] = yh.x, w.r1[(3 * K + 1) * spw] = yh.y, w.r1[(3 * K + 2) * spw] = yh.z;  // y-hat = D^-1 y
+                    w.lamv[(3 * K) * spw] = yh.x, w.lamv[(3 * K + 1) * spw] = yh.y, w.lamv[(3 * K + 2) * spw] = yh.z;  // y-hat = D^-1 y
                 }
 #pragma unroll 1
                 for (int ci = c0; ci < c1; ++ci) {
                     const int I = w.colrow[ci];
                     if (I % w.N != w.segi) continue;
                     double A[9], T[9];
-                    load9<S>(w.S0 + 9 * w.slot_tab[I * nb + K] * spw, A);
+                    load_block<S>(w, I * nb + K, A);
                     double* ri = w.r0 + 3 * I * spw;  // fused forward substitution
                     ri[0] -= fma(A[0], yh.x, fma(A[1], yh.y, A[2] * yh.z));
                     ri[spw] -= fma(A[3], yh.x, fma(A[4], yh.y, A[5] * yh.z));
@@ -777,7 +787,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                     for (int cj = c0; cj <= ci; ++cj) {  // every J <= I of the same column: (I, J) is in the pattern
                         const int J = w.colrow[cj];
                         double Bj[9];
-                        load9<S>(w.S0 + 9 * w.slot_tab[J * nb + K] * spw, Bj);
+                        load_block<S>(w, J * nb + K, Bj);
                         double* Sij = w.S0 + 9 * w.slot_tab[I * nb + J] * spw;
 #pragma unroll
                         for (int r = 0; r < 3; ++r)
@@ -790,8 +800,9 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                 }
             }
         }
-        __syncthreads();
-        // ---- G. backward substitution by the first warp: lambda_K = y-hat_K - D_K^-1 sum_I S_IK^T lambda_I
+        // ---- G. backward substitution by the first warp: lambda_K = y-hat_K - D_K^-1 sum_I S_IK^T lambda_I.
+        //         No barrier before it: the pivots of the last level are roots (empty columns), which only the
+        //         first warp touches, and everything below was closed by that level's barrier.
         if (w.segi == 0) {
 #pragma unroll 1
             for (int K = nb - 1; K >= 0; --K) {
@@ -800,7 +811,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                 for (int ci = w.colptr[K]; ci < w.colptr[K + 1]; ++ci) {
                     const int I = w.colrow[ci];
                     double A[9];
-                    load9<S>(w.S0 + 9 * w.slot_tab[I * nb + K] * spw, A);
+                    load_block<S>(w, I * nb + K, A);
                     const V3 li = mk(w.lamv[(3 * I) * spw], w.lamv[(3 * I + 1) * spw], w.lamv[(3 * I + 2) * spw]);
                     acc = axpy(li.x, mk(A[0], A[1], A[2]), axpy(li.y, mk(A[3], A[4], A[5]), axpy(li.z, mk(A[6], A[7], A[8]), acc)));
                 }
@@ -808,9 +819,9 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
 #pragma unroll
                 for (int i = 0; i < 6; ++i) di[i] = w.dinv[(6 * K + i) * spw];
                 const V3 corr = sym3_apply(di, acc);
-                w.lamv[(3 * K) * spw] = w.r1[(3 * K) * spw] - corr.x;
-                w.lamv[(3 * K + 1) * spw] = w.r1[(3 * K + 1) * spw] - corr.y;
-                w.lamv[(3 * K + 2) * spw] = w.r1[(3 * K + 2) * spw] - corr.z;
+                w.lamv[(3 * K) * spw] -= corr.x;
+                w.lamv[(3 * K + 1) * spw] -= corr.y;
+                w.lamv[(3 * K + 2) * spw] -= corr.z;
             }
         }
         __syncthreads();
