@@ -92,6 +92,31 @@ def test_results_do_not_depend_on_batch_position_or_size():
     assert torch.equal(Qf[idx], Qf2) and torch.equal(Qdf[idx], Qdf2)
 
 
+@pytest.mark.parametrize("name,kind", [("lower_limb", "tree"), ("knee_feikes", "knee"), ("full_body", "tree"), ("n_link_4", "chain")])
+def test_repeated_runs_are_bit_identical(name, kind):
+    """The warps of a CTA hand data to each other through shared memory with few barriers; any missing
+    ordering would show up as run-to-run differences.  Three runs of the same 20-step integration (and one
+    with a different batch size, i.e. a different CTA/SM schedule) must agree bit for bit."""
+    from bionc_b200.utils import states as st
+
+    case = load_case(name)
+    model = _model(name)
+    B = 150_001
+    if kind == "chain":
+        Qn, Qdn = st.planar_chain_states(model.table, 1 << 14, seed=31)
+        Q = torch.from_numpy(Qn).cuda().repeat(10, 1)[:B].contiguous()
+        Qd = torch.from_numpy(Qdn).cuda().repeat(10, 1)[:B].contiguous()
+    else:
+        Q, Qd = _tiled_states(kind, model, case, B, seed=31)
+    h = 5e-5 if kind == "knee" else 1e-3
+    ref = model.rk4(Q, Qd, h=h, n_steps=20, return_lambdas=True)
+    for _ in range(2):
+        out = model.rk4(Q, Qd, h=h, n_steps=20, return_lambdas=True)
+        assert all(torch.equal(a, b) for a, b in zip(ref, out))
+    sub = model.rk4(Q[:40_003].contiguous(), Qd[:40_003].contiguous(), h=h, n_steps=20, return_lambdas=True)
+    assert all(torch.equal(a[:40_003], b) for a, b in zip(ref, sub))
+
+
 def _rotate_about_z(X, ang):
     """Rotate every 3-vector of (B, 12N) states by `ang` (B,) about the global z axis (the gravity axis)."""
     B, n = X.shape
