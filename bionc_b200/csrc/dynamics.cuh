@@ -1,16 +1,18 @@
-// Constrained forward dynamics of natural-coordinate models, one LANE per SEGMENT.
+// Constrained forward dynamics of natural-coordinate models: one WARP per SEGMENT, one LANE per SYSTEM.
 //
 // System solved (reference bionc/bionc_numpy/biomechanical_model.py:404-426):
 //     [G K^T; K 0] [Qdd; lambda] = [f; -bias]        G = blockdiag(M4_i (x) I3)
 // The reference LU-factors the dense KKT matrix.  Here the same solution is obtained with a
 // fill-reducing block elimination of the Schur complement S = K G^-1 K^T:
-//   1. per segment (one lane, registers only): Sr_i = Kr_i G_i^-1 Kr_i^T (6x6) is factored LDL^T;
+//   1. per segment (one thread per system, registers only): Sr_i = Kr_i G_i^-1 Kr_i^T (6x6) is factored LDL^T;
 //      rigid-body rows of different segments never couple, so this is the block-diagonal leading
 //      part of S under the ordering "all rigid rows first";
 //   2. per constraint row touching the segment: q' = A_i k^T with the projected inverse mass
 //      A_i = G_i^-1 - G_i^-1 Kr_i^T Sr_i^-1 Kr_i G_i^-1, and the segment's contribution
-//      k_a . q'_b to the joint-level Schur complement S' (mj x mj, shared memory);
-//   3. S' lambda_j = rhs' is factored LDL^T cooperatively by the lanes of the system, in place;
+//      k_a . q'_b to the joint-level Schur complement S' (3x3 blocks in shared memory; closed form
+//      gamma I - B M B^T for pairs of point-to-point blocks);
+//   3. S' lambda_j = rhs' is factored as a sparse blocked LDL^T along a host-computed pattern
+//      (minimum-degree ordering, fill, elimination-tree levels), block rows dealt to the warps of the CTA;
 //   4. back-substitution per segment: F = f - Kj^T lambda_j, a = G^-1 F,
 //      lambda_r = Sr^-1 (Kr a + bias_r), Qdd = a - G^-1 Kr^T lambda_r.
 // LDL^T (no square roots) instead of Cholesky because the reference's mass matrix is not positive
@@ -24,7 +26,7 @@
 //   Qs, Qds  : N x 12 x 32   stage state (own segment at compile-time offsets, other segments at + 12*32*s)
 //   S0, S1   : 9 nslot x 32, 9 nslot2 x 32   stored 3x3 blocks of the joint-level Schur matrix; a block that
 //              two segments contribute to has a second copy written by the PARENT-role warp -> no atomics
-//   r0, r1, dinv : 3 nb, 3 nb, 6 nb (x 32)
+//   r0, r1, lamv, dinv : 3 nb, 3 nb, 3 nb, 6 nb (x 32)   rhs (child / parent copies), y-hat -> lambda_j, pivots
 //   knl      : N x rnl x 32   state-dependent vectors of the non-LIN3 rows (3 or 6 doubles per row and segment)
 #pragma once
 #include "model.cuh"
