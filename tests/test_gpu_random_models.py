@@ -165,3 +165,37 @@ def test_random_model_matches_oracle(seed, N, loops):
     for s in range(2):
         rq, rqd = om.rk4(Q[s], Qd[s], t, normalize=True)
         assert rel_err(np.concatenate([Qf[s], Qdf[s]]), np.concatenate([rq, rqd])) < 1e-8
+
+
+def test_indefinite_pseudo_inertia_fuzz():
+    """The reference's pseudo-inertia quirk makes M4 indefinite for many real models (SURVEY finding 1), where a
+    Cholesky of the Schur complement fails.  40 random models with random SYMMETRIC (indefinite) J: the unpivoted
+    LDL^T path must still match the oracle's pivoted LU, or flag the system."""
+    from bionc_oracle import OracleModel
+
+    from bionc_b200.bionc_cuda import BiomechanicalModel
+
+    rng = np.random.default_rng(0)
+    checked = 0
+    for trial in range(40):
+        N = int(rng.integers(1, 7))
+        table = random_table(5000 + trial, N, int(rng.integers(0, 3)) if N > 1 else 0)
+        for i in range(N):
+            A = rng.normal(size=(3, 3)) * 0.3
+            table.seg_J[i] = A + A.T
+        table.validate()
+        assert not table.is_mass_matrix_positive_definite or N == 0
+        model = BiomechanicalModel.from_table(table)
+        om = OracleModel(table)
+        Q, Qd = random_states(table, 3, trial)
+        qdd, lam, status = model.forward_dynamics(Q, Qd, return_status=True)
+        for s in range(3):
+            cond = np.linalg.cond(om.augmented_mass_matrix(Q[s]))
+            if cond > 1e10:
+                continue
+            rq, rl = om.forward_dynamics(Q[s], Qd[s])
+            tol = 1e-10 * max(1.0, cond / 1e5)
+            ok = rel_err(qdd[s], rq) < tol and rel_err(lam[s], rl) < tol
+            assert ok or status[s] != 0, (trial, N, s, cond)
+            checked += 1
+    assert checked > 100
