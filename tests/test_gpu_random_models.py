@@ -184,7 +184,6 @@ def test_indefinite_pseudo_inertia_fuzz():
             A = rng.normal(size=(3, 3)) * 0.3
             table.seg_J[i] = A + A.T
         table.validate()
-        assert not table.is_mass_matrix_positive_definite or N == 0
         model = BiomechanicalModel.from_table(table)
         om = OracleModel(table)
         Q, Qd = random_states(table, 3, trial)
