@@ -16,6 +16,7 @@ SYMBOLS = (
     "bionc_cuda_model_create",
     "bionc_cuda_model_destroy",
     "bionc_cuda_model_counts",
+    "bionc_cuda_model_layout",
     "bionc_cuda_forward_dynamics",
     "bionc_cuda_rk4",
     "bionc_cuda_eval",
@@ -92,6 +93,7 @@ def load():
     lib.bionc_cuda_model_create.argtypes = [C.POINTER(BioncModelDesc), C.c_int, C.POINTER(vp)]
     lib.bionc_cuda_model_destroy.argtypes = [vp]
     lib.bionc_cuda_model_counts.argtypes = [vp, c_int32_p, c_int32_p, c_int32_p]
+    lib.bionc_cuda_model_layout.argtypes = [vp, c_int32_p]
     lib.bionc_cuda_forward_dynamics.argtypes = [vp, vp, vp, optp, vp, vp, vp, i64, vp]
     lib.bionc_cuda_rk4.argtypes = [vp, vp, vp, dbl, vp, i64, i32, optp, vp, i64, vp, vp, i64, vp]
     lib.bionc_cuda_eval.argtypes = [vp, i32, vp, optp, vp, i64, vp]

@@ -482,6 +482,15 @@ int bionc_cuda_model_counts(const BioncModel* M, int32_t* nseg, int32_t* mj, int
     return BIONC_OK;
 }
 
+int bionc_cuda_model_layout(const BioncModel* M, int32_t* out) {
+    if (M == nullptr || out == nullptr) return fail(BIONC_E_INVALID, "null argument");
+    const DevHeader& h = M->hdr;
+    const int32_t v[10] = {h.N, h.mj, h.nb, h.nslot, h.nslot2, h.nlevel, h.rnl, h.nzero, M->blob_valid ? h.spw : 0,
+                           M->blob_valid ? (int32_t)M->smem_bytes : 0};
+    std::memcpy(out, v, sizeof(v));
+    return BIONC_OK;
+}
+
 int bionc_cuda_forward_dynamics(const BioncModel* Mc, const double* Q, const double* Qd, const BioncDynOptions* opt,
                                 double* Qdd, double* lam, int32_t* status, int64_t B, void* stream) {
     BioncModel* M = const_cast<BioncModel*>(Mc);

@@ -102,6 +102,12 @@ int bionc_cuda_model_destroy(BioncModel* model);
 int bionc_cuda_model_counts(const BioncModel* model, int32_t* nb_segments, int32_t* nb_joint_constraints,
                             int32_t* nb_holonomic_constraints);
 
+/* diagnostics: how the model was laid out for the kernels.  out[10] = {segments, joint rows, 3x3 nodes of the
+ * joint-level system, stored blocks, second copies, elimination-tree levels, doubles of per-segment row
+ * storage, zero-list entries, systems per CTA, shared-memory bytes per CTA}; the last two are 0 until the
+ * first launch has sized the CTA for the device */
+int bionc_cuda_model_layout(const BioncModel* model, int32_t* out);
+
 /* replaces BiomechanicalModel.forward_dynamics (bionc_numpy/biomechanical_model.py:351-429), batched.
  * lambda and status may be NULL. */
 int bionc_cuda_forward_dynamics(const BioncModel* model, const double* Q, const double* Qdot,

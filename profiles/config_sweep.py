@@ -100,7 +100,7 @@ def main():
             "systems": B, "rk4_steps_per_launch": S, "h": h, "kernel_ms": ms, "system_steps_per_s": rate,
             "flops_per_system_step": fl, "algorithmic_tflops": rate * fl / 1e12,
             "frac_of_measured_fp64_peak": rate * fl / 1e12 / sus.value, "fp64_peak_tflops": sus.value,
-            "flagged": int((status != 0).sum().item()),
+            "flagged": int((status != 0).sum().item()), "layout": model.kernel_layout(),
         }
         print(json.dumps(res), flush=True)
         results.append(res)
