@@ -139,23 +139,34 @@ int symbolic_analysis(BioncModel* M, int N) {
         for (int I : touched)
             for (int J : touched) contrib[I * nb + J] += 1;
     }
-    // greedy minimum-degree ordering on the node graph (with fill), ties broken by index
+    // Greedy minimum-degree ordering on the node graph (with fill), in rounds of "multiple elimination": every
+    // round eliminates an independent set of minimum-degree nodes, so that leaves of different branches end up
+    // on the same level of the elimination tree (fewer levels = fewer barriers in the kernel).
     std::vector<char> adj(nb * nb, 0), gone(nb, 0);
     for (int I = 0; I < nb; ++I)
         for (int J = 0; J < nb; ++J) adj[I * nb + J] = (I != J && contrib[I * nb + J] > 0);
     std::vector<int> order;
-    for (int step = 0; step < nb; ++step) {
-        int best = -1, best_deg = 1 << 30;
+    while ((int)order.size() < nb) {
+        int best_deg = 1 << 30;
+        std::vector<int> deg(nb, 0);
         for (int I = 0; I < nb; ++I) {
             if (gone[I]) continue;
-            int deg = 0;
-            for (int J = 0; J < nb; ++J) deg += (!gone[J] && adj[I * nb + J]);
-            if (deg < best_deg) best_deg = deg, best = I;
+            for (int J = 0; J < nb; ++J) deg[I] += (!gone[J] && adj[I * nb + J]);
+            if (deg[I] < best_deg) best_deg = deg[I];
         }
-        order.push_back(best), gone[best] = 1;
-        for (int I = 0; I < nb; ++I)
-            for (int J = 0; J < nb; ++J)
-                if (I != J && !gone[I] && !gone[J] && adj[I * nb + best] && adj[J * nb + best]) adj[I * nb + J] = 1;
+        std::vector<int> round;
+        for (int I = 0; I < nb; ++I) {
+            if (gone[I] || deg[I] != best_deg) continue;
+            bool independent = true;
+            for (int R : round) independent = independent && !adj[I * nb + R];
+            if (independent) round.push_back(I);
+        }
+        for (int best : round) {
+            order.push_back(best), gone[best] = 1;
+            for (int I = 0; I < nb; ++I)
+                for (int J = 0; J < nb; ++J)
+                    if (I != J && !gone[I] && !gone[J] && adj[I * nb + best] && adj[J * nb + best]) adj[I * nb + J] = 1;
+        }
     }
     std::vector<int> newidx(nb);
     for (int k = 0; k < nb; ++k) newidx[order[k]] = k;

@@ -743,7 +743,6 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                 }
             }
         }
-        __syncthreads();
 
         // ---- F. sparse blocked LDL^T of S' in place with 3x3 pivots along the host-computed pattern, level by
         //         level of the elimination tree (pivots of one level are independent: one barrier per level,
