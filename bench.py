@@ -8,7 +8,8 @@ Workload (config 3 of BASELINE.json): the 4-segment lower-limb model (PELVIS fre
 ankle spherical; geometry of the reference's examples/models/lower_limb.nc, inertia of SURVEY.md
 8(d)), B = 1e6 independent systems PER GPU with seeded, constraint-consistent random initial states,
 h = 0.01 s, post-step renormalisation on.  One bench "step" = one launch of the fused integrator
-advancing every system by `rk4_steps_per_launch` RK4 steps (4 forward-dynamics evaluations each).
+advancing every system by `rk4_steps_per_launch` (default 100) RK4 steps, 4 forward-dynamics evaluations
+each -- BASELINE.json's configurations integrate 1000 steps, i.e. ten such launches.
 Metric: RK4 system-steps/s, whole job (all GPUs).
 
   value        states resident in HBM, CUDA events on the launching stream, max over ranks
@@ -123,7 +124,9 @@ def run_reference_arm(args):
 
 # ----------------------------------------------------------------------------- GPU side
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons (B200_PROFILING.md recipe).  The sampler is started before the
+    warm-up (nvidia-smi takes a moment to come up, longer with 8 GPUs busy) and every row is stamped on
+    arrival; `summary(t0, t1)` keeps the rows that fall inside the timed region."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -134,7 +137,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -144,7 +147,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
     def __exit__(self, *exc):
         if self.proc is not None:
@@ -154,9 +157,11 @@ class ClockSampler:
             except subprocess.TimeoutExpired:
                 self.proc.kill()
 
-    def summary(self):
+    def summary(self, t0: float, t1: float):
         sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
+        for ts, r in self.rows:
+            if not (t0 <= ts <= t1 + 0.05):
+                continue
             try:
                 sm.append(float(r[0])), (mx := max(mx, float(r[1])))
             except (ValueError, IndexError):
@@ -230,6 +235,8 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    clocks = ClockSampler(local_rank)
+    clocks.__enter__()
     for _ in range(args.warmup):
         launch()
     barrier()
@@ -239,14 +246,16 @@ def run_gpu_arm(args):
     launches0 = lib.bionc_cuda_launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
-    with ClockSampler(local_rank) as clocks:
-        t_wall0 = time.perf_counter()
-        for e0, e1 in evs:
-            e0.record(stream)
-            launch()
-            e1.record(stream)
-        barrier()
-        t_wall = time.perf_counter() - t_wall0
+    t_wall0 = time.perf_counter()
+    for e0, e1 in evs:
+        e0.record(stream)
+        launch()
+        e1.record(stream)
+    barrier()
+    t_wall1 = time.perf_counter()
+    t_wall = t_wall1 - t_wall0
+    time.sleep(0.1)  # let the last samples of the window arrive
+    clocks.__exit__()
     gpu_launches = int(lib.bionc_cuda_launch_count() - launches0)
     kernel_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
     total_ms = evs[0][0].elapsed_time(evs[-1][1])  # first launch start -> last launch end, on the device
@@ -324,7 +333,7 @@ def run_gpu_arm(args):
                 "api": "bionc_cuda_rk4_host (C ABI, pinned host buffers, H2D + kernel + D2H timed)",
             },
             "gpu_launches": gpu_launches,
-            "clocks": clocks.summary(),
+            "clocks": clocks.summary(t_wall0, t_wall1),
             "status_flagged_systems": int(bad),
             "wall_s": t_wall,
         }
@@ -339,11 +348,11 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--batch", type=int, default=1_000_000, help="systems per GPU")
-    ap.add_argument("--rk4-steps-per-launch", type=int, default=10)
+    ap.add_argument("--rk4-steps-per-launch", type=int, default=100)
     ap.add_argument("--e2e-batch", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather-states", action="store_true")

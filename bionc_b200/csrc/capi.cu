@@ -346,6 +346,7 @@ KernelSet pick_kernels(bool general, int threads, int spc) {
     if (spc == 32) {
         if (threads <= 32) return BIONC_PICK(32, 32);
         if (threads <= 64) return BIONC_PICK(64, 32);
+        if (threads <= 96) return BIONC_PICK(96, 32);
         if (threads <= 128) return BIONC_PICK(128, 32);
         if (threads <= 256) return BIONC_PICK(256, 32);
         if (threads <= 384) return BIONC_PICK(384, 32);

@@ -6,7 +6,7 @@ namespace bionc {
 
 // Kernels are instantiated per CTA-size class (threads = 32 x segments); the register budget follows from
 // __launch_bounds__(MAXT, MinCtas<MAXT>): up to 64 threads -> 255 registers (shared memory limits residency
-// long before registers do), 128 threads x 4 CTAs -> 128 registers (barrier waits want resident CTAs more
+// long before registers do), 96 threads x 4 CTAs -> 168 registers, 128 threads x 4 CTAs -> 128 registers (barrier waits want resident CTAs more
 // than registers), 256 x 2 -> 128, 384 x 1 -> 168, 512 x 1 -> 128, 1024 x 1 -> 64.
 template <int MAXT>
 struct MinCtas {
@@ -154,6 +154,82 @@ __device__ __forceinline__ void load_constants(const WarpCtx& w, const double* _
     }
 }
 
+// ---- tensor memory as per-thread parking space ------------------------------------------------------
+// The fused integrator carries y0 and the k-accumulator (48 doubles per thread) across every stage
+// evaluation; in registers they would leave the evaluation ~30 registers, in local memory they turn into
+// L2 round trips and HBM write-backs.  The path issues no MMA, so the SM's 256 KB of tensor memory is
+// idle: each CTA allocates columns for its warps and every thread parks y0 (24 doubles = 48 32-bit words)
+// in its own TMEM lane (tcgen05.st / tcgen05.ld, shape 32x32b: lane = thread of the warp, columns = words).
+// A warp reaches the lane quarter 32 (warp % 4); warps 4.. of a CTA use the next group of 48 columns.
+// Measured on the lower limb (1e6 systems x 100 steps): y0 in TMEM 3.59e8 system-steps/s against 3.20e8
+// with everything left to the register allocator; parking the accumulator as well is slower (3.0e8, the
+// TMEM read port, 64 B/clk per SM, becomes the queue), so the accumulator stays with the compiler.
+template <int MAXT>
+struct TmemPark {
+    static constexpr int words = 48;  // per thread
+    static constexpr int groups = (MAXT + 127) / 128;
+    static constexpr int need = words * groups;
+    static constexpr int cols = need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : (need <= 256 ? 256 : 512)));
+    // CTAs per SM x columns must fit the 512 columns of an SM; small CTAs have registers to spare anyway
+    static constexpr bool use = MAXT >= 96 && need <= 512 && cols * MinCtas<MAXT>::value <= 512;
+};
+
+__device__ __forceinline__ void tmem_alloc(unsigned* slot_in_smem, unsigned ncols) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(slot_in_smem);
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(unsigned taddr, unsigned ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_put(unsigned taddr, const Q12& q) {  // 12 doubles -> 24 columns
+    unsigned r[24];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        r[6 * t + 0] = __double2loint(q.s[t].x), r[6 * t + 1] = __double2hiint(q.s[t].x);
+        r[6 * t + 2] = __double2loint(q.s[t].y), r[6 * t + 3] = __double2hiint(q.s[t].y);
+        r[6 * t + 4] = __double2loint(q.s[t].z), r[6 * t + 5] = __double2hiint(q.s[t].z);
+    }
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr + 16), "r"(r[16]),
+                 "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23])
+                 : "memory");
+}
+// loads are issued first (tmem_issue) and awaited together (tmem_wait): the registers are in/out operands of
+// the wait so that the compiler cannot read them before it
+struct TmemWords {
+    unsigned r[24];
+};
+__device__ __forceinline__ void tmem_issue(unsigned taddr, TmemWords& x) {
+    unsigned* r = x.r;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%24];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%16, %17, %18, %19, %20, %21, %22, %23}, [%25];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23])
+        : "r"(taddr), "r"(taddr + 16)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait(TmemWords& x, Q12& q) {
+    unsigned* r = x.r;
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23])
+                 :
+                 : "memory");
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+        q.s[t] = mk(__hiloint2double(r[6 * t + 1], r[6 * t + 0]), __hiloint2double(r[6 * t + 3], r[6 * t + 2]),
+                    __hiloint2double(r[6 * t + 5], r[6 * t + 4]));
+}
+__device__ __forceinline__ void tmem_stores_done() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------
 // forward_dynamics(Q, Qdot) -> Qddot, lambda       (biomechanical_model.py:351-429, batched)
 // ---------------------------------------------------------------------------------------------
@@ -194,8 +270,9 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
 // RK4 with the forward-dynamics closure fused in (utils/ode_solver.py:8-53, :107-120).
 // The state of a system stays on chip for all n_steps: HBM sees one read and one write of Q, Qdot
 // per launch (plus the optional trajectory snapshots).  The stage state lives in shared memory
-// (it has to be published there anyway for the two-segment joints); y0 and the k-accumulator are
-// per-thread values that the compiler keeps in registers or spills to L1/L2-resident local memory.
+// (it has to be published there anyway for the two-segment joints); y0 is parked in tensor memory
+// (TmemPark above) and the k-accumulator is a per-thread value that the compiler keeps in registers
+// or spills to L2-resident local memory.
 // ---------------------------------------------------------------------------------------------
 template <bool GENERAL, int MAXT, int S>
 __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
@@ -216,6 +293,16 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
     Q12 y0q, y0v;
     load_q12(Q + (size_t)gsys * n + 12 * w.segi, y0q);
     load_q12(Qd + (size_t)gsys * n + 12 * w.segi, y0v);
+    constexpr bool TM = TmemPark<MAXT>::use;
+    unsigned tm = 0;  // this thread's 48 columns: y0q, y0v (24 each)
+    unsigned* tm_slot = reinterpret_cast<unsigned*>(const_cast<int*>(w.hdr->pad));  // a free word of the header copy
+    if (TM) {
+        if (threadIdx.x < 32) tmem_alloc(tm_slot, TmemPark<MAXT>::cols);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tm = *tm_slot + (((threadIdx.x >> 5) & 3u) << 21) + (threadIdx.x >> 7) * TmemPark<MAXT>::words;
+    }
 
 #pragma unroll 1
     for (long long step = 0; step < n_steps; ++step) {
@@ -226,6 +313,7 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
             accq.s[t] = mk(0.0, 0.0, 0.0), accv.s[t] = mk(0.0, 0.0, 0.0);
             publish3<S>(w.Qo, t, y0q.s[t]), publish3<S>(w.Qdo, t, y0v.s[t]);
         }
+        if (TM) tmem_put(tm, y0q), tmem_put(tm + 24, y0v), tmem_stores_done();
         if (GENERAL) __syncthreads();  // only the general path reads other segments' published state
 #pragma unroll 1
         for (int stage = 0; stage < 4; ++stage) {
@@ -236,6 +324,11 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
             eval_forward_dynamics<GENERAL, S>(w, c, o, a, lam_sys, status);
             const double wt = (stage == 0 || stage == 3) ? 1.0 : 2.0;
             const double cn = (stage == 2) ? h : 0.5 * h;  // next stage is y0 + cn * k_stage
+            if (TM) {
+                TmemWords t0, t1;
+                tmem_issue(tm, t0), tmem_issue(tm + 24, t1);
+                tmem_wait(t0, y0q), tmem_wait(t1, y0v);
+            }
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 const V3 sv = own3<S>(w.Qdo, t);
@@ -263,6 +356,12 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
             store_q12(dst + 12 * w.segi, y0q);
             store_q12(dst + n + 12 * w.segi, y0v);
         }
+    }
+    if (TM) {  // every warp is done with its columns before warp 0 frees them
+        tmem_stores_done();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x < 32) tmem_dealloc(*tm_slot, TmemPark<MAXT>::cols);
     }
     if (live) {
         double chk = 0.0;
