@@ -46,12 +46,13 @@ MODEL = os.path.join(REPO, "tests", "golden", "models", "lower_limb.npz")
 WORKLOAD = "lower_limb_4seg (BASELINE.json configs[2]; PELVIS free + 3 spherical joints, n=48, m=33)"
 H = 0.01
 # DRAM traffic of ONE launch of the dominant kernel at the default configuration, from the committed
-# `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum): 0.84 GB read (the 768 MB of
-# state, once) + 8.12 GB written (768 MB of state + register spills evicted from L2: the kernel runs at 128
-# registers/thread to keep 4 CTAs per SM resident).  The algorithmic bytes of the same launch are
-# B * S * 1536 B = 15.4 GB: the state stays on chip for the S steps of a launch; DRAM runs at 3 % of peak.
-NCU_TRAFFIC = {"systems_per_gpu": 1_000_000, "rk4_steps_per_launch": 10, "bytes": 836.950016e6 + 8.117555e9,
-               "source": "profiles/r01_ncu_rk4_kernel_v7_benchconfig.txt"}
+# `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum): 0.80 GB read (the 768 MB of
+# state, once) + 8.89 GB written (768 MB of state + register spills evicted from L2: the kernel runs at 128
+# registers/thread to keep 4 CTAs per SM resident; before y0 moved to tensor memory the same launch wrote
+# 66 GB).  The algorithmic bytes of the same launch are B * S * 1536 B = 153.6 GB: the state stays on chip
+# for the S steps of a launch; DRAM runs below 1 % of peak.
+NCU_TRAFFIC = {"systems_per_gpu": 1_000_000, "rk4_steps_per_launch": 100, "bytes": 796.118784e6 + 8.887702e9,
+               "source": "profiles/r01_ncu_rk4_kernel_v8_benchconfig.txt"}
 METRIC = "rk4_forward_dynamics_system_steps_per_s"
 UNIT = "system-steps/s"
 
@@ -320,7 +321,7 @@ def run_gpu_arm(args):
                 "frac": achieved_tf / sustained.value,
                 "traffic": NCU_TRAFFIC["bytes"] if (B, S) == (NCU_TRAFFIC["systems_per_gpu"], NCU_TRAFFIC["rk4_steps_per_launch"]) else None,
                 "traffic_source": NCU_TRAFFIC["source"], "algorithmic_bytes_per_launch": B * S * by,
-                "kernel": "rk4_kernel<lean, 128 threads, 32 systems per CTA>", "kernel_ms": kernel_ms_mean,
+                "kernel": "rk4_kernel<lean, 128 threads, 32 systems per CTA, y0 in tensor memory>", "kernel_ms": kernel_ms_mean,
                 "flops_per_system_step": fl, "bytes_per_system_step": by,
                 "peak_source": "DFMA micro-benchmark in this run (bionc_cuda_measure_fp64_peak): sustained %.2f, best launch %.2f TFLOP/s"
                                % (sustained.value, best.value),
