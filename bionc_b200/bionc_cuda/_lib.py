@@ -18,6 +18,8 @@ SYMBOLS = (
     "bionc_cuda_model_counts",
     "bionc_cuda_model_layout",
     "bionc_cuda_forward_dynamics",
+    "bionc_cuda_dense_workspace_bytes",
+    "bionc_cuda_forward_dynamics_dense",
     "bionc_cuda_rk4",
     "bionc_cuda_eval",
     "bionc_cuda_mass_matrix",
@@ -95,6 +97,9 @@ def load():
     lib.bionc_cuda_model_counts.argtypes = [vp, c_int32_p, c_int32_p, c_int32_p]
     lib.bionc_cuda_model_layout.argtypes = [vp, c_int32_p]
     lib.bionc_cuda_forward_dynamics.argtypes = [vp, vp, vp, optp, vp, vp, vp, i64, vp]
+    lib.bionc_cuda_dense_workspace_bytes.argtypes = [vp, i64]
+    lib.bionc_cuda_dense_workspace_bytes.restype = C.c_size_t
+    lib.bionc_cuda_forward_dynamics_dense.argtypes = [vp, vp, vp, optp, vp, i64, vp, vp, vp, vp, C.c_size_t, vp]
     lib.bionc_cuda_rk4.argtypes = [vp, vp, vp, dbl, vp, i64, i32, optp, vp, i64, vp, vp, i64, vp]
     lib.bionc_cuda_eval.argtypes = [vp, i32, vp, optp, vp, i64, vp]
     lib.bionc_cuda_mass_matrix.argtypes = [vp, vp]
@@ -106,7 +111,7 @@ def load():
     lib.bionc_cuda_version.restype = C.c_char_p
     for name in SYMBOLS:
         fn = getattr(lib, name)
-        if name not in ("bionc_cuda_launch_count", "bionc_cuda_last_error", "bionc_cuda_version"):
+        if name not in ("bionc_cuda_launch_count", "bionc_cuda_last_error", "bionc_cuda_version", "bionc_cuda_dense_workspace_bytes"):
             fn.restype = C.c_int
     _lib = lib
     return lib

@@ -323,11 +323,20 @@ class BiomechanicalModel:
         stabilization: dict = None,
         inertial_parameters=None,
         return_status: bool = False,
+        pivoting: str = "auto",
     ):
         """biomechanical_model.py:351-429, batched.  ``joint_generalized_forces`` is accepted and ignored
         exactly like the reference (:391-413).  ``inertial_parameters`` (B, N, 10) optionally overrides
         the natural inertial parameters per system.  Returns ``(Qddot, lambdas)``; a single system whose
-        factorisation hits a zero pivot raises ``numpy.linalg.LinAlgError`` like the reference's solve."""
+        matrix is singular raises ``numpy.linalg.LinAlgError`` like the reference's solve.
+
+        ``pivoting``: ``"auto"`` (default) re-solves the systems the fast block-elimination kernel flags
+        (zero / small / non-finite pivot of the unpivoted LDL^T, e.g. indefinite mass matrices) with the dense
+        pivoted-LU kernel -- the reference's own algorithm (:335-349, :423-426) on the device -- and marks them
+        ``BIONC_STATUS_PIVOTED``; ``"never"`` keeps the fast result and its flags (no host synchronisation);
+        ``"always"`` solves every system with the dense kernel."""
+        if pivoting not in ("auto", "never", "always"):
+            raise ValueError("pivoting must be 'auto', 'never' or 'always'")
         q = _Batch(Q, self.nb_Q, self.device, "Q")
         qd = _Batch(Qdot, self.nb_Q, self.device, "Qdot")
         if q.B != qd.B:
@@ -338,12 +347,23 @@ class BiomechanicalModel:
         status = torch.empty((B,), dtype=torch.int32, device=self.device)
         opt, keep = self._options(external_forces, stabilization, inertial_parameters, B)
         with torch.cuda.device(self.device):
-            if B > 0:
+            if B > 0 and pivoting != "always":
                 rc = self._lib.bionc_cuda_forward_dynamics(
                     self._h, q.t.data_ptr(), qd.t.data_ptr(), C.byref(opt), qdd.data_ptr(), lam.data_ptr(),
                     status.data_ptr(), B, self._stream(),
                 )
                 _lib.check(rc, "forward_dynamics")
+            if B > 0 and pivoting != "never":
+                select = None if pivoting == "always" else torch.nonzero(status & 7).flatten()
+                count = B if select is None else int(select.numel())
+                if count > 0:
+                    nbytes = int(self._lib.bionc_cuda_dense_workspace_bytes(self._h, count))
+                    work = torch.empty((nbytes // 8,), dtype=torch.float64, device=self.device)
+                    rc = self._lib.bionc_cuda_forward_dynamics_dense(
+                        self._h, q.t.data_ptr(), qd.t.data_ptr(), C.byref(opt), None if select is None else select.data_ptr(),
+                        count, qdd.data_ptr(), lam.data_ptr(), status.data_ptr(), work.data_ptr(), nbytes, self._stream(),
+                    )
+                    _lib.check(rc, "forward_dynamics_dense")
         if q.single and B > 0 and not return_status:
             if int(status[0].item()) & 1:
                 raise np.linalg.LinAlgError("Singular matrix")
@@ -365,6 +385,7 @@ class BiomechanicalModel:
         return_lambdas: bool = False,
         return_status: bool = False,
         inplace: bool = False,
+        pivoting: str = "never",
     ):
         """Fused integrator: ``utils/ode_solver.py:8-53`` with the closure of ``:107-116`` inside the kernel.
 
@@ -373,7 +394,15 @@ class BiomechanicalModel:
         ``normalize_idx=model.normalized_coordinates``.  Returns ``(Q, Qdot)`` after the last step, plus
         the trajectory ``(n_steps // save_every, B, 2n)`` if ``save_every`` is given, the multipliers of
         the first stage of the last step if ``return_lambdas``, and the status flags if ``return_status``.
+
+        ``pivoting="auto"`` re-integrates the systems the fused kernel flags (zero / small / non-finite pivot of
+        the unpivoted LDL^T somewhere along the trajectory) from their initial state, stage by stage, with the
+        dense pivoted-LU kernel (``forward_dynamics(..., pivoting="always")``), and marks them
+        ``BIONC_STATUS_PIVOTED``; the default ``"never"`` returns the fused result with its flags and does not
+        synchronise with the host.
         """
+        if pivoting not in ("auto", "never"):
+            raise ValueError("pivoting must be 'auto' or 'never'")
         q = _Batch(Q, self.nb_Q, self.device, "Q")
         qd = _Batch(Qdot, self.nb_Q, self.device, "Qdot")
         if q.B != qd.B:
@@ -381,7 +410,9 @@ class BiomechanicalModel:
         B = q.B
         if not (inplace and q.torch_in and qd.torch_in and q.t.data_ptr() == Q.data_ptr()):
             q.t, qd.t = q.t.clone(), qd.t.clone()
+        start = (q.t.clone(), qd.t.clone()) if pivoting == "auto" else None
         h_steps = None
+        hs = None
         if t is not None:
             tt = np.asarray(t, dtype=np.float64).reshape(-1)
             hs = tt[1:] - tt[:-1]
@@ -404,6 +435,12 @@ class BiomechanicalModel:
                     int(save_every or 1), lam.data_ptr() if lam is not None else None, status.data_ptr(), B, self._stream(),
                 )
                 _lib.check(rc, "rk4")
+                if pivoting == "auto":
+                    sel = torch.nonzero(status & 7).flatten()
+                    if sel.numel() > 0:
+                        steps = hs if hs is not None else np.full(int(n_steps), float(h))
+                        self._rk4_stagewise_pivoted(sel, start, steps, normalize, external_forces, stabilization,
+                                                    inertial_parameters, q.t, qd.t, traj, save_every, lam, status)
             else:
                 status.zero_()
         res = [q.out(q.t), q.out(qd.t)]
@@ -414,6 +451,46 @@ class BiomechanicalModel:
         if return_status:
             res.append(q.out(status))
         return tuple(res)
+
+    def _rk4_stagewise_pivoted(self, sel, start, steps, normalize, external_forces, stabilization, inertial_parameters,
+                               Qout, Qdout, traj, save_every, lam, status):
+        """Classic RK4 (utils/ode_solver.py:8-53) on the systems ``sel``, one dense pivoted-LU launch per stage."""
+        yq, yv = start[0][sel].clone(), start[1][sel].clone()
+        ip = None
+        if inertial_parameters is not None:
+            it = inertial_parameters if isinstance(inertial_parameters, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(inertial_parameters, dtype=np.float64))
+            ip = it.to(self.device)[sel].contiguous()
+        bits = torch.zeros((sel.numel(),), dtype=torch.int32, device=self.device)
+
+        def f(qq, vv):
+            a, l, s = self.forward_dynamics(qq, vv, external_forces=external_forces, stabilization=stabilization,
+                                            inertial_parameters=ip, return_status=True, pivoting="always")
+            bits.bitwise_or_(s & 3)
+            return a, l
+
+        n_steps = len(steps)
+        for step in range(n_steps):
+            h = float(steps[step])
+            a1, lam1 = f(yq, yv)
+            v2 = yv + 0.5 * h * a1
+            a2, _ = f(yq + 0.5 * h * yv, v2)
+            v3 = yv + 0.5 * h * a2
+            a3, _ = f(yq + 0.5 * h * v2, v3)
+            v4 = yv + h * a3
+            a4, _ = f(yq + h * v3, v4)
+            yq = yq + (h / 6.0) * (yv + 2.0 * v2 + 2.0 * v3 + v4)
+            yv = yv + (h / 6.0) * (a1 + 2.0 * a2 + 2.0 * a3 + a4)
+            if normalize:  # ode_solver.py:50-52 on model.normalized_coordinates
+                y3 = yq.view(yq.shape[0], self.nb_segments, 4, 3)
+                y3[:, :, 0] /= y3[:, :, 0].norm(dim=-1, keepdim=True)
+                y3[:, :, 3] /= y3[:, :, 3].norm(dim=-1, keepdim=True)
+            if traj is not None and (step + 1) % save_every == 0:
+                traj[(step + 1) // save_every - 1, sel] = torch.cat([yq, yv], dim=1)
+            if lam is not None and step == n_steps - 1:
+                lam[sel] = lam1
+        Qout[sel], Qdout[sel] = yq, yv
+        bad = ~(torch.isfinite(yq).all(dim=1) & torch.isfinite(yv).all(dim=1))
+        status[sel] = bits | 8 | (bad.to(torch.int32) * 2)
 
     # ------------------------------------------------------------------ host-buffer path (C ABI with host pointers)
     def rk4_host(self, Q: np.ndarray, Qdot: np.ndarray, h: float, n_steps: int, normalize: bool = True,

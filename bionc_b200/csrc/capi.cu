@@ -467,6 +467,34 @@ int bionc_cuda_model_create(const BioncModelDesc* d, int device, BioncModel** ou
         S.side_end = (int)M->side.size();
         if (nl > rnl) rnl = nl;
     }
+    {  // nominal diagonal scale of every node of the joint-level system: a^T M4^-1 a summed over the two sides of a
+        // row (state-dependent factors taken as 1); the kernel flags pivots that have cancelled against it
+        const int nb = M->hdr.nb;
+        std::vector<double> sc(nb, 0.0);
+        auto quad = [&](int sgi, const double* a) {
+            const double* W = M->seg[sgi].W;
+            double q = 0.0;
+            for (int r = 0; r < 4; ++r)
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int lo = r < cc ? r : cc, hi = r < cc ? cc : r;
+                    q += a[r] * W[lo * 4 - lo * (lo - 1) / 2 + (hi - lo)] * a[cc];
+                }
+            return std::fabs(q);
+        };
+        for (int b = 0; b < nblk; ++b) {
+            const DevBlk& B = M->blk[b];
+            double g = quad(B.child, B.p + 4);
+            if (B.parent >= 0) g += quad(B.parent, B.p);
+            const int node = B.jrow / 3;
+            if (node < nb && g > sc[node]) sc[node] = g;
+        }
+        for (int I = 0; I < nb; ++I) {
+            const float f = (float)sc[I];
+            int bits;
+            std::memcpy(&bits, &f, sizeof(bits));
+            M->sym.push_back(bits);
+        }
+    }
     M->hdr.N = N, M->hdr.nblk = nblk, M->hdr.nside = (int)M->side.size();
     M->hdr.mj = mj, M->hdr.m = mj + 6 * N, M->hdr.spw = 32, M->hdr.rnl = rnl;  // spw is settled in build_blob
     *out = M;
@@ -523,6 +551,39 @@ int bionc_cuda_forward_dynamics(const BioncModel* Mc, const double* Q, const dou
     long long Bll = B;
     void* args[] = {&blob, &blob_bytes, &Q, &Qd, &inertia, &o, &Qdd, &lam, &status, &Bll};
     CUDA_TRY(cudaLaunchKernel(ks.fd, dim3(grid), dim3(block), args, M->smem_bytes, st));
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return BIONC_OK;
+}
+
+size_t bionc_cuda_dense_workspace_bytes(const BioncModel* M, int64_t count) {
+    if (M == nullptr || count < 1) return 0;
+    const size_t Mdim = (size_t)12 * M->hdr.N + (size_t)(M->hdr.mj + 6 * M->hdr.N);
+    const size_t per = (Mdim * (Mdim + 1) + Mdim) * sizeof(double);
+    const int64_t slots = count < 148 * 8 ? count : 148 * 8;
+    return per * (size_t)slots;
+}
+
+int bionc_cuda_forward_dynamics_dense(const BioncModel* Mc, const double* Q, const double* Qd, const BioncDynOptions* opt,
+                                      const int64_t* select, int64_t count, double* Qdd, double* lam, int32_t* status,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+    BioncModel* M = const_cast<BioncModel*>(Mc);
+    if (M == nullptr || Q == nullptr || Qd == nullptr || Qdd == nullptr || count < 0) return fail(BIONC_E_INVALID, "null argument");
+    if (count == 0) return BIONC_OK;
+    const size_t per = bionc_cuda_dense_workspace_bytes(M, 1);
+    if (workspace == nullptr || workspace_bytes < per) return fail(BIONC_E_INVALID, "workspace smaller than bionc_cuda_dense_workspace_bytes(model, 1)");
+    std::lock_guard<std::mutex> lock(M->mu);
+    DynOpts o;
+    int rc = prepare(M, opt, o);
+    if (rc != BIONC_OK) return rc;
+    long long slots = (long long)(workspace_bytes / per);
+    if (slots > count) slots = count;
+    if (slots > 148 * 8) slots = 148 * 8;
+    EvalArgs ea{0, M->hdr.N, M->hdr.nblk, M->hdr.mj, M->hdr.m};
+    const double* inertia = opt != nullptr ? opt->inertia : nullptr;
+    dense_kkt_kernel<<<(unsigned)slots, kDenseThreads, 0, (cudaStream_t)stream>>>(
+        M->d_blob, ea, Q, Qd, inertia, o, reinterpret_cast<const long long*>(select), (long long)count, Qdd, lam, status,
+        static_cast<double*>(workspace));
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return BIONC_OK;

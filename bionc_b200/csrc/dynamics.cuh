@@ -219,7 +219,7 @@ struct WarpCtx {
     double *Qo, *Qdo, *Qsys, *Qdsys;
     double *S0, *S1, *r0, *r1, *lamv, *dinv, *knl;
     // symbolic factorisation tables (host, capi.cu symbolic_analysis)
-    const int *slot_tab, *slot2_tab, *zero_list, *comb_list, *unit_list, *colptr, *colrow, *lvlptr, *lvlpiv;
+    const int *slot_tab, *slot2_tab, *zero_list, *comb_list, *unit_list, *colptr, *colrow, *lvlptr, *lvlpiv, *nscale;
     int N, mj, nb;
     int segi;  // this warp's segment
     int lane;  // this lane's system inside the CTA
@@ -762,6 +762,10 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                 double D[9], di[6];
                 load_block<S>(w, K * nb + K, D);
                 sym3_inverse(D[0], D[3], D[4], D[6], D[7], D[8], di, status);
+                // a pivot whose whole diagonal has cancelled against the node's nominal scale is a redundant node
+                // (e.g. the same joint declared twice): its remainder is rounding noise that the determinant test,
+                // relative to the block's own scale, cannot see
+                if (fmax(fabs(D[0]), fmax(fabs(D[4]), fabs(D[8]))) < kSmallPivot * (double)__int_as_float(w.nscale[K])) status |= 4;
                 const V3 yh = sym3_apply(di, mk(w.r0[(3 * K) * spw] + w.r1[(3 * K) * spw], w.r0[(3 * K + 1) * spw] + w.r1[(3 * K + 1) * spw],
                                                 w.r0[(3 * K + 2) * spw] + w.r1[(3 * K + 2) * spw]));
                 if (w.segi == 0) {

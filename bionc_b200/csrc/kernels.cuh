@@ -121,6 +121,7 @@ __device__ __forceinline__ void setup_cta(const unsigned char* __restrict__ blob
     w.colrow = w.colptr + w.nb + 1;
     w.lvlptr = w.colrow + h->ncol;
     w.lvlpiv = w.lvlptr + h->nlevel + 1;
+    w.nscale = w.lvlpiv + w.nb;
 }
 
 __device__ __forceinline__ void load_q12(const double* __restrict__ p, Q12& q) {
@@ -400,6 +401,99 @@ __device__ __forceinline__ void put_row(double* __restrict__ K, int ld, int row,
     }
 }
 
+// One item (segment or constraint block) of one system.  `vec` / `K` point at this system's output vector / matrix
+// (leading dimension ldK); X is this system's Q (or Qdot for the bias).
+__device__ __forceinline__ void eval_item(const DevSeg* __restrict__ seg, const DevBlk* __restrict__ blk,
+                                          const DevFext* __restrict__ fext, const EvalArgs& ea, int which, int item,
+                                          const double* __restrict__ X, double* __restrict__ vec, double* __restrict__ K,
+                                          int ldK) {
+    if (item < ea.N) {  // ---------------- segment items
+        const int i = item;
+        const DevSeg& sg = seg[i];
+        const V3 u = mk(X[12 * i], X[12 * i + 1], X[12 * i + 2]);
+        const V3 rp = mk(X[12 * i + 3], X[12 * i + 4], X[12 * i + 5]);
+        const V3 rd = mk(X[12 * i + 6], X[12 * i + 7], X[12 * i + 8]);
+        const V3 w = mk(X[12 * i + 9], X[12 * i + 10], X[12 * i + 11]);
+        const V3 v = rp - rd;
+        if (which == 0 || which == 4) {  // Phi_r rows
+            double* o = (which == 0) ? vec + 6 * i : vec + sg.rigid_row;
+            o[0] = dot(u, u) - 1.0;
+            o[1] = dot(u, v) - sg.phic[0];
+            o[2] = dot(u, w) - sg.phic[1];
+            o[3] = dot(v, v) - sg.phic[2];
+            o[4] = dot(v, w) - sg.phic[3];
+            o[5] = dot(w, w) - 1.0;
+        } else if (which == 6) {  // rigid bias (input is Qdot)
+            double* o = vec + sg.rigid_row;
+            o[0] = 2.0 * dot(u, u), o[1] = 2.0 * dot(u, v), o[2] = 2.0 * dot(u, w);
+            o[3] = 2.0 * dot(v, v), o[4] = 2.0 * dot(v, w), o[5] = 2.0 * dot(w, w);
+        } else if (which == 1 || which == 5) {  // K_r rows
+            const int r0 = (which == 1) ? 6 * i : sg.rigid_row;
+            const double eu[4] = {1, 0, 0, 0}, ev[4] = {0, 1, -1, 0}, ew[4] = {0, 0, 0, 1};
+            put_row(K, ldK, r0 + 0, i, eu, u, 2.0);
+            put_row(K, ldK, r0 + 1, i, eu, v, 1.0), put_row(K, ldK, r0 + 1, i, ev, u, 1.0);
+            put_row(K, ldK, r0 + 2, i, eu, w, 1.0), put_row(K, ldK, r0 + 2, i, ew, u, 1.0);
+            put_row(K, ldK, r0 + 3, i, ev, v, 2.0);
+            put_row(K, ldK, r0 + 4, i, ev, w, 1.0), put_row(K, ldK, r0 + 4, i, ew, v, 1.0);
+            put_row(K, ldK, r0 + 5, i, ew, w, 2.0);
+        } else if (which == 7) {  // natural external forces
+            double* o = vec + 12 * i;
+            SegCtx c;
+            c.u = u, c.v = v, c.w = w;
+            WarpCtx wc;
+            wc.fext = fext;
+            const Q12 f = external_forces(wc, sg, c, rp);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) o[3 * t] = f.s[t].x, o[3 * t + 1] = f.s[t].y, o[3 * t + 2] = f.s[t].z;
+        }
+    } else {  // ---------------- constraint-block items
+        if (which == 0 || which == 1 || which == 7) return;
+        const DevBlk& b = blk[item - ea.N];
+        const double* p = b.p;
+        const bool jorder = (which == 2 || which == 3);
+        const int row = jorder ? b.row_j : b.row_h;
+        const bool want_phi = (which == 2 || which == 4), want_K = (which == 3 || which == 5), want_b = (which == 6);
+        double* o = vec;
+        const V3 ex = mk(1, 0, 0), ey = mk(0, 1, 0), ez = mk(0, 0, 1);
+        if (b.type == LIN3) {
+            if (want_phi) {
+                V3 phi = mk(p[8], p[9], p[10]) - glin(X, b.child, p + 4);
+                if (b.parent >= 0) phi = phi + glin(X, b.parent, p);
+                o[row] = phi.x, o[row + 1] = phi.y, o[row + 2] = phi.z;
+            } else if (want_K) {
+                put_row(K, ldK, row, b.child, p + 4, ex, -1.0), put_row(K, ldK, row + 1, b.child, p + 4, ey, -1.0);
+                put_row(K, ldK, row + 2, b.child, p + 4, ez, -1.0);
+                if (b.parent >= 0) {
+                    put_row(K, ldK, row, b.parent, p, ex, 1.0), put_row(K, ldK, row + 1, b.parent, p, ey, 1.0);
+                    put_row(K, ldK, row + 2, b.parent, p, ez, 1.0);
+                }
+            }
+        } else if (b.type == DOT) {
+            const V3 Dc = glin(X, b.child, p + 4);
+            const V3 Dp = b.parent >= 0 ? glin(X, b.parent, p) : mk(p[0], p[1], p[2]);
+            if (want_phi) o[row] = dot(Dp, Dc) - p[8];
+            if (want_K) {
+                put_row(K, ldK, row, b.child, p + 4, Dp, 1.0);
+                if (b.parent >= 0) put_row(K, ldK, row, b.parent, p, Dc, 1.0);
+            }
+            if (want_b) o[row] = b.parent >= 0 ? 2.0 * dot(Dp, Dc) : 0.0;  // input is Qdot
+        } else if (b.type == CLEN) {
+            const V3 d = glin(X, b.parent, p) - glin(X, b.child, p + 4);
+            if (want_phi) o[row] = dot(d, d) - p[8];
+            if (want_K) put_row(K, ldK, row, b.parent, p, d, 2.0), put_row(K, ldK, row, b.child, p + 4, d, -2.0);
+            if (want_b) o[row] = 2.0 * dot(d, d);
+        } else {  // SOP
+            const V3 P = glin(X, b.parent, p), A = glin(X, b.child, p + 4), nn = glin(X, b.child, p + 8);
+            if (want_phi) o[row] = dot(P - A, nn) - p[12];
+            if (want_K) {
+                put_row(K, ldK, row, b.parent, p + 4, nn, -1.0), put_row(K, ldK, row, b.parent, p + 8, P - A, 1.0);
+                put_row(K, ldK, row, b.child, p, nn, 1.0);
+            }
+            if (want_b) o[row] = 2.0 * dot(P, nn) - 2.0 * dot(nn, A);
+        }
+    }
+}
+
 __global__ void eval_kernel(const unsigned char* __restrict__ blob, EvalArgs ea, const double* __restrict__ in,
                             double* __restrict__ out, long long B) {
     const DevHeader* h = reinterpret_cast<const DevHeader*>(blob);
@@ -409,100 +503,170 @@ __global__ void eval_kernel(const unsigned char* __restrict__ blob, EvalArgs ea,
     const int n = 12 * ea.N;
     const int nitem = ea.N + ea.nblk;
     const long long total = B * nitem;
+    const int which = ea.which;
+    const bool matrix = (which == 1 || which == 3 || which == 5);
+    const int rows = (which == 0 || which == 1) ? 6 * ea.N : ((which == 2 || which == 3) ? ea.mj : (which == 7 ? n : ea.m));
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const long long sys = idx / nitem;
         const int item = (int)(idx - sys * nitem);
-        const double* X = in + (size_t)sys * n;
-        const int which = ea.which;
-        if (item < ea.N) {  // ---------------- segment items
-            const int i = item;
-            const DevSeg& sg = seg[i];
-            const V3 u = mk(X[12 * i], X[12 * i + 1], X[12 * i + 2]);
-            const V3 rp = mk(X[12 * i + 3], X[12 * i + 4], X[12 * i + 5]);
-            const V3 rd = mk(X[12 * i + 6], X[12 * i + 7], X[12 * i + 8]);
-            const V3 w = mk(X[12 * i + 9], X[12 * i + 10], X[12 * i + 11]);
-            const V3 v = rp - rd;
-            if (which == 0 || which == 4) {  // Phi_r rows
-                double* o = (which == 0) ? out + (size_t)sys * 6 * ea.N + 6 * i : out + (size_t)sys * ea.m + sg.rigid_row;
-                o[0] = dot(u, u) - 1.0;
-                o[1] = dot(u, v) - sg.phic[0];
-                o[2] = dot(u, w) - sg.phic[1];
-                o[3] = dot(v, v) - sg.phic[2];
-                o[4] = dot(v, w) - sg.phic[3];
-                o[5] = dot(w, w) - 1.0;
-            } else if (which == 6) {  // rigid bias (input is Qdot)
-                double* o = out + (size_t)sys * ea.m + sg.rigid_row;
-                o[0] = 2.0 * dot(u, u), o[1] = 2.0 * dot(u, v), o[2] = 2.0 * dot(u, w);
-                o[3] = 2.0 * dot(v, v), o[4] = 2.0 * dot(v, w), o[5] = 2.0 * dot(w, w);
-            } else if (which == 1 || which == 5) {  // K_r rows
-                double* K = (which == 1) ? out + (size_t)sys * 6 * ea.N * n : out + (size_t)sys * ea.m * n;
-                const int r0 = (which == 1) ? 6 * i : sg.rigid_row;
-                const double eu[4] = {1, 0, 0, 0}, ev[4] = {0, 1, -1, 0}, ew[4] = {0, 0, 0, 1};
-                put_row(K, n, r0 + 0, i, eu, u, 2.0);
-                put_row(K, n, r0 + 1, i, eu, v, 1.0), put_row(K, n, r0 + 1, i, ev, u, 1.0);
-                put_row(K, n, r0 + 2, i, eu, w, 1.0), put_row(K, n, r0 + 2, i, ew, u, 1.0);
-                put_row(K, n, r0 + 3, i, ev, v, 2.0);
-                put_row(K, n, r0 + 4, i, ev, w, 1.0), put_row(K, n, r0 + 4, i, ew, v, 1.0);
-                put_row(K, n, r0 + 5, i, ew, w, 2.0);
-            } else if (which == 7) {  // natural external forces
-                double* o = out + (size_t)sys * n + 12 * i;
-                SegCtx c;
-                c.u = u, c.v = v, c.w = w;
-                WarpCtx wc;
-                wc.fext = fext;
-                const Q12 f = external_forces(wc, sg, c, rp);
+        double* o = out + (size_t)sys * rows * (matrix ? n : 1);
+        eval_item(seg, blk, fext, ea, which, item, in + (size_t)sys * n, o, o, n);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pivoted fallback: the reference's own algorithm on the device (biomechanical_model.py:335-349, :423-426):
+// dense augmented matrix [G K^T; K 0], right-hand side [f; -bias], LU with partial pivoting (the pivot rule
+// of LAPACK dgesv: first entry of largest modulus in the column), one CTA per system, the augmented matrix in
+// an L2-resident global scratch slot.  Meant for the few systems the fast path flags (SMALL_PIVOT /
+// SINGULAR): indefinite mass matrices whose unpivoted LDL^T meets a small pivot although the KKT system
+// itself is well conditioned.  `select` (optional) lists the systems to solve; outputs go to their rows.
+// ---------------------------------------------------------------------------------------------
+constexpr int kDenseThreads = 128;
+
+__global__ void __launch_bounds__(kDenseThreads)
+    dense_kkt_kernel(const unsigned char* __restrict__ blob, EvalArgs ea, const double* __restrict__ Q,
+                     const double* __restrict__ Qd, const double* __restrict__ inertia, DynOpts o,
+                     const long long* __restrict__ select, long long count, double* __restrict__ Qdd,
+                     double* __restrict__ lam, int* __restrict__ status_out, double* __restrict__ work) {
+    const DevHeader* h = reinterpret_cast<const DevHeader*>(blob);
+    const DevSeg* seg = reinterpret_cast<const DevSeg*>(blob + h->off_seg);
+    const DevBlk* blk = reinterpret_cast<const DevBlk*>(blob + h->off_blk);
+    const DevFext* fext = reinterpret_cast<const DevFext*>(blob + h->off_fext);
+    const int N = ea.N, n = 12 * N, m = ea.m, M = n + m, ld = M + 1, nitem = N + ea.nblk;
+    const int tid = threadIdx.x, lane = tid & 31;
+    double* A = work + (size_t)blockIdx.x * ((size_t)M * ld + M);  // [A | rhs], row-major
+    double* tmp = A + (size_t)M * ld;                               // M doubles
+    __shared__ int piv_row;
+    __shared__ double piv_abs;
+    for (long long it = blockIdx.x; it < count; it += gridDim.x) {
+        const long long sys = select != nullptr ? select[it] : it;
+        const double* Xq = Q + (size_t)sys * n;
+        const double* Xqd = Qd + (size_t)sys * n;
+        for (int e = tid; e < M * ld + M; e += kDenseThreads) A[e] = 0.0;
+        __syncthreads();
+        // K (rows n.., holonomic order) and the acceleration bias
+        for (int item = tid; item < nitem; item += kDenseThreads) {
+            eval_item(seg, blk, fext, ea, 5, item, Xq, nullptr, A + (size_t)n * ld, ld);
+            eval_item(seg, blk, fext, ea, 6, item, Xqd, tmp, nullptr, 0);
+        }
+        // G = blockdiag(M4_i (x) I3)  (natural_inertial_parameters.py:136-179)
+        for (int e = tid; e < 16 * N; e += kDenseThreads) {
+            const int i = e >> 4, a = (e >> 2) & 3, b = e & 3;
+            const double* ip = inertia != nullptr ? inertia + ((size_t)sys * N + i) * 10 : seg[i].mcj;
+            const double ms = ip[0], c0 = ip[1], c1 = ip[2], c2 = ip[3];
+            const double J00 = ip[4], J01 = ip[5], J02 = ip[6], J11 = ip[7], J12 = ip[8], J22 = ip[9];
+            const double M4[4][4] = {{J00, ms * c0 + J01, -J01, J02},
+                                     {ms * c0 + J01, ms + 2.0 * ms * c1 + J11, -(ms * c1 + J11), ms * c2 + J12},
+                                     {-J01, -(ms * c1 + J11), J11, -J12},
+                                     {J02, ms * c2 + J12, -J12, J22}};
+            double val = 0.0;
 #pragma unroll
-                for (int t = 0; t < 4; ++t) o[3 * t] = f.s[t].x, o[3 * t + 1] = f.s[t].y, o[3 * t + 2] = f.s[t].z;
+            for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+                for (int bb = 0; bb < 4; ++bb)
+                    if (aa == a && bb == b) val = M4[aa][bb];
+            for (int d = 0; d < 3; ++d) A[(size_t)(12 * i + 3 * a + d) * ld + 12 * i + 3 * b + d] = val;
+        }
+        __syncthreads();
+        for (int r = tid; r < m; r += kDenseThreads) A[(size_t)(n + r) * ld + M] = -tmp[r];
+        __syncthreads();
+        if (o.use_stab) {  // bias -= alpha Phi + beta K Qdot   (biomechanical_model.py:416-421)
+            for (int r = tid; r < m; r += kDenseThreads) tmp[r] = 0.0;
+            __syncthreads();
+            for (int item = tid; item < nitem; item += kDenseThreads) eval_item(seg, blk, fext, ea, 4, item, Xq, tmp, nullptr, 0);
+            __syncthreads();
+            for (int r = tid; r < m; r += kDenseThreads) {
+                double kqd = 0.0;
+                for (int c = 0; c < n; ++c) kqd = fma(A[(size_t)(n + r) * ld + c], Xqd[c], kqd);
+                A[(size_t)(n + r) * ld + M] -= o.alpha * tmp[r] + o.beta * kqd;
             }
-        } else {  // ---------------- constraint-block items
-            if (which == 0 || which == 1 || which == 7) continue;
-            const DevBlk& b = blk[item - ea.N];
-            const double* p = b.p;
-            const bool jorder = (which == 2 || which == 3);
-            const int row = jorder ? b.row_j : b.row_h;
-            const int nrows = jorder ? ea.mj : ea.m;
-            const bool want_phi = (which == 2 || which == 4), want_K = (which == 3 || which == 5), want_b = (which == 6);
-            double* o = out + (size_t)sys * nrows;
-            double* K = out + (size_t)sys * nrows * n;
-            const V3 ex = mk(1, 0, 0), ey = mk(0, 1, 0), ez = mk(0, 0, 1);
-            if (b.type == LIN3) {
-                if (want_phi) {
-                    V3 phi = mk(p[8], p[9], p[10]) - glin(X, b.child, p + 4);
-                    if (b.parent >= 0) phi = phi + glin(X, b.parent, p);
-                    o[row] = phi.x, o[row + 1] = phi.y, o[row + 2] = phi.z;
-                } else if (want_K) {
-                    put_row(K, n, row, b.child, p + 4, ex, -1.0), put_row(K, n, row + 1, b.child, p + 4, ey, -1.0);
-                    put_row(K, n, row + 2, b.child, p + 4, ez, -1.0);
-                    if (b.parent >= 0) {
-                        put_row(K, n, row, b.parent, p, ex, 1.0), put_row(K, n, row + 1, b.parent, p, ey, 1.0);
-                        put_row(K, n, row + 2, b.parent, p, ez, 1.0);
-                    }
+            __syncthreads();
+        }
+        // forces: gravity + natural external forces
+        for (int item = tid; item < N; item += kDenseThreads) eval_item(seg, blk, fext, ea, 7, item, Xq, tmp, nullptr, 0);
+        __syncthreads();
+        for (int e = tid; e < 4 * N; e += kDenseThreads) {
+            const int i = e >> 2, t = e & 3;
+            double fg;
+            if (inertia != nullptr) {
+                const double* ip = inertia + ((size_t)sys * N + i) * 10;
+                const double mg = ip[0] * -9.81;
+                fg = t == 0 ? ip[1] * mg : (t == 1 ? (1.0 + ip[2]) * mg : (t == 2 ? -ip[2] * mg : ip[3] * mg));
+            } else {
+                fg = seg[i].fg[t];
+            }
+            for (int d = 0; d < 3; ++d) A[(size_t)(12 * i + 3 * t + d) * ld + M] = tmp[12 * i + 3 * t + d] + (d == 2 ? fg : 0.0);
+        }
+        for (int e = tid; e < m * n; e += kDenseThreads) {  // K^T
+            const int r = e / n, c = e - r * n;
+            A[(size_t)c * ld + n + r] = A[(size_t)(n + r) * ld + c];
+        }
+        __syncthreads();
+        // LU with partial pivoting on [A | rhs]
+        int st = 8;  // BIONC_STATUS_PIVOTED
+        bool singular = false;
+        for (int k = 0; k < M; ++k) {
+            if (tid < 32) {
+                double best = -1.0;
+                int bi = k;
+                for (int i = k + lane; i < M; i += 32) {
+                    const double v = fabs(A[(size_t)i * ld + k]);
+                    if (v > best) best = v, bi = i;
                 }
-            } else if (b.type == DOT) {
-                const V3 Dc = glin(X, b.child, p + 4);
-                const V3 Dp = b.parent >= 0 ? glin(X, b.parent, p) : mk(p[0], p[1], p[2]);
-                if (want_phi) o[row] = dot(Dp, Dc) - p[8];
-                if (want_K) {
-                    put_row(K, n, row, b.child, p + 4, Dp, 1.0);
-                    if (b.parent >= 0) put_row(K, n, row, b.parent, p, Dc, 1.0);
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const double ov = __shfl_down_sync(0xffffffffu, best, off);
+                    const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+                    if (ov > best || (ov == best && oi < bi)) best = ov, bi = oi;
                 }
-                if (want_b) o[row] = b.parent >= 0 ? 2.0 * dot(Dp, Dc) : 0.0;  // input is Qdot
-            } else if (b.type == CLEN) {
-                const V3 d = glin(X, b.parent, p) - glin(X, b.child, p + 4);
-                if (want_phi) o[row] = dot(d, d) - p[8];
-                if (want_K) put_row(K, n, row, b.parent, p, d, 2.0), put_row(K, n, row, b.child, p + 4, d, -2.0);
-                if (want_b) o[row] = 2.0 * dot(d, d);
-            } else {  // SOP
-                const V3 P = glin(X, b.parent, p), A = glin(X, b.child, p + 4), nn = glin(X, b.child, p + 8);
-                if (want_phi) o[row] = dot(P - A, nn) - p[12];
-                if (want_K) {
-                    put_row(K, n, row, b.parent, p + 4, nn, -1.0), put_row(K, n, row, b.parent, p + 8, P - A, 1.0);
-                    put_row(K, n, row, b.child, p, nn, 1.0);
+                if (lane == 0) piv_row = bi, piv_abs = best;
+            }
+            __syncthreads();
+            const int p = piv_row;
+            if (!(piv_abs > 0.0) || !isfinite(piv_abs)) {  // exact zero column: numpy raises LinAlgError here
+                singular = true;
+                break;
+            }
+            if (p != k) {
+                for (int c = k + tid; c <= M; c += kDenseThreads) {
+                    const double x = A[(size_t)k * ld + c];
+                    A[(size_t)k * ld + c] = A[(size_t)p * ld + c];
+                    A[(size_t)p * ld + c] = x;
                 }
-                if (want_b) o[row] = 2.0 * dot(P, nn) - 2.0 * dot(nn, A);
+                __syncthreads();
+            }
+            const double akk = A[(size_t)k * ld + k];
+            const int rows = M - k - 1, cols = M - k;
+            for (int e = tid; e < rows * cols; e += kDenseThreads) {
+                const int i = k + 1 + e / cols, j = k + 1 + e % cols;
+                const double l = A[(size_t)i * ld + k] / akk;
+                A[(size_t)i * ld + j] -= l * A[(size_t)k * ld + j];
+            }
+            __syncthreads();
+        }
+        if (!singular && tid < 32) {  // back substitution, x overwrites the rhs column
+            for (int k = M - 1; k >= 0; --k) {
+                double sum = 0.0;
+                for (int j = k + 1 + lane; j < M; j += 32) sum = fma(A[(size_t)k * ld + j], A[(size_t)j * ld + M], sum);
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, off);
+                if (lane == 0) A[(size_t)k * ld + M] = (A[(size_t)k * ld + M] - sum) / A[(size_t)k * ld + k];
+                __syncwarp();
             }
         }
+        __syncthreads();
+        if (singular) st |= 1;
+        bool bad = false;
+        for (int c = tid; c < M; c += kDenseThreads) {
+            const double x = singular ? __longlong_as_double(0x7ff8000000000000LL) : A[(size_t)c * ld + M];
+            if (!isfinite(x)) bad = true;
+            if (c < n) Qdd[(size_t)sys * n + c] = x;
+            else if (lam != nullptr) lam[(size_t)sys * m + (c - n)] = x;
+        }
+        const int any_bad = __syncthreads_or(bad ? 1 : 0);
+        if (tid == 0 && status_out != nullptr) status_out[sys] = st | (any_bad && !singular ? 2 : 0);
     }
 }
 

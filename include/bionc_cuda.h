@@ -15,6 +15,7 @@
 #ifndef BIONC_CUDA_H
 #define BIONC_CUDA_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -46,6 +47,7 @@ extern "C" {
 #define BIONC_STATUS_NONFINITE 2 /* non-finite state or acceleration */
 #define BIONC_STATUS_SMALL_PIVOT 4 /* a pivot below 1e-11 of the diagonal scale: (near-)singular constraints, the
                                       unpivoted LDL^T result may be inaccurate (e.g. redundant constraints) */
+#define BIONC_STATUS_PIVOTED 8 /* the values of this system come from bionc_cuda_forward_dynamics_dense */
 
 /* which quantity bionc_cuda_eval computes */
 #define BIONC_EVAL_PHI_R 0  /* rigid_body_constraints(Q)                 -> (B, 6N)      biomechanical_model_segments.py:26-42 */
@@ -113,6 +115,21 @@ int bionc_cuda_model_layout(const BioncModel* model, int32_t* out);
 int bionc_cuda_forward_dynamics(const BioncModel* model, const double* Q, const double* Qdot,
                                 const BioncDynOptions* opt, double* Qddot, double* lambda, int32_t* status,
                                 int64_t B, void* stream);
+
+/* Pivoted variant = the reference's own algorithm on the device: the dense augmented matrix [G K^T; K 0] of
+ * BiomechanicalModel.augmented_mass_matrix (bionc_numpy/biomechanical_model.py:335-349) solved by LU with
+ * partial pivoting like numpy.linalg.solve -> LAPACK dgesv (biomechanical_model.py:423-426), one CTA per
+ * system.  Meant for the systems the fast path flags (indefinite mass matrices whose unpivoted LDL^T meets a
+ * small pivot); `select` lists `count` system indices (NULL -> systems 0..count-1).  Rows of Qddot / lambda /
+ * status that belong to the selected systems are overwritten; status becomes BIONC_STATUS_PIVOTED, plus
+ * SINGULAR for an exactly singular matrix (numpy: LinAlgError) or NONFINITE.  `workspace` is caller-owned
+ * device memory of at least bionc_cuda_dense_workspace_bytes(model, 1) bytes; more lets more systems run
+ * concurrently (bionc_cuda_dense_workspace_bytes(model, count) = enough for full concurrency). */
+size_t bionc_cuda_dense_workspace_bytes(const BioncModel* model, int64_t count);
+int bionc_cuda_forward_dynamics_dense(const BioncModel* model, const double* Q, const double* Qdot,
+                                      const BioncDynOptions* opt, const int64_t* select, int64_t count,
+                                      double* Qddot, double* lambda, int32_t* status, void* workspace,
+                                      size_t workspace_bytes, void* stream);
 
 /* replaces RK4 + the dynamics closure of forward_integration (utils/ode_solver.py:8-53, :107-120),
  * all four stages fused, n_steps steps per launch, in place on Q / Qdot.

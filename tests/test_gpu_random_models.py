@@ -81,7 +81,13 @@ def random_table(seed: int, N: int, loops: int = 0) -> ModelTable:
             joints.append((int(p), int(c), [(BLK_CLEN, np.concatenate([_point(rng), _point(rng), [0.09]]))]))
         else:
             joints.append((int(p), int(c), [(BLK_SOP, np.concatenate([_point(rng), _point(rng), _direction(rng), [0.01]]))]))
-    # bookkeeping: joint-index order = creation order; holonomic order = per child segment, then its rigid rows
+    return assemble_table(phic, geom, mass, com, J, joints)
+
+
+def assemble_table(phic, geom, mass, com, J, joints) -> ModelTable:
+    """Row bookkeeping for a list of joints (parent, child, [(block type, params)]): joint-index order = creation
+    order; holonomic order = per child segment its joints, then its rigid rows."""
+    N = phic.shape[0]
     row_j, jstart = 0, []
     for _, _, blocks in joints:
         jstart.append(row_j)
