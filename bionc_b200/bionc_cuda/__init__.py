@@ -17,7 +17,7 @@ from .natural_types import (  # noqa: F401
 )
 
 __all__ = [
-    "BiomechanicalModel", "BioncCudaError", "ExternalForceSet", "ModelTable", "UnsupportedModelError",
+    "BiomechanicalModel", "BioncCudaError", "NaturalSegment", "TimeSeriesUtils", "ExternalForceSet", "ModelTable", "UnsupportedModelError",
     "NaturalCoordinates", "NaturalVelocities", "NaturalAccelerations",
     "SegmentNaturalCoordinates", "SegmentNaturalVelocities", "SegmentNaturalAccelerations",
 ]
@@ -28,6 +28,14 @@ def __getattr__(name):
         from .biomechanical_model import BiomechanicalModel
 
         return BiomechanicalModel
+    if name == "NaturalSegment":
+        from .natural_segment import NaturalSegment
+
+        return NaturalSegment
+    if name == "TimeSeriesUtils":
+        from .time_series_utils import TimeSeriesUtils
+
+        return TimeSeriesUtils
     if name == "BioncCudaError":
         from ._lib import BioncCudaError
 

@@ -50,6 +50,9 @@ class BioncModelDesc(C.Structure):
         ("blk_row_h", c_int32_p),
         ("blk_row_j", c_int32_p),
         ("blk_param", c_double_p),
+        ("nb_markers", C.c_int32),
+        ("marker_segment", c_int32_p),
+        ("marker_position", c_double_p),
     ]
 
 

@@ -31,6 +31,7 @@ from .external_force import ExternalForceSet
 from .model_table import ModelTable
 
 EVAL_PHI_R, EVAL_K_R, EVAL_PHI_J, EVAL_K_J, EVAL_PHI_H, EVAL_K_H, EVAL_BIAS_H, EVAL_FEXT = range(8)
+EVAL_COM, EVAL_MARKERS, EVAL_KINETIC, EVAL_POTENTIAL, EVAL_RESIDUALS = range(8, 13)
 
 
 def _ptr(a: np.ndarray, typ):
@@ -92,6 +93,8 @@ class BiomechanicalModel:
             browh=np.ascontiguousarray(t.blk_row_h, dtype=np.int32),
             browj=np.ascontiguousarray(t.blk_row_j, dtype=np.int32),
             bpar_d=np.ascontiguousarray(t.blk_param, dtype=np.float64),
+            mkseg=np.ascontiguousarray(t.marker_segment, dtype=np.int32),
+            mkpos=np.ascontiguousarray(t.marker_position, dtype=np.float64),
         )
         k = self._keep
         desc = _lib.BioncModelDesc(
@@ -100,6 +103,7 @@ class BiomechanicalModel:
             _ptr(k["J"], _lib.c_double_p), _ptr(k["rrow"], _lib.c_int32_p), _ptr(k["btype"], _lib.c_int32_p),
             _ptr(k["bpar"], _lib.c_int32_p), _ptr(k["bchi"], _lib.c_int32_p), _ptr(k["browh"], _lib.c_int32_p),
             _ptr(k["browj"], _lib.c_int32_p), _ptr(k["bpar_d"], _lib.c_double_p),
+            t.nb_markers, _ptr(k["mkseg"], _lib.c_int32_p), _ptr(k["mkpos"], _lib.c_double_p),
         )
         handle = C.c_void_p()
         _lib.check(self._lib.bionc_cuda_model_create(C.byref(desc), self.device.index or 0, C.byref(handle)), "model_create")
@@ -289,25 +293,65 @@ class BiomechanicalModel:
         A[:, :n, n:] = K.transpose(1, 2)
         return b.out(A)
 
-    # ------------------------------------------------------------------ energies (post-processing, torch on the device)
+    # ------------------------------------------------------------------ post-processing on the device
     def kinetic_energy(self, Qdot):
         """biomechanical_model.py:98-113: ``1/2 Qdot^T G Qdot`` -> float / (B,)"""
-        b = _Batch(Qdot, self.nb_Q, self.device, "Qdot")
-        G = torch.from_numpy(self.mass_matrix).to(self.device)
-        E = 0.5 * ((b.t @ G) * b.t).sum(dim=1)
+        b, E = self._eval(EVAL_KINETIC, Qdot, None, None, "Qdot")
         return float(E[0].item()) if (b.single and not b.torch_in) else b.out(E)
 
     def potential_energy(self, Q):
         """biomechanical_model.py:115-133: ``sum_i m_i (N_com,i Q_i)[z]`` exactly as the reference codes it
         (``natural_segment.py:775-789``, no factor g) -> float / (B,)"""
-        b = _Batch(Q, self.nb_Q, self.device, "Q")
-        t = self.table
-        coef = np.zeros(self.nb_Q)
-        for i in range(self.nb_segments):
-            c, m = t.seg_com[i], t.seg_mass[i]
-            coef[12 * i + 2], coef[12 * i + 5], coef[12 * i + 8], coef[12 * i + 11] = m * c[0], m * (1 + c[1]), -m * c[1], m * c[2]
-        E = b.t @ torch.from_numpy(coef).to(self.device)
+        b, E = self._eval(EVAL_POTENTIAL, Q, None, None, "Q")
         return float(E[0].item()) if (b.single and not b.torch_in) else b.out(E)
+
+    @property
+    def nb_markers(self) -> int:
+        return self.table.nb_markers
+
+    @property
+    def nb_markers_technical(self) -> int:
+        return int(self.table.marker_technical.sum())
+
+    @property
+    def marker_names(self) -> list[str]:
+        return list(self.table.marker_names)
+
+    @property
+    def marker_names_technical(self) -> list[str]:
+        return [n for n, t in zip(self.table.marker_names, self.table.marker_technical) if t]
+
+    def markers(self, Q):
+        """Forward kinematics, biomechanical_model_markers.py:32-57 -> (3, nb_markers, 1) for one system like the
+        reference, (B, 3, nb_markers) for a batch."""
+        b, out = self._eval(EVAL_MARKERS, Q, 3, self.nb_markers, "Q")
+        return self._points_out(b, out)
+
+    def center_of_mass_position(self, Q):
+        """biomechanical_model_markers.py:59-79 -> (3, N, 1) for one system, (B, 3, N) for a batch."""
+        b, out = self._eval(EVAL_COM, Q, 3, self.nb_segments, "Q")
+        return self._points_out(b, out)
+
+    @staticmethod
+    def _points_out(b, out):
+        if b.single:
+            out = out[0].unsqueeze(-1)  # the reference's trailing frame axis
+            return out if b.torch_in else out.cpu().numpy()
+        return out if b.torch_in else out.cpu().numpy()
+
+    def constraint_residual_norms(self, Q):
+        """``[|Phi_r(Q)|_2, |Phi_j(Q)|_2]`` per system: the two numbers ``time_series_utils.total_rigid_body_constraints``
+        / ``total_joint_constraints`` (bionc_numpy/time_series_utils.py:6-41) compute per frame -> (2,) / (B, 2)."""
+        b, out = self._eval(EVAL_RESIDUALS, Q, 2, None, "Q")
+        return b.out(out)
+
+    def segment(self, index):
+        """Single-segment view (``model.segments[name]`` of the reference), by index or name."""
+        from .natural_segment import NaturalSegment
+
+        if isinstance(index, str):
+            index = self.table.segment_names.index(index)
+        return NaturalSegment(self, int(index))
 
     def lagrangian(self, Q, Qdot):
         """biomechanical_model.py:135-152"""

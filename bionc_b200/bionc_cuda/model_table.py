@@ -160,6 +160,11 @@ class ModelTable:
     blk_row_h: np.ndarray = None  # (nblk,) int32 first row in holonomic order
     blk_row_j: np.ndarray = None  # (nblk,) int32 first row in joint-index order
     blk_param: np.ndarray = None  # (nblk, BLK_NPARAM) float64
+    # markers (biomechanical_model_markers.py:32-57): model order = segment by segment; optional
+    marker_names: list[str] = field(default_factory=list)
+    marker_segment: np.ndarray = None  # (nmk,) int32
+    marker_position: np.ndarray = None  # (nmk, 3) natural coordinates (n_u, n_v, n_w) of the marker in its segment
+    marker_technical: np.ndarray = None  # (nmk,) int32 0/1
 
     # ------------------------------------------------------------------ counts (protocols/biomechanical_model.py:347-453)
     @property
@@ -173,6 +178,10 @@ class ModelTable:
     @property
     def nb_blocks(self) -> int:
         return int(self.blk_type.shape[0])
+
+    @property
+    def nb_markers(self) -> int:
+        return 0 if self.marker_segment is None else int(self.marker_segment.shape[0])
 
     @property
     def nb_rigid_body_constraints(self) -> int:
@@ -221,6 +230,14 @@ class ModelTable:
             a = getattr(self, name)
             want = np.int32 if name.startswith("blk_") and name != "blk_param" or name == "seg_rigid_row" else np.float64
             setattr(self, name, np.ascontiguousarray(a, dtype=want))
+        nmk = len(self.marker_names)
+        self.marker_segment = np.ascontiguousarray(self.marker_segment if self.marker_segment is not None else np.zeros(0), dtype=np.int32)
+        self.marker_position = np.ascontiguousarray(
+            self.marker_position if self.marker_position is not None else np.zeros((0, 3)), dtype=np.float64).reshape(-1, 3)
+        self.marker_technical = np.ascontiguousarray(self.marker_technical if self.marker_technical is not None else np.zeros(0), dtype=np.int32)
+        assert self.marker_segment.shape == (nmk,) and self.marker_position.shape == (nmk, 3) and self.marker_technical.shape == (nmk,)
+        if nmk:
+            assert self.marker_segment.min() >= 0 and self.marker_segment.max() < N
         assert self.seg_phi_const.shape == (N, 4) and self.seg_J.shape == (N, 3, 3)
         assert self.blk_param.shape == (self.nb_blocks, BLK_NPARAM)
         if self.nb_blocks:
@@ -238,8 +255,12 @@ class ModelTable:
     def save(self, filename: str) -> None:
         np.savez(
             filename,
-            format_version=np.int32(1),
+            format_version=np.int32(2),
             segment_names=np.array(self.segment_names),
+            marker_names=np.array(self.marker_names, dtype=str),
+            marker_segment=self.marker_segment,
+            marker_position=self.marker_position,
+            marker_technical=self.marker_technical,
             joint_names=np.array(self.joint_names),
             joint_kinds=np.array(self.joint_kinds),
             **{k: getattr(self, k) for k in self._ARRAYS},
@@ -248,9 +269,13 @@ class ModelTable:
     @classmethod
     def load(cls, filename: str) -> "ModelTable":
         with np.load(filename, allow_pickle=False) as z:
-            if int(z["format_version"]) != 1:
-                raise ValueError(f"unknown model table version {int(z['format_version'])}")
+            version = int(z["format_version"])
+            if version not in (1, 2):  # 2 = 1 + the marker arrays
+                raise ValueError(f"unknown model table version {version}")
             kw = {k: z[k] for k in cls._ARRAYS}
+            if version >= 2:
+                kw.update(marker_names=[str(s) for s in z["marker_names"]], marker_segment=z["marker_segment"],
+                          marker_position=z["marker_position"], marker_technical=z["marker_technical"])
             return cls(
                 segment_names=[str(s) for s in z["segment_names"]],
                 joint_names=[str(s) for s in z["joint_names"]],
@@ -329,6 +354,14 @@ class ModelTable:
             seg_rigid_row[i] = row_h
             row_h += 6
 
+        # markers in model order (biomechanical_model_markers.py: indexes() walks the segments in order)
+        mk_names, mk_seg, mk_pos, mk_tech = [], [], [], []
+        for i, s in enumerate(segments):
+            for mk in s._markers:
+                mk_names.append(str(mk.name)), mk_seg.append(i)
+                mk_pos.append(np.asarray(mk.position, dtype=np.float64).reshape(3))
+                mk_tech.append(1 if mk.is_technical else 0)
+
         nb = len(blocks)
         param = np.zeros((nb, BLK_NPARAM))
         for b, blk in enumerate(blocks):
@@ -351,6 +384,10 @@ class ModelTable:
             blk_row_h=np.array([b["row_h"] for b in blocks], dtype=np.int32),
             blk_row_j=np.array([b["row_j"] for b in blocks], dtype=np.int32),
             blk_param=param,
+            marker_names=mk_names,
+            marker_segment=np.array(mk_seg, dtype=np.int32),
+            marker_position=np.array(mk_pos, dtype=np.float64).reshape(len(mk_seg), 3),
+            marker_technical=np.array(mk_tech, dtype=np.int32),
         ).validate()
         if row_h != model.nb_holonomic_constraints:
             raise AssertionError("holonomic row count differs from the reference model")

@@ -76,6 +76,8 @@ struct BioncModel {
     std::vector<DevBlk> blk;
     std::vector<DevSide> side;
     std::vector<int> sym;  // symbolic factorisation tables (see DevHeader::off_sym)
+    int nb_markers = 0;
+    DevMarker* d_markers = nullptr;  // marker table (device), outside the blob: the dynamics kernels never see it
     // device blob for the current external-force set (rebuilt when the set changes)
     std::vector<unsigned char> fext_key;
     unsigned char* d_blob = nullptr;
@@ -497,6 +499,28 @@ int bionc_cuda_model_create(const BioncModelDesc* d, int device, BioncModel** ou
     }
     M->hdr.N = N, M->hdr.nblk = nblk, M->hdr.nside = (int)M->side.size();
     M->hdr.mj = mj, M->hdr.m = mj + 6 * N, M->hdr.spw = 32, M->hdr.rnl = rnl;  // spw is settled in build_blob
+    if (d->nb_markers > 0) {
+        if (d->marker_segment == nullptr || d->marker_position == nullptr) {
+            delete M;
+            return fail(BIONC_E_INVALID, "nb_markers > 0 without marker arrays");
+        }
+        std::vector<DevMarker> mk(d->nb_markers);
+        for (int k = 0; k < d->nb_markers; ++k) {
+            if (d->marker_segment[k] < 0 || d->marker_segment[k] >= N) {
+                delete M;
+                return fail(BIONC_E_INVALID, "marker attached to a segment outside [0, N)");
+            }
+            mk[k].segment = d->marker_segment[k], mk[k].pad = 0;
+            for (int e = 0; e < 3; ++e) mk[k].pos[e] = d->marker_position[3 * k + e];
+        }
+        if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&M->d_markers, mk.size() * sizeof(DevMarker)) != cudaSuccess ||
+            cudaMemcpy(M->d_markers, mk.data(), mk.size() * sizeof(DevMarker), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaGetLastError();
+            delete M;
+            return fail(BIONC_E_CUDA, "marker table upload failed");
+        }
+        M->nb_markers = d->nb_markers;
+    }
     *out = M;
     return BIONC_OK;
 }
@@ -505,6 +529,7 @@ int bionc_cuda_model_destroy(BioncModel* M) {
     if (M == nullptr) return BIONC_OK;
     cudaSetDevice(M->device);
     cudaFree(M->d_blob);
+    cudaFree(M->d_markers);
     cudaFree(M->d_Q), cudaFree(M->d_Qd), cudaFree(M->d_Qdd), cudaFree(M->d_lam), cudaFree(M->d_inertia), cudaFree(M->d_h);
     cudaFree(M->d_status);
     if (M->stream != nullptr) cudaStreamDestroy(M->stream);
@@ -621,13 +646,34 @@ int bionc_cuda_rk4(const BioncModel* Mc, double* Q, double* Qd, double h, const 
 int bionc_cuda_eval(const BioncModel* Mc, int32_t which, const double* in, const BioncDynOptions* opt, double* out,
                     int64_t B, void* stream) {
     BioncModel* M = const_cast<BioncModel*>(Mc);
-    if (M == nullptr || in == nullptr || out == nullptr || B < 0 || which < 0 || which > 7) return fail(BIONC_E_INVALID, "bad argument");
+    if (M == nullptr || in == nullptr || out == nullptr || B < 0 || which < 0 || which > 12) return fail(BIONC_E_INVALID, "bad argument");
     if (B == 0) return BIONC_OK;
     std::lock_guard<std::mutex> lock(M->mu);
     DynOpts o;
     int rc = prepare(M, opt, o);
     if (rc != BIONC_OK) return rc;
     const int N = M->hdr.N, n = 12 * N, mj = M->hdr.mj, m = M->hdr.m;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (which >= BIONC_EVAL_COM) {  // post-processing evaluators: every output element is written, no zero fill
+        if (which == BIONC_EVAL_COM || which == BIONC_EVAL_MARKERS) {
+            const int nitem = which == BIONC_EVAL_COM ? N : M->nb_markers;
+            if (nitem == 0) return BIONC_OK;
+            const long long total = B * (long long)nitem;
+            long long grid = (total + 255) / 256;
+            if (grid > 148LL * 32) grid = 148LL * 32;
+            point_kernel<<<(unsigned)grid, 256, 0, st>>>(M->d_blob, M->d_markers, which, N, nitem, in, out, B);
+        } else {
+            int G = 1;  // lanes per system: segments rounded up to a power of two
+            while (G < N) G <<= 1;
+            const long long threads = B * (long long)G;
+            long long grid = (threads + 255) / 256;
+            if (grid > 148LL * 32) grid = 148LL * 32;
+            reduce_kernel<<<(unsigned)grid, 256, 0, st>>>(M->d_blob, which, N, M->hdr.nblk, G, in, out, B);
+        }
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+        return BIONC_OK;
+    }
     size_t out_elems = 0;
     switch (which) {
         case BIONC_EVAL_PHI_R: out_elems = (size_t)6 * N; break;
@@ -639,8 +685,9 @@ int bionc_cuda_eval(const BioncModel* Mc, int32_t which, const double* in, const
         case BIONC_EVAL_FEXT: out_elems = n; break;
     }
     if (out_elems == 0) return BIONC_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    CUDA_TRY(cudaMemsetAsync(out, 0, out_elems * B * sizeof(double), st));
+    // vector outputs are written row by row in full; only the (sparse) Jacobians need the zero fill
+    if (which == BIONC_EVAL_K_R || which == BIONC_EVAL_K_J || which == BIONC_EVAL_K_H)
+        CUDA_TRY(cudaMemsetAsync(out, 0, out_elems * B * sizeof(double), st));
     EvalArgs ea{which, N, M->hdr.nblk, mj, m};
     const long long total = B * (long long)(N + M->hdr.nblk);
     const int block = 128;

@@ -460,6 +460,8 @@ __device__ __forceinline__ void eval_item(const DevSeg* __restrict__ seg, const 
                 V3 phi = mk(p[8], p[9], p[10]) - glin(X, b.child, p + 4);
                 if (b.parent >= 0) phi = phi + glin(X, b.parent, p);
                 o[row] = phi.x, o[row + 1] = phi.y, o[row + 2] = phi.z;
+            } else if (want_b) {
+                o[row] = 0.0, o[row + 1] = 0.0, o[row + 2] = 0.0;  // point-to-point rows are linear: no bias
             } else if (want_K) {
                 put_row(K, ldK, row, b.child, p + 4, ex, -1.0), put_row(K, ldK, row + 1, b.child, p + 4, ey, -1.0);
                 put_row(K, ldK, row + 2, b.child, p + 4, ez, -1.0);
@@ -512,6 +514,137 @@ __global__ void eval_kernel(const unsigned char* __restrict__ blob, EvalArgs ea,
         const int item = (int)(idx - sys * nitem);
         double* o = out + (size_t)sys * rows * (matrix ? n : 1);
         eval_item(seg, blk, fext, ea, which, item, in + (size_t)sys * n, o, o, n);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Post-processing evaluators: what the reference's users compute frame by frame after an
+// integration -- marker / centre-of-mass kinematics, energies, constraint-residual norms -- on the device, so a
+// trajectory does not have to go back to the host to be checked.  All of them stream Q once: HBM-bound.
+// ---------------------------------------------------------------------------------------------
+struct DevMarker {
+    double pos[3];  // natural coordinates (n_u, n_v, n_w) of the point in its segment
+    int segment, pad;
+};
+
+// natural point -> global: n_u u + (1 + n_v) rp - n_v rd + n_w w   (natural_vector.py: interpolate())
+__device__ __forceinline__ V3 natural_point(const double* __restrict__ X, int seg, double nu, double nv, double nw) {
+    const double* q = X + 12 * seg;
+    return mk(fma(nu, q[0], fma(1.0 + nv, q[3], fma(-nv, q[6], nw * q[9]))),
+              fma(nu, q[1], fma(1.0 + nv, q[4], fma(-nv, q[7], nw * q[10]))),
+              fma(nu, q[2], fma(1.0 + nv, q[5], fma(-nv, q[8], nw * q[11]))));
+}
+
+// which = 8: centre-of-mass positions (biomechanical_model_markers.py:59-79) -> (B, 3, N)
+// which = 9: marker positions / forward kinematics (biomechanical_model_markers.py:32-57) -> (B, 3, nb_markers)
+__global__ void point_kernel(const unsigned char* __restrict__ blob, const DevMarker* __restrict__ markers, int which,
+                             int N, int nitem, const double* __restrict__ Q, double* __restrict__ out, long long B) {
+    const DevHeader* h = reinterpret_cast<const DevHeader*>(blob);
+    const DevSeg* seg = reinterpret_cast<const DevSeg*>(blob + h->off_seg);
+    const int n = 12 * N;
+    const long long total = B * nitem;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long sys = idx / nitem;
+        const int item = (int)(idx - sys * nitem);
+        const double* X = Q + (size_t)sys * n;
+        V3 p;
+        if (which == 8) {
+            const double* c = seg[item].mcj + 1;
+            p = natural_point(X, item, c[0], c[1], c[2]);
+        } else {
+            const DevMarker mkr = markers[item];
+            p = natural_point(X, mkr.segment, mkr.pos[0], mkr.pos[1], mkr.pos[2]);
+        }
+        double* o = out + (size_t)sys * 3 * nitem + item;
+        o[0] = p.x, o[nitem] = p.y, o[2 * nitem] = p.z;
+    }
+}
+
+// residual rows of one constraint block (the Phi branch of eval_item); returns the number of rows
+__device__ __forceinline__ int block_residual(const DevBlk& b, const double* __restrict__ X, double (&phi)[3]) {
+    const double* p = b.p;
+    if (b.type == LIN3) {
+        V3 r = mk(p[8], p[9], p[10]) - glin(X, b.child, p + 4);
+        if (b.parent >= 0) r = r + glin(X, b.parent, p);
+        phi[0] = r.x, phi[1] = r.y, phi[2] = r.z;
+        return 3;
+    }
+    if (b.type == DOT) {
+        const V3 Dc = glin(X, b.child, p + 4);
+        const V3 Dp = b.parent >= 0 ? glin(X, b.parent, p) : mk(p[0], p[1], p[2]);
+        phi[0] = dot(Dp, Dc) - p[8];
+    } else if (b.type == CLEN) {
+        const V3 d = glin(X, b.parent, p) - glin(X, b.child, p + 4);
+        phi[0] = dot(d, d) - p[8];
+    } else {
+        const V3 P = glin(X, b.parent, p), A = glin(X, b.child, p + 4), nn = glin(X, b.child, p + 8);
+        phi[0] = dot(P - A, nn) - p[12];
+    }
+    return 1;
+}
+
+// A group of G lanes per system (G = segments rounded up to a power of two, so a warp carries 32 / G systems
+// and all its lanes load): lane-in-group = segment (then blocks in strides of G), fixed-order xor-shuffle
+// reduction inside the group, so the sums are reproducible.  A group reads its system's 12N doubles contiguously.
+// which = 10: kinetic energy 1/2 Qdot^T G Qdot (biomechanical_model.py:98-113)            -> (B)
+// which = 11: potential energy sum_i m_i (N_com Q_i)[z] as coded, no g (natural_segment.py:775-789) -> (B)
+// which = 12: norms of the rigid-body and joint residual vectors (time_series_utils.py:6-41) -> (B, 2)
+__global__ void __launch_bounds__(256)
+    reduce_kernel(const unsigned char* __restrict__ blob, int which, int N, int nblk, int G, const double* __restrict__ in,
+                  double* __restrict__ out, long long B) {
+    const DevHeader* h = reinterpret_cast<const DevHeader*>(blob);
+    const DevSeg* seg = reinterpret_cast<const DevSeg*>(blob + h->off_seg);
+    const DevBlk* blk = reinterpret_cast<const DevBlk*>(blob + h->off_blk);
+    const int n = 12 * N;
+    const int gl = threadIdx.x & (G - 1);  // lane inside the group
+    const long long groups = ((long long)gridDim.x * blockDim.x) / G;
+    const long long rounds = (B + groups - 1) / groups;  // every lane of a warp runs the same number of rounds
+    long long sys = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    for (long long r = 0; r < rounds; ++r, sys += groups) {
+        const bool live = sys < B;
+        const double* X = in + (size_t)(live ? sys : 0) * n;
+        double s0 = 0.0, s1 = 0.0;
+        if (live && gl < N) {
+            const int i = gl;
+            const DevSeg& sg = seg[i];
+            const V3 u = mk(X[12 * i], X[12 * i + 1], X[12 * i + 2]);
+            const V3 rp = mk(X[12 * i + 3], X[12 * i + 4], X[12 * i + 5]);
+            const V3 rd = mk(X[12 * i + 6], X[12 * i + 7], X[12 * i + 8]);
+            const V3 w = mk(X[12 * i + 9], X[12 * i + 10], X[12 * i + 11]);
+            if (which == 10) {
+                const double* ip = sg.mcj;
+                const double ms = ip[0], c0 = ip[1], c1 = ip[2], c2 = ip[3];
+                const double J00 = ip[4], J01 = ip[5], J02 = ip[6], J11 = ip[7], J12 = ip[8], J22 = ip[9];
+                // diagonal and off-diagonal entries of M4 over the slots (u, rp, rd, w)
+                s0 = 0.5 * (J00 * dot(u, u) + (ms + 2.0 * ms * c1 + J11) * dot(rp, rp) + J11 * dot(rd, rd) + J22 * dot(w, w)) +
+                     (ms * c0 + J01) * dot(u, rp) - J01 * dot(u, rd) + J02 * dot(u, w) - (ms * c1 + J11) * dot(rp, rd) +
+                     (ms * c2 + J12) * dot(rp, w) - J12 * dot(rd, w);
+            } else if (which == 11) {
+                const double* c = sg.mcj + 1;
+                s0 = sg.mcj[0] * fma(c[0], u.z, fma(1.0 + c[1], rp.z, fma(-c[1], rd.z, c[2] * w.z)));
+            } else {
+                const V3 v = rp - rd;
+                const double r0 = dot(u, u) - 1.0, r1 = dot(u, v) - sg.phic[0], r2 = dot(u, w) - sg.phic[1];
+                const double r3 = dot(v, v) - sg.phic[2], r4 = dot(v, w) - sg.phic[3], r5 = dot(w, w) - 1.0;
+                s0 = r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3 + r4 * r4 + r5 * r5;
+            }
+        }
+        if (which == 12 && live) {
+            for (int b = gl; b < nblk; b += G) {
+                double phi[3];
+                const int rows = block_residual(blk[b], X, phi);
+                for (int q = 0; q < rows; ++q) s1 = fma(phi[q], phi[q], s1);
+            }
+        }
+        for (int off = G >> 1; off > 0; off >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+        }
+        if (live && gl == 0) {
+            if (which == 12) out[2 * sys] = sqrt(s0), out[2 * sys + 1] = sqrt(s1);
+            else out[sys] = s0;
+        }
     }
 }
 

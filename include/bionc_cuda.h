@@ -58,6 +58,12 @@ extern "C" {
 #define BIONC_EVAL_K_H 5    /* holonomic_constraints_jacobian(Q)         -> (B, m, 12N)  biomechanical_model.py:199-258 */
 #define BIONC_EVAL_BIAS_H 6 /* holonomic_constraints_acceleration_bias(Qdot) -> (B, m)   biomechanical_model.py:260-317 */
 #define BIONC_EVAL_FEXT 7   /* ExternalForceSet.to_natural_external_forces(Q) -> (B, 12N) external_force.py:143-166 */
+/* post-processing: what users evaluate frame by frame after an integration */
+#define BIONC_EVAL_COM 8        /* center_of_mass_position(Q)  -> (B, 3, N)          biomechanical_model_markers.py:59-79 */
+#define BIONC_EVAL_MARKERS 9    /* markers(Q), forward kinematics -> (B, 3, nb_markers) biomechanical_model_markers.py:32-57 */
+#define BIONC_EVAL_KINETIC 10   /* kinetic_energy(Qdot)        -> (B)                biomechanical_model.py:98-113 */
+#define BIONC_EVAL_POTENTIAL 11 /* potential_energy(Q)         -> (B)                biomechanical_model.py:115-133 */
+#define BIONC_EVAL_RESIDUALS 12 /* [|Phi_r(Q)|_2, |Phi_j(Q)|_2] -> (B, 2)            bionc_numpy/time_series_utils.py:6-41 */
 
 /* Flat model description: the arrays of a compiled ModelTable (host pointers, copied at create). */
 typedef struct BioncModelDesc {
@@ -74,6 +80,9 @@ typedef struct BioncModelDesc {
     const int32_t* blk_row_h;    /* (nblk)  first row, holonomic order                                               */
     const int32_t* blk_row_j;    /* (nblk)  first row, joint-index order                                             */
     const double* blk_param;     /* (nblk, BIONC_BLK_NPARAM)                                                         */
+    int32_t nb_markers;          /* markers in model order (0 = none), natural_marker.py:39-71                       */
+    const int32_t* marker_segment; /* (nb_markers) segment index                                                     */
+    const double* marker_position; /* (nb_markers, 3) natural coordinates (n_u, n_v, n_w)                            */
 } BioncModelDesc;
 
 /* External forces shared by every system of the batch (ExternalForceSet, external_force.py:13-180). */

@@ -44,6 +44,17 @@ class OracleModel:
         else:
             d = {k: np.array(getattr(table, k)) for k in _ARRAYS}
         self.__dict__.update(d)
+        # markers are optional (model table format 2)
+        if isinstance(table, (str, bytes)) or hasattr(table, "__fspath__"):
+            with np.load(table, allow_pickle=False) as z:
+                has = "marker_segment" in z.files
+                self.marker_segment = np.array(z["marker_segment"]) if has else np.zeros(0, dtype=np.int32)
+                self.marker_position = np.array(z["marker_position"]) if has else np.zeros((0, 3))
+        else:
+            ms = getattr(table, "marker_segment", None)
+            self.marker_segment = np.zeros(0, dtype=np.int32) if ms is None else np.array(ms)
+            mp = getattr(table, "marker_position", None)
+            self.marker_position = np.zeros((0, 3)) if mp is None else np.array(mp).reshape(-1, 3)
         # optional per-system inertial-parameter override (config 5: perturbed inertial parameters)
         if seg_mass is not None:
             self.seg_mass = np.asarray(seg_mass, dtype=np.float64)
@@ -113,6 +124,51 @@ class OracleModel:
             c = self.seg_com[i]
             E += self.seg_mass[i] * (np.kron(np.array([[c[0], 1 + c[1], -c[1], c[2]]]), np.eye(3)) @ Q[12 * i : 12 * i + 12])[2]
         return E
+
+    # ----------------------------------------------------------------- kinematics of points (post-processing)
+    def center_of_mass_position(self, Q):
+        """biomechanical_model_markers.py:59-79 / natural_segment.py:551-560: N_com,i Q_i -> (3, N)."""
+        Q = np.asarray(Q, float).reshape(-1)
+        out = np.zeros((3, self.nb_segments))
+        for i in range(self.nb_segments):
+            c = self.seg_com[i]
+            out[:, i] = self._N([c[0], 1 + c[1], -c[1], c[2]]) @ Q[12 * i : 12 * i + 12]
+        return out
+
+    def markers(self, Q):
+        """biomechanical_model_markers.py:32-57: interpolation matrix of every marker times its segment's Q_i
+        (natural_marker.py:159-172, natural_vector.py interpolate()) -> (3, nb_markers)."""
+        Q = np.asarray(Q, float).reshape(-1)
+        out = np.zeros((3, self.marker_segment.shape[0]))
+        for k, (i, p) in enumerate(zip(self.marker_segment, self.marker_position)):
+            out[:, k] = self._N([p[0], 1 + p[1], -p[1], p[2]]) @ Q[12 * int(i) : 12 * int(i) + 12]
+        return out
+
+    def total_rigid_body_constraints(self, Q):
+        """time_series_utils.py:6-12, :24-26 for one frame."""
+        return float(np.sqrt(np.sum(self.rigid_body_constraints(Q) ** 2)))
+
+    def total_joint_constraints(self, Q):
+        """time_series_utils.py:6-12, :34-36 for one frame."""
+        return float(np.sqrt(np.sum(self.joint_constraints(Q) ** 2)))
+
+    def segment_differential_algebraic_equation(self, i, Qi, Qdoti, stabilization=None):
+        """natural_segment.py:574-633: the 18x18 system [G_i Kr^T; Kr 0][Qddot_i; lambda_i] = [gravity_i; -bias_i].
+        The reference's own `stabilization` branch cannot run (:617 in-place shape error); the formula it intends
+        is applied here when a dict is given."""
+        Qi, Qdoti = np.asarray(Qi, float).reshape(-1), np.asarray(Qdoti, float).reshape(-1)
+        G = self._G[12 * i : 12 * i + 12, 12 * i : 12 * i + 12]
+        Kr = self._rigid_jacobian(Qi)
+        bias = -self._rigid_bias(Qdoti)
+        if stabilization is not None:
+            u, v, w = self._uvw(Qi)
+            c = self.seg_phi_const[i]
+            phi = np.array([u @ u - 1, u @ v - c[0], u @ w - c[1], v @ v - c[2], v @ w - c[3], w @ w - 1])
+            bias = bias - stabilization["alpha"] * phi - stabilization["beta"] * (Kr @ Qdoti)
+        A = np.zeros((18, 18))
+        A[:12, :12], A[12:, :12], A[:12, 12:] = G, Kr, Kr.T
+        x = np.linalg.solve(A, np.concatenate([self._fg[12 * i : 12 * i + 12], bias]))
+        return x[:12], x[12:]
 
     # ----------------------------------------------------------------- rigid body (per segment)
     @staticmethod

@@ -103,6 +103,7 @@ def fext_to_arrays(fext: ExternalForceSet | None):
 def evaluate(model, Q, Qdot, fext=None, stab=(0.7, 1.3)):
     """Reference outputs for a batch of states, one system at a time (the reference has no batch axis)."""
     out = {k: [] for k in "phi_r phi_j K_j phi_h K_h bias fext Qddot lam Qddot_stab lam_stab kinetic potential".split()}
+    post = {k: [] for k in "com markers dae_Qddot dae_lam".split()}
     for q, qd in zip(Q, Qdot):
         Qn, Qdn = NaturalCoordinates(q), NaturalVelocities(qd)
         out["phi_r"].append(np.asarray(model.rigid_body_constraints(Qn)).reshape(-1))
@@ -119,7 +120,21 @@ def evaluate(model, Q, Qdot, fext=None, stab=(0.7, 1.3)):
         out["Qddot"].append(np.asarray(qdd).reshape(-1)), out["lam"].append(np.asarray(lam).reshape(-1))
         qdd, lam = model.forward_dynamics(Qn, Qdn, external_forces=fext, stabilization=dict(alpha=stab[0], beta=stab[1]))
         out["Qddot_stab"].append(np.asarray(qdd).reshape(-1)), out["lam_stab"].append(np.asarray(lam).reshape(-1))
+        # post-processing / single-segment rows
+        post["markers"].append(np.asarray(model.markers(Qn))[:, :, 0])  # (3, nb_markers)
+        post["com"].append(np.asarray(model.center_of_mass_position(Qn))[:, :, 0])  # (3, N)
+        dq, dl = [], []
+        for i, seg in enumerate(model.segments_no_ground.values()):
+            # natural_segment.py:574-633.  The `stabilization` branch of this function cannot run in the reference
+            # (:617 subtracts a (6,) from a (6,1) in place -> ValueError), so only the plain DAE has a golden.
+            a, l = seg.differential_algebraic_equation(Qn.vector(i), Qdn.vector(i))
+            dq.append(np.asarray(a).reshape(-1)), dl.append(np.asarray(l).reshape(-1))
+        post["dae_Qddot"].append(np.array(dq)), post["dae_lam"].append(np.array(dl))
     res = {"ref_" + k: np.array(v) for k, v in out.items()}
+    res.update({"ref_" + k: np.array(v) for k, v in post.items()})
+    # time_series_utils.py:6-41: norm of the residual vector per frame
+    res["ref_total_rigid"] = np.sqrt(np.sum(res["ref_phi_r"] ** 2, axis=1))
+    res["ref_total_joint"] = np.sqrt(np.sum(res["ref_phi_j"] ** 2, axis=1))
     res["stab_alpha_beta"] = np.array(stab)
     return res
 

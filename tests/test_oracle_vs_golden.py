@@ -30,6 +30,14 @@ def test_oracle_components_match_reference(name):
         np.testing.assert_allclose(om.natural_external_forces(Q, fext), case["ref_fext"][s], rtol=1e-12, atol=1e-12)
         np.testing.assert_allclose(om.kinetic_energy(Qd), case["ref_kinetic"][s], rtol=1e-13, atol=1e-13)
         np.testing.assert_allclose(om.potential_energy(Q), case["ref_potential"][s], rtol=1e-13, atol=1e-13)
+        # post-processing rows and the single-segment DAE (natural_segment.py:574-633)
+        np.testing.assert_allclose(om.center_of_mass_position(Q), case["ref_com"][s], **tol)
+        np.testing.assert_allclose(om.markers(Q), case["ref_markers"][s], **tol)
+        np.testing.assert_allclose(om.total_rigid_body_constraints(Q), case["ref_total_rigid"][s], **tol)
+        np.testing.assert_allclose(om.total_joint_constraints(Q), case["ref_total_joint"][s], **tol)
+        for i in range(om.nb_segments):
+            a, l = om.segment_differential_algebraic_equation(i, Q[12 * i : 12 * i + 12], Qd[12 * i : 12 * i + 12])
+            assert rel_err(a, case["ref_dae_Qddot"][s, i]) < 1e-10 and rel_err(l, case["ref_dae_lam"][s, i]) < 1e-10
 
 
 @pytest.mark.parametrize("name", CASES)
