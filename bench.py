@@ -291,7 +291,8 @@ def run_gpu_arm(args):
     if distributed:
         # the only collective of the workload: a final gather (of per-rank checksums by default;
         # --gather-states gathers the full states, 768 MB per rank at the default batch)
-        chk = torch.stack([Q.sum(), Qd.sum()])[None]
+        ok = (status == 0).to(torch.float64)[:, None]  # a handful of systems diverge in 800+ unstabilised steps, as the reference does
+        chk = torch.stack([torch.nan_to_num(Q * ok).sum(), torch.nan_to_num(Qd * ok).sum()])[None]
         allchk = gather_states(chk, world)
         assert allchk.shape == (world, 2) and bool(torch.isfinite(allchk).all())
         if args.gather_states:
