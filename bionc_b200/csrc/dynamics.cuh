@@ -570,10 +570,11 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
         //         rows); padding rows get a unit diagonal and a zero right-hand side.  Lean models have
         //         neither, so this phase and its barrier vanish for them.
         if (hd->nzero > 0 || hd->nunit > 0) {
-            for (int it = w.segi; it < 9 * hd->nzero; it += w.N) {
-                const int z = w.zero_list[it / 9], e = it - 9 * (it / 9);
-                double* dst = z >= 0 ? w.S0 + (9 * z + e) * spw : w.S1 + (9 * (-z - 1) + e) * spw;
-                *dst = 0.0;
+            for (int zi = w.segi; zi < hd->nzero; zi += w.N) {
+                const int z = w.zero_list[zi];
+                double* dst = z >= 0 ? w.S0 + 9 * z * spw : w.S1 + 9 * (-z - 1) * spw;
+#pragma unroll
+                for (int e = 0; e < 9; ++e) dst[e * spw] = 0.0;
             }
             __syncthreads();
             if (w.segi == 0) {
