@@ -241,6 +241,15 @@ int symbolic_analysis(BioncModel* M, int N) {
     auto append = [&](const std::vector<int>& v) { M->sym.insert(M->sym.end(), v.begin(), v.end()); };
     append(slot_tab), append(slot2_tab), append(zero), append(comb), append(unit), append(colptr), append(colrow);
     append(lvlptr), append(lvlpiv);
+    // block row I is handled by warp I mod N; pivot K occupies warp 0 and the owners of the rows of its column
+    std::vector<int> owner(nb), pivmask(nb);
+    for (int I = 0; I < nb; ++I) owner[I] = I % N;
+    for (int K = 0; K < nb; ++K) {
+        unsigned mask = 1u;
+        for (int ci = colptr[K]; ci < colptr[K + 1]; ++ci) mask |= 1u << owner[colrow[ci]];
+        pivmask[K] = (int)mask;
+    }
+    append(owner), append(pivmask);
     M->hdr.nlevel = nlevel;
     M->hdr.nb = nb, M->hdr.nslot = nslot, M->hdr.nslot2 = nslot2;
     M->hdr.nzero = (int)zero.size(), M->hdr.ncomb = (int)comb.size() / 2, M->hdr.nunit = (int)unit.size();

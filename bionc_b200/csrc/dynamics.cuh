@@ -219,7 +219,7 @@ struct WarpCtx {
     double *Qo, *Qdo, *Qsys, *Qdsys;
     double *S0, *S1, *r0, *r1, *lamv, *dinv, *knl;
     // symbolic factorisation tables (host, capi.cu symbolic_analysis)
-    const int *slot_tab, *slot2_tab, *zero_list, *comb_list, *unit_list, *colptr, *colrow, *lvlptr, *lvlpiv, *nscale;
+    const int *slot_tab, *slot2_tab, *zero_list, *comb_list, *unit_list, *colptr, *colrow, *lvlptr, *lvlpiv, *owner, *pivmask, *nscale;
     int N, mj, nb;
     int segi;  // this warp's segment
     int lane;  // this lane's system inside the CTA
@@ -514,6 +514,29 @@ __device__ __forceinline__ V3 sym3_apply(const double (&di)[6], V3 x) {
               fma(di[3], x.x, fma(di[4], x.y, di[5] * x.z)));
 }
 
+// lambda_K = y-hat_K - D_K^-1 sum_{I in column K} S_IK^T lambda_I   (in place in lamv)
+template <int spw>
+__device__ __forceinline__ void back_substitute(const WarpCtx& w, int K) {
+    const int c0 = w.colptr[K], c1 = w.colptr[K + 1];
+    if (c0 == c1) return;  // root: lambda = y-hat
+    V3 acc = mk(0.0, 0.0, 0.0);
+#pragma unroll 1
+    for (int ci = c0; ci < c1; ++ci) {
+        const int I = w.colrow[ci];
+        double A[9];
+        load_block<spw>(w, I * w.nb + K, A);
+        const V3 li = mk(w.lamv[(3 * I) * spw], w.lamv[(3 * I + 1) * spw], w.lamv[(3 * I + 2) * spw]);
+        acc = axpy(li.x, mk(A[0], A[1], A[2]), axpy(li.y, mk(A[3], A[4], A[5]), axpy(li.z, mk(A[6], A[7], A[8]), acc)));
+    }
+    double di[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) di[i] = w.dinv[(6 * K + i) * spw];
+    const V3 corr = sym3_apply(di, acc);
+    w.lamv[(3 * K) * spw] -= corr.x;
+    w.lamv[(3 * K + 1) * spw] -= corr.y;
+    w.lamv[(3 * K + 2) * spw] -= corr.z;
+}
+
 template <bool GENERAL, int S>
 __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& c, const DynOpts& o, Q12& Qdd,
                                                       double* lam_out, int& status) {
@@ -757,9 +780,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
             for (int pi = w.lvlptr[lv]; pi < w.lvlptr[lv + 1]; ++pi) {
                 const int K = w.lvlpiv[pi];
                 const int c0 = w.colptr[K], c1 = w.colptr[K + 1];
-                bool mine = (w.segi == 0);
-                for (int ci = c0; ci < c1; ++ci) mine = mine || (w.colrow[ci] % w.N == w.segi);
-                if (!mine) continue;
+                if (((w.pivmask[K] >> w.segi) & 1) == 0) continue;  // neither warp 0 nor the owner of a row of column K
                 double D[9], di[6];
                 load_block<S>(w, K * nb + K, D);
                 sym3_inverse(D[0], D[3], D[4], D[6], D[7], D[8], di, status);
@@ -777,7 +798,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
 #pragma unroll 1
                 for (int ci = c0; ci < c1; ++ci) {
                     const int I = w.colrow[ci];
-                    if (I % w.N != w.segi) continue;
+                    if (w.owner[I] != w.segi) continue;
                     double A[9], T[9];
                     load_block<S>(w, I * nb + K, A);
                     double* ri = w.r0 + 3 * I * spw;  // fused forward substitution
@@ -806,28 +827,22 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                 }
             }
         }
-        // ---- G. backward substitution by the first warp: lambda_K = y-hat_K - D_K^-1 sum_I S_IK^T lambda_I.
-        //         No barrier before it: the pivots of the last level are roots (empty columns), which only the
-        //         first warp touches, and everything below was closed by that level's barrier.
-        if (w.segi == 0) {
+        // ---- G. backward substitution: lambda_K = y-hat_K - D_K^-1 sum_I S_IK^T lambda_I.
+        //         Small trees (<= 2 levels): by the first warp, and no barrier before it -- the pivots of the last
+        //         level are roots (empty columns), which only the first warp touches, and everything below was closed
+        //         by that level's barrier.  Deeper trees: level by level from the roots down, the pivots of a level
+        //         spread over the warps (they only read lambda of higher levels), one barrier per level.
+        if (hd->nlevel <= 2) {
+            if (w.segi == 0) {
 #pragma unroll 1
-            for (int K = nb - 1; K >= 0; --K) {
-                V3 acc = mk(0.0, 0.0, 0.0);
+                for (int K = nb - 1; K >= 0; --K) back_substitute<S>(w, K);
+            }
+        } else {
 #pragma unroll 1
-                for (int ci = w.colptr[K]; ci < w.colptr[K + 1]; ++ci) {
-                    const int I = w.colrow[ci];
-                    double A[9];
-                    load_block<S>(w, I * nb + K, A);
-                    const V3 li = mk(w.lamv[(3 * I) * spw], w.lamv[(3 * I + 1) * spw], w.lamv[(3 * I + 2) * spw]);
-                    acc = axpy(li.x, mk(A[0], A[1], A[2]), axpy(li.y, mk(A[3], A[4], A[5]), axpy(li.z, mk(A[6], A[7], A[8]), acc)));
-                }
-                double di[6];
-#pragma unroll
-                for (int i = 0; i < 6; ++i) di[i] = w.dinv[(6 * K + i) * spw];
-                const V3 corr = sym3_apply(di, acc);
-                w.lamv[(3 * K) * spw] -= corr.x;
-                w.lamv[(3 * K + 1) * spw] -= corr.y;
-                w.lamv[(3 * K + 2) * spw] -= corr.z;
+            for (int lv = hd->nlevel - 2; lv >= 0; --lv) {  // the last level holds roots only: lambda = y-hat already
+                __syncthreads();
+#pragma unroll 1
+                for (int pi = w.lvlptr[lv] + w.segi; pi < w.lvlptr[lv + 1]; pi += w.N) back_substitute<S>(w, w.lvlpiv[pi]);
             }
         }
         __syncthreads();

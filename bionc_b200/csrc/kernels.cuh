@@ -121,7 +121,9 @@ __device__ __forceinline__ void setup_cta(const unsigned char* __restrict__ blob
     w.colrow = w.colptr + w.nb + 1;
     w.lvlptr = w.colrow + h->ncol;
     w.lvlpiv = w.lvlptr + h->nlevel + 1;
-    w.nscale = w.lvlpiv + w.nb;
+    w.owner = w.lvlpiv + w.nb;
+    w.pivmask = w.owner + w.nb;
+    w.nscale = w.pivmask + w.nb;
 }
 
 __device__ __forceinline__ void load_q12(const double* __restrict__ p, Q12& q) {
