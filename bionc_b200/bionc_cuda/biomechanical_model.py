@@ -575,10 +575,10 @@ class BiomechanicalModel:
     def kernel_layout(self) -> dict:
         """How the model is laid out for the kernels (diagnostics): joint-level nodes, stored blocks, tree levels,
         systems per CTA and shared memory per CTA (the last two are known after the first launch)."""
-        out = (C.c_int32 * 10)()
+        out = (C.c_int32 * 11)()
         _lib.check(self._lib.bionc_cuda_model_layout(self._h, out), "model_layout")
         keys = ("segments", "joint_rows", "nodes", "stored_blocks", "second_copies", "tree_levels", "row_storage_doubles",
-                "zero_list", "systems_per_cta", "smem_bytes_per_cta")
+                "zero_list", "systems_per_cta", "smem_bytes_per_cta", "serial_joint_level_schedule")
         return dict(zip(keys, [int(v) for v in out]))
 
     @staticmethod

@@ -250,6 +250,45 @@ int symbolic_analysis(BioncModel* M, int N) {
         pivmask[K] = (int)mask;
     }
     append(owner), append(pivmask);
+    // Schedule of the joint-level phases: level-parallel (one barrier per level, rows spread over the warps) or serial
+    // on the first warp (no inner barriers, no pivot inverted twice).  Crude cost model in units of a 3x3 block
+    // product: inverse 3, row (forward substitution + T) 2, pair update 2, back-substitution term 1, barrier 3.
+    {
+        const double c_inv = 3, c_row = 2, c_pair = 2, c_back = 1, c_bar = 3;
+        double serial = 0, parallel = 0;
+        for (int K = 0; K < nb; ++K) {
+            const int c = colptr[K + 1] - colptr[K];
+            serial += c_inv + c * c_row + 0.5 * c * (c + 1) * c_pair + (c > 0 ? 1 + c * c_back : 0);
+        }
+        for (int L = 0; L < nlevel; ++L) {
+            std::vector<double> load(N, 0.0);
+            for (int K = 0; K < nb; ++K) {
+                if (level[K] != L) continue;
+                for (int wi = 0; wi < N; ++wi)
+                    if ((pivmask[K] >> wi) & 1) load[wi] += c_inv;
+                for (int ci = colptr[K]; ci < colptr[K + 1]; ++ci) load[owner[colrow[ci]]] += c_row + (ci - colptr[K] + 1) * c_pair;
+            }
+            parallel += c_bar + *std::max_element(load.begin(), load.end());
+        }
+        if (nlevel <= 2) {
+            for (int K = 0; K < nb; ++K) {
+                const int c = colptr[K + 1] - colptr[K];
+                parallel += c > 0 ? 1 + c * c_back : 0;
+            }
+        } else {
+            for (int L = nlevel - 2; L >= 0; --L) {
+                std::vector<double> load(N, 0.0);
+                int k = 0;
+                for (int K = 0; K < nb; ++K)
+                    if (level[K] == L) {
+                        const int c = colptr[K + 1] - colptr[K];
+                        load[k++ % N] += c > 0 ? 1 + c * c_back : 0;
+                    }
+                parallel += c_bar + *std::max_element(load.begin(), load.end());
+            }
+        }
+        M->hdr.serial_solve = serial <= parallel ? 1 : 0;
+    }
     M->hdr.nlevel = nlevel;
     M->hdr.nb = nb, M->hdr.nslot = nslot, M->hdr.nslot2 = nslot2;
     M->hdr.nzero = (int)zero.size(), M->hdr.ncomb = (int)comb.size() / 2, M->hdr.nunit = (int)unit.size();
@@ -559,8 +598,8 @@ int bionc_cuda_model_counts(const BioncModel* M, int32_t* nseg, int32_t* mj, int
 int bionc_cuda_model_layout(const BioncModel* M, int32_t* out) {
     if (M == nullptr || out == nullptr) return fail(BIONC_E_INVALID, "null argument");
     const DevHeader& h = M->hdr;
-    const int32_t v[10] = {h.N, h.mj, h.nb, h.nslot, h.nslot2, h.nlevel, h.rnl, h.nzero, M->blob_valid ? h.spw : 0,
-                           M->blob_valid ? (int32_t)M->smem_bytes : 0};
+    const int32_t v[11] = {h.N, h.mj, h.nb, h.nslot, h.nslot2, h.nlevel, h.rnl, h.nzero, M->blob_valid ? h.spw : 0,
+                           M->blob_valid ? (int32_t)M->smem_bytes : 0, h.serial_solve};
     std::memcpy(out, v, sizeof(v));
     return BIONC_OK;
 }

@@ -514,6 +514,58 @@ __device__ __forceinline__ V3 sym3_apply(const double (&di)[6], V3 x) {
               fma(di[3], x.x, fma(di[4], x.y, di[5] * x.z)));
 }
 
+// Pivot K of the blocked LDL^T: invert D_K, y-hat_K = D_K^-1 r_K, then for the rows I of column K that this warp
+// owns (ALL: every row) the fused forward substitution and the Schur updates S_IJ -= S_IK D_K^-1 S_JK^T.
+template <bool ALL, int spw>
+__device__ __forceinline__ void eliminate_pivot(const WarpCtx& w, int K, int& status) {
+    const int nb = w.nb;
+    const int c0 = w.colptr[K], c1 = w.colptr[K + 1];
+    double D[9], di[6];
+    load_block<spw>(w, K * nb + K, D);
+    sym3_inverse(D[0], D[3], D[4], D[6], D[7], D[8], di, status);
+    // a pivot whose whole diagonal has cancelled against the node's nominal scale is a redundant node (e.g. the same
+    // joint declared twice): its remainder is rounding noise that the determinant test, relative to the block's own
+    // scale, cannot see
+    if (fmax(fabs(D[0]), fmax(fabs(D[4]), fabs(D[8]))) < kSmallPivot * (double)__int_as_float(w.nscale[K])) status |= 4;
+    const V3 yh = sym3_apply(di, mk(w.r0[(3 * K) * spw] + w.r1[(3 * K) * spw], w.r0[(3 * K + 1) * spw] + w.r1[(3 * K + 1) * spw],
+                                    w.r0[(3 * K + 2) * spw] + w.r1[(3 * K + 2) * spw]));
+    if (ALL || w.segi == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) w.dinv[(6 * K + i) * spw] = di[i];
+        w.lamv[(3 * K) * spw] = yh.x, w.lamv[(3 * K + 1) * spw] = yh.y, w.lamv[(3 * K + 2) * spw] = yh.z;  // y-hat = D^-1 y
+    }
+#pragma unroll 1
+    for (int ci = c0; ci < c1; ++ci) {
+        const int I = w.colrow[ci];
+        if (!ALL && w.owner[I] != w.segi) continue;
+        double A[9], T[9];
+        load_block<spw>(w, I * nb + K, A);
+        double* ri = w.r0 + 3 * I * spw;  // fused forward substitution
+        ri[0] -= fma(A[0], yh.x, fma(A[1], yh.y, A[2] * yh.z));
+        ri[spw] -= fma(A[3], yh.x, fma(A[4], yh.y, A[5] * yh.z));
+        ri[2 * spw] -= fma(A[6], yh.x, fma(A[7], yh.y, A[8] * yh.z));
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {  // T = A Dinv
+            const V3 t = sym3_apply(di, mk(A[3 * r], A[3 * r + 1], A[3 * r + 2]));
+            T[3 * r] = t.x, T[3 * r + 1] = t.y, T[3 * r + 2] = t.z;
+        }
+#pragma unroll 1
+        for (int cj = c0; cj <= ci; ++cj) {  // every J <= I of the same column: (I, J) is in the pattern
+            const int J = w.colrow[cj];
+            double Bj[9];
+            load_block<spw>(w, J * nb + K, Bj);
+            double* Sij = w.S0 + 9 * w.slot_tab[I * nb + J] * spw;
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const double upd = fma(T[3 * r], Bj[3 * q], fma(T[3 * r + 1], Bj[3 * q + 1], T[3 * r + 2] * Bj[3 * q + 2]));
+                    Sij[(3 * r + q) * spw] -= upd;
+                }
+        }
+    }
+}
+
 // lambda_K = y-hat_K - D_K^-1 sum_{I in column K} S_IK^T lambda_I   (in place in lamv)
 template <int spw>
 __device__ __forceinline__ void back_substitute(const WarpCtx& w, int K) {
@@ -768,81 +820,51 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
             }
         }
 
-        // ---- F. sparse blocked LDL^T of S' in place with 3x3 pivots along the host-computed pattern, level by
-        //         level of the elimination tree (pivots of one level are independent: one barrier per level,
-        //         the first one also closes the assembly).  A block row I is always handled by warp I mod N,
-        //         so concurrent pivots never write the same block.  The forward substitution is fused in
-        //         (r_I -= S_IK D_K^-1 r_K); S_IK is kept unscaled (L_IK = S_IK D_K^-1 acts through y-hat).
-#pragma unroll 1
-        for (int lv = 0; lv < hd->nlevel; ++lv) {
+        // ---- F. sparse blocked LDL^T of S' in place with 3x3 pivots along the host-computed pattern.  The forward
+        //         substitution is fused in (r_I -= S_IK D_K^-1 r_K); S_IK is kept unscaled (L_IK = S_IK D_K^-1 acts
+        //         through y-hat).
+        //    G. backward substitution: lambda_K = y-hat_K - D_K^-1 sum_I S_IK^T lambda_I.
+        if (hd->serial_solve != 0) {
+            // serial schedule (host decision: the elimination offers no parallelism across warps, e.g. the lower
+            // limb's hip / ankle pivots both update the knee block): the first warp factors and solves everything
+            // between two barriers -- no barrier per level, no pivot inverted twice.
             __syncthreads();
-#pragma unroll 1
-            for (int pi = w.lvlptr[lv]; pi < w.lvlptr[lv + 1]; ++pi) {
-                const int K = w.lvlpiv[pi];
-                const int c0 = w.colptr[K], c1 = w.colptr[K + 1];
-                if (((w.pivmask[K] >> w.segi) & 1) == 0) continue;  // neither warp 0 nor the owner of a row of column K
-                double D[9], di[6];
-                load_block<S>(w, K * nb + K, D);
-                sym3_inverse(D[0], D[3], D[4], D[6], D[7], D[8], di, status);
-                // a pivot whose whole diagonal has cancelled against the node's nominal scale is a redundant node
-                // (e.g. the same joint declared twice): its remainder is rounding noise that the determinant test,
-                // relative to the block's own scale, cannot see
-                if (fmax(fabs(D[0]), fmax(fabs(D[4]), fabs(D[8]))) < kSmallPivot * (double)__int_as_float(w.nscale[K])) status |= 4;
-                const V3 yh = sym3_apply(di, mk(w.r0[(3 * K) * spw] + w.r1[(3 * K) * spw], w.r0[(3 * K + 1) * spw] + w.r1[(3 * K + 1) * spw],
-                                                w.r0[(3 * K + 2) * spw] + w.r1[(3 * K + 2) * spw]));
-                if (w.segi == 0) {
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) w.dinv[(6 * K + i) * spw] = di[i];
-                    w.lamv[(3 * K) * spw] = yh.x, w.lamv[(3 * K + 1) * spw] = yh.y, w.lamv[(3 * K + 2) * spw] = yh.z;  // y-hat = D^-1 y
-                }
-#pragma unroll 1
-                for (int ci = c0; ci < c1; ++ci) {
-                    const int I = w.colrow[ci];
-                    if (w.owner[I] != w.segi) continue;
-                    double A[9], T[9];
-                    load_block<S>(w, I * nb + K, A);
-                    double* ri = w.r0 + 3 * I * spw;  // fused forward substitution
-                    ri[0] -= fma(A[0], yh.x, fma(A[1], yh.y, A[2] * yh.z));
-                    ri[spw] -= fma(A[3], yh.x, fma(A[4], yh.y, A[5] * yh.z));
-                    ri[2 * spw] -= fma(A[6], yh.x, fma(A[7], yh.y, A[8] * yh.z));
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) {  // T = A Dinv
-                        const V3 t = sym3_apply(di, mk(A[3 * r], A[3 * r + 1], A[3 * r + 2]));
-                        T[3 * r] = t.x, T[3 * r + 1] = t.y, T[3 * r + 2] = t.z;
-                    }
-#pragma unroll 1
-                    for (int cj = c0; cj <= ci; ++cj) {  // every J <= I of the same column: (I, J) is in the pattern
-                        const int J = w.colrow[cj];
-                        double Bj[9];
-                        load_block<S>(w, J * nb + K, Bj);
-                        double* Sij = w.S0 + 9 * w.slot_tab[I * nb + J] * spw;
-#pragma unroll
-                        for (int r = 0; r < 3; ++r)
-#pragma unroll
-                            for (int q = 0; q < 3; ++q) {
-                                const double upd = fma(T[3 * r], Bj[3 * q], fma(T[3 * r + 1], Bj[3 * q + 1], T[3 * r + 2] * Bj[3 * q + 2]));
-                                Sij[(3 * r + q) * spw] -= upd;
-                            }
-                    }
-                }
-            }
-        }
-        // ---- G. backward substitution: lambda_K = y-hat_K - D_K^-1 sum_I S_IK^T lambda_I.
-        //         Small trees (<= 2 levels): by the first warp, and no barrier before it -- the pivots of the last
-        //         level are roots (empty columns), which only the first warp touches, and everything below was closed
-        //         by that level's barrier.  Deeper trees: level by level from the roots down, the pivots of a level
-        //         spread over the warps (they only read lambda of higher levels), one barrier per level.
-        if (hd->nlevel <= 2) {
             if (w.segi == 0) {
+#pragma unroll 1
+                for (int K = 0; K < nb; ++K) eliminate_pivot<true, S>(w, K, status);
 #pragma unroll 1
                 for (int K = nb - 1; K >= 0; --K) back_substitute<S>(w, K);
             }
         } else {
+            // level by level of the elimination tree (pivots of one level are independent: one barrier per level, the
+            // first one also closes the assembly).  A block row I is always handled by warp owner[I], so concurrent
+            // pivots never write the same block.
 #pragma unroll 1
-            for (int lv = hd->nlevel - 2; lv >= 0; --lv) {  // the last level holds roots only: lambda = y-hat already
+            for (int lv = 0; lv < hd->nlevel; ++lv) {
                 __syncthreads();
 #pragma unroll 1
-                for (int pi = w.lvlptr[lv] + w.segi; pi < w.lvlptr[lv + 1]; pi += w.N) back_substitute<S>(w, w.lvlpiv[pi]);
+                for (int pi = w.lvlptr[lv]; pi < w.lvlptr[lv + 1]; ++pi) {
+                    const int K = w.lvlpiv[pi];
+                    if (((w.pivmask[K] >> w.segi) & 1) == 0) continue;  // neither warp 0 nor the owner of a row of column K
+                    eliminate_pivot<false, S>(w, K, status);
+                }
+            }
+            // Back substitution.  Small trees (<= 2 levels): by the first warp, and no barrier before it -- the pivots of
+            // the last level are roots (empty columns), which only the first warp touches, and everything below was
+            // closed by that level's barrier.  Deeper trees: level by level from the roots down, the pivots of a level
+            // spread over the warps (they only read lambda of higher levels), one barrier per level.
+            if (hd->nlevel <= 2) {
+                if (w.segi == 0) {
+#pragma unroll 1
+                    for (int K = nb - 1; K >= 0; --K) back_substitute<S>(w, K);
+                }
+            } else {
+#pragma unroll 1
+                for (int lv = hd->nlevel - 2; lv >= 0; --lv) {  // the last level holds roots only: lambda = y-hat already
+                    __syncthreads();
+#pragma unroll 1
+                    for (int pi = w.lvlptr[lv] + w.segi; pi < w.lvlptr[lv + 1]; pi += w.N) back_substitute<S>(w, w.lvlpiv[pi]);
+                }
             }
         }
         __syncthreads();

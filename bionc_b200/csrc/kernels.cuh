@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
     load_q12(Qd + (size_t)gsys * n + 12 * w.segi, y0v);
     constexpr bool TM = TmemPark<MAXT>::use;
     unsigned tm = 0;  // this thread's 48 columns: y0q, y0v (24 each)
-    unsigned* tm_slot = reinterpret_cast<unsigned*>(const_cast<int*>(w.hdr->pad));  // a free word of the header copy
+    unsigned* tm_slot = reinterpret_cast<unsigned*>(const_cast<int*>(&w.hdr->tmem_slot));  // a free word of the header copy
     if (TM) {
         if (threadIdx.x < 32) tmem_alloc(tm_slot, TmemPark<MAXT>::cols);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -40,7 +40,8 @@ struct DevHeader {
                   // owner[nb] (warp of block row I) pivmask[nb] (warps taking part in pivot K)
                   // nscale[nb] (float bits: nominal diagonal scale of each node)
     int nlevel;   // levels of the elimination tree: pivots of one level are mutually independent
-    int pad[2];   // pad[0]: scratch word of the shared-memory copy (TMEM base address of the CTA)
+    int tmem_slot;     // scratch word of the shared-memory copy: TMEM base address of the CTA
+    int serial_solve;  // 1: the joint-level factorisation and solve run on the first warp between two barriers
 };
 
 struct DevSeg {

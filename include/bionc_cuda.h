@@ -113,10 +113,10 @@ int bionc_cuda_model_destroy(BioncModel* model);
 int bionc_cuda_model_counts(const BioncModel* model, int32_t* nb_segments, int32_t* nb_joint_constraints,
                             int32_t* nb_holonomic_constraints);
 
-/* diagnostics: how the model was laid out for the kernels.  out[10] = {segments, joint rows, 3x3 nodes of the
+/* diagnostics: how the model was laid out for the kernels.  out[11] = {segments, joint rows, 3x3 nodes of the
  * joint-level system, stored blocks, second copies, elimination-tree levels, doubles of per-segment row
- * storage, zero-list entries, systems per CTA, shared-memory bytes per CTA}; the last two are 0 until the
- * first launch has sized the CTA for the device */
+ * storage, zero-list entries, systems per CTA, shared-memory bytes per CTA, serial joint-level schedule (0/1)};
+ * systems and bytes per CTA are 0 until the first launch has sized the CTA for the device */
 int bionc_cuda_model_layout(const BioncModel* model, int32_t* out);
 
 /* replaces BiomechanicalModel.forward_dynamics (bionc_numpy/biomechanical_model.py:351-429), batched.
