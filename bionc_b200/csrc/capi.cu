@@ -288,6 +288,11 @@ int symbolic_analysis(BioncModel* M, int N) {
             }
         }
         M->hdr.serial_solve = serial <= parallel ? 1 : 0;
+        // two leaves against one root (hip / ankle against the knee), the root's diagonal and right-hand side with
+        // their second copies: the leaves are eliminated by two warps at once (solve_two_leaves)
+        if (nb == 3 && N >= 2 && slot_tab[1 * nb + 0] < 0 && slot_tab[2 * nb + 0] >= 0 && slot_tab[2 * nb + 1] >= 0 &&
+            slot2_tab[2 * nb + 2] >= 0 && zero.empty() && unit.empty())
+            M->hdr.serial_solve = 2;
     }
     M->hdr.nlevel = nlevel;
     M->hdr.nb = nb, M->hdr.nslot = nslot, M->hdr.nslot2 = nslot2;

@@ -589,6 +589,58 @@ __device__ __forceinline__ void back_substitute(const WarpCtx& w, int K) {
     w.lamv[(3 * K + 2) * spw] -= corr.z;
 }
 
+// Joint-level system of three nodes shaped like an arrow: nodes 0 and 1 are leaves coupled only with the root 2
+// (the lower limb: hip and ankle against the knee).  The two leaves are eliminated concurrently by the first two
+// warps; their updates of the root go to the two exclusive-writer copies of D_2 and r_2, so no write is shared.
+// After one barrier both warps invert the root (cheaper than a second barrier) and each finishes its own leaf:
+// lambda_leaf = y-hat_leaf - T^T lambda_2 with T = S_2,leaf D_leaf^-1 kept in the block's first copy.
+template <int spw>
+__device__ __forceinline__ void solve_two_leaves(const WarpCtx& w, int& status) {
+    constexpr int nb = 3;
+    if (w.segi < 2) {
+        const int K = w.segi;
+        double D[9], di[6], A[9], T[9];
+        load_block<spw>(w, K * nb + K, D);
+        sym3_inverse(D[0], D[3], D[4], D[6], D[7], D[8], di, status);
+        if (fmax(fabs(D[0]), fmax(fabs(D[4]), fabs(D[8]))) < kSmallPivot * (double)__int_as_float(w.nscale[K])) status |= 4;
+        const V3 yh = sym3_apply(di, mk(w.r0[(3 * K) * spw] + w.r1[(3 * K) * spw], w.r0[(3 * K + 1) * spw] + w.r1[(3 * K + 1) * spw],
+                                        w.r0[(3 * K + 2) * spw] + w.r1[(3 * K + 2) * spw]));
+        w.lamv[(3 * K) * spw] = yh.x, w.lamv[(3 * K + 1) * spw] = yh.y, w.lamv[(3 * K + 2) * spw] = yh.z;
+        load_block<spw>(w, 2 * nb + K, A);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const V3 t = sym3_apply(di, mk(A[3 * r], A[3 * r + 1], A[3 * r + 2]));
+            T[3 * r] = t.x, T[3 * r + 1] = t.y, T[3 * r + 2] = t.z;
+        }
+        double* Sd = K == 0 ? w.S0 + 9 * w.slot_tab[2 * nb + 2] * spw : w.S1 + 9 * w.slot2_tab[2 * nb + 2] * spw;
+        double* rr = (K == 0 ? w.r0 : w.r1) + 6 * spw;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                Sd[(3 * r + q) * spw] -= fma(T[3 * r], A[3 * q], fma(T[3 * r + 1], A[3 * q + 1], T[3 * r + 2] * A[3 * q + 2]));
+            rr[r * spw] -= fma(A[3 * r], yh.x, fma(A[3 * r + 1], yh.y, A[3 * r + 2] * yh.z));
+        }
+        double* Sa = w.S0 + 9 * w.slot_tab[2 * nb + K] * spw;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Sa[e * spw] = T[e];
+    }
+    __syncthreads();
+    if (w.segi < 2) {
+        const int K = w.segi;
+        double D[9], di[6], T[9];
+        load_block<spw>(w, 2 * nb + 2, D);
+        sym3_inverse(D[0], D[3], D[4], D[6], D[7], D[8], di, status);
+        if (fmax(fabs(D[0]), fmax(fabs(D[4]), fabs(D[8]))) < kSmallPivot * (double)__int_as_float(w.nscale[2])) status |= 4;
+        const V3 l2 = sym3_apply(di, mk(w.r0[6 * spw] + w.r1[6 * spw], w.r0[7 * spw] + w.r1[7 * spw], w.r0[8 * spw] + w.r1[8 * spw]));
+        if (K == 0) w.lamv[6 * spw] = l2.x, w.lamv[7 * spw] = l2.y, w.lamv[8 * spw] = l2.z;
+        load9<spw>(w.S0 + 9 * w.slot_tab[2 * nb + K] * spw, T);
+        w.lamv[(3 * K) * spw] -= fma(T[0], l2.x, fma(T[3], l2.y, T[6] * l2.z));
+        w.lamv[(3 * K + 1) * spw] -= fma(T[1], l2.x, fma(T[4], l2.y, T[7] * l2.z));
+        w.lamv[(3 * K + 2) * spw] -= fma(T[2], l2.x, fma(T[5], l2.y, T[8] * l2.z));
+    }
+}
+
 template <bool GENERAL, int S>
 __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& c, const DynOpts& o, Q12& Qdd,
                                                       double* lam_out, int& status) {
@@ -824,7 +876,10 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
         //         substitution is fused in (r_I -= S_IK D_K^-1 r_K); S_IK is kept unscaled (L_IK = S_IK D_K^-1 acts
         //         through y-hat).
         //    G. backward substitution: lambda_K = y-hat_K - D_K^-1 sum_I S_IK^T lambda_I.
-        if (hd->serial_solve != 0) {
+        if (hd->serial_solve == 2) {
+            __syncthreads();  // closes the assembly
+            solve_two_leaves<S>(w, status);
+        } else if (hd->serial_solve != 0) {
             // serial schedule (host decision: the elimination offers no parallelism across warps, e.g. the lower
             // limb's hip / ankle pivots both update the knee block): the first warp factors and solves everything
             // between two barriers -- no barrier per level, no pivot inverted twice.

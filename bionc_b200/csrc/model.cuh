@@ -41,7 +41,7 @@ struct DevHeader {
                   // nscale[nb] (float bits: nominal diagonal scale of each node)
     int nlevel;   // levels of the elimination tree: pivots of one level are mutually independent
     int tmem_slot;     // scratch word of the shared-memory copy: TMEM base address of the CTA
-    int serial_solve;  // 1: the joint-level factorisation and solve run on the first warp between two barriers
+    int serial_solve;  // joint-level schedule: 0 level-parallel, 1 serial on the first warp, 2 two leaves + root on two warps
 };
 
 struct DevSeg {
