@@ -46,13 +46,13 @@ MODEL = os.path.join(REPO, "tests", "golden", "models", "lower_limb.npz")
 WORKLOAD = "lower_limb_4seg (BASELINE.json configs[2]; PELVIS free + 3 spherical joints, n=48, m=33)"
 H = 0.01
 # DRAM traffic of ONE launch of the dominant kernel at the default configuration, from the committed
-# `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum): 0.80 GB read (the 768 MB of
-# state, once) + 11.5 GB written (768 MB of state + register spills evicted from L2: the kernel runs at 128
+# `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum): 0.79 GB read (the 768 MB of
+# state, once) + 8.9 GB written (768 MB of state + register spills evicted from L2: the kernel runs at 128
 # registers/thread to keep 4 CTAs per SM resident; before y0 moved to tensor memory the same launch wrote
 # 66 GB).  The algorithmic bytes of the same launch are B * S * 1536 B = 153.6 GB: the state stays on chip
 # for the S steps of a launch; DRAM runs below 1 % of peak.
-NCU_TRAFFIC = {"systems_per_gpu": 1_000_000, "rk4_steps_per_launch": 100, "bytes": 795.0144e6 + 11.513645e9,
-               "source": "profiles/r01_ncu_rk4_kernel_v11_benchconfig.txt"}
+NCU_TRAFFIC = {"systems_per_gpu": 1_000_000, "rk4_steps_per_launch": 100, "bytes": 792.342528e6 + 8.927182e9,
+               "source": "profiles/r01_ncu_rk4_kernel_v12_benchconfig.txt"}
 METRIC = "rk4_forward_dynamics_system_steps_per_s"
 UNIT = "system-steps/s"
 
