@@ -242,14 +242,17 @@ int symbolic_analysis(BioncModel* M, int N) {
     append(slot_tab), append(slot2_tab), append(zero), append(comb), append(unit), append(colptr), append(colrow);
     append(lvlptr), append(lvlpiv);
     // block row I is handled by warp I mod N; pivot K occupies warp 0 and the owners of the rows of its column
-    std::vector<int> owner(nb), pivmask(nb);
+    // The inverse pivot and y-hat of pivot K are stored by one of the warps that needs them anyway (the owner of the
+    // first row of its column; roots are spread round-robin), so no single warp has to invert every pivot of a level.
+    std::vector<int> owner(nb), pivmask(nb), pivwriter(nb);
     for (int I = 0; I < nb; ++I) owner[I] = I % N;
     for (int K = 0; K < nb; ++K) {
-        unsigned mask = 1u;
+        pivwriter[K] = colptr[K + 1] > colptr[K] ? owner[colrow[colptr[K]]] : K % N;
+        unsigned mask = 1u << pivwriter[K];
         for (int ci = colptr[K]; ci < colptr[K + 1]; ++ci) mask |= 1u << owner[colrow[ci]];
         pivmask[K] = (int)mask;
     }
-    append(owner), append(pivmask);
+    append(owner), append(pivmask), append(pivwriter);
     // Schedule of the joint-level phases: level-parallel (one barrier per level, rows spread over the warps) or serial
     // on the first warp (no inner barriers, no pivot inverted twice).  Crude cost model in units of a 3x3 block
     // product: inverse 3, row (forward substitution + T) 2, pair update 2, back-substitution term 1, barrier 3.
@@ -270,22 +273,15 @@ int symbolic_analysis(BioncModel* M, int N) {
             }
             parallel += c_bar + *std::max_element(load.begin(), load.end());
         }
-        if (nlevel <= 2) {
-            for (int K = 0; K < nb; ++K) {
-                const int c = colptr[K + 1] - colptr[K];
-                parallel += c > 0 ? 1 + c * c_back : 0;
-            }
-        } else {
-            for (int L = nlevel - 2; L >= 0; --L) {
-                std::vector<double> load(N, 0.0);
-                int k = 0;
-                for (int K = 0; K < nb; ++K)
-                    if (level[K] == L) {
-                        const int c = colptr[K + 1] - colptr[K];
-                        load[k++ % N] += c > 0 ? 1 + c * c_back : 0;
-                    }
-                parallel += c_bar + *std::max_element(load.begin(), load.end());
-            }
+        for (int L = nlevel - 2; L >= 0; --L) {
+            std::vector<double> load(N, 0.0);
+            int k = 0;
+            for (int K = 0; K < nb; ++K)
+                if (level[K] == L) {
+                    const int c = colptr[K + 1] - colptr[K];
+                    load[k++ % N] += c > 0 ? 1 + c * c_back : 0;
+                }
+            parallel += c_bar + *std::max_element(load.begin(), load.end());
         }
         M->hdr.serial_solve = serial <= parallel ? 1 : 0;
         // two leaves against one root (hip / ankle against the knee), the root's diagonal and right-hand side with

@@ -219,7 +219,7 @@ struct WarpCtx {
     double *Qo, *Qdo, *Qsys, *Qdsys;
     double *S0, *S1, *r0, *r1, *lamv, *dinv, *knl;
     // symbolic factorisation tables (host, capi.cu symbolic_analysis)
-    const int *slot_tab, *slot2_tab, *zero_list, *comb_list, *unit_list, *colptr, *colrow, *lvlptr, *lvlpiv, *owner, *pivmask, *nscale;
+    const int *slot_tab, *slot2_tab, *zero_list, *comb_list, *unit_list, *colptr, *colrow, *lvlptr, *lvlpiv, *owner, *pivmask, *pivwriter, *nscale;
     int N, mj, nb;
     int segi;  // this warp's segment
     int lane;  // this lane's system inside the CTA
@@ -529,7 +529,7 @@ __device__ __forceinline__ void eliminate_pivot(const WarpCtx& w, int K, int& st
     if (fmax(fabs(D[0]), fmax(fabs(D[4]), fabs(D[8]))) < kSmallPivot * (double)__int_as_float(w.nscale[K])) status |= 4;
     const V3 yh = sym3_apply(di, mk(w.r0[(3 * K) * spw] + w.r1[(3 * K) * spw], w.r0[(3 * K + 1) * spw] + w.r1[(3 * K + 1) * spw],
                                     w.r0[(3 * K + 2) * spw] + w.r1[(3 * K + 2) * spw]));
-    if (ALL || w.segi == 0) {
+    if (ALL || w.segi == w.pivwriter[K]) {
 #pragma unroll
         for (int i = 0; i < 6; ++i) w.dinv[(6 * K + i) * spw] = di[i];
         w.lamv[(3 * K) * spw] = yh.x, w.lamv[(3 * K + 1) * spw] = yh.y, w.lamv[(3 * K + 2) * spw] = yh.z;  // y-hat = D^-1 y
@@ -900,26 +900,18 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
 #pragma unroll 1
                 for (int pi = w.lvlptr[lv]; pi < w.lvlptr[lv + 1]; ++pi) {
                     const int K = w.lvlpiv[pi];
-                    if (((w.pivmask[K] >> w.segi) & 1) == 0) continue;  // neither warp 0 nor the owner of a row of column K
+                    if (((w.pivmask[K] >> w.segi) & 1) == 0) continue;  // neither the pivot's writer nor the owner of a row of column K
                     eliminate_pivot<false, S>(w, K, status);
                 }
             }
-            // Back substitution.  Small trees (<= 2 levels): by the first warp, and no barrier before it -- the pivots of
-            // the last level are roots (empty columns), which only the first warp touches, and everything below was
-            // closed by that level's barrier.  Deeper trees: level by level from the roots down, the pivots of a level
-            // spread over the warps (they only read lambda of higher levels), one barrier per level.
-            if (hd->nlevel <= 2) {
-                if (w.segi == 0) {
+            // Back substitution level by level from the roots down, the pivots of a level spread over the warps (they
+            // only read lambda of higher levels); the barrier of a level also closes the y-hat / inverse pivots that the
+            // factorisation stored above it.
 #pragma unroll 1
-                    for (int K = nb - 1; K >= 0; --K) back_substitute<S>(w, K);
-                }
-            } else {
+            for (int lv = hd->nlevel - 2; lv >= 0; --lv) {  // the last level holds roots only: lambda = y-hat already
+                __syncthreads();
 #pragma unroll 1
-                for (int lv = hd->nlevel - 2; lv >= 0; --lv) {  // the last level holds roots only: lambda = y-hat already
-                    __syncthreads();
-#pragma unroll 1
-                    for (int pi = w.lvlptr[lv] + w.segi; pi < w.lvlptr[lv + 1]; pi += w.N) back_substitute<S>(w, w.lvlpiv[pi]);
-                }
+                for (int pi = w.lvlptr[lv] + w.segi; pi < w.lvlptr[lv + 1]; pi += w.N) back_substitute<S>(w, w.lvlpiv[pi]);
             }
         }
         __syncthreads();

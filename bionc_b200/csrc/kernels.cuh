@@ -123,7 +123,8 @@ __device__ __forceinline__ void setup_cta(const unsigned char* __restrict__ blob
     w.lvlpiv = w.lvlptr + h->nlevel + 1;
     w.owner = w.lvlpiv + w.nb;
     w.pivmask = w.owner + w.nb;
-    w.nscale = w.pivmask + w.nb;
+    w.pivwriter = w.pivmask + w.nb;
+    w.nscale = w.pivwriter + w.nb;
 }
 
 __device__ __forceinline__ void load_q12(const double* __restrict__ p, Q12& q) {

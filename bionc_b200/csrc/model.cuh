@@ -38,6 +38,7 @@ struct DevHeader {
     int off_sym;  // byte offset of the symbolic tables (ints): slot_tab[nb*nb] slot2_tab[nb*nb] zero[nzero]
                   // comb[2*ncomb] unit[nunit] colptr[nb+1] colrow[ncol] lvlptr[nlevel+1] lvlpiv[nb]
                   // owner[nb] (warp of block row I) pivmask[nb] (warps taking part in pivot K)
+                  // pivwriter[nb] (warp that stores the inverse pivot and y-hat of pivot K)
                   // nscale[nb] (float bits: nominal diagonal scale of each node)
     int nlevel;   // levels of the elimination tree: pivots of one level are mutually independent
     int tmem_slot;     // scratch word of the shared-memory copy: TMEM base address of the CTA
