@@ -437,9 +437,9 @@ __device__ __forceinline__ void sr_solve3(const SegCtx& c, double (&y)[6][3]) {
 // signed coefficient vector of a LIN3 block restricted to one side: rows are  as (x) e_c
 __device__ __forceinline__ void lin3_coefs(const DevBlk& b, int role, double (&as)[4]) {
     const double* a = b.p + (role == CHILD ? 4 : 0);
-    const double sgn = role == CHILD ? -1.0 : 1.0;
+    const int flip = role == CHILD ? (int)0x80000000 : 0;  // sign flip on the integer pipe: the FP64 pipe is the scarce one
 #pragma unroll
-    for (int t = 0; t < 4; ++t) as[t] = sgn * a[t];
+    for (int t = 0; t < 4; ++t) as[t] = __hiloint2double(__double2hiint(a[t]) ^ flip, __double2loint(a[t]));
 }
 // beta = W as, and its (u, v, w) reduction b3 = E^T beta with E = [e_u, e_rp - e_rd, e_w]
 __device__ __forceinline__ void lin3_beta(const SegCtx& c, const double (&as)[4], double (&beta)[4], double (&b3)[3]) {
