@@ -220,3 +220,74 @@ def test_status_flags_mirror_the_reference_linalg_error():
     for s in good[:2]:
         rq, rqd = om.rk4(Q[s], Qd[s], t, normalize=True)
         assert np.abs(np.concatenate([Qf[s] - rq, Qdf[s] - rqd])).max() < 1e-8
+
+
+def test_pendulum_with_force_1000_steps_full_batch():
+    """Config 2: pendulum_with_force.nmod with the `no_equilibrium` external force, 1e6 hinge states,
+    h = 1/60, 1000 steps, normalize=True.  Every trajectory stays on the hinge (rp pinned, |Phi| at drift level,
+    nothing flagged); a seeded subsample follows the oracle's (reference algorithm) 1000-step trajectory to 1e-8."""
+    from bionc_oracle import OracleModel
+
+    from helpers import fext_list
+
+    case = load_case("pendulum_force_batch")
+    model = _model("pendulum_force_batch")
+    fext = _fext(model, case)
+    Q, Qd = _tiled_states("hinge", model, case, B_FULL, seed=21)
+    h, steps = 1.0 / 60.0, 1000
+    Qf, Qdf, status = model.rk4(Q, Qd, h=h, n_steps=steps, normalize=True, external_forces=fext, return_status=True)
+    assert int(status.count_nonzero().item()) == 0
+    assert bool(torch.isfinite(Qf).all()) and bool(torch.isfinite(Qdf).all())
+    norms = model.constraint_residual_norms(Qf)
+    # unstabilised drift over 16.7 s of simulated time (worst system 3.9e-3; the oracle comparison below shows the
+    # reference algorithm drifts identically): a bound on blow-ups, not an accuracy claim
+    assert float(norms.max().item()) < 2e-2
+    v = Qf.reshape(B_FULL, 1, 4, 3)
+    assert float((v[:, :, 0].norm(dim=-1) - 1).abs().max().item()) < 1e-14
+    om = OracleModel(model_path("pendulum_force_batch"))
+    t = np.arange(steps + 1) * h
+    for s in (0, 12345, 999_999):
+        rq, rqd = om.rk4(Q[s].cpu().numpy(), Qd[s].cpu().numpy(), t, normalize=True, fext=fext_list(case))
+        got = np.concatenate([Qf[s].cpu().numpy(), Qdf[s].cpu().numpy()])
+        ref = np.concatenate([rq, rqd])
+        # t is an arange here and a constant h on the device: the step sizes differ in the last bit
+        assert np.abs(got - ref).max() / max(1.0, np.abs(ref).max()) < 1e-8, s
+
+
+def test_full_body_perturbed_inertia_full_batch():
+    """Config 5: the 10-segment full body with per-system natural inertial parameters (masses x U(0.9,
+    1.1), COM x U(0.95, 1.05), inertias x U(0.9, 1.1)), 1.25e6 systems (the per-GPU share of 1e7 on 8 GPUs), 100
+    steps.  Nothing flagged, unit vectors kept, and a subsample against the oracle rebuilt with that system's
+    parameters (forward dynamics of every sampled system, one full 100-step trajectory)."""
+    from bionc_oracle import OracleModel
+
+    from bionc_b200.utils import states as st
+
+    B = 1_250_000
+    case = load_case("full_body")
+    model = _model("full_body")
+    Q, Qd = _tiled_states("tree", model, case, B, seed=22)
+    pool = 1 << 12
+    mass, com, J = st.perturbed_inertial_parameters(model.table, pool, seed=23)
+    ip_pool = np.concatenate(
+        [mass[..., None], com, np.stack([J[..., 0, 0], J[..., 0, 1], J[..., 0, 2], J[..., 1, 1], J[..., 1, 2], J[..., 2, 2]], axis=-1)], axis=-1)
+    reps = (B + pool - 1) // pool
+    ip = torch.from_numpy(ip_pool).cuda().repeat(reps, 1, 1)[:B].contiguous()
+    h, steps = 0.001, 100
+    Qf, Qdf, status = model.rk4(Q, Qd, h=h, n_steps=steps, normalize=True, inertial_parameters=ip, return_status=True)
+    assert int(status.count_nonzero().item()) == 0
+    v = Qf.reshape(B, model.nb_segments, 4, 3)
+    assert float((v[:, :, 0].norm(dim=-1) - 1).abs().max().item()) < 1e-14
+    assert float(model.constraint_residual_norms(Qf).max().item()) < 1e-6
+    qdd, lam = model.forward_dynamics(Q[:pool], Qd[:pool], inertial_parameters=ip[:pool])
+    for s in (0, 7, 4095):
+        om = OracleModel(model_path("full_body"), seg_mass=mass[s], seg_com=com[s], seg_J=J[s])
+        rq, rl = om.forward_dynamics(Q[s].cpu().numpy(), Qd[s].cpu().numpy())
+        assert np.abs(qdd[s].cpu().numpy() - rq).max() / max(1.0, np.abs(rq).max()) < 1e-10
+        assert np.abs(lam[s].cpu().numpy() - rl).max() / max(1.0, np.abs(rl).max()) < 1e-10
+    s = 4095 + pool  # a tiled copy: same state and parameters as system 4095
+    om = OracleModel(model_path("full_body"), seg_mass=mass[4095], seg_com=com[4095], seg_J=J[4095])
+    rq, rqd = om.rk4(Q[s].cpu().numpy(), Qd[s].cpu().numpy(), np.arange(steps + 1) * h, normalize=True)
+    got = np.concatenate([Qf[s].cpu().numpy(), Qdf[s].cpu().numpy()])
+    ref = np.concatenate([rq, rqd])
+    assert np.abs(got - ref).max() / max(1.0, np.abs(ref).max()) < 1e-8
