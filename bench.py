@@ -45,6 +45,46 @@ sys.path.insert(0, REPO)
 MODEL = os.path.join(REPO, "tests", "golden", "models", "lower_limb.npz")
 WORKLOAD = "lower_limb_4seg (BASELINE.json configs[2]; PELVIS free + 3 spherical joints, n=48, m=33)"
 H = 0.01
+# The default workload is the one BASELINE.json's metric is quoted on (the 4-segment lower limb).  `--workload`
+# runs the other BASELINE configurations through the same measurement (SURVEY 8(d) definitions); they are not
+# bench lines of the driver, which calls bench.py without that flag.
+WORKLOADS = {
+    "lower_limb": dict(model="lower_limb", states="tree", h=0.01, fext=False, inertia=False, desc=WORKLOAD),
+    "pendulum_force": dict(model="pendulum_force_batch", states="hinge", h=1.0 / 60.0, fext=True, inertia=False,
+                           desc="pendulum_with_force.nmod + no_equilibrium force (BASELINE.json configs[1]; ground hinge, n=12, m=11)"),
+    "knee": dict(model="knee_feikes", states="knee", h=5e-5, fext=False, inertia=False,
+                 desc="knee_feikes parallel mechanism (BASELINE.json configs[3]; closed loops, n=24, m=20)"),
+    "full_body": dict(model="full_body", states="tree", h=0.001, fext=False, inertia=True,
+                      desc="synthetic full body, per-system inertial parameters (BASELINE.json configs[4]; 10 segments, n=120, m=87)"),
+}
+
+
+def workload_paths(name):
+    w = WORKLOADS[name]
+    return (os.path.join(REPO, "tests", "golden", "models", w["model"] + ".npz"),
+            os.path.join(REPO, "tests", "golden", "cases", w["model"] + ".npz"))
+
+
+def workload_states(name, table, count, seed):
+    """Seeded consistent initial states of a workload (numpy, SURVEY 8(d) generators)."""
+    from bionc_b200.utils import states as st
+
+    kind = WORKLOADS[name]["states"]
+    if kind == "tree":
+        return st.tree_states(table, count, seed=seed)
+    if kind == "hinge":
+        return st.hinge_pendulum_states(count, seed=seed)
+    with np.load(workload_paths(name)[1]) as z:  # knee: rigid motions of the reference's own initial state
+        q0 = np.array(z["Q"][0])
+    return st.rigidly_moved_states(q0, count, seed=seed, angle_max=0.3, omega_sigma=0.0)
+
+
+def workload_fext(name):
+    """(segment, kind, param) arrays of the workload's external forces (from the golden case), or None."""
+    if not WORKLOADS[name]["fext"]:
+        return None
+    with np.load(workload_paths(name)[1]) as z:
+        return np.array(z["fext_seg"]), np.array(z["fext_kind"]), np.array(z["fext_param"])
 # DRAM traffic of ONE launch of the dominant kernel at the default configuration, from the committed
 # `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum): 0.79 GB read (the 768 MB of
 # state, once) + 8.9 GB written (768 MB of state + register spills evicted from L2: the kernel runs at 128
@@ -60,7 +100,7 @@ UNIT = "system-steps/s"
 # ----------------------------------------------------------------------------- CPU side (oracle port)
 def _cpu_worker(args):
     """One host core: integrate `nsys` systems for `nsteps` RK4 steps with the oracle port."""
-    seed, nsys, nsteps = args
+    seed, nsys, nsteps, workload = args
     os.environ["OMP_NUM_THREADS"] = "1"
     sys.path.insert(0, os.path.join(REPO, "oracle"))
     from bionc_oracle import OracleModel  # noqa: E402  (the CPU baseline leg is allowed to run the oracle)
@@ -68,23 +108,31 @@ def _cpu_worker(args):
     from bionc_b200.bionc_cuda.model_table import ModelTable
     from bionc_b200.utils import states as st
 
-    table = ModelTable.load(MODEL)
-    om = OracleModel(MODEL)
-    Q, Qd = st.tree_states(table, nsys, seed=seed)
-    t = np.arange(nsteps + 1) * H
+    model_file = workload_paths(workload)[0]
+    table = ModelTable.load(model_file)
+    om = OracleModel(model_file)
+    Q, Qd = workload_states(workload, table, nsys, seed)
+    fx = workload_fext(workload)
+    fext = None if fx is None else [(int(a), int(b), c) for a, b, c in zip(*fx)]
+    per_system = None
+    if WORKLOADS[workload]["inertia"]:
+        per_system = st.perturbed_inertial_parameters(table, nsys, seed=seed)
+    t = np.arange(nsteps + 1) * WORKLOADS[workload]["h"]
     t0 = time.perf_counter()
     for s in range(nsys):
-        om.rk4(Q[s], Qd[s], t, normalize=True)
+        if per_system is not None:  # like the reference, one model object per parameter set (a few ms, inside the timing)
+            om = OracleModel(model_file, seg_mass=per_system[0][s], seg_com=per_system[1][s], seg_J=per_system[2][s])
+        om.rk4(Q[s], Qd[s], t, normalize=True, fext=fext)
     return time.perf_counter() - t0
 
 
-def cpu_rate(nsys_per_core: int, nsteps: int, cores: int, seed0: int = 1000):
+def cpu_rate(nsys_per_core: int, nsteps: int, cores: int, seed0: int = 1000, workload: str = "lower_limb"):
     """Aggregate system-steps/s of `cores` worker processes, wall clock of the slowest worker."""
     import multiprocessing as mp
 
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
-        times = pool.map(_cpu_worker, [(seed0 + c, nsys_per_core, nsteps) for c in range(cores)])
+        times = pool.map(_cpu_worker, [(seed0 + c, nsys_per_core, nsteps, workload) for c in range(cores)])
     wall = max(times)  # integration time of the slowest worker (process start-up and imports excluded)
     return cores * nsys_per_core * nsteps / wall, wall
 
@@ -105,17 +153,17 @@ def run_reference_arm(args):
     cores = host_cores()
     nsys, nsteps = 4, 100  # ~1 s per core per bench step at a few hundred system-steps/s/core
     for _ in range(args.warmup):
-        cpu_rate(nsys, nsteps, cores)
+        cpu_rate(nsys, nsteps, cores, workload=args.workload)
     wall = 0.0
     for k in range(args.steps):
-        wall += cpu_rate(nsys, nsteps, cores, seed0=2000 + 100 * k)[1]
+        wall += cpu_rate(nsys, nsteps, cores, seed0=2000 + 100 * k, workload=args.workload)[1]
     value = args.steps * cores * nsys * nsteps / wall
     sample = f"{cores} cores x {nsys} systems x {nsteps} RK4 steps per bench step (oracle port, numpy dense KKT LU)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "h": H, "normalize": True},
+        "config": {"workload": WORKLOADS[args.workload]["desc"], "h": WORKLOADS[args.workload]["h"], "normalize": True},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -192,7 +240,9 @@ def run_gpu_arm(args):
     if not distributed and not args.no_cpu_baseline:
         cores = host_cores()
         nsys, nsteps = 8, 1000  # ~10-25 s of CPU work per core at a few hundred system-steps/s/core
-        rate, wall = cpu_rate(nsys, nsteps, cores)
+        if WORKLOADS[args.workload]['model'] == 'full_body':
+            nsys, nsteps = 4, 250  # 2.4 ms per evaluation
+        rate, wall = cpu_rate(nsys, nsteps, cores, workload=args.workload)
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"{cores} cores x {nsys} systems x {nsteps} RK4 steps, same model/h/normalize ({wall:.1f} s wall)"}
 
@@ -212,11 +262,13 @@ def run_gpu_arm(args):
         dist.init_process_group("nccl", device_id=dev)
 
     B, S = args.batch, args.rk4_steps_per_launch
-    model = BiomechanicalModel.load(MODEL, device=dev)
+    wl = WORKLOADS[args.workload]
+    h_step = wl["h"]
+    model = BiomechanicalModel.load(workload_paths(args.workload)[0], device=dev)
     n = model.nb_Q
     # seeded synthetic initial states: a pool of 2^16 consistent states (numpy), tiled to B on the device
     pool = min(B, 1 << 16)
-    Qp, Qdp = st.tree_states(model.table, pool, seed=1 + rank)
+    Qp, Qdp = workload_states(args.workload, model.table, pool, seed=1 + rank)
     reps = (B + pool - 1) // pool
     Q0 = torch.from_numpy(Qp).to(dev).repeat(reps, 1)[:B].contiguous()
     Qd0 = torch.from_numpy(Qdp).to(dev).repeat(reps, 1)[:B].contiguous()
@@ -224,10 +276,27 @@ def run_gpu_arm(args):
     status = torch.zeros(B, dtype=torch.int32, device=dev)
     lib = _lib.load()
     opt = _lib.BioncDynOptions()
+    keep = []
+    fx = workload_fext(args.workload)
+    if fx is not None:
+        seg, kind, par = (np.ascontiguousarray(fx[0], dtype=np.int32), np.ascontiguousarray(fx[1], dtype=np.int32),
+                          np.ascontiguousarray(fx[2], dtype=np.float64))
+        fdesc = _lib.BioncFextDesc(int(seg.size), seg.ctypes.data_as(_lib.c_int32_p), kind.ctypes.data_as(_lib.c_int32_p),
+                                   par.ctypes.data_as(_lib.c_double_p))
+        keep += [seg, kind, par, fdesc]
+        opt.fext = C.pointer(fdesc)
+    ip_pool = None
+    if wl["inertia"]:  # config 5: per-system natural inertial parameters (B, N, 10), resident on the device
+        mass, com, J = st.perturbed_inertial_parameters(model.table, pool, seed=100 + rank)
+        ip_pool = np.ascontiguousarray(np.concatenate(
+            [mass[..., None], com, np.stack([J[..., 0, 0], J[..., 0, 1], J[..., 0, 2], J[..., 1, 1], J[..., 1, 2], J[..., 2, 2]], axis=-1)], axis=-1))
+        ip_dev = torch.from_numpy(ip_pool).to(dev).repeat(reps, 1, 1)[:B].contiguous()
+        keep.append(ip_dev)
+        opt.inertia = ip_dev.data_ptr()
     stream = torch.cuda.current_stream(dev)
 
     def launch():
-        rc = lib.bionc_cuda_rk4(model._h, Q.data_ptr(), Qd.data_ptr(), H, None, S, 1, C.byref(opt), None, 1, None,
+        rc = lib.bionc_cuda_rk4(model._h, Q.data_ptr(), Qd.data_ptr(), h_step, None, S, 1, C.byref(opt), None, 1, None,
                                 status.data_ptr(), B, C.c_void_p(stream.cuda_stream))
         _lib.check(rc, "rk4")
 
@@ -269,8 +338,17 @@ def run_gpu_arm(args):
     Qh0, Qdh0 = Qh.clone(), Qdh.clone()
     sth = torch.zeros(Be, dtype=torch.int32).pin_memory()
 
+    opt_host = _lib.BioncDynOptions()
+    opt_host.fext = opt.fext
+    extra_h2d = 0
+    if ip_pool is not None:  # the host entry point takes the per-system parameters from host memory and uploads them
+        iph = torch.from_numpy(np.ascontiguousarray(ip_pool[:Be] if Be <= pool else np.tile(ip_pool, (reps, 1, 1))[:Be])).pin_memory()
+        keep.append(iph)
+        opt_host.inertia = iph.data_ptr()
+        extra_h2d = int(iph.numel() * 8)
+
     def e2e_call():
-        rc = lib.bionc_cuda_rk4_host(model._h, Qh.data_ptr(), Qdh.data_ptr(), H, None, S, 1, C.byref(opt), sth.data_ptr(), Be)
+        rc = lib.bionc_cuda_rk4_host(model._h, Qh.data_ptr(), Qdh.data_ptr(), h_step, None, S, 1, C.byref(opt_host), sth.data_ptr(), Be)
         _lib.check(rc, "rk4_host")
 
     e2e_call()  # warm-up: allocates the library's device scratch
@@ -307,22 +385,27 @@ def run_gpu_arm(args):
         value = world * B * S * args.steps / (total_ms * 1e-3)
         per_gpu_rate = B * S / (kernel_ms_mean * 1e-3)  # dominant kernel, one launch, one GPU
         fl, by = rf.flops_per_step(model.table), rf.bytes_per_step(model.table)
+        lay = model.kernel_layout()
+        general = fx is not None or any(int(t) != 0 for t in model.table.blk_type)
+        kernel_name = "rk4_kernel<%s, %d threads, %d systems per CTA%s>" % (
+            "general" if general else "lean", 32 * model.nb_segments, lay["systems_per_cta"],
+            ", y0 in tensor memory" if model.nb_segments >= 3 else "")
         achieved_tf = per_gpu_rate * fl / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": WORKLOAD, "systems_per_gpu": B, "rk4_steps_per_launch": S, "h": H, "normalize": True,
+                "workload": wl["desc"], "systems_per_gpu": B, "rk4_steps_per_launch": S, "h": h_step, "normalize": True,
                 "l2": "state per GPU = %.0f MB, larger than the 126 MB L2; every launch re-reads it from HBM" % (B * 2 * n * 8 / 1e6),
                 "parallelism": f"batch sharded over {world} GPU(s), no collective on the step path",
             },
             "roofline": {
                 "bound": "fp64", "achieved": achieved_tf, "peak": sustained.value, "unit": "TFLOP/s",
                 "frac": achieved_tf / sustained.value,
-                "traffic": NCU_TRAFFIC["bytes"] if (B, S) == (NCU_TRAFFIC["systems_per_gpu"], NCU_TRAFFIC["rk4_steps_per_launch"]) else None,
+                "traffic": NCU_TRAFFIC["bytes"] if (args.workload, B, S) == ("lower_limb", NCU_TRAFFIC["systems_per_gpu"], NCU_TRAFFIC["rk4_steps_per_launch"]) else None,
                 "traffic_source": NCU_TRAFFIC["source"], "algorithmic_bytes_per_launch": B * S * by,
-                "kernel": "rk4_kernel<lean, 128 threads, 32 systems per CTA, y0 in tensor memory>", "kernel_ms": kernel_ms_mean,
+                "kernel": kernel_name, "kernel_ms": kernel_ms_mean,
                 "flops_per_system_step": fl, "bytes_per_system_step": by,
                 "peak_source": "DFMA micro-benchmark in this run (bionc_cuda_measure_fp64_peak): sustained %.2f, best launch %.2f TFLOP/s"
                                % (sustained.value, best.value),
@@ -330,7 +413,7 @@ def run_gpu_arm(args):
                         "frac": per_gpu_rate * by / 1e9 / peaks.get("hbm_gbs", 6650.0), "peak_source": peak_src},
             },
             "e2e": {
-                "value": world * Be * S / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(2 * Be * n * 8),
+                "value": world * Be * S / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(2 * Be * n * 8) + extra_h2d,
                 "d2h_bytes_per_step": int(2 * Be * n * 8 + Be * 4), "systems": Be,
                 "api": "bionc_cuda_rk4_host (C ABI, pinned host buffers, H2D + kernel + D2H timed)",
             },
@@ -358,6 +441,8 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather-states", action="store_true")
+    ap.add_argument("--workload", default="lower_limb", choices=sorted(WORKLOADS),
+                    help="default: the configuration BASELINE.json's metric is quoted on; the others are its remaining GPU configs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "cuda":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
