@@ -74,3 +74,63 @@ def test_product_path_fails_loudly_without_cuda():
 
     with pytest.raises(BioncCudaError):
         BiomechanicalModel.load(model_path("lower_limb"))
+
+
+def test_struct_layouts_and_constants_match_the_header(tmp_path):
+    """The ctypes mirrors in _lib.py against the C compiler's view of include/bionc_cuda.h (sizes, field offsets) and
+    the Python-side constants against the header's #defines."""
+    import shutil
+    import subprocess
+
+    from bionc_b200.bionc_cuda import _lib, model_table as mt
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    fields = {
+        "BioncModelDesc": [n for n, _ in _lib.BioncModelDesc._fields_],
+        "BioncFextDesc": [n for n, _ in _lib.BioncFextDesc._fields_],
+        "BioncDynOptions": [n for n, _ in _lib.BioncDynOptions._fields_],
+    }
+    consts = ["BIONC_BLK_LIN3", "BIONC_BLK_DOT", "BIONC_BLK_CLEN", "BIONC_BLK_SOP", "BIONC_BLK_NPARAM", "BIONC_FEXT_NPARAM",
+              "BIONC_FEXT_GLOBAL_ON_PROXIMAL", "BIONC_FEXT_GLOBAL_LOCAL_POINT", "BIONC_FEXT_GLOBAL", "BIONC_FEXT_LOCAL",
+              "BIONC_EVAL_PHI_R", "BIONC_EVAL_K_R", "BIONC_EVAL_PHI_J", "BIONC_EVAL_K_J", "BIONC_EVAL_PHI_H", "BIONC_EVAL_K_H",
+              "BIONC_EVAL_BIAS_H", "BIONC_EVAL_FEXT", "BIONC_EVAL_COM", "BIONC_EVAL_MARKERS", "BIONC_EVAL_KINETIC",
+              "BIONC_EVAL_POTENTIAL", "BIONC_EVAL_RESIDUALS", "BIONC_STATUS_SINGULAR", "BIONC_STATUS_NONFINITE",
+              "BIONC_STATUS_SMALL_PIVOT", "BIONC_STATUS_PIVOTED"]
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "bionc_cuda.h"', "int main(void) {"]
+    for st, names in fields.items():
+        lines.append(f'printf("sizeof {st} %zu\\n", sizeof({st}));')
+        lines += [f'printf("offset {st}.{n} %zu\\n", offsetof({st}, {n}));' for n in names]
+    lines += [f'printf("const {c} %d\\n", (int){c});' for c in consts]
+    lines += ["return 0; }"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(REPO, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    got = {}
+    for ln in out.splitlines():
+        kind, name, val = ln.split()
+        got[(kind, name)] = int(val)
+    for st in fields:
+        cls = getattr(_lib, st)
+        assert got[("sizeof", st)] == ctypes.sizeof(cls), st
+        for n in fields[st]:
+            assert got[("offset", f"{st}.{n}")] == getattr(cls, n).offset, f"{st}.{n}"
+    c = {name: val for (kind, name), val in got.items() if kind == "const"}
+    assert (c["BIONC_BLK_LIN3"], c["BIONC_BLK_DOT"], c["BIONC_BLK_CLEN"], c["BIONC_BLK_SOP"]) == (mt.BLK_LIN3, mt.BLK_DOT, mt.BLK_CLEN, mt.BLK_SOP)
+    assert c["BIONC_BLK_NPARAM"] == mt.BLK_NPARAM and c["BIONC_FEXT_NPARAM"] == mt.FEXT_NPARAM
+    assert (c["BIONC_FEXT_GLOBAL_ON_PROXIMAL"], c["BIONC_FEXT_GLOBAL_LOCAL_POINT"], c["BIONC_FEXT_GLOBAL"], c["BIONC_FEXT_LOCAL"]) == (
+        mt.FEXT_GLOBAL_ON_PROXIMAL, mt.FEXT_GLOBAL_LOCAL_POINT, mt.FEXT_GLOBAL, mt.FEXT_LOCAL)
+    evals = ["PHI_R", "K_R", "PHI_J", "K_J", "PHI_H", "K_H", "BIAS_H", "FEXT", "COM", "MARKERS", "KINETIC", "POTENTIAL", "RESIDUALS"]
+    import importlib
+
+    try:
+        bm_mod = importlib.import_module("bionc_b200.bionc_cuda.biomechanical_model")
+    except Exception:  # torch missing: the constants are plain ints at module level, nothing else to check
+        bm_mod = None
+    if bm_mod is not None:
+        for k, e in enumerate(evals):
+            assert c["BIONC_EVAL_" + e] == k == getattr(bm_mod, "EVAL_" + e)
+    assert (c["BIONC_STATUS_SINGULAR"], c["BIONC_STATUS_NONFINITE"], c["BIONC_STATUS_SMALL_PIVOT"], c["BIONC_STATUS_PIVOTED"]) == (1, 2, 4, 8)
