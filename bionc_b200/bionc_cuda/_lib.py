@@ -75,6 +75,39 @@ class BioncDynOptions(C.Structure):
     ]
 
 
+def model_desc(table, with_markers: bool = True):
+    """``BioncModelDesc`` for a (validated) ModelTable plus the arrays it points into (keep them alive as long as
+    the descriptor is used)."""
+    import numpy as np
+
+    def ptr(a, typ):
+        return a.ctypes.data_as(typ)
+
+    k = dict(
+        phic=np.ascontiguousarray(table.seg_phi_const, dtype=np.float64),
+        mass=np.ascontiguousarray(table.seg_mass, dtype=np.float64),
+        com=np.ascontiguousarray(table.seg_com, dtype=np.float64),
+        J=np.ascontiguousarray(table.seg_J, dtype=np.float64).reshape(-1, 9),
+        rrow=np.ascontiguousarray(table.seg_rigid_row, dtype=np.int32),
+        btype=np.ascontiguousarray(table.blk_type, dtype=np.int32),
+        bpar=np.ascontiguousarray(table.blk_parent, dtype=np.int32),
+        bchi=np.ascontiguousarray(table.blk_child, dtype=np.int32),
+        browh=np.ascontiguousarray(table.blk_row_h, dtype=np.int32),
+        browj=np.ascontiguousarray(table.blk_row_j, dtype=np.int32),
+        bpar_d=np.ascontiguousarray(table.blk_param, dtype=np.float64),
+        mkseg=np.ascontiguousarray(table.marker_segment, dtype=np.int32),
+        mkpos=np.ascontiguousarray(table.marker_position, dtype=np.float64),
+    )
+    desc = BioncModelDesc(
+        table.nb_segments, table.nb_blocks,
+        ptr(k["phic"], c_double_p), ptr(k["mass"], c_double_p), ptr(k["com"], c_double_p), ptr(k["J"], c_double_p),
+        ptr(k["rrow"], c_int32_p), ptr(k["btype"], c_int32_p), ptr(k["bpar"], c_int32_p), ptr(k["bchi"], c_int32_p),
+        ptr(k["browh"], c_int32_p), ptr(k["browj"], c_int32_p), ptr(k["bpar_d"], c_double_p),
+        table.nb_markers if with_markers else 0, ptr(k["mkseg"], c_int32_p), ptr(k["mkpos"], c_double_p),
+    )
+    return desc, k
+
+
 class BioncCudaError(RuntimeError):
     pass
 

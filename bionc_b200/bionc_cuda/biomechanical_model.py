@@ -80,31 +80,7 @@ class BiomechanicalModel:
         if self.device.type != "cuda":
             raise ValueError("bionc_cuda models live on CUDA devices only")
         self._lib = _lib.load()
-        t = self.table
-        self._keep = dict(
-            phic=np.ascontiguousarray(t.seg_phi_const, dtype=np.float64),
-            mass=np.ascontiguousarray(t.seg_mass, dtype=np.float64),
-            com=np.ascontiguousarray(t.seg_com, dtype=np.float64),
-            J=np.ascontiguousarray(t.seg_J, dtype=np.float64).reshape(-1, 9),
-            rrow=np.ascontiguousarray(t.seg_rigid_row, dtype=np.int32),
-            btype=np.ascontiguousarray(t.blk_type, dtype=np.int32),
-            bpar=np.ascontiguousarray(t.blk_parent, dtype=np.int32),
-            bchi=np.ascontiguousarray(t.blk_child, dtype=np.int32),
-            browh=np.ascontiguousarray(t.blk_row_h, dtype=np.int32),
-            browj=np.ascontiguousarray(t.blk_row_j, dtype=np.int32),
-            bpar_d=np.ascontiguousarray(t.blk_param, dtype=np.float64),
-            mkseg=np.ascontiguousarray(t.marker_segment, dtype=np.int32),
-            mkpos=np.ascontiguousarray(t.marker_position, dtype=np.float64),
-        )
-        k = self._keep
-        desc = _lib.BioncModelDesc(
-            t.nb_segments, t.nb_blocks,
-            _ptr(k["phic"], _lib.c_double_p), _ptr(k["mass"], _lib.c_double_p), _ptr(k["com"], _lib.c_double_p),
-            _ptr(k["J"], _lib.c_double_p), _ptr(k["rrow"], _lib.c_int32_p), _ptr(k["btype"], _lib.c_int32_p),
-            _ptr(k["bpar"], _lib.c_int32_p), _ptr(k["bchi"], _lib.c_int32_p), _ptr(k["browh"], _lib.c_int32_p),
-            _ptr(k["browj"], _lib.c_int32_p), _ptr(k["bpar_d"], _lib.c_double_p),
-            t.nb_markers, _ptr(k["mkseg"], _lib.c_int32_p), _ptr(k["mkpos"], _lib.c_double_p),
-        )
+        desc, self._keep = _lib.model_desc(self.table)
         handle = C.c_void_p()
         _lib.check(self._lib.bionc_cuda_model_create(C.byref(desc), self.device.index or 0, C.byref(handle)), "model_create")
         self._h = handle
