@@ -717,7 +717,9 @@ int bionc_cuda_eval(const BioncModel* Mc, int32_t which, const double* in, const
             const long long threads = B * (long long)G;
             long long grid = (threads + 255) / 256;
             if (grid > 148LL * 32) grid = 148LL * 32;
-            reduce_kernel<<<(unsigned)grid, 256, 0, st>>>(M->d_blob, which, N, M->hdr.nblk, G, in, out, B);
+            if (which == BIONC_EVAL_KINETIC) reduce_kernel<10><<<(unsigned)grid, 256, 0, st>>>(M->d_blob, N, M->hdr.nblk, G, in, out, B);
+            else if (which == BIONC_EVAL_POTENTIAL) reduce_kernel<11><<<(unsigned)grid, 256, 0, st>>>(M->d_blob, N, M->hdr.nblk, G, in, out, B);
+            else reduce_kernel<12><<<(unsigned)grid, 256, 0, st>>>(M->d_blob, N, M->hdr.nblk, G, in, out, B);
         }
         g_launches++;
         CUDA_TRY(cudaGetLastError());

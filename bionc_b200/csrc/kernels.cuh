@@ -587,14 +587,44 @@ __device__ __forceinline__ int block_residual(const DevBlk& b, const double* __r
     return 1;
 }
 
+// the same on the two segments held in registers (qp: parent, qc: child)
+__device__ __forceinline__ V3 qlin(const Q12& q, const double* a) {
+    V3 r = mk(0.0, 0.0, 0.0);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) r = axpy(a[t], q.s[t], r);
+    return r;
+}
+__device__ __forceinline__ int block_residual_q(const DevBlk& b, const Q12& qp, const Q12& qc, double (&phi)[3]) {
+    const double* p = b.p;
+    if (b.type == LIN3) {
+        V3 r = mk(p[8], p[9], p[10]) - qlin(qc, p + 4);
+        if (b.parent >= 0) r = r + qlin(qp, p);
+        phi[0] = r.x, phi[1] = r.y, phi[2] = r.z;
+        return 3;
+    }
+    if (b.type == DOT) {
+        const V3 Dc = qlin(qc, p + 4);
+        const V3 Dp = b.parent >= 0 ? qlin(qp, p) : mk(p[0], p[1], p[2]);
+        phi[0] = dot(Dp, Dc) - p[8];
+    } else if (b.type == CLEN) {
+        const V3 d = qlin(qp, p) - qlin(qc, p + 4);
+        phi[0] = dot(d, d) - p[8];
+    } else {
+        const V3 P = qlin(qp, p), A = qlin(qc, p + 4), nn = qlin(qc, p + 8);
+        phi[0] = dot(P - A, nn) - p[12];
+    }
+    return 1;
+}
+
 // A group of G lanes per system (G = segments rounded up to a power of two, so a warp carries 32 / G systems
 // and all its lanes load): lane-in-group = segment (then blocks in strides of G), fixed-order xor-shuffle
 // reduction inside the group, so the sums are reproducible.  A group reads its system's 12N doubles contiguously.
 // which = 10: kinetic energy 1/2 Qdot^T G Qdot (biomechanical_model.py:98-113)            -> (B)
 // which = 11: potential energy sum_i m_i (N_com Q_i)[z] as coded, no g (natural_segment.py:775-789) -> (B)
 // which = 12: norms of the rigid-body and joint residual vectors (time_series_utils.py:6-41) -> (B, 2)
+template <int which>  // one instantiation per quantity: each keeps only the registers it needs
 __global__ void __launch_bounds__(256)
-    reduce_kernel(const unsigned char* __restrict__ blob, int which, int N, int nblk, int G, const double* __restrict__ in,
+    reduce_kernel(const unsigned char* __restrict__ blob, int N, int nblk, int G, const double* __restrict__ in,
                   double* __restrict__ out, long long B) {
     const DevHeader* h = reinterpret_cast<const DevHeader*>(blob);
     const DevSeg* seg = reinterpret_cast<const DevSeg*>(blob + h->off_seg);
@@ -608,13 +638,21 @@ __global__ void __launch_bounds__(256)
         const bool live = sys < B;
         const double* X = in + (size_t)(live ? sys : 0) * n;
         double s0 = 0.0, s1 = 0.0;
+        Q12 q;  // this lane's segment (u, rp, rd, w); zeros on idle lanes
+#pragma unroll
+        for (int t = 0; t < 4; ++t) q.s[t] = mk(0.0, 0.0, 0.0);
+        if (live && gl < N) {
+            if (which == 11) {  // the potential energy only reads the z components
+                const double* x = X + 12 * gl;
+                q.s[0].z = x[2], q.s[1].z = x[5], q.s[2].z = x[8], q.s[3].z = x[11];
+            } else {
+                load_q12(X + 12 * gl, q);  // 16-byte loads: 12 N doubles per system keep the alignment
+            }
+        }
         if (live && gl < N) {
             const int i = gl;
             const DevSeg& sg = seg[i];
-            const V3 u = mk(X[12 * i], X[12 * i + 1], X[12 * i + 2]);
-            const V3 rp = mk(X[12 * i + 3], X[12 * i + 4], X[12 * i + 5]);
-            const V3 rd = mk(X[12 * i + 6], X[12 * i + 7], X[12 * i + 8]);
-            const V3 w = mk(X[12 * i + 9], X[12 * i + 10], X[12 * i + 11]);
+            const V3 u = q.s[0], rp = q.s[1], rd = q.s[2], w = q.s[3];
             if (which == 10) {
                 const double* ip = sg.mcj;
                 const double ms = ip[0], c0 = ip[1], c1 = ip[2], c2 = ip[3];
@@ -633,11 +671,28 @@ __global__ void __launch_bounds__(256)
                 s0 = r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3 + r4 * r4 + r5 * r5;
             }
         }
-        if (which == 12 && live) {
-            for (int b = gl; b < nblk; b += G) {
-                double phi[3];
-                const int rows = block_residual(blk[b], X, phi);
-                for (int q = 0; q < rows; ++q) s1 = fma(phi[q], phi[q], s1);
+        if (which == 12) {
+            // joint residuals: lane gl of the group takes blocks gl, gl + G, ...; the two segments of a block come from
+            // the registers of the lanes that loaded them (shuffles inside the group), not from memory again
+            const int lane0 = (threadIdx.x & 31) & ~(G - 1);
+            for (int b0 = 0; b0 < nblk; b0 += G) {
+                const int b = b0 + gl;
+                const bool has = live && b < nblk;
+                const DevBlk& bk = blk[has ? b : 0];
+                const int sp = bk.parent >= 0 ? bk.parent : 0, sc = bk.child;
+                Q12 qp, qc;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    qp.s[t] = mk(__shfl_sync(0xffffffffu, q.s[t].x, lane0 + sp), __shfl_sync(0xffffffffu, q.s[t].y, lane0 + sp),
+                                 __shfl_sync(0xffffffffu, q.s[t].z, lane0 + sp));
+                    qc.s[t] = mk(__shfl_sync(0xffffffffu, q.s[t].x, lane0 + sc), __shfl_sync(0xffffffffu, q.s[t].y, lane0 + sc),
+                                 __shfl_sync(0xffffffffu, q.s[t].z, lane0 + sc));
+                }
+                if (has) {
+                    double phi[3];
+                    const int rows = block_residual_q(bk, qp, qc, phi);
+                    for (int e = 0; e < rows; ++e) s1 = fma(phi[e], phi[e], s1);
+                }
             }
         }
         for (int off = G >> 1; off > 0; off >>= 1) {
