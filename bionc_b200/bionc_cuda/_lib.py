@@ -17,6 +17,7 @@ SYMBOLS = (
     "bionc_cuda_model_destroy",
     "bionc_cuda_model_counts",
     "bionc_cuda_model_layout",
+    "bionc_cuda_model_joint_rows",
     "bionc_cuda_forward_dynamics",
     "bionc_cuda_dense_workspace_bytes",
     "bionc_cuda_forward_dynamics_dense",
@@ -62,6 +63,8 @@ class BioncFextDesc(C.Structure):
         ("segment", c_int32_p),
         ("kind", c_int32_p),
         ("param", c_double_p),
+        ("values", C.c_void_p),  # optional per-system (torque, force): (values_steps, B, F, 6)
+        ("values_steps", C.c_int64),
     ]
 
 
@@ -132,6 +135,7 @@ def load():
     lib.bionc_cuda_model_destroy.argtypes = [vp]
     lib.bionc_cuda_model_counts.argtypes = [vp, c_int32_p, c_int32_p, c_int32_p]
     lib.bionc_cuda_model_layout.argtypes = [vp, c_int32_p]
+    lib.bionc_cuda_model_joint_rows.argtypes = [vp, c_int32_p]
     lib.bionc_cuda_forward_dynamics.argtypes = [vp, vp, vp, optp, vp, vp, vp, i64, vp]
     lib.bionc_cuda_dense_workspace_bytes.argtypes = [vp, i64]
     lib.bionc_cuda_dense_workspace_bytes.restype = C.c_size_t

@@ -179,7 +179,11 @@ class BiomechanicalModel:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _options(self, external_forces=None, stabilization=None, inertia=None, B=None):
+    def _options(self, external_forces=None, stabilization=None, inertia=None, B=None, force_values=None, host=False):
+        """``BioncDynOptions`` of one call plus the objects it points into.  ``force_values``: optional per-system
+        (torque, force) values ``(B, F, 6)`` -- or ``(steps, B, F, 6)`` for ``rk4`` -- replacing the values stored in
+        ``external_forces`` (forces in the order ``ExternalForceSet.to_arrays`` lists them: by segment, then insertion);
+        ``host``: the call goes to a ``_host`` entry point (values stay on the host)."""
         keep = []
         opt = _lib.BioncDynOptions()
         opt.use_stabilization = 0
@@ -196,8 +200,29 @@ class BiomechanicalModel:
             seg, kind, par = external_forces.to_arrays()
             if seg.size:
                 fx = _lib.BioncFextDesc(int(seg.size), _ptr(seg, _lib.c_int32_p), _ptr(kind, _lib.c_int32_p), _ptr(par, _lib.c_double_p))
+                if force_values is not None:
+                    F = int(seg.size)
+                    if host:
+                        fv = np.ascontiguousarray(force_values, dtype=np.float64)
+                    else:
+                        fv = force_values if isinstance(force_values, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(force_values, dtype=np.float64))
+                        fv = fv.to(device=self.device, dtype=torch.float64).contiguous()
+                    shape = tuple(fv.shape)
+                    if shape == (B, F, 6):
+                        steps = 1
+                    elif len(shape) == 4 and shape[1:] == (B, F, 6) and shape[0] >= 1:
+                        steps = int(shape[0])
+                    else:
+                        raise ValueError(f"external force values must have shape ({B}, {F}, 6) or (steps, {B}, {F}, 6); got {shape}")
+                    fx.values = fv.ctypes.data if host else fv.data_ptr()
+                    fx.values_steps = steps
+                    keep.append(fv)
                 keep += [seg, kind, par, fx]
                 opt.fext = C.pointer(fx)
+            elif force_values is not None:
+                raise ValueError("external force values given for an empty force set")
+        elif force_values is not None:
+            raise ValueError("external_force_values needs external_forces (the list of application points)")
         if inertia is not None:
             it = inertia if isinstance(inertia, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(inertia, dtype=np.float64))
             it = it.to(device=self.device, dtype=torch.float64).contiguous()
@@ -344,10 +369,13 @@ class BiomechanicalModel:
         inertial_parameters=None,
         return_status: bool = False,
         pivoting: str = "auto",
+        external_force_values=None,
     ):
         """biomechanical_model.py:351-429, batched.  ``joint_generalized_forces`` is accepted and ignored
         exactly like the reference (:391-413).  ``inertial_parameters`` (B, N, 10) optionally overrides
-        the natural inertial parameters per system.  Returns ``(Qddot, lambdas)``; a single system whose
+        the natural inertial parameters per system; ``external_force_values`` (B, F, 6) gives every system its own
+        (torque, force) for the forces of ``external_forces`` (the reference builds one ``ExternalForceSet`` per call,
+        external_force.py:143-180).  Returns ``(Qddot, lambdas)``; a single system whose
         matrix is singular raises ``numpy.linalg.LinAlgError`` like the reference's solve.
 
         ``pivoting``: ``"auto"`` (default) re-solves the systems the fast block-elimination kernel flags
@@ -365,7 +393,7 @@ class BiomechanicalModel:
         qdd = torch.empty_like(q.t)
         lam = torch.empty((B, self.nb_holonomic_constraints), dtype=torch.float64, device=self.device)
         status = torch.empty((B,), dtype=torch.int32, device=self.device)
-        opt, keep = self._options(external_forces, stabilization, inertial_parameters, B)
+        opt, keep = self._options(external_forces, stabilization, inertial_parameters, B, external_force_values)
         with torch.cuda.device(self.device):
             if B > 0 and pivoting != "always":
                 rc = self._lib.bionc_cuda_forward_dynamics(
@@ -406,6 +434,7 @@ class BiomechanicalModel:
         return_status: bool = False,
         inplace: bool = False,
         pivoting: str = "never",
+        external_force_values=None,
     ):
         """Fused integrator: ``utils/ode_solver.py:8-53`` with the closure of ``:107-116`` inside the kernel.
 
@@ -446,7 +475,7 @@ class BiomechanicalModel:
             traj = torch.empty((n_steps // save_every, B, 2 * self.nb_Q), dtype=torch.float64, device=self.device)
         lam = torch.empty((B, self.nb_holonomic_constraints), dtype=torch.float64, device=self.device) if return_lambdas else None
         status = torch.empty((B,), dtype=torch.int32, device=self.device)
-        opt, keep = self._options(external_forces, stabilization, inertial_parameters, B)
+        opt, keep = self._options(external_forces, stabilization, inertial_parameters, B, external_force_values)
         with torch.cuda.device(self.device):
             if B > 0 and n_steps > 0:
                 rc = self._lib.bionc_cuda_rk4(
@@ -460,7 +489,8 @@ class BiomechanicalModel:
                     if sel.numel() > 0:
                         steps = hs if hs is not None else np.full(int(n_steps), float(h))
                         self._rk4_stagewise_pivoted(sel, start, steps, normalize, external_forces, stabilization,
-                                                    inertial_parameters, q.t, qd.t, traj, save_every, lam, status)
+                                                    inertial_parameters, q.t, qd.t, traj, save_every, lam, status,
+                                                    external_force_values)
             else:
                 status.zero_()
         res = [q.out(q.t), q.out(qd.t)]
@@ -473,7 +503,7 @@ class BiomechanicalModel:
         return tuple(res)
 
     def _rk4_stagewise_pivoted(self, sel, start, steps, normalize, external_forces, stabilization, inertial_parameters,
-                               Qout, Qdout, traj, save_every, lam, status):
+                               Qout, Qdout, traj, save_every, lam, status, force_values=None):
         """Classic RK4 (utils/ode_solver.py:8-53) on the systems ``sel``, one dense pivoted-LU launch per stage."""
         yq, yv = start[0][sel].clone(), start[1][sel].clone()
         ip = None
@@ -481,16 +511,26 @@ class BiomechanicalModel:
             it = inertial_parameters if isinstance(inertial_parameters, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(inertial_parameters, dtype=np.float64))
             ip = it.to(self.device)[sel].contiguous()
         bits = torch.zeros((sel.numel(),), dtype=torch.int32, device=self.device)
+        fv = None
+        if force_values is not None:
+            fv = force_values if isinstance(force_values, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(force_values, dtype=np.float64))
+            fv = fv.to(self.device)
+            fv = fv[None] if fv.dim() == 3 else fv
+            fv = fv[:, sel].contiguous()
+        step_now = [0]
 
         def f(qq, vv):
+            fvs = None if fv is None else fv[min(step_now[0], fv.shape[0] - 1)]
             a, l, s = self.forward_dynamics(qq, vv, external_forces=external_forces, stabilization=stabilization,
-                                            inertial_parameters=ip, return_status=True, pivoting="always")
+                                            inertial_parameters=ip, return_status=True, pivoting="always",
+                                            external_force_values=fvs)
             bits.bitwise_or_(s & 3)
             return a, l
 
         n_steps = len(steps)
         for step in range(n_steps):
             h = float(steps[step])
+            step_now[0] = step
             a1, lam1 = f(yq, yv)
             v2 = yv + 0.5 * h * a1
             a2, _ = f(yq + 0.5 * h * yv, v2)
@@ -514,14 +554,15 @@ class BiomechanicalModel:
 
     # ------------------------------------------------------------------ host-buffer path (C ABI with host pointers)
     def rk4_host(self, Q: np.ndarray, Qdot: np.ndarray, h: float, n_steps: int, normalize: bool = True,
-                 external_forces=None, stabilization: dict = None, status: np.ndarray | None = None):
+                 external_forces=None, stabilization: dict = None, status: np.ndarray | None = None,
+                 external_force_values=None):
         """End-to-end call through ``bionc_cuda_rk4_host``: ``Q``/``Qdot`` are HOST arrays (B, n), float64,
         C-contiguous (pinned for full copy bandwidth), advanced in place; the library does H2D, the fused
         kernel and D2H and returns when the results are on the host."""
         for a in (Q, Qdot):
             if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.ndim == 2 and a.shape[1] == self.nb_Q):
                 raise ValueError("rk4_host needs C-contiguous float64 host arrays of shape (B, 12N)")
-        opt, keep = self._options(external_forces, stabilization)
+        opt, keep = self._options(external_forces, stabilization, B=int(Q.shape[0]), force_values=external_force_values, host=True)
         _lib.check(
             self._lib.bionc_cuda_rk4_host(
                 self._h, Q.ctypes.data, Qdot.ctypes.data, float(h), None, int(n_steps), 1 if normalize else 0, C.byref(opt),
@@ -531,7 +572,8 @@ class BiomechanicalModel:
         )
         return Q, Qdot
 
-    def forward_dynamics_host(self, Q: np.ndarray, Qdot: np.ndarray, external_forces=None, stabilization: dict = None):
+    def forward_dynamics_host(self, Q: np.ndarray, Qdot: np.ndarray, external_forces=None, stabilization: dict = None,
+                              external_force_values=None):
         """End-to-end call through ``bionc_cuda_forward_dynamics_host`` with host arrays (B, n)."""
         Q = np.ascontiguousarray(Q, dtype=np.float64)
         Qdot = np.ascontiguousarray(Qdot, dtype=np.float64)
@@ -539,7 +581,7 @@ class BiomechanicalModel:
         qdd = np.empty_like(Q)
         lam = np.empty((B, self.nb_holonomic_constraints))
         status = np.empty((B,), dtype=np.int32)
-        opt, keep = self._options(external_forces, stabilization)
+        opt, keep = self._options(external_forces, stabilization, B=B, force_values=external_force_values, host=True)
         _lib.check(
             self._lib.bionc_cuda_forward_dynamics_host(
                 self._h, Q.ctypes.data, Qdot.ctypes.data, C.byref(opt), qdd.ctypes.data, lam.ctypes.data, status.ctypes.data, B

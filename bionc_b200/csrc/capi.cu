@@ -69,6 +69,14 @@ bool invert4(const double M[4][4], double W[4][4]) {
 
 }  // namespace
 
+// Launch geometry of the dynamics kernels for one model and one size of the per-call force table
+struct LaunchPlan {
+    int spw = 0;        // systems per CTA (32 or 16)
+    size_t smem = 0;    // dynamic shared memory per CTA
+};
+
+// Immutable after bionc_cuda_model_create: the device entry points only read it (re-entrant, any stream, any host
+// thread).  The scratch of the host-buffer entry points is the one mutable part; it is guarded by host_mu.
 struct BioncModel {
     int device = 0;
     DevHeader hdr{};
@@ -78,19 +86,22 @@ struct BioncModel {
     std::vector<int> sym;  // symbolic factorisation tables (see DevHeader::off_sym)
     int nb_markers = 0;
     DevMarker* d_markers = nullptr;  // marker table (device), outside the blob: the dynamics kernels never see it
-    // device blob for the current external-force set (rebuilt when the set changes)
-    std::vector<unsigned char> fext_key;
+    // device copy of the table: uploaded once, by the first call that needs the device (std::call_once), so that a
+    // model can be compiled -- and its layout inspected -- on a machine without a GPU
+    std::once_flag device_once;
+    int device_rc = BIONC_OK;
+    std::string device_err;
     unsigned char* d_blob = nullptr;
     int blob_bytes = 0;
-    bool blob_valid = false;
-    size_t smem_bytes = 0;
-    std::mutex mu;
+    int dev_smem_optin = 0, sm_smem = 0;
+    LaunchPlan plan0;  // without external forces
     // host-path scratch
+    std::mutex host_mu;
     cudaStream_t stream = nullptr;
     cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};  // chunk pipeline of the host-buffer entry points
-    double *d_Q = nullptr, *d_Qd = nullptr, *d_Qdd = nullptr, *d_lam = nullptr, *d_inertia = nullptr, *d_h = nullptr;
+    double *d_Q = nullptr, *d_Qd = nullptr, *d_Qdd = nullptr, *d_lam = nullptr, *d_inertia = nullptr, *d_h = nullptr, *d_fvals = nullptr;
     int* d_status = nullptr;
-    long long cap_B = 0, cap_h = 0;
+    long long cap_B = 0, cap_h = 0, cap_fvals = 0;
 };
 
 namespace {
@@ -298,102 +309,142 @@ int symbolic_analysis(BioncModel* M, int N) {
 }
 
 
-int build_blob(BioncModel* M, const BioncFextDesc* fx) {
-    // key = raw bytes of the force description
-    std::vector<unsigned char> key;
-    std::vector<DevFext> fext;
-    const int N = M->hdr.N;
-    if (fx != nullptr && fx->nb_forces > 0) {
-        for (int i = 0; i < fx->nb_forces; ++i) {
-            if (fx->segment[i] < 0 || fx->segment[i] >= N) return fail(BIONC_E_INVALID, "external force on a segment that does not exist");
-            if (fx->kind[i] < 0 || fx->kind[i] > 3) return fail(BIONC_E_INVALID, "unknown external force kind");
-        }
-        key.resize(sizeof(int) + fx->nb_forces * (2 * sizeof(int) + kFextNParam * sizeof(double)));
-        unsigned char* k = key.data();
-        std::memcpy(k, &fx->nb_forces, sizeof(int)), k += sizeof(int);
-        std::memcpy(k, fx->segment, fx->nb_forces * sizeof(int)), k += fx->nb_forces * sizeof(int);
-        std::memcpy(k, fx->kind, fx->nb_forces * sizeof(int)), k += fx->nb_forces * sizeof(int);
-        std::memcpy(k, fx->param, fx->nb_forces * kFextNParam * sizeof(double));
+// RAII: the calling thread's current device is switched to the model's for the duration of an entry point
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
     }
-    if (M->blob_valid && key == M->fext_key) return BIONC_OK;
-
-    std::vector<DevSeg> seg = M->seg;
-    for (int s = 0; s < N; ++s) {  // forces grouped by segment, insertion order kept inside a segment
-        seg[s].fext_begin = (int)fext.size();
-        if (fx != nullptr)
-            for (int i = 0; i < fx->nb_forces; ++i)
-                if (fx->segment[i] == s) {
-                    DevFext f{};
-                    std::memcpy(f.p, fx->param + (size_t)i * kFextNParam, kFextNParam * sizeof(double));
-                    f.segment = s, f.kind = fx->kind[i];
-                    fext.push_back(f);
-                }
-        seg[s].fext_end = (int)fext.size();
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
     }
-    DevHeader h = M->hdr;
-    h.nfext = (int)fext.size();
-    h.off_seg = align16(sizeof(DevHeader));
-    h.off_blk = align16(h.off_seg + (int)(seg.size() * sizeof(DevSeg)));
-    h.off_side = align16(h.off_blk + (int)(M->blk.size() * sizeof(DevBlk)));
-    h.off_fext = align16(h.off_side + (int)(M->side.size() * sizeof(DevSide)));
-    h.off_sym = align16(h.off_fext + (int)(fext.size() * sizeof(DevFext)));
-    h.blob_bytes = align16(h.off_sym + (int)(M->sym.size() * sizeof(int)));
-    std::vector<unsigned char> blob(h.blob_bytes, 0);
-    std::memcpy(blob.data(), &h, sizeof(h));
-    std::memcpy(blob.data() + h.off_seg, seg.data(), seg.size() * sizeof(DevSeg));
-    if (!M->blk.empty()) std::memcpy(blob.data() + h.off_blk, M->blk.data(), M->blk.size() * sizeof(DevBlk));
-    if (!M->side.empty()) std::memcpy(blob.data() + h.off_side, M->side.data(), M->side.size() * sizeof(DevSide));
-    if (!fext.empty()) std::memcpy(blob.data() + h.off_fext, fext.data(), fext.size() * sizeof(DevFext));
-    if (!M->sym.empty()) std::memcpy(blob.data() + h.off_sym, M->sym.data(), M->sym.size() * sizeof(int));
+};
+#define BIONC_ON_DEVICE(M)                                                                      \
+    DeviceGuard guard__((M)->device);                                                           \
+    if (!guard__.ok) return fail(BIONC_E_CUDA, "cudaSetDevice failed for the model's device");  \
+    {                                                                                           \
+        const int rc__ = ensure_device(M);                                                      \
+        if (rc__ != BIONC_OK) return rc__;                                                      \
+    }
 
-    // shared-memory budget of one CTA (32 systems, one warp per segment)
-    int dev_smem = 0;
-    CUDA_TRY(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, M->device));
-    // Systems per CTA: 32 (every lane busy) or 16 (upper half-warps idle).  Pick what keeps more systems
-    // resident per SM: large per-system working sets (many joint rows) can fit three 16-system CTAs where
-    // only one 32-system CTA fits.
-    int sm_smem = 0;
-    CUDA_TRY(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, M->device));
-    size_t cta_bytes = 0;
-    int best_spc = 0, best_resident = 0;
+// Systems per CTA and shared memory for a force table of `ftab_bytes` bytes behind the blob: 32 systems (every lane
+// busy) or 16 (upper half-warps mirror), whichever keeps more systems resident per SM.
+int make_plan(const BioncModel* M, int ftab_bytes, LaunchPlan& plan) {
+    const DevHeader& h = M->hdr;
+    int best_resident = 0;
+    plan = LaunchPlan{};
     for (int spc = 32; spc >= 16; spc >>= 1) {
-        const size_t bytes = h.blob_bytes + (size_t)cta_smem_doubles(spc, h.N, h.nb, h.nslot, h.nslot2, h.rnl) * sizeof(double);
-        if (bytes > (size_t)dev_smem) continue;
-        int ctas = (int)((size_t)sm_smem / (bytes + 1024));  // 1 KB per CTA is reserved by the driver
+        const size_t bytes = (size_t)h.blob_bytes + ftab_bytes + (size_t)cta_smem_doubles(spc, h.N, h.nb, h.nslot, h.nslot2, h.rnl) * sizeof(double);
+        if (bytes > (size_t)M->dev_smem_optin) continue;
+        int ctas = (int)((size_t)M->sm_smem / (bytes + 1024));  // 1 KB per CTA is reserved by the driver
         const int by_threads = 2048 / (32 * h.N);
         if (ctas > by_threads) ctas = by_threads;
         if (ctas > 32) ctas = 32;
-        if (ctas * spc > best_resident) best_resident = ctas * spc, best_spc = spc, cta_bytes = bytes;
+        if (ctas * spc > best_resident) best_resident = ctas * spc, plan.spw = spc, plan.smem = bytes;
     }
-    if (best_spc == 0) return fail(BIONC_E_TOO_LARGE, "model needs more shared memory per CTA than one SM has");
-    h.spw = best_spc;
-
-    CUDA_TRY(cudaSetDevice(M->device));
-    if (M->d_blob != nullptr && M->blob_bytes < h.blob_bytes) {
-        CUDA_TRY(cudaFree(M->d_blob));
-        M->d_blob = nullptr;
-    }
-    if (M->d_blob == nullptr) CUDA_TRY(cudaMalloc(&M->d_blob, h.blob_bytes));
-    // synchronous copy: the blob is a few KB and changes only when the force set changes
-    CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaMemcpy(M->d_blob, blob.data(), h.blob_bytes, cudaMemcpyHostToDevice));
-    M->blob_bytes = h.blob_bytes;
-    M->hdr = h;
-    M->smem_bytes = cta_bytes;
-    M->fext_key.swap(key);
-    M->blob_valid = true;
+    if (plan.spw == 0) return fail(BIONC_E_TOO_LARGE, "model needs more shared memory per CTA than one SM has");
     return BIONC_OK;
 }
 
-// kernel instantiations by CTA-size class (threads = 32 x segments) and path (lean / general)
+// The model blob: built and uploaded once (ensure_device).
+int build_blob(BioncModel* M) {
+    DevHeader h = M->hdr;
+    h.off_seg = align16(sizeof(DevHeader));
+    h.off_blk = align16(h.off_seg + (int)(M->seg.size() * sizeof(DevSeg)));
+    h.off_side = align16(h.off_blk + (int)(M->blk.size() * sizeof(DevBlk)));
+    h.off_sym = align16(h.off_side + (int)(M->side.size() * sizeof(DevSide)));
+    h.blob_bytes = align16(h.off_sym + (int)(M->sym.size() * sizeof(int)));
+    CUDA_TRY(cudaDeviceGetAttribute(&M->dev_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, M->device));
+    CUDA_TRY(cudaDeviceGetAttribute(&M->sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, M->device));
+    M->hdr = h;
+    int rc = make_plan(M, 0, M->plan0);
+    if (rc != BIONC_OK) return rc;
+    h.spw = M->plan0.spw;
+    M->hdr = h;
+    std::vector<unsigned char> blob(h.blob_bytes, 0);
+    std::memcpy(blob.data(), &h, sizeof(h));
+    std::memcpy(blob.data() + h.off_seg, M->seg.data(), M->seg.size() * sizeof(DevSeg));
+    if (!M->blk.empty()) std::memcpy(blob.data() + h.off_blk, M->blk.data(), M->blk.size() * sizeof(DevBlk));
+    if (!M->side.empty()) std::memcpy(blob.data() + h.off_side, M->side.data(), M->side.size() * sizeof(DevSide));
+    if (!M->sym.empty()) std::memcpy(blob.data() + h.off_sym, M->sym.data(), M->sym.size() * sizeof(int));
+    CUDA_TRY(cudaMalloc(&M->d_blob, h.blob_bytes));
+    CUDA_TRY(cudaMemcpy(M->d_blob, blob.data(), h.blob_bytes, cudaMemcpyHostToDevice));
+    M->blob_bytes = h.blob_bytes;
+    return BIONC_OK;
+}
+
+// First use of the device by this model.  Thread-safe; every later call only reads what this leaves behind.
+int ensure_device(const BioncModel* Mc) {
+    BioncModel* M = const_cast<BioncModel*>(Mc);
+    std::call_once(M->device_once, [M]() {
+        M->device_rc = build_blob(M);
+        if (M->device_rc != BIONC_OK) M->device_err = g_last_error;
+    });
+    if (M->device_rc != BIONC_OK) return fail(M->device_rc, M->device_err);
+    return BIONC_OK;
+}
+
+// External forces of one call: the table (a few hundred bytes) is built on the host, uploaded into a stream-ordered
+// allocation on the caller's stream and freed on that stream after the launch; nothing of it is kept in the model.
+struct FextCall {
+    FextArgs args{};
+    void* d_tab = nullptr;
+    cudaStream_t st = nullptr;
+    int upload(const BioncModel* M, const BioncFextDesc* fx, cudaStream_t stream) {
+        st = stream;
+        args = FextArgs{};
+        if (fx == nullptr || fx->nb_forces <= 0) return BIONC_OK;
+        const int N = M->hdr.N, nf = fx->nb_forces;
+        if (fx->segment == nullptr || fx->kind == nullptr || fx->param == nullptr) return fail(BIONC_E_INVALID, "external force arrays missing");
+        for (int i = 0; i < nf; ++i) {
+            if (fx->segment[i] < 0 || fx->segment[i] >= N) return fail(BIONC_E_INVALID, "external force on a segment that does not exist");
+            if (fx->kind[i] < 0 || fx->kind[i] > 3) return fail(BIONC_E_INVALID, "unknown external force kind");
+        }
+        const int bytes = align16((int)(sizeof(DevFextTab) + (size_t)nf * sizeof(DevFext)));
+        std::vector<unsigned char> host(bytes, 0);
+        DevFextTab* tab = reinterpret_cast<DevFextTab*>(host.data());
+        DevFext* f = reinterpret_cast<DevFext*>(host.data() + sizeof(DevFextTab));
+        tab->nf = nf;
+        int k = 0;
+        for (int s = 0; s < N; ++s) {  // forces grouped by segment, insertion order kept inside a segment
+            tab->begin[s] = k;
+            for (int i = 0; i < nf; ++i)
+                if (fx->segment[i] == s) {
+                    std::memcpy(f[k].p, fx->param + (size_t)i * kFextNParam, kFextNParam * sizeof(double));
+                    f[k].segment = s, f[k].kind = fx->kind[i], f[k].slot = i, f[k].pad0 = 0;
+                    ++k;
+                }
+        }
+        for (int s = N; s < kMaxSegments + 4; ++s) tab->begin[s] = k;
+        CUDA_TRY(cudaMallocAsync(&d_tab, bytes, st));
+        // pageable source: the runtime stages it before returning, so `host` may go out of scope
+        CUDA_TRY(cudaMemcpyAsync(d_tab, host.data(), bytes, cudaMemcpyHostToDevice, st));
+        args.tab = static_cast<const unsigned char*>(d_tab);
+        args.tab_bytes = bytes, args.nf = nf;
+        args.vals = fx->values;
+        args.steps = fx->values != nullptr ? (fx->values_steps > 1 ? fx->values_steps : 1) : 0;
+        args.step_stride = 0;  // set by the caller, who knows B
+        return BIONC_OK;
+    }
+    ~FextCall() {
+        if (d_tab != nullptr) cudaFreeAsync(d_tab, st);
+    }
+};
+
+// kernel instantiations by CTA-size class (threads = 32 x segments) and path:
+//   0 lean (point-to-point blocks only, no forces)   1 lean + Baumgarte   2 general (every block kind, forces, Baumgarte)
 struct KernelSet {
     const void* fd;
     const void* rk4;
 };
-#define BIONC_PICK(T, S)                                                                                          \
-    (general ? KernelSet{(const void*)forward_dynamics_kernel<true, T, S>, (const void*)rk4_kernel<true, T, S>}    \
-             : KernelSet{(const void*)forward_dynamics_kernel<false, T, S>, (const void*)rk4_kernel<false, T, S>})
-KernelSet pick_kernels(bool general, int threads, int spc) {
+#define BIONC_PICK(T, S)                                                                                                         \
+    (path == 2   ? KernelSet{(const void*)forward_dynamics_kernel<true, true, T, S>, (const void*)rk4_kernel<true, true, T, S>}    \
+     : path == 1 ? KernelSet{(const void*)forward_dynamics_kernel<false, true, T, S>, (const void*)rk4_kernel<false, true, T, S>}  \
+                 : KernelSet{(const void*)forward_dynamics_kernel<false, false, T, S>, (const void*)rk4_kernel<false, false, T, S>})
+KernelSet pick_kernels(int path, int threads, int spc) {
     if (spc == 32) {
         if (threads <= 32) return BIONC_PICK(32, 32);
         if (threads <= 64) return BIONC_PICK(64, 32);
@@ -411,31 +462,31 @@ KernelSet pick_kernels(bool general, int threads, int spc) {
     return BIONC_PICK(1024, 16);
 }
 
-int ensure_smem(const void* kernel, size_t bytes) {
+// opt a kernel in to the device's full shared memory, once per (device, kernel)
+int ensure_smem(int device, const void* kernel, int optin_bytes) {
     static std::mutex mu;
-    static std::vector<std::pair<const void*, size_t>> done;
+    static std::vector<std::pair<int, const void*>> done;
     std::lock_guard<std::mutex> lock(mu);
     for (auto& d : done)
-        if (d.first == kernel && d.second >= bytes) return BIONC_OK;
-    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        if (d.first == device && d.second == kernel) return BIONC_OK;
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin_bytes));
     // as much shared memory as the SM has: residency is limited by the per-CTA working sets
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    done.emplace_back(kernel, bytes);
+    done.emplace_back(device, kernel);
     return BIONC_OK;
 }
 
-int prepare(BioncModel* M, const BioncDynOptions* opt, DynOpts& o) {
+void dyn_options(const BioncDynOptions* opt, DynOpts& o) {
     o.use_stab = (opt != nullptr && opt->use_stabilization) ? 1 : 0;
     o.alpha = opt != nullptr ? opt->alpha : 0.0;
     o.beta = opt != nullptr ? opt->beta : 0.0;
-    return build_blob(M, opt != nullptr ? opt->fext : nullptr);
 }
 
-// the lean kernel instantiation covers models made of point-to-point (LIN3) blocks only, without
-// external forces or Baumgarte stabilisation; everything else takes the general one
-bool needs_general(const BioncModel* M, const DynOpts& o) { return M->hdr.rnl > 0 || M->hdr.nfext > 0 || o.use_stab != 0; }
-
-unsigned grid_for(const BioncModel* M, long long B) { return (unsigned)((B + M->hdr.spw - 1) / M->hdr.spw); }
+// kernel path of a call (see pick_kernels)
+int kernel_path(const BioncModel* M, const DynOpts& o, const FextArgs& fx) {
+    if (M->hdr.rnl > 0 || fx.tab != nullptr) return 2;
+    return o.use_stab != 0 ? 1 : 0;
+}
 
 }  // namespace
 
@@ -467,6 +518,7 @@ int bionc_cuda_model_create(const BioncModelDesc* d, int device, BioncModel** ou
     }
     const int mj = symbolic_analysis(M, N);
     int rnl = 0;
+    std::vector<std::vector<double>> Winv(N);
     for (int i = 0; i < N; ++i) {
         DevSeg& S = M->seg[i];
         std::memset(&S, 0, sizeof(S));
@@ -486,14 +538,22 @@ int bionc_cuda_model_create(const BioncModelDesc* d, int device, BioncModel** ou
         M4[3][3] = J[8];
         for (int r = 0; r < 4; ++r)
             for (int cc = 0; cc < r; ++cc) M4[r][cc] = M4[cc][r];
-        double W[4][4];
-        if (!invert4(M4, W)) {
+        if (!(std::fabs(m) > 0.0) || !std::isfinite(m)) {
             delete M;
-            return fail(BIONC_E_INVALID, "singular segment mass matrix");  // reference: LinAlgError at solve time
+            return fail(BIONC_E_INVALID, "segment without mass");  // reference: LinAlgError at solve time
         }
-        int k = 0;
-        for (int r = 0; r < 4; ++r)
-            for (int cc = r; cc < 4; ++cc) S.W[k++] = 0.5 * (W[r][cc] + W[cc][r]);
+        // M4^-1 only serves the nominal scale of the joint-level nodes below; a singular M4 just disables that check
+        double W[4][4];
+        Winv[i].assign(10, 0.0);
+        if (invert4(M4, W)) {
+            int k = 0;
+            for (int r = 0; r < 4; ++r)
+                for (int cc = r; cc < 4; ++cc) Winv[i][k++] = 0.5 * (W[r][cc] + W[cc][r]);
+        }
+        // N3 = J - m c c^T (second moments about the centre of mass, natural coordinates), c, m, 1/m
+        S.kc[0] = J[0] - m * c[0] * c[0], S.kc[1] = J[1] - m * c[0] * c[1], S.kc[2] = J[2] - m * c[0] * c[2];
+        S.kc[3] = J[4] - m * c[1] * c[1], S.kc[4] = J[5] - m * c[1] * c[2], S.kc[5] = J[8] - m * c[2] * c[2];
+        S.kc[6] = c[0], S.kc[7] = c[1], S.kc[8] = c[2], S.kc[9] = m, S.kc[10] = 1.0 / m, S.kc[11] = 0.0;
         const double g = -9.81;
         S.fg[0] = c[0] * m * g, S.fg[1] = (1 + c[1]) * m * g, S.fg[2] = -c[1] * m * g, S.fg[3] = c[2] * m * g;
         std::memcpy(S.phic, d->seg_phi_const + 4 * i, 4 * sizeof(double));
@@ -523,7 +583,7 @@ int bionc_cuda_model_create(const BioncModelDesc* d, int device, BioncModel** ou
         const int nb = M->hdr.nb;
         std::vector<double> sc(nb, 0.0);
         auto quad = [&](int sgi, const double* a) {
-            const double* W = M->seg[sgi].W;
+            const double* W = Winv[sgi].data();
             double q = 0.0;
             for (int r = 0; r < 4; ++r)
                 for (int cc = 0; cc < 4; ++cc) {
@@ -562,7 +622,8 @@ int bionc_cuda_model_create(const BioncModelDesc* d, int device, BioncModel** ou
             mk[k].segment = d->marker_segment[k], mk[k].pad = 0;
             for (int e = 0; e < 3; ++e) mk[k].pos[e] = d->marker_position[3 * k + e];
         }
-        if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&M->d_markers, mk.size() * sizeof(DevMarker)) != cudaSuccess ||
+        DeviceGuard guard(device);
+        if (!guard.ok || cudaMalloc(&M->d_markers, mk.size() * sizeof(DevMarker)) != cudaSuccess ||
             cudaMemcpy(M->d_markers, mk.data(), mk.size() * sizeof(DevMarker), cudaMemcpyHostToDevice) != cudaSuccess) {
             cudaGetLastError();
             delete M;
@@ -576,11 +637,15 @@ int bionc_cuda_model_create(const BioncModelDesc* d, int device, BioncModel** ou
 
 int bionc_cuda_model_destroy(BioncModel* M) {
     if (M == nullptr) return BIONC_OK;
-    cudaSetDevice(M->device);
+    if (M->d_blob == nullptr && M->d_markers == nullptr && M->d_Q == nullptr) {  // the device was never touched
+        delete M;
+        return BIONC_OK;
+    }
+    DeviceGuard guard(M->device);
     cudaFree(M->d_blob);
     cudaFree(M->d_markers);
     cudaFree(M->d_Q), cudaFree(M->d_Qd), cudaFree(M->d_Qdd), cudaFree(M->d_lam), cudaFree(M->d_inertia), cudaFree(M->d_h);
-    cudaFree(M->d_status);
+    cudaFree(M->d_status), cudaFree(M->d_fvals);
     if (M->stream != nullptr) cudaStreamDestroy(M->stream);
     for (auto& ps : M->pipe)
         if (ps != nullptr) cudaStreamDestroy(ps);
@@ -596,35 +661,56 @@ int bionc_cuda_model_counts(const BioncModel* M, int32_t* nseg, int32_t* mj, int
     return BIONC_OK;
 }
 
+int bionc_cuda_model_joint_rows(const BioncModel* M, int32_t* jrow) {
+    if (M == nullptr || jrow == nullptr) return fail(BIONC_E_INVALID, "null argument");
+    for (size_t b = 0; b < M->blk.size(); ++b) jrow[b] = M->blk[b].jrow;
+    return BIONC_OK;
+}
+
 int bionc_cuda_model_layout(const BioncModel* M, int32_t* out) {
     if (M == nullptr || out == nullptr) return fail(BIONC_E_INVALID, "null argument");
     const DevHeader& h = M->hdr;
-    const int32_t v[11] = {h.N, h.mj, h.nb, h.nslot, h.nslot2, h.nlevel, h.rnl, h.nzero, M->blob_valid ? h.spw : 0,
-                           M->blob_valid ? (int32_t)M->smem_bytes : 0, h.serial_solve};
+    const int32_t v[11] = {h.N, h.mj, h.nb, h.nslot, h.nslot2, h.nlevel, h.rnl, h.nzero, M->plan0.spw, (int32_t)M->plan0.smem, h.serial_solve};
     std::memcpy(out, v, sizeof(v));
     return BIONC_OK;
 }
 
-int bionc_cuda_forward_dynamics(const BioncModel* Mc, const double* Q, const double* Qd, const BioncDynOptions* opt,
+// per-call launch state shared by the dynamics entry points
+struct DynCall {
+    DynOpts o{};
+    FextCall fx;
+    LaunchPlan plan;
+    KernelSet ks{};
+    int prepare(const BioncModel* M, const BioncDynOptions* opt, int64_t B, cudaStream_t st) {
+        dyn_options(opt, o);
+        int rc = fx.upload(M, opt != nullptr ? opt->fext : nullptr, st);
+        if (rc != BIONC_OK) return rc;
+        fx.args.step_stride = (long long)B * fx.args.nf * 6;
+        plan = M->plan0;
+        if (fx.args.tab != nullptr && (rc = make_plan(M, fx.args.tab_bytes, plan)) != BIONC_OK) return rc;
+        ks = pick_kernels(kernel_path(M, o, fx.args), 32 * M->hdr.N, plan.spw);
+        return BIONC_OK;
+    }
+};
+
+int bionc_cuda_forward_dynamics(const BioncModel* M, const double* Q, const double* Qd, const BioncDynOptions* opt,
                                 double* Qdd, double* lam, int32_t* status, int64_t B, void* stream) {
-    BioncModel* M = const_cast<BioncModel*>(Mc);
     if (M == nullptr || Q == nullptr || Qd == nullptr || Qdd == nullptr || B < 0) return fail(BIONC_E_INVALID, "null argument");
     if (B == 0) return BIONC_OK;
-    std::lock_guard<std::mutex> lock(M->mu);
-    DynOpts o;
-    int rc = prepare(M, opt, o);
-    if (rc != BIONC_OK) return rc;
+    BIONC_ON_DEVICE(M);
     cudaStream_t st = (cudaStream_t)stream;
+    DynCall call;
+    int rc = call.prepare(M, opt, B, st);
+    if (rc != BIONC_OK) return rc;
     if (status != nullptr) CUDA_TRY(cudaMemsetAsync(status, 0, B * sizeof(int32_t), st));
     const double* inertia = opt != nullptr ? opt->inertia : nullptr;
-    const unsigned grid = grid_for(M, B), block = 32 * M->hdr.N;
-    const KernelSet ks = pick_kernels(needs_general(M, o), (int)block, M->hdr.spw);
-    if ((rc = ensure_smem(ks.fd, M->smem_bytes)) != BIONC_OK) return rc;
+    const unsigned grid = (unsigned)((B + call.plan.spw - 1) / call.plan.spw), block = 32 * M->hdr.N;
+    if ((rc = ensure_smem(M->device, call.ks.fd, M->dev_smem_optin)) != BIONC_OK) return rc;
     const unsigned char* blob = M->d_blob;
     int blob_bytes = M->blob_bytes;
     long long Bll = B;
-    void* args[] = {&blob, &blob_bytes, &Q, &Qd, &inertia, &o, &Qdd, &lam, &status, &Bll};
-    CUDA_TRY(cudaLaunchKernel(ks.fd, dim3(grid), dim3(block), args, M->smem_bytes, st));
+    void* args[] = {&blob, &blob_bytes, &call.fx.args, &Q, &Qd, &inertia, &call.o, &Qdd, &lam, &status, &Bll};
+    CUDA_TRY(cudaLaunchKernel(call.ks.fd, dim3(grid), dim3(block), args, call.plan.smem, st));
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return BIONC_OK;
@@ -638,69 +724,65 @@ size_t bionc_cuda_dense_workspace_bytes(const BioncModel* M, int64_t count) {
     return per * (size_t)slots;
 }
 
-int bionc_cuda_forward_dynamics_dense(const BioncModel* Mc, const double* Q, const double* Qd, const BioncDynOptions* opt,
+int bionc_cuda_forward_dynamics_dense(const BioncModel* M, const double* Q, const double* Qd, const BioncDynOptions* opt,
                                       const int64_t* select, int64_t count, double* Qdd, double* lam, int32_t* status,
                                       void* workspace, size_t workspace_bytes, void* stream) {
-    BioncModel* M = const_cast<BioncModel*>(Mc);
     if (M == nullptr || Q == nullptr || Qd == nullptr || Qdd == nullptr || count < 0) return fail(BIONC_E_INVALID, "null argument");
     if (count == 0) return BIONC_OK;
     const size_t per = bionc_cuda_dense_workspace_bytes(M, 1);
     if (workspace == nullptr || workspace_bytes < per) return fail(BIONC_E_INVALID, "workspace smaller than bionc_cuda_dense_workspace_bytes(model, 1)");
-    std::lock_guard<std::mutex> lock(M->mu);
+    BIONC_ON_DEVICE(M);
+    cudaStream_t st = (cudaStream_t)stream;
     DynOpts o;
-    int rc = prepare(M, opt, o);
+    dyn_options(opt, o);
+    FextCall fx;
+    int rc = fx.upload(M, opt != nullptr ? opt->fext : nullptr, st);
     if (rc != BIONC_OK) return rc;
     long long slots = (long long)(workspace_bytes / per);
     if (slots > count) slots = count;
     if (slots > 148 * 8) slots = 148 * 8;
     EvalArgs ea{0, M->hdr.N, M->hdr.nblk, M->hdr.mj, M->hdr.m};
     const double* inertia = opt != nullptr ? opt->inertia : nullptr;
-    dense_kkt_kernel<<<(unsigned)slots, kDenseThreads, 0, (cudaStream_t)stream>>>(
-        M->d_blob, ea, Q, Qd, inertia, o, reinterpret_cast<const long long*>(select), (long long)count, Qdd, lam, status,
+    dense_kkt_kernel<<<(unsigned)slots, kDenseThreads, 0, st>>>(
+        M->d_blob, fx.args, ea, Q, Qd, inertia, o, reinterpret_cast<const long long*>(select), (long long)count, Qdd, lam, status,
         static_cast<double*>(workspace));
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return BIONC_OK;
 }
 
-int bionc_cuda_rk4(const BioncModel* Mc, double* Q, double* Qd, double h, const double* h_steps, int64_t n_steps,
+int bionc_cuda_rk4(const BioncModel* M, double* Q, double* Qd, double h, const double* h_steps, int64_t n_steps,
                    int32_t normalize, const BioncDynOptions* opt, double* traj, int64_t traj_every, double* lam_last,
                    int32_t* status, int64_t B, void* stream) {
-    BioncModel* M = const_cast<BioncModel*>(Mc);
     if (M == nullptr || Q == nullptr || Qd == nullptr || B < 0 || n_steps < 0) return fail(BIONC_E_INVALID, "null argument");
     if (traj != nullptr && traj_every < 1) return fail(BIONC_E_INVALID, "traj_every must be >= 1");
     if (B == 0 || n_steps == 0) return BIONC_OK;
-    std::lock_guard<std::mutex> lock(M->mu);
-    DynOpts o;
-    int rc = prepare(M, opt, o);
-    if (rc != BIONC_OK) return rc;
+    BIONC_ON_DEVICE(M);
     cudaStream_t st = (cudaStream_t)stream;
+    DynCall call;
+    int rc = call.prepare(M, opt, B, st);
+    if (rc != BIONC_OK) return rc;
     if (status != nullptr) CUDA_TRY(cudaMemsetAsync(status, 0, B * sizeof(int32_t), st));
     const double* inertia = opt != nullptr ? opt->inertia : nullptr;
-    const unsigned grid = grid_for(M, B), block = 32 * M->hdr.N;
+    const unsigned grid = (unsigned)((B + call.plan.spw - 1) / call.plan.spw), block = 32 * M->hdr.N;
     if (traj == nullptr) traj_every = 1;
-    const KernelSet ks = pick_kernels(needs_general(M, o), (int)block, M->hdr.spw);
-    if ((rc = ensure_smem(ks.rk4, M->smem_bytes)) != BIONC_OK) return rc;
+    if ((rc = ensure_smem(M->device, call.ks.rk4, M->dev_smem_optin)) != BIONC_OK) return rc;
     const unsigned char* blob = M->d_blob;
     int blob_bytes = M->blob_bytes;
     long long Bll = B, nsteps = n_steps, tevery = traj_every;
     int norm = normalize;
-    void* args[] = {&blob, &blob_bytes, &Q, &Qd, &inertia, &o, &h, &h_steps, &nsteps, &norm, &traj, &tevery, &lam_last, &status, &Bll};
-    CUDA_TRY(cudaLaunchKernel(ks.rk4, dim3(grid), dim3(block), args, M->smem_bytes, st));
+    void* args[] = {&blob, &blob_bytes, &call.fx.args, &Q, &Qd, &inertia, &call.o, &h, &h_steps, &nsteps, &norm, &traj, &tevery, &lam_last, &status, &Bll};
+    CUDA_TRY(cudaLaunchKernel(call.ks.rk4, dim3(grid), dim3(block), args, call.plan.smem, st));
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return BIONC_OK;
 }
 
-int bionc_cuda_eval(const BioncModel* Mc, int32_t which, const double* in, const BioncDynOptions* opt, double* out,
+int bionc_cuda_eval(const BioncModel* M, int32_t which, const double* in, const BioncDynOptions* opt, double* out,
                     int64_t B, void* stream) {
-    BioncModel* M = const_cast<BioncModel*>(Mc);
     if (M == nullptr || in == nullptr || out == nullptr || B < 0 || which < 0 || which > 12) return fail(BIONC_E_INVALID, "bad argument");
     if (B == 0) return BIONC_OK;
-    std::lock_guard<std::mutex> lock(M->mu);
-    DynOpts o;
-    int rc = prepare(M, opt, o);
-    if (rc != BIONC_OK) return rc;
+    BIONC_ON_DEVICE(M);
     const int N = M->hdr.N, n = 12 * N, mj = M->hdr.mj, m = M->hdr.m;
     cudaStream_t st = (cudaStream_t)stream;
     if (which >= BIONC_EVAL_COM) {  // post-processing evaluators: every output element is written, no zero fill
@@ -736,6 +818,12 @@ int bionc_cuda_eval(const BioncModel* Mc, int32_t which, const double* in, const
         case BIONC_EVAL_FEXT: out_elems = n; break;
     }
     if (out_elems == 0) return BIONC_OK;
+    FextCall fx;
+    if (which == BIONC_EVAL_FEXT) {
+        int rc = fx.upload(M, opt != nullptr ? opt->fext : nullptr, st);
+        if (rc != BIONC_OK) return rc;
+        fx.args.step_stride = (long long)B * fx.args.nf * 6;
+    }
     // vector outputs are written row by row in full; only the (sparse) Jacobians need the zero fill
     if (which == BIONC_EVAL_K_R || which == BIONC_EVAL_K_J || which == BIONC_EVAL_K_H)
         CUDA_TRY(cudaMemsetAsync(out, 0, out_elems * B * sizeof(double), st));
@@ -744,7 +832,7 @@ int bionc_cuda_eval(const BioncModel* Mc, int32_t which, const double* in, const
     const int block = 128;
     long long grid = (total + block - 1) / block;
     if (grid > 148LL * 64) grid = 148LL * 64;
-    eval_kernel<<<(unsigned)grid, block, 0, st>>>(M->d_blob, ea, in, out, B);
+    eval_kernel<<<(unsigned)grid, block, 0, st>>>(M->d_blob, fx.args, ea, in, out, B);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return BIONC_OK;
@@ -769,27 +857,43 @@ int bionc_cuda_mass_matrix(const BioncModel* M, double* G) {
 }
 
 // ------------------------------------------------------------------------------------------ host path
-static int ensure_host_scratch(BioncModel* M, long long B, long long nh, bool want_inertia) {
-    CUDA_TRY(cudaSetDevice(M->device));
+}  // extern "C"
+// (re)allocate one scratch array; on failure the pointer stays null and the capacity 0
+template <typename T>
+static int regrow(T*& p, size_t count) {
+    if (p != nullptr) cudaFree(p);
+    p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, count * sizeof(T)));
+    return BIONC_OK;
+}
+extern "C" {
+
+// host_mu must be held
+static int ensure_host_scratch(BioncModel* M, long long B, long long nh, bool want_inertia, long long fvals_doubles) {
     if (M->stream == nullptr) CUDA_TRY(cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking));
     for (auto& ps : M->pipe)
         if (ps == nullptr) CUDA_TRY(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
     const size_t n = 12 * (size_t)M->hdr.N;
+    int rc;
     if (B > M->cap_B) {
-        cudaFree(M->d_Q), cudaFree(M->d_Qd), cudaFree(M->d_Qdd), cudaFree(M->d_lam), cudaFree(M->d_status), cudaFree(M->d_inertia);
-        M->d_inertia = nullptr;
-        CUDA_TRY(cudaMalloc(&M->d_Q, B * n * sizeof(double)));
-        CUDA_TRY(cudaMalloc(&M->d_Qd, B * n * sizeof(double)));
-        CUDA_TRY(cudaMalloc(&M->d_Qdd, B * n * sizeof(double)));
-        CUDA_TRY(cudaMalloc(&M->d_lam, B * (size_t)M->hdr.m * sizeof(double)));
-        CUDA_TRY(cudaMalloc(&M->d_status, B * sizeof(int)));
+        M->cap_B = 0;  // stays 0 unless every allocation below succeeds
+        if (M->d_inertia != nullptr) cudaFree(M->d_inertia), M->d_inertia = nullptr;
+        if ((rc = regrow(M->d_Q, B * n)) != BIONC_OK || (rc = regrow(M->d_Qd, B * n)) != BIONC_OK ||
+            (rc = regrow(M->d_Qdd, B * n)) != BIONC_OK || (rc = regrow(M->d_lam, B * (size_t)M->hdr.m)) != BIONC_OK ||
+            (rc = regrow(M->d_status, (size_t)B)) != BIONC_OK)
+            return rc;
         M->cap_B = B;
     }
-    if (want_inertia && M->d_inertia == nullptr) CUDA_TRY(cudaMalloc(&M->d_inertia, M->cap_B * (size_t)M->hdr.N * 10 * sizeof(double)));
+    if (want_inertia && M->d_inertia == nullptr && (rc = regrow(M->d_inertia, M->cap_B * (size_t)M->hdr.N * 10)) != BIONC_OK) return rc;
     if (nh > M->cap_h) {
-        cudaFree(M->d_h);
-        CUDA_TRY(cudaMalloc(&M->d_h, nh * sizeof(double)));
+        M->cap_h = 0;
+        if ((rc = regrow(M->d_h, (size_t)nh)) != BIONC_OK) return rc;
         M->cap_h = nh;
+    }
+    if (fvals_doubles > M->cap_fvals) {
+        M->cap_fvals = 0;
+        if ((rc = regrow(M->d_fvals, (size_t)fvals_doubles)) != BIONC_OK) return rc;
+        M->cap_fvals = fvals_doubles;
     }
     return BIONC_OK;
 }
@@ -806,12 +910,61 @@ static int64_t host_chunk(int64_t B) {
     return (c + 4095) / 4096 * 4096;
 }
 
+// drain the chunk pipeline (also on the error paths: no copy into the caller's buffers may be left in flight)
+static int drain(BioncModel* M, int rc) {
+    for (auto& ps : M->pipe)
+        if (ps != nullptr) {
+            const cudaError_t e = cudaStreamSynchronize(ps);
+            if (e != cudaSuccess && rc == BIONC_OK) rc = fail(BIONC_E_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
+        }
+    return rc;
+}
+#define PIPE_TRY(expr)                                                                                       \
+    do {                                                                                                     \
+        cudaError_t e__ = (expr);                                                                            \
+        if (e__ != cudaSuccess) return drain(M, fail(BIONC_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__))); \
+    } while (0)
+
+// per-chunk options of the host path: device copies of the per-system inertia / force values of the chunk
+struct HostChunkOpts {
+    BioncDynOptions o{};
+    BioncFextDesc fx{};
+};
+static int stage_chunk_options(BioncModel* M, const BioncDynOptions* opt, int64_t B, int64_t lo, int64_t b, cudaStream_t st, HostChunkOpts& out) {
+    out.o = opt != nullptr ? *opt : BioncDynOptions{};
+    if (opt != nullptr && opt->inertia != nullptr) {
+        const size_t ni = (size_t)M->hdr.N * 10;
+        CUDA_TRY(cudaMemcpyAsync(M->d_inertia + lo * ni, opt->inertia + lo * ni, (size_t)b * ni * sizeof(double), cudaMemcpyHostToDevice, st));
+        out.o.inertia = M->d_inertia + lo * ni;
+    }
+    if (opt != nullptr && opt->fext != nullptr && opt->fext->values != nullptr && opt->fext->nb_forces > 0) {
+        // (steps, B, F, 6) on the host -> (steps, b, F, 6) of this chunk, slices packed back to back in the scratch
+        out.fx = *opt->fext;
+        const size_t per = (size_t)opt->fext->nb_forces * 6;
+        const int64_t steps = opt->fext->values_steps > 1 ? opt->fext->values_steps : 1;
+        double* dst = M->d_fvals + (size_t)lo * per * steps;
+        for (int64_t k = 0; k < steps; ++k)
+            CUDA_TRY(cudaMemcpyAsync(dst + (size_t)k * b * per, opt->fext->values + ((size_t)k * B + lo) * per, (size_t)b * per * sizeof(double),
+                                     cudaMemcpyHostToDevice, st));
+        out.fx.values = dst;
+        out.o.fext = &out.fx;
+    }
+    return BIONC_OK;
+}
+static long long host_fvals_doubles(const BioncDynOptions* opt, int64_t B) {
+    if (opt == nullptr || opt->fext == nullptr || opt->fext->values == nullptr || opt->fext->nb_forces <= 0) return 0;
+    const int64_t steps = opt->fext->values_steps > 1 ? opt->fext->values_steps : 1;
+    return (long long)B * opt->fext->nb_forces * 6 * steps;
+}
+
 int bionc_cuda_forward_dynamics_host(BioncModel* M, const double* Q, const double* Qd, const BioncDynOptions* opt,
                                      double* Qdd, double* lam, int32_t* status, int64_t B) {
     if (M == nullptr || Q == nullptr || Qd == nullptr || Qdd == nullptr || B < 0) return fail(BIONC_E_INVALID, "null argument");
     if (B == 0) return BIONC_OK;
+    BIONC_ON_DEVICE(M);
+    std::lock_guard<std::mutex> lock(M->host_mu);
     const bool per_sys = opt != nullptr && opt->inertia != nullptr;
-    int rc = ensure_host_scratch(M, B, 0, per_sys);
+    int rc = ensure_host_scratch(M, B, 0, per_sys, host_fvals_doubles(opt, B));
     if (rc != BIONC_OK) return rc;
     const size_t n = 12 * (size_t)M->hdr.N, m = (size_t)M->hdr.m;
     const int64_t chunk = host_chunk(B);
@@ -820,31 +973,28 @@ int bionc_cuda_forward_dynamics_host(BioncModel* M, const double* Q, const doubl
         const int64_t b = (B - lo < chunk) ? B - lo : chunk;
         cudaStream_t st = M->pipe[k % 3];
         const size_t nb = (size_t)b * n * sizeof(double);
-        CUDA_TRY(cudaMemcpyAsync(M->d_Q + lo * n, Q + lo * n, nb, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(M->d_Qd + lo * n, Qd + lo * n, nb, cudaMemcpyHostToDevice, st));
-        BioncDynOptions o2 = opt != nullptr ? *opt : BioncDynOptions{};
-        if (per_sys) {
-            const size_t ni = (size_t)M->hdr.N * 10;
-            CUDA_TRY(cudaMemcpyAsync(M->d_inertia + lo * ni, opt->inertia + lo * ni, (size_t)b * ni * sizeof(double), cudaMemcpyHostToDevice, st));
-            o2.inertia = M->d_inertia + lo * ni;
-        }
-        rc = bionc_cuda_forward_dynamics(M, M->d_Q + lo * n, M->d_Qd + lo * n, &o2, M->d_Qdd + lo * n,
+        PIPE_TRY(cudaMemcpyAsync(M->d_Q + lo * n, Q + lo * n, nb, cudaMemcpyHostToDevice, st));
+        PIPE_TRY(cudaMemcpyAsync(M->d_Qd + lo * n, Qd + lo * n, nb, cudaMemcpyHostToDevice, st));
+        HostChunkOpts co;
+        if ((rc = stage_chunk_options(M, opt, B, lo, b, st, co)) != BIONC_OK) return drain(M, rc);
+        rc = bionc_cuda_forward_dynamics(M, M->d_Q + lo * n, M->d_Qd + lo * n, &co.o, M->d_Qdd + lo * n,
                                          lam != nullptr ? M->d_lam + lo * m : nullptr, status != nullptr ? M->d_status + lo : nullptr, b, st);
-        if (rc != BIONC_OK) return rc;
-        CUDA_TRY(cudaMemcpyAsync(Qdd + lo * n, M->d_Qdd + lo * n, nb, cudaMemcpyDeviceToHost, st));
-        if (lam != nullptr) CUDA_TRY(cudaMemcpyAsync(lam + lo * m, M->d_lam + lo * m, (size_t)b * m * sizeof(double), cudaMemcpyDeviceToHost, st));
-        if (status != nullptr) CUDA_TRY(cudaMemcpyAsync(status + lo, M->d_status + lo, (size_t)b * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (rc != BIONC_OK) return drain(M, rc);
+        PIPE_TRY(cudaMemcpyAsync(Qdd + lo * n, M->d_Qdd + lo * n, nb, cudaMemcpyDeviceToHost, st));
+        if (lam != nullptr) PIPE_TRY(cudaMemcpyAsync(lam + lo * m, M->d_lam + lo * m, (size_t)b * m * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (status != nullptr) PIPE_TRY(cudaMemcpyAsync(status + lo, M->d_status + lo, (size_t)b * sizeof(int), cudaMemcpyDeviceToHost, st));
     }
-    for (auto& ps : M->pipe) CUDA_TRY(cudaStreamSynchronize(ps));
-    return BIONC_OK;
+    return drain(M, BIONC_OK);
 }
 
 int bionc_cuda_rk4_host(BioncModel* M, double* Q, double* Qd, double h, const double* h_steps, int64_t n_steps,
                         int32_t normalize, const BioncDynOptions* opt, int32_t* status, int64_t B) {
     if (M == nullptr || Q == nullptr || Qd == nullptr || B < 0 || n_steps < 0) return fail(BIONC_E_INVALID, "null argument");
     if (B == 0 || n_steps == 0) return BIONC_OK;
+    BIONC_ON_DEVICE(M);
+    std::lock_guard<std::mutex> lock(M->host_mu);
     const bool per_sys = opt != nullptr && opt->inertia != nullptr;
-    int rc = ensure_host_scratch(M, B, h_steps != nullptr ? n_steps : 0, per_sys);
+    int rc = ensure_host_scratch(M, B, h_steps != nullptr ? n_steps : 0, per_sys, host_fvals_doubles(opt, B));
     if (rc != BIONC_OK) return rc;
     const size_t n = 12 * (size_t)M->hdr.N;
     if (h_steps != nullptr) {
@@ -857,30 +1007,26 @@ int bionc_cuda_rk4_host(BioncModel* M, double* Q, double* Qd, double h, const do
         const int64_t b = (B - lo < chunk) ? B - lo : chunk;
         cudaStream_t st = M->pipe[k % 3];
         const size_t nb = (size_t)b * n * sizeof(double);
-        CUDA_TRY(cudaMemcpyAsync(M->d_Q + lo * n, Q + lo * n, nb, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(M->d_Qd + lo * n, Qd + lo * n, nb, cudaMemcpyHostToDevice, st));
-        BioncDynOptions o2 = opt != nullptr ? *opt : BioncDynOptions{};
-        if (per_sys) {
-            const size_t ni = (size_t)M->hdr.N * 10;
-            CUDA_TRY(cudaMemcpyAsync(M->d_inertia + lo * ni, opt->inertia + lo * ni, (size_t)b * ni * sizeof(double), cudaMemcpyHostToDevice, st));
-            o2.inertia = M->d_inertia + lo * ni;
-        }
+        PIPE_TRY(cudaMemcpyAsync(M->d_Q + lo * n, Q + lo * n, nb, cudaMemcpyHostToDevice, st));
+        PIPE_TRY(cudaMemcpyAsync(M->d_Qd + lo * n, Qd + lo * n, nb, cudaMemcpyHostToDevice, st));
+        HostChunkOpts co;
+        if ((rc = stage_chunk_options(M, opt, B, lo, b, st, co)) != BIONC_OK) return drain(M, rc);
         rc = bionc_cuda_rk4(M, M->d_Q + lo * n, M->d_Qd + lo * n, h, h_steps != nullptr ? M->d_h : nullptr, n_steps, normalize,
-                            &o2, nullptr, 1, nullptr, status != nullptr ? M->d_status + lo : nullptr, b, st);
-        if (rc != BIONC_OK) return rc;
-        CUDA_TRY(cudaMemcpyAsync(Q + lo * n, M->d_Q + lo * n, nb, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(Qd + lo * n, M->d_Qd + lo * n, nb, cudaMemcpyDeviceToHost, st));
-        if (status != nullptr) CUDA_TRY(cudaMemcpyAsync(status + lo, M->d_status + lo, (size_t)b * sizeof(int), cudaMemcpyDeviceToHost, st));
+                            &co.o, nullptr, 1, nullptr, status != nullptr ? M->d_status + lo : nullptr, b, st);
+        if (rc != BIONC_OK) return drain(M, rc);
+        PIPE_TRY(cudaMemcpyAsync(Q + lo * n, M->d_Q + lo * n, nb, cudaMemcpyDeviceToHost, st));
+        PIPE_TRY(cudaMemcpyAsync(Qd + lo * n, M->d_Qd + lo * n, nb, cudaMemcpyDeviceToHost, st));
+        if (status != nullptr) PIPE_TRY(cudaMemcpyAsync(status + lo, M->d_status + lo, (size_t)b * sizeof(int), cudaMemcpyDeviceToHost, st));
     }
-    for (auto& ps : M->pipe) CUDA_TRY(cudaStreamSynchronize(ps));
-    return BIONC_OK;
+    return drain(M, BIONC_OK);
 }
 
 // FP64 roofline denominator: a DFMA-only kernel (8 independent accumulator chains per thread,
 // 2048 threads per SM resident) timed with CUDA events; MEASURED_PEAKS.json has no FP64 figure.
 int bionc_cuda_measure_fp64_peak(int device, int repeats, double* tflops_best, double* tflops_sustained) {
     if (tflops_best == nullptr) return fail(BIONC_E_INVALID, "null argument");
-    CUDA_TRY(cudaSetDevice(device));
+    DeviceGuard guard__(device);
+    if (!guard__.ok) return fail(BIONC_E_CUDA, "cudaSetDevice failed");
     int sms = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     const int block = 256, grid = sms * 8, iters = 1 << 14;

@@ -2,21 +2,34 @@
 //
 // System solved (reference bionc/bionc_numpy/biomechanical_model.py:404-426):
 //     [G K^T; K 0] [Qdd; lambda] = [f; -bias]        G = blockdiag(M4_i (x) I3)
-// The reference LU-factors the dense KKT matrix.  Here the same solution is obtained with a
-// fill-reducing block elimination of the Schur complement S = K G^-1 K^T:
-//   1. per segment (one thread per system, registers only): Sr_i = Kr_i G_i^-1 Kr_i^T (6x6) is factored LDL^T;
-//      rigid-body rows of different segments never couple, so this is the block-diagonal leading
-//      part of S under the ordering "all rigid rows first";
-//   2. per constraint row touching the segment: q' = A_i k^T with the projected inverse mass
-//      A_i = G_i^-1 - G_i^-1 Kr_i^T Sr_i^-1 Kr_i G_i^-1, and the segment's contribution
-//      k_a . q'_b to the joint-level Schur complement S' (3x3 blocks in shared memory; closed form
-//      gamma I - B M B^T for pairs of point-to-point blocks);
+// The reference LU-factors the dense KKT matrix.  The kernels obtain the same solution by eliminating the
+// rigid-body rows of every segment in closed form (null-space form) and the joint rows with a sparse block LDL^T:
+//
+//   1. Rigid-body rows, per segment (one thread per system, registers only).  The six rows of Kr are the gradients of
+//      u.u, u.v, u.w, v.v, v.w, w.w (natural_segment.py:450-483); for ANY invertible basis B = [u v w] (drifted
+//      or not) the null space of Kr is the set of rigid motions  dQ = (al x u, t, t - al x v, al x w), and
+//      [A_u A_v A_w] = -1/2 B^-T Bsym solves  Kr q_p = -b_r  when Bsym is the symmetric matrix of the six
+//      right-hand sides b_r (bias: Bsym = 2 Ud^T Ud).  So  Qdd_i = T_i (al_i, tc_i) + q_p,i  with six unknowns per
+//      segment: the angular acceleration al and the acceleration tc of the centre of mass.  Projecting
+//      G_i Qdd_i + Kr^T lambda_r + Kj^T lambda_j = f_i  with T_i^T removes lambda_r and leaves Newton-Euler:
+//          m tc = F - sum_rows fdir lambda          Ic al = tau_c - eta - sum_rows n lambda
+//      m = total mass, Ic = tr(Y) I - Y with Y = B N3 B^T and N3 = J - m c c^T the second-moment matrix about
+//      the centre of mass in natural coordinates, eta = sum_ij N3_ij B_i x A_j, (tau_c, F) the applied wrench about
+//      the centre of mass (gravity: pure force).  Only 3x3 matrices are inverted; G^-1 never appears, so an
+//      indefinite M4 costs nothing as long as m != 0 and Ic is regular.
+//   2. Every joint row restricted to a segment, k = a1 (x) d1 [+ a2 (x) d2] (a: constant 4 coefficients over
+//      (u, rp, rd, w), d: 3-vector), acts on (al, tc) through the 6-vector (n, fdir) = (rho' x d, sigma d) with
+//      sigma = a_rp + a_rd, rho' = B (a~ - sigma c), a~ = (a_u, -a_rd, a_w), and on q_p through kappa = d . A (a~ - sigma c).
+//      The segment's contribution to the joint-level Schur complement S' is
+//          S'_ab = fdir_a . fdir_b / m + n_a . Ic^-1 n_b
+//      (3x3 blocks gamma I - [rho_a]x Ic^-1 [rho_b]x for two point-to-point sides), its right-hand side
+//          n . al_free + fdir . tc_free + kappa (+ bias + Baumgarte terms, added by the child side).
 //   3. S' lambda_j = rhs' is factored as a sparse blocked LDL^T along a host-computed pattern
-//      (minimum-degree ordering, fill, elimination-tree levels), block rows dealt to the warps of the CTA;
-//   4. back-substitution per segment: F = f - Kj^T lambda_j, a = G^-1 F,
-//      lambda_r = Sr^-1 (Kr a + bias_r), Qdd = a - G^-1 Kr^T lambda_r.
-// LDL^T (no square roots) instead of Cholesky because the reference's mass matrix is not positive
-// definite in general (SURVEY.md finding 1); a zero / non-finite pivot raises the status flag.
+//      (minimum-degree ordering, fill, elimination-tree levels), block rows dealt to the warps of the CTA.
+//   4. Back-substitution per segment: (al, tc) from Newton-Euler with the joint multipliers, Qdd = T (al, tc) + q_p;
+//      lambda_r, when asked for, from  Kr^T lambda_r = f - Kj^T lambda_j - G Qdd  through B^-1.
+// The result is algebraically identical to the reference's KKT solution (tests: 1e-10 on Qdd and lambda); a zero /
+// non-finite determinant raises the status flag.
 //
 // Thread mapping: one CTA integrates 32 systems; WARP = SEGMENT, LANE = SYSTEM.  All lanes of a warp walk
 // the same constraint-block lists (no divergence between segments), every shared-memory array is indexed
@@ -78,122 +91,47 @@ struct Q12 {
     V3 s[4];
 };
 
-// index of W(t, s) in the packed upper triangle
+// index of entry (t, s) of a symmetric 4x4 in the packed upper triangle (uu ur ud uw rr rd rw dd dw ww)
 __device__ __forceinline__ constexpr int widx(int t, int s) {
     return t <= s ? (t * 4 - t * (t - 1) / 2 + (s - t)) : (s * 4 - s * (s - 1) / 2 + (t - s));
 }
 
 // Per-lane view of one segment in one system.
 struct SegCtx {
-    double W[10];  // M4^-1
-    double fg[4];
-    V3 u, v, w;       // v = rp - rd
-    double L[15];     // unit lower factor of Sr, packed rows: (1,0) (2,0) (2,1) (3,0) ...
-    double dinv[6];
+    // constants of the segment: from the model table, or from the per-system inertial parameters (config 5)
+    double N3[6];  // J - m c c^T, packed xx xy xz yy yz zz: second-moment matrix about the centre of mass, natural coordinates
+    double cn[3];  // natural centre of mass
+    double m, minv;
+    // state-dependent, set by segment_setup
+    V3 u, v, w;        // v = rp - rd
+    V3 Au, Av, Aw;     // particular accelerations of u, v, w:  [Au Av Aw] = B^-T S,  S = -1/2 Bsym
+    double Ii[6];      // inverse of the inertia tensor about the centre of mass (sym3_inverse layout: 00 10 11 20 21 22)
+    V3 tau0, F0;       // applied wrench about the centre of mass, gyroscopic term eta already subtracted from tau0
 };
 
-__device__ __forceinline__ constexpr int lidx(int r, int c) { return r * (r - 1) / 2 + c; }  // r > c
-
-// x = G^-1 k  (W (x) I3 applied to a 12-vector)
-__device__ __forceinline__ Q12 apply_W(const double (&W)[10], const Q12& k) {
-    Q12 q;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        V3 acc = W[widx(t, 0)] * k.s[0];
-#pragma unroll
-        for (int s = 1; s < 4; ++s) acc = axpy(W[widx(t, s)], k.s[s], acc);
-        q.s[t] = acc;
-    }
-    return q;
+// sum_i x[i] * (u, v, w)[i]
+__device__ __forceinline__ V3 in_basis(const SegCtx& c, double x0, double x1, double x2) {
+    return axpy(x0, c.u, axpy(x1, c.v, x2 * c.w));
+}
+// same combination of the particular accelerations
+__device__ __forceinline__ V3 in_accel(const SegCtx& c, double x0, double x1, double x2) {
+    return axpy(x0, c.Au, axpy(x1, c.Av, x2 * c.Aw));
 }
 
-// Kr x for a 12-vector x (natural_segment.py:450-483 contracted): 6 numbers
-__device__ __forceinline__ void kr_apply(const SegCtx& c, const Q12& x, double (&out)[6]) {
-    const V3 xv = x.s[1] - x.s[2];
-    out[0] = 2.0 * dot(c.u, x.s[0]);
-    out[1] = dot(c.v, x.s[0]) + dot(c.u, xv);
-    out[2] = dot(c.w, x.s[0]) + dot(c.u, x.s[3]);
-    out[3] = 2.0 * dot(c.v, xv);
-    out[4] = dot(c.w, xv) + dot(c.v, x.s[3]);
-    out[5] = 2.0 * dot(c.w, x.s[3]);
-}
-
-// G^-1 Kr^T y for a 6-vector y
-__device__ __forceinline__ Q12 ginv_krt(const SegCtx& c, const double (&y)[6]) {
-    const V3 su = axpy(2.0 * y[0], c.u, axpy(y[1], c.v, y[2] * c.w));
-    const V3 p = axpy(y[1], c.u, axpy(2.0 * y[3], c.v, y[4] * c.w));  // rp slot; rd slot is -p
-    const V3 sw = axpy(y[2], c.u, axpy(y[4], c.v, (2.0 * y[5]) * c.w));
-    Q12 x;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        const double wv = c.W[widx(t, 1)] - c.W[widx(t, 2)];
-        x.s[t] = axpy(c.W[widx(t, 0)], su, axpy(wv, p, c.W[widx(t, 3)] * sw));
-    }
-    return x;
-}
-
-// solve Sr y = rhs in place with the LDL^T factors held in registers
-__device__ __forceinline__ void sr_solve(const SegCtx& c, double (&y)[6]) {
-#pragma unroll
-    for (int k = 0; k < 6; ++k)
-#pragma unroll
-        for (int r = k + 1; r < 6; ++r) y[r] = fma(-c.L[lidx(r, k)], y[k], y[r]);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) y[k] *= c.dinv[k];
-#pragma unroll
-    for (int k = 5; k >= 0; --k)
-#pragma unroll
-        for (int r = k + 1; r < 6; ++r) y[k] = fma(-c.L[lidx(r, k)], y[r], y[k]);
-}
-
-// Build Sr = Kr G^-1 Kr^T from the Gram matrix of (u, v, w) and omega = E^T W E, E = [e_u, e_rp - e_rd, e_w],
-// and factor it.  Row (a,b) of Kr is e_a (x) b + e_b (x) a, so
-//   Sr[(a,b),(c,d)] = om_ac g_bd + om_ad g_bc + om_bc g_ad + om_bd g_ac.
-__device__ __forceinline__ void sr_factor(SegCtx& c, int& status) {
-    double g[3][3], om[3][3];
-    g[0][0] = dot(c.u, c.u);
-    g[0][1] = g[1][0] = dot(c.u, c.v);
-    g[0][2] = g[2][0] = dot(c.u, c.w);
-    g[1][1] = dot(c.v, c.v);
-    g[1][2] = g[2][1] = dot(c.v, c.w);
-    g[2][2] = dot(c.w, c.w);
-    om[0][0] = c.W[widx(0, 0)];
-    om[0][1] = om[1][0] = c.W[widx(0, 1)] - c.W[widx(0, 2)];
-    om[0][2] = om[2][0] = c.W[widx(0, 3)];
-    om[1][1] = c.W[widx(1, 1)] - 2.0 * c.W[widx(1, 2)] + c.W[widx(2, 2)];
-    om[1][2] = om[2][1] = c.W[widx(1, 3)] - c.W[widx(2, 3)];
-    om[2][2] = c.W[widx(3, 3)];
-    constexpr int pa[6] = {0, 0, 0, 1, 1, 2};
-    constexpr int pb[6] = {0, 1, 2, 1, 2, 2};
-    double A[6][6];
-#pragma unroll
-    for (int r = 0; r < 6; ++r)
-#pragma unroll
-        for (int q = 0; q <= r; ++q) {
-            const int a = pa[r], b = pb[r], cc = pa[q], d = pb[q];
-            A[r][q] = fma(om[a][cc], g[b][d], fma(om[a][d], g[b][cc], fma(om[b][cc], g[a][d], om[b][d] * g[a][cc])));
-        }
-    double dmax = 0.0;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) dmax = fmax(dmax, fabs(A[k][k]));
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        const double piv = A[k][k];
-        if (!(fabs(piv) > 0.0) || !isfinite(piv)) status |= 1;
-        else if (fabs(piv) < kSmallPivot * dmax) status |= 4;
-        const double inv = fast_rcp(piv);
-        c.dinv[k] = inv;
-        double col[6];
-#pragma unroll
-        for (int r = k + 1; r < 6; ++r) {
-            col[r] = A[r][k];
-            c.L[lidx(r, k)] = col[r] * inv;
-        }
-#pragma unroll
-        for (int r = k + 1; r < 6; ++r)
-#pragma unroll
-            for (int q = k + 1; q <= r; ++q) A[r][q] = fma(-c.L[lidx(r, k)], col[q], A[r][q]);
-    }
+// A constant coefficient vector a over the slots (u, rp, rd, w) as seen from the centre of mass:
+// sum_s a[s] Qdd_s = sigma tc + al x rho' + kappa',  sigma = a_rp + a_rd,  rho' = B r,  kappa' = A r,
+// r = (a_u, -a_rd, a_w) - sigma c.
+struct Lever {
+    double sigma;
+    double r[3];
+};
+__device__ __forceinline__ Lever lever_of(const SegCtx& c, const double (&a)[4]) {
+    Lever l;
+    l.sigma = a[1] + a[2];
+    l.r[0] = fma(-l.sigma, c.cn[0], a[0]);
+    l.r[1] = fma(-l.sigma, c.cn[1], -a[2]);
+    l.r[2] = fma(-l.sigma, c.cn[2], a[3]);
+    return l;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -215,7 +153,9 @@ struct WarpCtx {
     const DevSeg* seg;
     const DevBlk* blk;
     const DevSide* side;
+    const DevFextTab* ftab;  // this call's external forces (shared-memory copy), nullptr without forces
     const DevFext* fext;
+    const double* fvals;     // per-system (torque, force) values of this lane's system at the current step, or nullptr
     double *Qo, *Qdo, *Qsys, *Qdsys;
     double *S0, *S1, *r0, *r1, *lamv, *dinv, *knl;
     // symbolic factorisation tables (host, capi.cu symbolic_analysis)
@@ -339,45 +279,74 @@ __device__ __forceinline__ Q12 load_nonlin_k(const WarpCtx& w, const DevBlk& b, 
     return nonlin_k(b, role, d1, d2);
 }
 
-// External forces on this lane's segment (external_force.py:143-180 and the four force classes).
-__device__ __forceinline__ Q12 external_forces(const WarpCtx& w, const DevSeg& sg, const SegCtx& c, V3 rp) {
+// External forces (external_force.py:143-180 and the four force classes).  The force table lives outside the model
+// blob: DevFextTab | DevFext[nf], sorted by segment (begin[s] .. begin[s+1]).  `vals` (optional) holds per-system
+// values: 6 doubles (torque, force) per force, indexed by the force's position in the caller's list (DevFext::slot).
+// fext_transport returns the force and its torque about rp.
+__device__ __forceinline__ void fext_transport(const DevFext& fe, const double* __restrict__ vals, V3 u, V3 v, V3 w, V3 rp,
+                                               V3& tau, V3& F) {
+    if (vals != nullptr) {
+        const double* x = vals + 6 * fe.slot;
+        tau = mk(x[0], x[1], x[2]), F = mk(x[3], x[4], x[5]);
+    } else {
+        tau = mk(fe.p[0], fe.p[1], fe.p[2]), F = mk(fe.p[3], fe.p[4], fe.p[5]);
+    }
+    const V3 pt = mk(fe.p[6], fe.p[7], fe.p[8]);
+    if (fe.kind == 3) {  // in local: rotate by [u v w] Tinv (external_force_in_local.py:85-91)
+        const double* T = fe.p + 9;
+        const V3 c0 = axpy(T[0], u, axpy(T[3], v, T[6] * w));
+        const V3 c1 = axpy(T[1], u, axpy(T[4], v, T[7] * w));
+        const V3 c2 = axpy(T[2], u, axpy(T[5], v, T[8] * w));
+        const V3 Fg = axpy(F.x, c0, axpy(F.y, c1, F.z * c2));
+        const V3 tg = axpy(tau.x, c0, axpy(tau.y, c1, tau.z * c2));
+        F = Fg;
+        tau = tg;
+    }
+    if (fe.kind == 1 || fe.kind == 3) {  // local application point (external_force_global_local_point.py:68-100)
+        // rp - P = -(pt0 u + pt1 (rp - rd) + pt2 w)
+        const V3 lever = mk(0.0, 0.0, 0.0) - axpy(pt.x, u, axpy(pt.y, v, pt.z * w));
+        tau = tau + cross(lever, F);
+    } else if (fe.kind == 2) {  // global application point (external_force_global.py:67-96)
+        tau = tau + cross(rp - pt, F);
+    }
+}
+
+// Natural external forces of one segment as the reference forms them: the torque goes through the pseudo
+// interpolation matrix (natural_coordinates.py:132-158), f = N_prox^T F + N*^T tau.  Used by the FEXT evaluator, the
+// dense kernel and the lambda_r output; the dynamics only need the wrench (below).
+__device__ __forceinline__ Q12 external_forces(const DevFext* __restrict__ fext, int begin, int end,
+                                               const double* __restrict__ vals, V3 u, V3 v, V3 w, V3 rp) {
     Q12 f;
 #pragma unroll
     for (int t = 0; t < 4; ++t) f.s[t] = mk(0.0, 0.0, 0.0);
-    for (int e = sg.fext_begin; e < sg.fext_end; ++e) {
-        const DevFext& fe = w.fext[e];
-        V3 tau = mk(fe.p[0], fe.p[1], fe.p[2]), F = mk(fe.p[3], fe.p[4], fe.p[5]);
-        const V3 pt = mk(fe.p[6], fe.p[7], fe.p[8]);
-        if (fe.kind == 3) {  // in local: rotate by [u v w] Tinv (external_force_in_local.py:85-91)
-            const double* T = fe.p + 9;
-            const V3 c0 = axpy(T[0], c.u, axpy(T[3], c.v, T[6] * c.w));
-            const V3 c1 = axpy(T[1], c.u, axpy(T[4], c.v, T[7] * c.w));
-            const V3 c2 = axpy(T[2], c.u, axpy(T[5], c.v, T[8] * c.w));
-            const V3 Fg = axpy(F.x, c0, axpy(F.y, c1, F.z * c2));
-            const V3 tg = axpy(tau.x, c0, axpy(tau.y, c1, tau.z * c2));
-            F = Fg;
-            tau = tg;
-        }
-        if (fe.kind == 1 || fe.kind == 3) {  // local application point (external_force_global_local_point.py:68-100)
-            // rp - P = -(pt0 u + pt1 (rp - rd) + pt2 w)
-            const V3 lever = mk(0.0, 0.0, 0.0) - axpy(pt.x, c.u, axpy(pt.y, c.v, pt.z * c.w));
-            tau = tau + cross(lever, F);
-        } else if (fe.kind == 2) {  // global application point (external_force_global.py:67-96)
-            tau = tau + cross(rp - pt, F);
-        }
-        // pseudo interpolation matrix (natural_coordinates.py:132-158): solve [w x u, u x v, -v x w] x = tau
-        const V3 b0 = cross(c.w, c.u), b1 = cross(c.u, c.v), b2 = cross(c.w, c.v);  // -v x w = w x v
+    for (int e = begin; e < end; ++e) {
+        V3 tau, F;
+        fext_transport(fext[e], vals, u, v, w, rp, tau, F);
+        // solve [w x u, u x v, -v x w] x = tau
+        const V3 b0 = cross(w, u), b1 = cross(u, v), b2 = cross(w, v);  // -v x w = w x v
         const double det = dot(b0, cross(b1, b2));
         const double idet = fast_rcp(det);
         const double x0 = dot(tau, cross(b1, b2)) * idet;
         const double x1 = dot(b0, cross(tau, b2)) * idet;
         const double x2 = dot(b0, cross(b1, tau)) * idet;
-        f.s[0] = axpy(x1, c.v, f.s[0]);
-        f.s[1] = f.s[1] + F - x2 * c.w;
-        f.s[2] = axpy(x2, c.w, f.s[2]);
-        f.s[3] = axpy(x0, c.u, f.s[3]);
+        f.s[0] = axpy(x1, v, f.s[0]);
+        f.s[1] = f.s[1] + F - x2 * w;
+        f.s[2] = axpy(x2, w, f.s[2]);
+        f.s[3] = axpy(x0, u, f.s[3]);
     }
     return f;
+}
+
+// The same forces as a wrench about rp.  T^T f of the natural force above is exactly (tau, F): the pseudo interpolation
+// is built so that u x f_u - v x f_rd + w x f_w = tau, hence the dynamics never need the 3x3 solve.
+__device__ __forceinline__ void external_wrench(const DevFext* __restrict__ fext, int begin, int end,
+                                                const double* __restrict__ vals, V3 u, V3 v, V3 w, V3 rp, V3& tau_sum, V3& F_sum) {
+    tau_sum = mk(0.0, 0.0, 0.0), F_sum = mk(0.0, 0.0, 0.0);
+    for (int e = begin; e < end; ++e) {
+        V3 tau, F;
+        fext_transport(fext[e], vals, u, v, w, rp, tau, F);
+        tau_sum = tau_sum + tau, F_sum = F_sum + F;
+    }
 }
 
 // this lane's own segment, slot t, from / to the published stage state (Xo = w.Qo or w.Qdo)
@@ -390,86 +359,6 @@ __device__ __forceinline__ void publish3(double* Xo, int t, V3 v) {
     Xo[(3 * t) * S] = v.x, Xo[(3 * t + 1) * S] = v.y, Xo[(3 * t + 2) * S] = v.z;
 }
 
-// rigid-body right-hand side term: bias_r (+ alpha Phi_r + beta Kr Qdot)   (natural_segment.py:429-448, :508-545)
-template <int S>
-__device__ __forceinline__ void rigid_bterm(const WarpCtx& w, const SegCtx& c, const DevSeg& sg, const DynOpts& o,
-                                            double (&b)[6]) {
-    Q12 Qd;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) Qd.s[t] = own3<S>(w.Qdo, t);
-    const V3 ud = Qd.s[0], vd = Qd.s[1] - Qd.s[2], wd = Qd.s[3];
-    b[0] = 2.0 * dot(ud, ud);
-    b[1] = 2.0 * dot(ud, vd);
-    b[2] = 2.0 * dot(ud, wd);
-    b[3] = 2.0 * dot(vd, vd);
-    b[4] = 2.0 * dot(vd, wd);
-    b[5] = 2.0 * dot(wd, wd);
-    if (o.use_stab) {
-        double kqd[6];
-        kr_apply(c, Qd, kqd);
-        const double phi[6] = {dot(c.u, c.u) - 1.0,         dot(c.u, c.v) - sg.phic[0], dot(c.u, c.w) - sg.phic[1],
-                               dot(c.v, c.v) - sg.phic[2], dot(c.v, c.w) - sg.phic[3], dot(c.w, c.w) - 1.0};
-#pragma unroll
-        for (int i = 0; i < 6; ++i) b[i] += o.alpha * phi[i] + o.beta * kqd[i];
-    }
-}
-
-// three right-hand sides at once (the three rows of a LIN3 block): 3-way instruction-level parallelism
-__device__ __forceinline__ void sr_solve3(const SegCtx& c, double (&y)[6][3]) {
-#pragma unroll
-    for (int k = 0; k < 6; ++k)
-#pragma unroll
-        for (int r = k + 1; r < 6; ++r)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) y[r][j] = fma(-c.L[lidx(r, k)], y[k][j], y[r][j]);
-#pragma unroll
-    for (int k = 0; k < 6; ++k)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) y[k][j] *= c.dinv[k];
-#pragma unroll
-    for (int k = 5; k >= 0; --k)
-#pragma unroll
-        for (int r = k + 1; r < 6; ++r)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) y[k][j] = fma(-c.L[lidx(r, k)], y[r][j], y[k][j]);
-}
-
-// signed coefficient vector of a LIN3 block restricted to one side: rows are  as (x) e_c
-__device__ __forceinline__ void lin3_coefs(const DevBlk& b, int role, double (&as)[4]) {
-    const double* a = b.p + (role == CHILD ? 4 : 0);
-    const int flip = role == CHILD ? (int)0x80000000 : 0;  // sign flip on the integer pipe: the FP64 pipe is the scarce one
-#pragma unroll
-    for (int t = 0; t < 4; ++t) as[t] = __hiloint2double(__double2hiint(a[t]) ^ flip, __double2loint(a[t]));
-}
-// beta = W as, and its (u, v, w) reduction b3 = E^T beta with E = [e_u, e_rp - e_rd, e_w]
-__device__ __forceinline__ void lin3_beta(const SegCtx& c, const double (&as)[4], double (&beta)[4], double (&b3)[3]) {
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        double acc = 0.0;
-#pragma unroll
-        for (int s = 0; s < 4; ++s) acc = fma(c.W[widx(t, s)], as[s], acc);
-        beta[t] = acc;
-    }
-    b3[0] = beta[0], b3[1] = beta[1] - beta[2], b3[2] = beta[3];
-}
-
-// ---------------------------------------------------------------------------------------------
-// One forward-dynamics evaluation for the whole warp.
-// Precondition: every lane has published its segment's stage state (Q, Qdot) in w.Qs / w.Qds.
-// Every lane receives Qddot of its segment; lambda (holonomic order) goes to lam_out if non-null.
-// Every thread of the CTA must call this (it contains __syncthreads).
-//
-// GENERAL=false is the lean instantiation for models whose joints are all point-to-point (LIN3:
-// spherical / ground spherical / weld halves), without external forces or stabilisation -- the
-// lower-limb and full-body trees.  GENERAL=true handles everything.
-//
-// For two LIN3 block sides a, b on one segment (rows as_a (x) e_c', as_b (x) e_c) the contribution to
-// the joint-level Schur complement has the closed form
-//     S'_ab = (as_a . W as_b) I3 - B M_ab B^T,   M_ab = Gamma(a3)^T Sr^-1 Gamma(b3),   B = [u v w]
-// with Gamma(b3) the 6x3 matrix [[2bu,0,0],[bv,bu,0],[bw,0,bu],[0,2bv,0],[0,bw,bv],[0,0,2bw]]
-// (Kr G^-1 (as_b (x) e_c)^T = Gamma(b3) B[c,:]^T), so the three rows of a block share one
-// three-right-hand-side solve Z_b = Sr^-1 Gamma(b3).
-// ---------------------------------------------------------------------------------------------
 // 3x3 helpers for the blocked joint-level factorisation (blocks are stored row-major, element e = 3 r + c)
 template <int spw>
 __device__ __forceinline__ void load9(const double* p, double (&A)[9]) {
@@ -512,6 +401,121 @@ __device__ __forceinline__ void sym3_inverse(double a00, double a10, double a11,
 __device__ __forceinline__ V3 sym3_apply(const double (&di)[6], V3 x) {
     return mk(fma(di[0], x.x, fma(di[1], x.y, di[3] * x.z)), fma(di[1], x.x, fma(di[2], x.y, di[4] * x.z)),
               fma(di[3], x.x, fma(di[4], x.y, di[5] * x.z)));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase B: everything about this lane's segment that depends on the stage state only.
+//   B = [u v w], reciprocal basis b_i (rows of det B^-1), Ic^-1, particular accelerations A = B^-T S with
+//   S = -1/2 Bsym,  Bsym = 2 Ud^T Ud  (+ alpha Phi_r + beta Kr Qdot as symmetric matrices when stabilised:
+//   natural_segment.py:429-448, :508-545, biomechanical_model.py:416-421), gyroscopic term eta, applied wrench.
+// ---------------------------------------------------------------------------------------------
+template <bool GENERAL, bool STAB, int S>
+__device__ __forceinline__ void segment_setup(const WarpCtx& w, SegCtx& c, const DevSeg& sg, const DynOpts& o, int& status) {
+    const V3 rp = own3<S>(w.Qo, 1);
+    c.u = own3<S>(w.Qo, 0), c.v = rp - own3<S>(w.Qo, 2), c.w = own3<S>(w.Qo, 3);
+    const V3 b0 = cross(c.v, c.w), b1 = cross(c.w, c.u), b2 = cross(c.u, c.v);
+    const double det = dot(c.u, b0);
+    const double guu = dot(c.u, c.u), gvv = dot(c.v, c.v), gww = dot(c.w, c.w);
+    if (!(fabs(det) > 0.0) || !isfinite(det)) status |= 1;
+    else if (det * det < (kSmallPivot * kSmallPivot) * (guu * gvv * gww)) status |= 4;
+    const double idet = fast_rcp(det);
+    const double* N = c.N3;
+    {   // Y = B N3 B^T,  Ic = tr(Y) I - Y
+        const V3 X0 = in_basis(c, N[0], N[1], N[2]), X1 = in_basis(c, N[1], N[3], N[4]), X2 = in_basis(c, N[2], N[4], N[5]);
+        const double Yxx = fma(X0.x, c.u.x, fma(X1.x, c.v.x, X2.x * c.w.x));
+        const double Yyy = fma(X0.y, c.u.y, fma(X1.y, c.v.y, X2.y * c.w.y));
+        const double Yzz = fma(X0.z, c.u.z, fma(X1.z, c.v.z, X2.z * c.w.z));
+        const double Yxy = fma(X0.x, c.u.y, fma(X1.x, c.v.y, X2.x * c.w.y));
+        const double Yxz = fma(X0.x, c.u.z, fma(X1.x, c.v.z, X2.x * c.w.z));
+        const double Yyz = fma(X0.y, c.u.z, fma(X1.y, c.v.z, X2.y * c.w.z));
+        sym3_inverse(Yyy + Yzz, -Yxy, Yxx + Yzz, -Yxz, -Yyz, Yxx + Yyy, c.Ii, status);
+    }
+    const V3 ud = own3<S>(w.Qdo, 0), vd = own3<S>(w.Qdo, 1) - own3<S>(w.Qdo, 2), wd = own3<S>(w.Qdo, 3);
+    double s00 = -dot(ud, ud), s01 = -dot(ud, vd), s02 = -dot(ud, wd), s11 = -dot(vd, vd), s12 = -dot(vd, wd), s22 = -dot(wd, wd);
+    if (STAB && o.use_stab) {
+        const double ha = 0.5 * o.alpha, hb = 0.5 * o.beta;
+        s00 -= fma(ha, guu - 1.0, hb * (2.0 * dot(c.u, ud)));
+        s01 -= fma(ha, dot(c.u, c.v) - sg.phic[0], hb * (dot(c.u, vd) + dot(ud, c.v)));
+        s02 -= fma(ha, dot(c.u, c.w) - sg.phic[1], hb * (dot(c.u, wd) + dot(ud, c.w)));
+        s11 -= fma(ha, gvv - sg.phic[2], hb * (2.0 * dot(c.v, vd)));
+        s12 -= fma(ha, dot(c.v, c.w) - sg.phic[3], hb * (dot(c.v, wd) + dot(vd, c.w)));
+        s22 -= fma(ha, gww - 1.0, hb * (2.0 * dot(c.w, wd)));
+    }
+    s00 *= idet, s01 *= idet, s02 *= idet, s11 *= idet, s12 *= idet, s22 *= idet;
+    c.Au = axpy(s00, b0, axpy(s01, b1, s02 * b2));
+    c.Av = axpy(s01, b0, axpy(s11, b1, s12 * b2));
+    c.Aw = axpy(s02, b0, axpy(s12, b1, s22 * b2));
+    {   // eta = sum_ij N3_ij B_i x A_j
+        const V3 Z0 = in_accel(c, N[0], N[1], N[2]), Z1 = in_accel(c, N[1], N[3], N[4]), Z2 = in_accel(c, N[2], N[4], N[5]);
+        const V3 eta = cross(c.u, Z0) + cross(c.v, Z1) + cross(c.w, Z2);
+        c.tau0 = mk(-eta.x, -eta.y, -eta.z);
+    }
+    c.F0 = mk(0.0, 0.0, -9.81 * c.m);  // gravity acts at the centre of mass: no torque (natural_segment.py:562-572)
+    if (GENERAL && w.fext != nullptr) {
+        const int fb = w.ftab->begin[w.segi], fe = w.ftab->begin[w.segi + 1];
+        if (fe > fb) {
+            V3 te, Fe;
+            external_wrench(w.fext, fb, fe, w.fvals, c.u, c.v, c.w, rp, te, Fe);
+            const V3 cbar = in_basis(c, c.cn[0], c.cn[1], c.cn[2]);
+            c.F0 = c.F0 + Fe;
+            c.tau0 = c.tau0 + te - cross(cbar, Fe);
+        }
+    }
+}
+
+// One term a (x) d of a non-LIN3 row (a: 4 constant coefficients times `scale`, d: 3-vector) as it acts on the
+// segment's six unknowns and on the particular acceleration: n += rho' x d, f += sigma d, kappa += d . A r.
+struct Row6 {
+    V3 n, f;
+    double kap;
+};
+template <bool KAP>
+__device__ __forceinline__ void row6_term(const SegCtx& c, const double* a, double scale, V3 d, Row6& r) {
+    const double as[4] = {scale * a[0], scale * a[1], scale * a[2], scale * a[3]};
+    const Lever lv = lever_of(c, as);
+    r.n = r.n + cross(in_basis(c, lv.r[0], lv.r[1], lv.r[2]), d);
+    r.f = axpy(lv.sigma, d, r.f);
+    if (KAP) r.kap += dot(d, in_accel(c, lv.r[0], lv.r[1], lv.r[2]));
+}
+// (n, fdir, kappa) of a non-LIN3 row restricted to this lane's segment; same case analysis as nonlin_k
+template <bool KAP>
+__device__ __forceinline__ Row6 nonlin_row6(const SegCtx& c, const DevBlk& b, int role, V3 d1, V3 d2) {
+    Row6 r;
+    r.n = mk(0.0, 0.0, 0.0), r.f = mk(0.0, 0.0, 0.0), r.kap = 0.0;
+    const double* p = b.p;
+    if (b.type == DOT) {
+        row6_term<KAP>(c, role == CHILD ? p + 4 : p, 1.0, d1, r);
+    } else if (b.type == CLEN) {
+        row6_term<KAP>(c, role == CHILD ? p + 4 : p, role == CHILD ? -2.0 : 2.0, d1, r);
+    } else if (role == CHILD) {  // SOP, blocks as coded (swapped)
+        row6_term<KAP>(c, p, 1.0, d1, r);
+    } else {
+        row6_term<KAP>(c, p + 4, -1.0, d1, r);
+        row6_term<KAP>(c, p + 8, 1.0, d2, r);
+    }
+    return r;
+}
+template <bool KAP, int S>
+__device__ __forceinline__ Row6 load_row6(const WarpCtx& w, const SegCtx& c, const DevBlk& b, int role, int q) {
+    const double* src = w.knl + q * S;
+    const V3 d1 = mk(src[0], src[S], src[2 * S]);
+    const V3 d2 = nonlin_two_terms(b, role) ? mk(src[3 * S], src[4 * S], src[5 * S]) : mk(0.0, 0.0, 0.0);
+    return nonlin_row6<KAP>(c, b, role, d1, d2);
+}
+
+// Ic^-1 (rho x e_c), c = 0..2: the three columns of Ic^-1 [rho]x^T a point-to-point side needs for its pair blocks
+__device__ __forceinline__ void lever_columns(const double (&di)[6], V3 rho, V3 (&V)[3]) {
+    V[0] = mk(fma(di[1], rho.z, -(di[3] * rho.y)), fma(di[2], rho.z, -(di[4] * rho.y)), fma(di[4], rho.z, -(di[5] * rho.y)));
+    V[1] = mk(fma(di[3], rho.x, -(di[0] * rho.z)), fma(di[4], rho.x, -(di[1] * rho.z)), fma(di[5], rho.x, -(di[3] * rho.z)));
+    V[2] = mk(fma(di[0], rho.y, -(di[1] * rho.x)), fma(di[1], rho.y, -(di[2] * rho.x)), fma(di[3], rho.y, -(di[4] * rho.x)));
+}
+
+// signed coefficient vector of a LIN3 block restricted to one side: rows are  as (x) e_c
+__device__ __forceinline__ void lin3_coefs(const DevBlk& b, int role, double (&as)[4]) {
+    const double* a = b.p + (role == CHILD ? 4 : 0);
+    const int flip = role == CHILD ? (int)0x80000000 : 0;  // sign flip on the integer pipe: the FP64 pipe is the scarce one
+#pragma unroll
+    for (int t = 0; t < 4; ++t) as[t] = __hiloint2double(__double2hiint(a[t]) ^ flip, __double2loint(a[t]));
 }
 
 // Pivot K of the blocked LDL^T: invert D_K, y-hat_K = D_K^-1 r_K, then for the rows I of column K that this warp
@@ -641,57 +645,84 @@ __device__ __forceinline__ void solve_two_leaves(const WarpCtx& w, int& status) 
     }
 }
 
+// lambda_r of this lane's segment from  Kr^T lambda_r = R,  R = f - Kj^T lambda_j - G Qdd  (the rows of the reference's
+// KKT system that the null-space form never touches).  Kr^T lambda_r reads  R_u = 2 l0 u + l1 v + l2 w,
+// R_rp = l1 u + 2 l3 v + l4 w = -R_rd,  R_w = l2 u + l4 v + 2 l5 w,  so  B^-1 [R_u R_rp R_w] = [[2 l0, l1, l2], [l1, 2 l3, l4],
+// [l2, l4, 2 l5]]; the off-diagonal pairs agree up to rounding and are averaged.  Output path only (forward_dynamics,
+// the last step of rk4 when lambda is asked for): it is kept out of line so that it does not weigh on the hot loop.
 template <bool GENERAL, int S>
+__device__ __noinline__ void rigid_multipliers(const WarpCtx& w, const SegCtx& c, const DevSeg& sg, const Q12& Qdd, double* lam_r) {
+    constexpr int spw = S;
+    // M4 rows u, rp, w from (m, c, J), J = N3 + m c c^T   (natural_inertial_parameters.py:153-177)
+    const double m = c.m, c0 = c.cn[0], c1 = c.cn[1], c2 = c.cn[2];
+    const double J00 = fma(m * c0, c0, c.N3[0]), J01 = fma(m * c0, c1, c.N3[1]), J02 = fma(m * c0, c2, c.N3[2]);
+    const double J11 = fma(m * c1, c1, c.N3[3]), J12 = fma(m * c1, c2, c.N3[4]), J22 = fma(m * c2, c2, c.N3[5]);
+    const double Mu[4] = {J00, m * c0 + J01, -J01, J02};
+    const double Mr[4] = {m * c0 + J01, m + 2.0 * m * c1 + J11, -(m * c1 + J11), m * c2 + J12};
+    const double Mw[4] = {J02, m * c2 + J12, -J12, J22};
+    const V3 rp = own3<S>(w.Qo, 1);
+    const double g = -9.81 * m;
+    V3 Ru = mk(0.0, 0.0, g * c0), Rr = mk(0.0, 0.0, g * (1.0 + c1)), Rw = mk(0.0, 0.0, g * c2);
+    if (GENERAL && w.fext != nullptr) {
+        const Q12 fe = external_forces(w.fext, w.ftab->begin[w.segi], w.ftab->begin[w.segi + 1], w.fvals, c.u, c.v, c.w, rp);
+        Ru = Ru + fe.s[0], Rr = Rr + fe.s[1], Rw = Rw + fe.s[3];
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        Ru = axpy(-Mu[t], Qdd.s[t], Ru);
+        Rr = axpy(-Mr[t], Qdd.s[t], Rr);
+        Rw = axpy(-Mw[t], Qdd.s[t], Rw);
+    }
+    for (int e = sg.side_begin; e < sg.side_end; ++e) {
+        const DevSide sd = w.side[e];
+        const DevBlk& b = w.blk[sd.blk];
+        const double* lj = w.lamv + b.jrow * spw;
+        if (!GENERAL || b.type == LIN3) {
+            double as[4];
+            lin3_coefs(b, sd.role, as);
+            const V3 lam = mk(lj[0], lj[spw], lj[2 * spw]);
+            Ru = axpy(-as[0], lam, Ru), Rr = axpy(-as[1], lam, Rr), Rw = axpy(-as[3], lam, Rw);
+        } else {
+            const Q12 k = load_nonlin_k<S>(w, b, sd.role, sd.nl_slot);
+            Ru = axpy(-lj[0], k.s[0], Ru), Rr = axpy(-lj[0], k.s[1], Rr), Rw = axpy(-lj[0], k.s[3], Rw);
+        }
+    }
+    const V3 b0 = cross(c.v, c.w), b1 = cross(c.w, c.u), b2 = cross(c.u, c.v);
+    const double idet = 1.0 / dot(c.u, b0);
+    lam_r[0] = 0.5 * idet * dot(b0, Ru);
+    lam_r[1] = 0.5 * idet * (dot(b1, Ru) + dot(b0, Rr));
+    lam_r[2] = 0.5 * idet * (dot(b2, Ru) + dot(b0, Rw));
+    lam_r[3] = 0.5 * idet * dot(b1, Rr);
+    lam_r[4] = 0.5 * idet * (dot(b2, Rr) + dot(b1, Rw));
+    lam_r[5] = 0.5 * idet * dot(b2, Rw);
+}
+
+// ---------------------------------------------------------------------------------------------
+// One forward-dynamics evaluation for the whole warp.
+// Precondition: every lane has published its segment's stage state (Q, Qdot) in w.Qs / w.Qds.
+// Every lane receives Qddot of its segment; lambda (holonomic order) goes to lam_out if non-null.
+// Every thread of the CTA must call this (it contains __syncthreads).
+//
+// GENERAL=false is the lean instantiation for models whose joints are all point-to-point (LIN3: spherical / ground
+// spherical / weld halves) without external forces -- the lower-limb and full-body trees; GENERAL=true handles every
+// block kind and the forces.  STAB compiles the Baumgarte terms in (they read the other segment of a joint, so the
+// caller must order the publication of a stage state with a barrier when STAB or GENERAL is set).
+// ---------------------------------------------------------------------------------------------
+template <bool GENERAL, bool STAB, int S>
 __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& c, const DynOpts& o, Q12& Qdd,
                                                       double* lam_out, int& status) {
     constexpr int spw = S;
     const DevSeg& sg = w.seg[w.segi];
+    const bool stab = STAB && o.use_stab;
 
-    // ---- B. segment-local factorisation
-    const V3 rp = own3<S>(w.Qo, 1);
-    c.u = own3<S>(w.Qo, 0), c.v = rp - own3<S>(w.Qo, 2), c.w = own3<S>(w.Qo, 3);
-    sr_factor(c, status);
-    Q12 f;  // natural forces: gravity + external
-    if (GENERAL && sg.fext_end > sg.fext_begin) {
-        f = external_forces(w, sg, c, rp);
-    } else {
-#pragma unroll
-        for (int t = 0; t < 4; ++t) f.s[t] = mk(0.0, 0.0, 0.0);
-    }
-#pragma unroll
-    for (int t = 0; t < 4; ++t) f.s[t].z += c.fg[t];
-    DynOpts oo = o;
-    if (!GENERAL) oo.use_stab = 0;
+    // ---- B. segment-local quantities
+    segment_setup<GENERAL, STAB, S>(w, c, sg, o, status);
+    V3 tau = c.tau0, F = c.F0;  // Newton-Euler right-hand sides, joint multipliers subtracted in phase H
 
-    // Two passes over the same segment solve  x = A_i f + (particular part):
-    //   pass 0 with f = applied forces gives the free acceleration abar that feeds the joint-level system,
-    //   pass 1 with f - Kj^T lambda_j gives Qddot and lambda_r.
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-        Q12 x;
-        double z[6];
-        {
-            const Q12 a = apply_W(c.W, f);
-            kr_apply(c, a, z);
-            double br[6];  // recomputed in both passes rather than kept alive across the joint-level phases
-            rigid_bterm<S>(w, c, sg, oo, br);
-#pragma unroll
-            for (int i = 0; i < 6; ++i) z[i] += br[i];
-            sr_solve(c, z);
-            const Q12 corr = ginv_krt(c, z);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) x.s[t] = a.s[t] - corr.s[t];
-        }
-        if (pass == 1 || w.mj == 0) {
-            Qdd = x;
-            if (lam_out != nullptr) {
-#pragma unroll
-                for (int i = 0; i < 6; ++i) lam_out[sg.rigid_row + i] = z[i];  // lambda_r
-            }
-            break;
-        }
+    if (w.mj > 0) {
         const int nb = w.nb, mjp = 3 * nb;
         const DevHeader* hd = w.hdr;
+        const V3 afree = sym3_apply(c.Ii, c.tau0), tfree = c.minv * c.F0;  // free accelerations (no joint forces)
 
         // ---- C. zero what the assembly does not overwrite (pure fill blocks, blocks of nodes made of single
         //         rows); padding rows get a unit diagonal and a zero right-hand side.  Lean models have
@@ -710,92 +741,70 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
             }
         }
 
-        // ---- D. right-hand side rhs' = Kj abar + b_j (copy `role` of each row is written by exactly one
-        //         lane) and the explicit rows of non-LIN3 blocks
-        {
-            for (int e = sg.side_begin; e < sg.side_end; ++e) {
-                const DevSide sd = w.side[e];
-                const DevBlk& b = w.blk[sd.blk];
-                double* rr = (sd.role == CHILD ? w.r0 : w.r1) + b.jrow * spw;
-                if (!GENERAL || b.type == LIN3) {
-                    double as[4];
-                    lin3_coefs(b, sd.role, as);
-                    V3 r = mk(0.0, 0.0, 0.0);
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) r = axpy(as[t], x.s[t], r);
-                    if (GENERAL && sd.role == CHILD && o.use_stab) {
-                        // Phi = c0 + N_p Q_p - N_c Q_c ; K Qdot = N_p Qdot_p - N_c Qdot_c
-                        V3 phi = mk(b.p[8], b.p[9], b.p[10]) - lin_form<S>(w, w.Qsys, b.child, b.p + 4);
-                        V3 kqd = mk(0.0, 0.0, 0.0) - lin_form<S>(w, w.Qdsys, b.child, b.p + 4);
-                        if (b.parent >= 0) {
-                            phi = phi + lin_form<S>(w, w.Qsys, b.parent, b.p);
-                            kqd = kqd + lin_form<S>(w, w.Qdsys, b.parent, b.p);
-                        }
-                        r = axpy(o.alpha, phi, axpy(o.beta, kqd, r));
+        // ---- D. right-hand side rhs' = J a_free + kappa + b_j: every segment adds its share into its own copy of the
+        //         row (copy `role`, written by exactly one lane); the child side also carries the row's bias terms
+        for (int e = sg.side_begin; e < sg.side_end; ++e) {
+            const DevSide sd = w.side[e];
+            const DevBlk& b = w.blk[sd.blk];
+            double* rr = (sd.role == CHILD ? w.r0 : w.r1) + b.jrow * spw;
+            if (!GENERAL || b.type == LIN3) {
+                double as[4];
+                lin3_coefs(b, sd.role, as);
+                const Lever lv = lever_of(c, as);
+                const V3 rho = in_basis(c, lv.r[0], lv.r[1], lv.r[2]);
+                V3 r = axpy(lv.sigma, tfree, cross(afree, rho) + in_accel(c, lv.r[0], lv.r[1], lv.r[2]));
+                if (stab && sd.role == CHILD) {
+                    // Phi = c0 + N_p Q_p - N_c Q_c ; K Qdot = N_p Qdot_p - N_c Qdot_c
+                    V3 phi = mk(b.p[8], b.p[9], b.p[10]) - lin_form<S>(w, w.Qsys, b.child, b.p + 4);
+                    V3 kqd = mk(0.0, 0.0, 0.0) - lin_form<S>(w, w.Qdsys, b.child, b.p + 4);
+                    if (b.parent >= 0) {
+                        phi = phi + lin_form<S>(w, w.Qsys, b.parent, b.p);
+                        kqd = kqd + lin_form<S>(w, w.Qdsys, b.parent, b.p);
                     }
-                    rr[0] = r.x, rr[spw] = r.y, rr[2 * spw] = r.z;
-                    if (b.parent < 0) {  // no parent lane: the child also settles the second copy
-                        double* r1p = w.r1 + b.jrow * spw;
-                        r1p[0] = 0.0, r1p[spw] = 0.0, r1p[2 * spw] = 0.0;
-                    }
-                } else {
-                    V3 d1, d2;
-                    double bterm;
-                    nonlin_row<S>(w, b, sd.role, o, d1, d2, bterm);
-                    const Q12 k = nonlin_k(b, sd.role, d1, d2);
-                    double acc = bterm;
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) acc += dot(k.s[t], x.s[t]);
-                    double* dst = w.knl + sd.nl_slot * S;
-                    dst[0] = d1.x, dst[S] = d1.y, dst[2 * S] = d1.z;
-                    if (nonlin_two_terms(b, sd.role)) dst[3 * S] = d2.x, dst[4 * S] = d2.y, dst[5 * S] = d2.z;
-                    rr[0] = acc;
-                    if (b.parent < 0) w.r1[b.jrow * spw] = 0.0;
+                    r = axpy(o.alpha, phi, axpy(o.beta, kqd, r));
                 }
+                rr[0] = r.x, rr[spw] = r.y, rr[2 * spw] = r.z;
+                if (b.parent < 0) {  // no parent lane: the child also settles the second copy
+                    double* r1p = w.r1 + b.jrow * spw;
+                    r1p[0] = 0.0, r1p[spw] = 0.0, r1p[2 * spw] = 0.0;
+                }
+            } else {
+                V3 d1, d2;
+                double bterm;
+                nonlin_row<S>(w, b, sd.role, o, d1, d2, bterm);
+                const Row6 r6 = nonlin_row6<true>(c, b, sd.role, d1, d2);
+                double* dst = w.knl + sd.nl_slot * S;
+                dst[0] = d1.x, dst[S] = d1.y, dst[2 * S] = d1.z;
+                if (nonlin_two_terms(b, sd.role)) dst[3 * S] = d2.x, dst[4 * S] = d2.y, dst[5 * S] = d2.z;
+                rr[0] = dot(r6.n, afree) + dot(r6.f, tfree) + r6.kap + bterm;
+                if (b.parent < 0) w.r1[b.jrow * spw] = 0.0;
             }
         }
 
-        // ---- E1. LIN3 x LIN3 pairs on this segment: S'_ab = gamma I3 - B M_ab B^T, one 3x3 block each
-        {
-            for (int e = sg.side_begin; e < sg.side_end; ++e) {
-                const DevSide sd = w.side[e];
-                const DevBlk& b = w.blk[sd.blk];
-                if (GENERAL && b.type != LIN3) continue;
-                double asb[4], betab[4], b3[3];
+        // ---- E. this segment's contribution to S':  S'_ab = fdir_a . fdir_b / m + n_a . Ic^-1 n_b
+        for (int e = sg.side_begin; e < sg.side_end; ++e) {
+            const DevSide sd = w.side[e];
+            const DevBlk& b = w.blk[sd.blk];
+            if (!GENERAL || b.type == LIN3) {
+                // point-to-point side b against the point-to-point sides a >= b: 3x3 block gamma I + [V_c x rho_a]
+                double asb[4];
                 lin3_coefs(b, sd.role, asb);
-                lin3_beta(c, asb, betab, b3);
-                double Z[6][3];  // Sr^-1 Gamma(b3)
-                Z[0][0] = 2.0 * b3[0], Z[0][1] = 0.0, Z[0][2] = 0.0;
-                Z[1][0] = b3[1], Z[1][1] = b3[0], Z[1][2] = 0.0;
-                Z[2][0] = b3[2], Z[2][1] = 0.0, Z[2][2] = b3[0];
-                Z[3][0] = 0.0, Z[3][1] = 2.0 * b3[1], Z[3][2] = 0.0;
-                Z[4][0] = 0.0, Z[4][1] = b3[2], Z[4][2] = b3[1];
-                Z[5][0] = 0.0, Z[5][1] = 0.0, Z[5][2] = 2.0 * b3[2];
-                sr_solve3(c, Z);
+                const Lever lb = lever_of(c, asb);
+                V3 V[3];
+                lever_columns(c.Ii, in_basis(c, lb.r[0], lb.r[1], lb.r[2]), V);
+                const double sbm = lb.sigma * c.minv;
                 const int Jb = b.jrow / 3;
                 for (int e2 = e; e2 < sg.side_end; ++e2) {
                     const DevSide sa = w.side[e2];
                     const DevBlk& a = w.blk[sa.blk];
                     if (GENERAL && a.type != LIN3) continue;
-                    double asa[4], betaa[4], a3[3];
+                    double asa[4];
                     lin3_coefs(a, sa.role, asa);
-                    lin3_beta(c, asa, betaa, a3);
-                    double gamma = 0.0;
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) gamma = fma(asa[t], betab[t], gamma);
-                    // M = Gamma(a3)^T Z (3x3), P = B M (columns), block = gamma I - P B^T
-                    V3 Pc[3];
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) {
-                        const double m0 = fma(2.0 * a3[0], Z[0][j], fma(a3[1], Z[1][j], a3[2] * Z[2][j]));
-                        const double m1 = fma(a3[0], Z[1][j], fma(2.0 * a3[1], Z[3][j], a3[2] * Z[4][j]));
-                        const double m2 = fma(a3[0], Z[2][j], fma(a3[1], Z[4][j], (2.0 * a3[2]) * Z[5][j]));
-                        Pc[j] = axpy(m0, c.u, axpy(m1, c.v, m2 * c.w));
-                    }
-                    // element (row r of a, row cc of b) = gamma delta - sum_j Pc[j][r] * B[cc][j],  B[cc] = (u_cc, v_cc, w_cc)
-                    const V3 col0 = mk(0, 0, 0) - axpy(c.u.x, Pc[0], axpy(c.v.x, Pc[1], c.w.x * Pc[2]));
-                    const V3 col1 = mk(0, 0, 0) - axpy(c.u.y, Pc[0], axpy(c.v.y, Pc[1], c.w.y * Pc[2]));
-                    const V3 col2 = mk(0, 0, 0) - axpy(c.u.z, Pc[0], axpy(c.v.z, Pc[1], c.w.z * Pc[2]));
+                    const Lever la = lever_of(c, asa);
+                    const V3 rho_a = in_basis(c, la.r[0], la.r[1], la.r[2]);
+                    const double gamma = la.sigma * sbm;
+                    // element (row r of a, row cc of b) = gamma delta + (rho_a x e_r) . V_cc = gamma delta + (V_cc x rho_a)_r
+                    const V3 col0 = cross(V[0], rho_a), col1 = cross(V[1], rho_a), col2 = cross(V[2], rho_a);
                     const int Ia = a.jrow / 3;
                     if (Ia >= Jb) {  // block (Ia, Jb): rows of a, columns of b
                         const int s2 = w.slot2_tab[Ia * nb + Jb];
@@ -811,26 +820,10 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                         Sc[6 * spw] = col2.x, Sc[7 * spw] = col2.y, Sc[8 * spw] = col2.z + gamma;
                     }
                 }
-            }
-        }
-
-        // ---- E2. pairs with at least one non-LIN3 row: explicit q' = A_i k_b^T of the non-LIN3 row b
-        if (GENERAL) {
-            for (int e = sg.side_begin; e < sg.side_end; ++e) {
-                const DevSide sd = w.side[e];
-                const DevBlk& b = w.blk[sd.blk];
-                if (b.type == LIN3) continue;
-                const Q12 kb = load_nonlin_k<S>(w, b, sd.role, sd.nl_slot);
-                Q12 q;
-                {
-                    double y[6];
-                    q = apply_W(c.W, kb);
-                    kr_apply(c, q, y);
-                    sr_solve(c, y);
-                    const Q12 corr = ginv_krt(c, y);
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) q.s[t] = q.s[t] - corr.s[t];
-                }
+            } else {
+                // single row b against every point-to-point side and against the single rows a >= b
+                const Row6 rb6 = load_row6<false, S>(w, c, b, sd.role, sd.nl_slot);
+                const V3 yb = sym3_apply(c.Ii, rb6.n), fbm = c.minv * rb6.f;
                 const int Ib = b.jrow / 3, rb = b.jrow - 3 * Ib;
                 for (int e2 = sg.side_begin; e2 < sg.side_end; ++e2) {
                     const DevSide sa = w.side[e2];
@@ -839,9 +832,9 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                     if (a.type == LIN3) {
                         double asa[4];
                         lin3_coefs(a, sa.role, asa);
-                        V3 r = mk(0.0, 0.0, 0.0);
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) r = axpy(asa[t], q.s[t], r);
+                        const Lever la = lever_of(c, asa);
+                        const V3 rho_a = in_basis(c, la.r[0], la.r[1], la.r[2]);
+                        const V3 r = axpy(la.sigma, fbm, cross(yb, rho_a));
                         const int Ia = a.jrow / 3;  // LIN3 blocks are whole nodes, never Ib
                         if (Ia > Ib) {  // rows of a, column rb
                             const int s2 = w.slot2_tab[Ia * nb + Ib];
@@ -853,10 +846,8 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                             Sc[0] = r.x, Sc[spw] = r.y, Sc[2 * spw] = r.z;
                         }
                     } else if (e2 >= e) {  // every pair of single rows once
-                        const Q12 ka = load_nonlin_k<S>(w, a, sa.role, sa.nl_slot);
-                        double acc = 0.0;
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) acc += dot(ka.s[t], q.s[t]);
+                        const Row6 ra6 = load_row6<false, S>(w, c, a, sa.role, sa.nl_slot);
+                        const double acc = dot(ra6.f, fbm) + dot(ra6.n, yb);
                         const int Ia = a.jrow / 3, ra = a.jrow - 3 * Ia;
                         // the larger ROW decides the block orientation and whose role picks the copy
                         const bool a_larger = a.jrow >= b.jrow;
@@ -880,9 +871,8 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
             __syncthreads();  // closes the assembly
             solve_two_leaves<S>(w, status);
         } else if (hd->serial_solve != 0) {
-            // serial schedule (host decision: the elimination offers no parallelism across warps, e.g. the lower
-            // limb's hip / ankle pivots both update the knee block): the first warp factors and solves everything
-            // between two barriers -- no barrier per level, no pivot inverted twice.
+            // serial schedule (host decision: the elimination offers no parallelism across warps): the first warp
+            // factors and solves everything between two barriers -- no barrier per level, no pivot inverted twice.
             __syncthreads();
             if (w.segi == 0) {
 #pragma unroll 1
@@ -916,36 +906,41 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
         }
         __syncthreads();
 
-        // ---- H. f <- f - Kj^T lambda_j for the second pass.  Without external forces f is just gravity: it is
-        //         rebuilt here instead of being kept alive (24 registers) across the joint-level phases.
-        if (!GENERAL) {
-#pragma unroll
-            for (int t = 0; t < 4; ++t) f.s[t] = mk(0.0, 0.0, c.fg[t]);
-        }
-        {
-            for (int e = sg.side_begin; e < sg.side_end; ++e) {
-                const DevSide sd = w.side[e];
-                const DevBlk& b = w.blk[sd.blk];
-                const double* lj = w.lamv + b.jrow * spw;
-                if (!GENERAL || b.type == LIN3) {
-                    double as[4];
-                    lin3_coefs(b, sd.role, as);
-                    const V3 lam = mk(lj[0], lj[spw], lj[2 * spw]);
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) f.s[t] = axpy(-as[t], lam, f.s[t]);
-                    if (lam_out != nullptr && sd.role == CHILD) {
-                        lam_out[b.row_h + 0] = lam.x, lam_out[b.row_h + 1] = lam.y, lam_out[b.row_h + 2] = lam.z;
-                    }
-                } else {
-                    const double lam = lj[0];
-                    const Q12 k = load_nonlin_k<S>(w, b, sd.role, sd.nl_slot);
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) f.s[t] = axpy(-lam, k.s[t], f.s[t]);
-                    if (lam_out != nullptr && sd.role == CHILD) lam_out[b.row_h] = lam;
+        // ---- H. joint forces on this segment:  F -= sum fdir lambda,  tau -= sum n lambda
+        for (int e = sg.side_begin; e < sg.side_end; ++e) {
+            const DevSide sd = w.side[e];
+            const DevBlk& b = w.blk[sd.blk];
+            const double* lj = w.lamv + b.jrow * spw;
+            if (!GENERAL || b.type == LIN3) {
+                double as[4];
+                lin3_coefs(b, sd.role, as);
+                const Lever lv = lever_of(c, as);
+                const V3 lam = mk(lj[0], lj[spw], lj[2 * spw]);
+                F = axpy(-lv.sigma, lam, F);
+                tau = tau - cross(in_basis(c, lv.r[0], lv.r[1], lv.r[2]), lam);
+                if (lam_out != nullptr && sd.role == CHILD) {
+                    lam_out[b.row_h + 0] = lam.x, lam_out[b.row_h + 1] = lam.y, lam_out[b.row_h + 2] = lam.z;
                 }
+            } else {
+                const double lam = lj[0];
+                const Row6 r6 = load_row6<false, S>(w, c, b, sd.role, sd.nl_slot);
+                F = axpy(-lam, r6.f, F);
+                tau = axpy(-lam, r6.n, tau);
+                if (lam_out != nullptr && sd.role == CHILD) lam_out[b.row_h] = lam;
             }
         }
     }
+
+    // ---- I. Newton-Euler and back to natural accelerations:  Qdd = T (al, tc) + q_p
+    {
+        const V3 al = sym3_apply(c.Ii, tau), tc = c.minv * F;
+        const V3 cbar = in_basis(c, c.cn[0], c.cn[1], c.cn[2]);
+        Qdd.s[0] = cross(al, c.u) + c.Au;
+        Qdd.s[3] = cross(al, c.w) + c.Aw;
+        Qdd.s[1] = tc - cross(al, cbar) - in_accel(c, c.cn[0], c.cn[1], c.cn[2]);
+        Qdd.s[2] = Qdd.s[1] - (cross(al, c.v) + c.Av);
+    }
+    if (lam_out != nullptr) rigid_multipliers<GENERAL, S>(w, c, sg, Qdd, lam_out + sg.rigid_row);
     // No barrier here: lambda_j lives in its own array, so the next evaluation may start assembling while
     // slower warps still read it; the barriers inside the next evaluation order everything else.
 }

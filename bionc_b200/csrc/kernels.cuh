@@ -13,81 +13,30 @@ struct MinCtas {
     static constexpr int value = MAXT <= 32 ? 8 : (MAXT <= 64 ? 4 : (MAXT <= 128 ? 4 : (MAXT <= 256 ? 2 : 1)));
 };
 
-// ---- inverse of a symmetric 4x4 given by its packed upper triangle (LDL^T, no pivoting) ----------
-__device__ __forceinline__ void sym4_inverse(const double (&M)[10], double (&Wout)[10], int& status) {
-    double A[4][4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c <= r; ++c) A[r][c] = M[widx(r, c)];
-    double dinv[4], L[4][4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const double piv = A[k][k];
-        if (!(fabs(piv) > 0.0) || !isfinite(piv)) status |= 1;
-        dinv[k] = fast_rcp(piv);
-        double col[4];
-#pragma unroll
-        for (int r = k + 1; r < 4; ++r) {
-            col[r] = A[r][k];
-            L[r][k] = col[r] * dinv[k];
-        }
-#pragma unroll
-        for (int r = k + 1; r < 4; ++r)
-#pragma unroll
-            for (int c = k + 1; c <= r; ++c) A[r][c] = fma(-L[r][k], col[c], A[r][c]);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {  // column j of the inverse, rows >= j are enough (symmetric)
-        double y[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) y[r] = (r == j) ? 1.0 : 0.0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-            for (int r = k + 1; r < 4; ++r) y[r] = fma(-L[r][k], y[k], y[r]);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) y[k] *= dinv[k];
-#pragma unroll
-        for (int k = 3; k >= 0; --k)
-#pragma unroll
-            for (int r = k + 1; r < 4; ++r) y[k] = fma(-L[r][k], y[r], y[k]);
-#pragma unroll
-        for (int r = j; r < 4; ++r) Wout[widx(j, r)] = y[r];
-    }
-}
-
-// M4 from natural inertial parameters (natural_inertial_parameters.py:153-177) and gravity (natural_segment.py:562-572)
-__device__ __forceinline__ void inertia_to_constants(const double* ip, double (&W)[10], double (&fg)[4], int& status) {
+// What the dynamics need of the natural inertial parameters ip = [m, c(3), J00 J01 J02 J11 J12 J22]
+// (natural_inertial_parameters.py:153-177): N3 = J - m c c^T, c, m, 1/m.  No inverse of M4 is involved.
+__device__ __forceinline__ void inertia_to_constants(const double* __restrict__ ip, SegCtx& c, int& status) {
     const double m = ip[0], c0 = ip[1], c1 = ip[2], c2 = ip[3];
-    const double J00 = ip[4], J01 = ip[5], J02 = ip[6], J11 = ip[7], J12 = ip[8], J22 = ip[9];
-    double M[10];
-    M[widx(0, 0)] = J00;
-    M[widx(0, 1)] = m * c0 + J01;
-    M[widx(0, 2)] = -J01;
-    M[widx(0, 3)] = J02;
-    M[widx(1, 1)] = m + 2.0 * m * c1 + J11;
-    M[widx(1, 2)] = -(m * c1 + J11);
-    M[widx(1, 3)] = m * c2 + J12;
-    M[widx(2, 2)] = J11;
-    M[widx(2, 3)] = -J12;
-    M[widx(3, 3)] = J22;
-    sym4_inverse(M, W, status);
-    const double g = -9.81;
-    fg[0] = c0 * m * g;
-    fg[1] = (1.0 + c1) * m * g;
-    fg[2] = -c1 * m * g;
-    fg[3] = c2 * m * g;
+    c.N3[0] = fma(-m * c0, c0, ip[4]), c.N3[1] = fma(-m * c0, c1, ip[5]), c.N3[2] = fma(-m * c0, c2, ip[6]);
+    c.N3[3] = fma(-m * c1, c1, ip[7]), c.N3[4] = fma(-m * c1, c2, ip[8]), c.N3[5] = fma(-m * c2, c2, ip[9]);
+    c.cn[0] = c0, c.cn[1] = c1, c.cn[2] = c2;
+    c.m = m, c.minv = 1.0 / m;
+    if (!(fabs(m) > 0.0) || !isfinite(m)) status |= 1;
 }
 
 // ---- per-CTA setup: copy the model blob to shared memory, carve the working set ----------------------
 template <int S>
-__device__ __forceinline__ void setup_cta(const unsigned char* __restrict__ blob, int blob_bytes, unsigned char* smem,
-                                          WarpCtx& w) {
+__device__ __forceinline__ void setup_cta(const unsigned char* __restrict__ blob, int blob_bytes, const FextArgs& fx,
+                                          unsigned char* smem, WarpCtx& w) {
     {
         const int4* src = reinterpret_cast<const int4*>(blob);
         int4* dst = reinterpret_cast<int4*>(smem);
         for (int i = threadIdx.x; i < blob_bytes / 16; i += blockDim.x) dst[i] = src[i];
+        if (fx.tab != nullptr) {  // this call's force table behind the blob
+            const int4* fsrc = reinterpret_cast<const int4*>(fx.tab);
+            int4* fdst = reinterpret_cast<int4*>(smem + blob_bytes);
+            for (int i = threadIdx.x; i < fx.tab_bytes / 16; i += blockDim.x) fdst[i] = fsrc[i];
+        }
     }
     __syncthreads();
     const DevHeader* h = reinterpret_cast<const DevHeader*>(smem);
@@ -95,11 +44,13 @@ __device__ __forceinline__ void setup_cta(const unsigned char* __restrict__ blob
     w.seg = reinterpret_cast<const DevSeg*>(smem + h->off_seg);
     w.blk = reinterpret_cast<const DevBlk*>(smem + h->off_blk);
     w.side = reinterpret_cast<const DevSide*>(smem + h->off_side);
-    w.fext = reinterpret_cast<const DevFext*>(smem + h->off_fext);
+    w.ftab = fx.tab != nullptr ? reinterpret_cast<const DevFextTab*>(smem + blob_bytes) : nullptr;
+    w.fext = fx.tab != nullptr ? reinterpret_cast<const DevFext*>(smem + blob_bytes + sizeof(DevFextTab)) : nullptr;
+    w.fvals = nullptr;
     w.N = h->N, w.mj = h->mj, w.nb = h->nb;
     w.segi = threadIdx.x >> 5;       // warp = segment
     w.lane = threadIdx.x & (S - 1);  // lane = system; with S < 32 systems per CTA the upper lanes mirror the lower ones
-    double* base = reinterpret_cast<double*>(smem + blob_bytes);
+    double* base = reinterpret_cast<double*>(smem + blob_bytes + (fx.tab != nullptr ? fx.tab_bytes : 0));
     double* Qs = base;
     double* Qds = Qs + 12 * S * w.N;
     w.Qsys = Qs + w.lane, w.Qdsys = Qds + w.lane;
@@ -148,13 +99,14 @@ __device__ __forceinline__ void store_q12(double* __restrict__ p, const Q12& q) 
 __device__ __forceinline__ void load_constants(const WarpCtx& w, const double* __restrict__ inertia, long long gsys,
                                                SegCtx& c, int& status) {
     if (inertia != nullptr) {
-        inertia_to_constants(inertia + ((size_t)gsys * w.N + w.segi) * 10, c.W, c.fg, status);
+        inertia_to_constants(inertia + ((size_t)gsys * w.N + w.segi) * 10, c, status);
     } else {
         const DevSeg& sg = w.seg[w.segi];
 #pragma unroll
-        for (int i = 0; i < 10; ++i) c.W[i] = sg.W[i];
+        for (int i = 0; i < 6; ++i) c.N3[i] = sg.kc[i];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) c.fg[i] = sg.fg[i];
+        for (int i = 0; i < 3; ++i) c.cn[i] = sg.kc[6 + i];
+        c.m = sg.kc[9], c.minv = sg.kc[10];
     }
 }
 
@@ -237,15 +189,15 @@ __device__ __forceinline__ void tmem_stores_done() { asm volatile("tcgen05.wait:
 // ---------------------------------------------------------------------------------------------
 // forward_dynamics(Q, Qdot) -> Qddot, lambda       (biomechanical_model.py:351-429, batched)
 // ---------------------------------------------------------------------------------------------
-template <bool GENERAL, int MAXT, int S>
+template <bool GENERAL, bool STAB, int MAXT, int S>
 __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
-    forward_dynamics_kernel(const unsigned char* __restrict__ blob, int blob_bytes, const double* __restrict__ Q,
+    forward_dynamics_kernel(const unsigned char* __restrict__ blob, int blob_bytes, FextArgs fx, const double* __restrict__ Q,
                             const double* __restrict__ Qd, const double* __restrict__ inertia, DynOpts o,
                             double* __restrict__ Qdd, double* __restrict__ lam, int* __restrict__ status_out,
                             long long B) {
     extern __shared__ __align__(16) unsigned char smem[];
     WarpCtx w;
-    setup_cta<S>(blob, blob_bytes, smem, w);
+    setup_cta<S>(blob, blob_bytes, fx, smem, w);
     long long gsys = (long long)blockIdx.x * S + w.lane;
     const bool live = (int)(threadIdx.x & 31) < S && gsys < B;
     if (gsys >= B) gsys = B - 1;  // tail lanes recompute the last system, stores are masked
@@ -253,6 +205,7 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
     int status = 0;
     SegCtx c;
     load_constants(w, inertia, gsys, c, status);
+    if (GENERAL && fx.vals != nullptr) w.fvals = fx.vals + (size_t)gsys * fx.nf * 6;
     {
         Q12 q, qd;
         load_q12(Q + (size_t)gsys * n + 12 * w.segi, q);
@@ -263,7 +216,7 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
     __syncthreads();
     Q12 qdd;
     double* lam_sys = (lam != nullptr && live) ? lam + (size_t)gsys * w.hdr->m : nullptr;
-    eval_forward_dynamics<GENERAL, S>(w, c, o, qdd, lam_sys, status);
+    eval_forward_dynamics<GENERAL, STAB, S>(w, c, o, qdd, lam_sys, status);
     if (live) {
         store_q12(Qdd + (size_t)gsys * n + 12 * w.segi, qdd);
         if (status_out != nullptr && status != 0) atomicOr(status_out + gsys, status);
@@ -276,17 +229,19 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
 // per launch (plus the optional trajectory snapshots).  The stage state lives in shared memory
 // (it has to be published there anyway for the two-segment joints); y0 is parked in tensor memory
 // (TmemPark above) and the k-accumulator is a per-thread value that the compiler keeps in registers
-// or spills to L2-resident local memory.
+// or spills to L2-resident local memory.  Per-system external-force values may change from step to
+// step (fx.steps slices, held over the four stages of a step).
 // ---------------------------------------------------------------------------------------------
-template <bool GENERAL, int MAXT, int S>
+template <bool GENERAL, bool STAB, int MAXT, int S>
 __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
-    rk4_kernel(const unsigned char* __restrict__ blob, int blob_bytes, double* __restrict__ Q, double* __restrict__ Qd,
+    rk4_kernel(const unsigned char* __restrict__ blob, int blob_bytes, FextArgs fx, double* __restrict__ Q, double* __restrict__ Qd,
                const double* __restrict__ inertia, DynOpts o, double h_const, const double* __restrict__ h_steps,
                long long n_steps, int normalize, double* __restrict__ traj, long long traj_every,
                double* __restrict__ lam_last, int* __restrict__ status_out, long long B) {
     extern __shared__ __align__(16) unsigned char smem[];
+    constexpr bool XSEG = GENERAL || STAB;  // an evaluation reads other segments' published state
     WarpCtx w;
-    setup_cta<S>(blob, blob_bytes, smem, w);
+    setup_cta<S>(blob, blob_bytes, fx, smem, w);
     long long gsys = (long long)blockIdx.x * S + w.lane;
     const bool live = (int)(threadIdx.x & 31) < S && gsys < B;
     if (gsys >= B) gsys = B - 1;
@@ -294,6 +249,7 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
     int status = 0;
     SegCtx c;
     load_constants(w, inertia, gsys, c, status);
+    const double* fvals0 = (GENERAL && fx.vals != nullptr) ? fx.vals + (size_t)gsys * fx.nf * 6 : nullptr;
     Q12 y0q, y0v;
     load_q12(Q + (size_t)gsys * n + 12 * w.segi, y0q);
     load_q12(Qd + (size_t)gsys * n + 12 * w.segi, y0v);
@@ -311,6 +267,7 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
 #pragma unroll 1
     for (long long step = 0; step < n_steps; ++step) {
         const double h = h_steps != nullptr ? h_steps[step] : h_const;
+        if (GENERAL && fvals0 != nullptr) w.fvals = fvals0 + (step < fx.steps ? step : fx.steps - 1) * fx.step_stride;
         Q12 accq, accv;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -318,14 +275,14 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
             publish3<S>(w.Qo, t, y0q.s[t]), publish3<S>(w.Qdo, t, y0v.s[t]);
         }
         if (TM) tmem_put(tm, y0q), tmem_put(tm + 24, y0v), tmem_stores_done();
-        if (GENERAL) __syncthreads();  // only the general path reads other segments' published state
+        if (XSEG) __syncthreads();
 #pragma unroll 1
         for (int stage = 0; stage < 4; ++stage) {
             // k_stage = f(stage state): (stage velocity, Qddot)
             Q12 a;
             double* lam_sys = (lam_last != nullptr && live && stage == 0 && step == n_steps - 1)
                                   ? lam_last + (size_t)gsys * w.hdr->m : nullptr;
-            eval_forward_dynamics<GENERAL, S>(w, c, o, a, lam_sys, status);
+            eval_forward_dynamics<GENERAL, STAB, S>(w, c, o, a, lam_sys, status);
             const double wt = (stage == 0 || stage == 3) ? 1.0 : 2.0;
             const double cn = (stage == 2) ? h : 0.5 * h;  // next stage is y0 + cn * k_stage
             if (TM) {
@@ -333,6 +290,7 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
                 tmem_issue(tm, t0), tmem_issue(tm + 24, t1);
                 tmem_wait(t0, y0q), tmem_wait(t1, y0v);
             }
+            // other segments' published state is only read before the barriers inside the evaluation: no barrier here
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 const V3 sv = own3<S>(w.Qdo, t);
@@ -343,7 +301,7 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
                     publish3<S>(w.Qdo, t, axpy(cn, a.s[t], y0v.s[t]));
                 }
             }
-            if (GENERAL) __syncthreads();
+            if (XSEG) __syncthreads();
         }
         const double h6 = h / 6.0;
 #pragma unroll
@@ -406,8 +364,21 @@ __device__ __forceinline__ void put_row(double* __restrict__ K, int ld, int row,
 
 // One item (segment or constraint block) of one system.  `vec` / `K` point at this system's output vector / matrix
 // (leading dimension ldK); X is this system's Q (or Qdot for the bias).
+struct FextView {  // a call's force table as the evaluators see it (global memory)
+    const DevFextTab* tab;
+    const DevFext* f;
+    const double* vals;  // this system's (torque, force) values or nullptr
+};
+__device__ __forceinline__ FextView fext_view(const FextArgs& fx, long long sys) {
+    FextView v;
+    v.tab = reinterpret_cast<const DevFextTab*>(fx.tab);
+    v.f = fx.tab != nullptr ? reinterpret_cast<const DevFext*>(fx.tab + sizeof(DevFextTab)) : nullptr;
+    v.vals = fx.vals != nullptr ? fx.vals + (size_t)sys * fx.nf * 6 : nullptr;
+    return v;
+}
+
 __device__ __forceinline__ void eval_item(const DevSeg* __restrict__ seg, const DevBlk* __restrict__ blk,
-                                          const DevFext* __restrict__ fext, const EvalArgs& ea, int which, int item,
+                                          const FextView& fext, const EvalArgs& ea, int which, int item,
                                           const double* __restrict__ X, double* __restrict__ vec, double* __restrict__ K,
                                           int ldK) {
     if (item < ea.N) {  // ---------------- segment items
@@ -441,11 +412,13 @@ __device__ __forceinline__ void eval_item(const DevSeg* __restrict__ seg, const 
             put_row(K, ldK, r0 + 5, i, ew, w, 2.0);
         } else if (which == 7) {  // natural external forces
             double* o = vec + 12 * i;
-            SegCtx c;
-            c.u = u, c.v = v, c.w = w;
-            WarpCtx wc;
-            wc.fext = fext;
-            const Q12 f = external_forces(wc, sg, c, rp);
+            Q12 f;
+            if (fext.tab != nullptr) {
+                f = external_forces(fext.f, fext.tab->begin[i], fext.tab->begin[i + 1], fext.vals, u, v, w, rp);
+            } else {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) f.s[t] = mk(0.0, 0.0, 0.0);
+            }
 #pragma unroll
             for (int t = 0; t < 4; ++t) o[3 * t] = f.s[t].x, o[3 * t + 1] = f.s[t].y, o[3 * t + 2] = f.s[t].z;
         }
@@ -499,12 +472,11 @@ __device__ __forceinline__ void eval_item(const DevSeg* __restrict__ seg, const 
     }
 }
 
-__global__ void eval_kernel(const unsigned char* __restrict__ blob, EvalArgs ea, const double* __restrict__ in,
+__global__ void eval_kernel(const unsigned char* __restrict__ blob, FextArgs fx, EvalArgs ea, const double* __restrict__ in,
                             double* __restrict__ out, long long B) {
     const DevHeader* h = reinterpret_cast<const DevHeader*>(blob);
     const DevSeg* seg = reinterpret_cast<const DevSeg*>(blob + h->off_seg);
     const DevBlk* blk = reinterpret_cast<const DevBlk*>(blob + h->off_blk);
-    const DevFext* fext = reinterpret_cast<const DevFext*>(blob + h->off_fext);
     const int n = 12 * ea.N;
     const int nitem = ea.N + ea.nblk;
     const long long total = B * nitem;
@@ -516,7 +488,7 @@ __global__ void eval_kernel(const unsigned char* __restrict__ blob, EvalArgs ea,
         const long long sys = idx / nitem;
         const int item = (int)(idx - sys * nitem);
         double* o = out + (size_t)sys * rows * (matrix ? n : 1);
-        eval_item(seg, blk, fext, ea, which, item, in + (size_t)sys * n, o, o, n);
+        eval_item(seg, blk, fext_view(fx, sys), ea, which, item, in + (size_t)sys * n, o, o, n);
     }
 }
 
@@ -717,14 +689,13 @@ __global__ void __launch_bounds__(256)
 constexpr int kDenseThreads = 128;
 
 __global__ void __launch_bounds__(kDenseThreads)
-    dense_kkt_kernel(const unsigned char* __restrict__ blob, EvalArgs ea, const double* __restrict__ Q,
+    dense_kkt_kernel(const unsigned char* __restrict__ blob, FextArgs fx, EvalArgs ea, const double* __restrict__ Q,
                      const double* __restrict__ Qd, const double* __restrict__ inertia, DynOpts o,
                      const long long* __restrict__ select, long long count, double* __restrict__ Qdd,
                      double* __restrict__ lam, int* __restrict__ status_out, double* __restrict__ work) {
     const DevHeader* h = reinterpret_cast<const DevHeader*>(blob);
     const DevSeg* seg = reinterpret_cast<const DevSeg*>(blob + h->off_seg);
     const DevBlk* blk = reinterpret_cast<const DevBlk*>(blob + h->off_blk);
-    const DevFext* fext = reinterpret_cast<const DevFext*>(blob + h->off_fext);
     const int N = ea.N, n = 12 * N, m = ea.m, M = n + m, ld = M + 1, nitem = N + ea.nblk;
     const int tid = threadIdx.x, lane = tid & 31;
     double* A = work + (size_t)blockIdx.x * ((size_t)M * ld + M);  // [A | rhs], row-major
@@ -733,6 +704,7 @@ __global__ void __launch_bounds__(kDenseThreads)
     __shared__ double piv_abs;
     for (long long it = blockIdx.x; it < count; it += gridDim.x) {
         const long long sys = select != nullptr ? select[it] : it;
+        const FextView fext = fext_view(fx, sys);
         const double* Xq = Q + (size_t)sys * n;
         const double* Xqd = Qd + (size_t)sys * n;
         for (int e = tid; e < M * ld + M; e += kDenseThreads) A[e] = 0.0;

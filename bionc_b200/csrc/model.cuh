@@ -1,9 +1,11 @@
 // Device-side model table ("blob") shared by every kernel.
 //
-// The host lowers a BioncModelDesc (include/bionc_cuda.h) to one contiguous blob:
-//   DevHeader | DevSeg[N] | DevBlk[nblk] | DevSide[nside] | DevFext[nfext]
+// The host lowers a BioncModelDesc (include/bionc_cuda.h) to one contiguous, immutable blob:
+//   DevHeader | DevSeg[N] | DevBlk[nblk] | DevSide[nside] | symbolic tables
 // which each CTA copies into shared memory once.  Everything a lane needs about "its" segment and
-// the constraint blocks touching it is found through DevSeg::side_begin/side_end.
+// the constraint blocks touching it is found through DevSeg::side_begin/side_end.  External forces are
+// not part of the model: a call that has them passes its own table (DevFextTab | DevFext[nf]), copied
+// to shared memory behind the blob.
 #pragma once
 #include <stdint.h>
 
@@ -23,11 +25,11 @@ struct DevHeader {
     int mj;       // joint-constraint rows
     int nb;       // 3x3 block rows ("nodes") of the joint-level Schur system (mj padded up to a multiple of 3)
     int m;        // holonomic rows = mj + 6 N
-    int spw;      // systems per CTA: 32 (one lane per system), or 16 when the working set of 32 does not fit
+    int spw;      // systems per CTA without external forces: 32 (one lane per system), or 16 when the working set of 32 does not fit
     int rnl;      // doubles of shared memory per lane for the d-vectors of the non-LIN3 rows touching a segment
-    int nfext;    // external forces
+    int pad0;
     int blob_bytes;
-    int off_seg, off_blk, off_side, off_fext;  // byte offsets inside the blob
+    int off_seg, off_blk, off_side, pad1;  // byte offsets inside the blob
     // symbolic factorisation of the joint-level Schur complement (computed on the host, see capi.cu)
     int nslot;    // stored 3x3 blocks of the lower triangle: structural non-zeros + fill
     int nslot2;   // blocks that can receive contributions from two segments (second, exclusive-writer copy)
@@ -46,13 +48,13 @@ struct DevHeader {
 };
 
 struct DevSeg {
-    double W[10];    // M4^{-1}, upper triangle row-major over (u, rp, rd, w): uu ur ud uw rr rd rw dd dw ww
+    double kc[12];   // what the dynamics need of (m, c, J): N3 = J - m c c^T (xx xy xz yy yz zz), c (3), m, 1/m, pad
     double fg[4];    // gravity: natural force on slot s is fg[s] * e_z   (natural_segment.py:562-572)
     double phic[4];  // L cos(gamma), cos(beta), L^2, L cos(alpha)         (natural_segment.py:441-446)
     double mcj[10];  // mass, c(3), J00 J01 J02 J11 J12 J22 (for bionc_cuda_mass_matrix / documentation)
     int side_begin, side_end;
     int rigid_row;  // first holonomic row of the 6 rigid-body rows
-    int fext_begin, fext_end, pad0, pad1, pad2;
+    int pad0, pad1, pad2, pad3, pad4;
 };
 
 struct DevBlk {
@@ -73,7 +75,25 @@ struct DevSide {
 
 struct DevFext {
     double p[kFextNParam];  // torque(3) force(3) point(3) Tinv(9, row-major)
-    int segment, kind, pad0, pad1;
+    int segment, kind;
+    int slot;  // position in the caller's force list: per-system values are (B, F, 6) in that order
+    int pad0;
+};
+
+// header of a call's force table; the forces follow it, sorted by segment
+struct DevFextTab {
+    int nf, pad0, pad1, pad2;
+    int begin[kMaxSegments + 4];  // forces of segment s: begin[s] .. begin[s + 1]
+};
+
+// external forces of one launch (kernel parameter)
+struct FextArgs {
+    const unsigned char* tab;  // device: DevFextTab | DevFext[nf], or nullptr
+    int tab_bytes;             // multiple of 16
+    int nf;
+    const double* vals;        // device, optional: per-system (torque, force), (steps, B, nf, 6)
+    long long step_stride;     // doubles between the slices of two RK4 steps (0: one slice for every step)
+    long long steps;           // slices
 };
 
 // Shared-memory working set of one CTA (spc systems, one warp per segment), in doubles (layout: dynamics.cuh).

@@ -85,19 +85,30 @@ typedef struct BioncModelDesc {
     const double* marker_position; /* (nb_markers, 3) natural coordinates (n_u, n_v, n_w)                            */
 } BioncModelDesc;
 
-/* External forces shared by every system of the batch (ExternalForceSet, external_force.py:13-180). */
+/* External forces of one call (ExternalForceSet, external_force.py:13-180).  The list (segment, kind, application
+ * point, local frame) is shared by the batch; the (torque, force) values are either shared too (those in `param`) or
+ * given per system -- the reference evaluates ExternalForceSet.to_natural_external_forces(Q) for every call of its
+ * dynamics closure (external_force.py:143-180, utils/ode_solver.py:107-116), so every trajectory may carry its own
+ * loads and change them from step to step.  Nothing of this is kept in the model: the description is read during the
+ * call and may be freed or changed as soon as the call returns. */
 typedef struct BioncFextDesc {
     int32_t nb_forces;
-    const int32_t* segment; /* (F) */
-    const int32_t* kind;    /* (F) BIONC_FEXT_* */
-    const double* param;    /* (F, BIONC_FEXT_NPARAM), torque first (external_force.py:84-85) */
+    const int32_t* segment; /* (F) host */
+    const int32_t* kind;    /* (F) host, BIONC_FEXT_* */
+    const double* param;    /* (F, BIONC_FEXT_NPARAM) host, torque first (external_force.py:84-85) */
+    /* optional per-system values replacing torque(3), force(3) of `param`: (values_steps, B, F, 6), forces in the order
+     * of this list.  DEVICE pointer for the device entry points, HOST pointer for the _host ones; NULL = shared values.
+     * values_steps <= 1: one slice for the whole call.  values_steps > 1 (rk4 only): step k of the launch uses slice
+     * min(k, values_steps - 1), held over the four stages of the step. */
+    const double* values;
+    int64_t values_steps;
 } BioncFextDesc;
 
 /* Options common to forward_dynamics and rk4. */
 typedef struct BioncDynOptions {
     int32_t use_stabilization; /* Baumgarte, biomechanical_model.py:416-421 */
     double alpha, beta;
-    const BioncFextDesc* fext; /* NULL = none (HOST pointers inside; uploaded per call, a few hundred bytes) */
+    const BioncFextDesc* fext; /* NULL = none (uploaded per call on the caller's stream, a few hundred bytes) */
     /* optional per-system natural inertial parameters (device for the device entry points, host
      * for the _host ones): (B, N, 10) = [mass, c0, c1, c2, J00, J01, J02, J11, J12, J22]; NULL = use
      * the model's own (config 5: "perturbed inertial parameters") */
@@ -118,6 +129,10 @@ int bionc_cuda_model_counts(const BioncModel* model, int32_t* nb_segments, int32
  * storage, zero-list entries, systems per CTA, shared-memory bytes per CTA, serial joint-level schedule (0/1)};
  * systems and bytes per CTA are 0 until the first launch has sized the CTA for the device */
 int bionc_cuda_model_layout(const BioncModel* model, int32_t* out);
+/* diagnostics: first row of every constraint block (in the order of BioncModelDesc::blk_*) inside the joint-level
+ * system as the kernels order it: node = row / 3 is eliminated in ascending order (fill-reducing ordering of the host
+ * symbolic analysis); lets a host program replay the block elimination.  out: nb_blocks values */
+int bionc_cuda_model_joint_rows(const BioncModel* model, int32_t* first_row_of_block);
 
 /* replaces BiomechanicalModel.forward_dynamics (bionc_numpy/biomechanical_model.py:351-429), batched.
  * lambda and status may be NULL. */
