@@ -199,7 +199,7 @@ def test_indefinite_pseudo_inertia_fuzz():
             if cond > 1e10:
                 continue
             rq, rl = om.forward_dynamics(Q[s], Qd[s])
-                tol = 1e-10 * max(1.0, cond / 1e4)  # indefinite S': eps * cond * growth of the unpivoted block elimination
+            tol = 1e-10 * max(1.0, cond / 1e4)  # indefinite S': eps * cond * growth of the unpivoted block elimination
             ok = rel_err(qdd[s], rq) < tol and rel_err(lam[s], rl) < tol
             assert ok or status[s] != 0, (trial, N, s, cond)
             checked += 1
