@@ -6,21 +6,30 @@
 
 Workload (config 3 of BASELINE.json): the 4-segment lower-limb model (PELVIS free, hip / knee /
 ankle spherical; geometry of the reference's examples/models/lower_limb.nc, inertia of SURVEY.md
-8(d)), B = 1e6 independent systems PER GPU with seeded, constraint-consistent random initial states,
-h = 0.01 s, post-step renormalisation on.  One bench "step" = one launch of the fused integrator
-advancing every system by `rk4_steps_per_launch` (default 100) RK4 steps, 4 forward-dynamics evaluations
-each -- BASELINE.json's configurations integrate 1000 steps, i.e. ten such launches.
+8(d)), B = 1e6 independent systems PER GPU with seeded, constraint-consistent, pairwise distinct random
+initial states, h = 0.01 s, post-step renormalisation on.  One bench "step" = one launch of the fused
+integrator advancing every system by `rk4_steps_per_launch` (default 100) RK4 steps, 4 forward-dynamics
+evaluations each; the states are put back to the initial ones every 1000 steps, so the timed region is a
+sequence of the configuration's own 1000-step integrations (10 launches each).
 Metric: RK4 system-steps/s, whole job (all GPUs).
 
   value        states resident in HBM, CUDA events on the launching stream, max over ranks
   e2e          the same through the C ABI's host-buffer entry point (bionc_cuda_rk4_host): pinned
                host arrays in, H2D + kernel + D2H inside the timed region
-  roofline     algorithmic FLOPs (SURVEY.md 8(d) count) / measured kernel time vs the FP64 DFMA peak
-               measured in this run, plus the HBM fraction against MEASURED_PEAKS.json
-  cpu_baseline the numpy oracle port of the reference algorithm on this box's host cores (N=1, rank 0)
+  roofline     bound: the FP64 pipe.  `frac` = FP64 operations the kernel EXECUTES (ncu opcode counts of a committed
+               capture of this kernel and configuration: 2 DFMA + DMUL + DADD per system-step) / measured kernel time /
+               the DFMA peak measured in this run.  `algorithmic_frac` is the same with SURVEY.md 8(d)'s operation count
+               of the reference-shaped algorithm (dense m^3/3 factorisation), which the kernel does not execute: it can
+               exceed 1.  `traffic` (ncu DRAM bytes per launch) against the algorithmic bytes of a launch (the state
+               read once and written once: it stays on chip for all steps of a launch) gives `traffic_ratio`.
+  cpu_baseline the UNMODIFIED reference (bionc.RK4 + bionc_numpy forward_dynamics, installed in baseline/_ref) on
+               this box's host cores, one process per core (N = 1, rank 0); falls back to the numpy oracle port
+               (kind "port") when the reference install is missing
+  stabilized   the same launch with Baumgarte stabilisation (what long simulations use): rate and flagged systems
+  strong       (N > 1) the configuration's own scaling run: B = 1e6 systems IN TOTAL, 1e6 / N per GPU
+  gather       (N > 1) the one collective of the workload: all_gather_into_tensor of the final states
 
-`--impl reference` times the reference's CPU algorithm (oracle port; the reference itself is pure
-Python + numpy and does not travel to the GPU box) on all host cores.
+`--impl reference` times the reference's own CPU implementation on all host cores (bounded sample per step).
 """
 
 from __future__ import annotations
@@ -36,27 +45,44 @@ import subprocess
 import sys
 import threading
 import time
+import warnings
 
 import numpy as np
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
-MODEL = os.path.join(REPO, "tests", "golden", "models", "lower_limb.npz")
 WORKLOAD = "lower_limb_4seg (BASELINE.json configs[2]; PELVIS free + 3 spherical joints, n=48, m=33)"
-H = 0.01
 # The default workload is the one BASELINE.json's metric is quoted on (the 4-segment lower limb).  `--workload`
 # runs the other BASELINE configurations through the same measurement (SURVEY 8(d) definitions); they are not
-# bench lines of the driver, which calls bench.py without that flag.
+# bench lines of the driver, which calls bench.py without that flag.  `ref`: the configuration's builder in
+# baseline/reference_models.py (the live reference).
 WORKLOADS = {
-    "lower_limb": dict(model="lower_limb", states="tree", h=0.01, fext=False, inertia=False, desc=WORKLOAD),
-    "pendulum_force": dict(model="pendulum_force_batch", states="hinge", h=1.0 / 60.0, fext=True, inertia=False,
+    "lower_limb": dict(model="lower_limb", ref="lower_limb", states="tree", h=0.01, fext=False, inertia=False, desc=WORKLOAD),
+    "pendulum_force": dict(model="pendulum_force_batch", ref="pendulum_force", states="hinge", h=1.0 / 60.0, fext=True, inertia=False,
                            desc="pendulum_with_force.nmod + no_equilibrium force (BASELINE.json configs[1]; ground hinge, n=12, m=11)"),
-    "knee": dict(model="knee_feikes", states="knee", h=5e-5, fext=False, inertia=False,
+    "knee": dict(model="knee_feikes", ref="knee", states="knee", h=5e-5, fext=False, inertia=False,
                  desc="knee_feikes parallel mechanism (BASELINE.json configs[3]; closed loops, n=24, m=20)"),
-    "full_body": dict(model="full_body", states="tree", h=0.001, fext=False, inertia=True,
+    "full_body": dict(model="full_body", ref="full_body", states="tree", h=0.001, fext=False, inertia=True,
                       desc="synthetic full body, per-system inertial parameters (BASELINE.json configs[4]; 10 segments, n=120, m=87)"),
+    "n_link_4": dict(model="n_link_4", ref=None, states="chain", h=0.005, fext=False, inertia=False,
+                     desc="4-link hinge pendulum (tests/test_forward_dynamics.py of the reference; 4 hinges, n=48, m=44)"),
 }
+STAB = dict(alpha=50.0, beta=20.0)  # Baumgarte gains of the stabilised leg: examples/forward_dynamics/actuated_3d_pendulum.py:155
+
+# What one launch of the dominant kernel does on the device, from the committed `ncu --set full` captures of THIS kernel
+# version at the bench configuration (B = 1e6 systems, 100 steps per launch): executed FP64 thread instructions
+# (smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on.sum), all warp instructions, FP64 pipe utilisation and
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum).  Filled from profiles/ by profiles/ncu_raw_summary.py.
+NCU = {}
+try:
+    with open(os.path.join(REPO, "profiles", "ncu_constants.json")) as _f:
+        NCU = json.load(_f)
+except OSError:
+    pass
+
+METRIC = "rk4_forward_dynamics_system_steps_per_s"
+UNIT = "system-steps/s"
 
 
 def workload_paths(name):
@@ -66,7 +92,7 @@ def workload_paths(name):
 
 
 def workload_states(name, table, count, seed):
-    """Seeded consistent initial states of a workload (numpy, SURVEY 8(d) generators)."""
+    """Seeded consistent initial states of a workload (numpy, SURVEY 8(d) generators); every system its own draw."""
     from bionc_b200.utils import states as st
 
     kind = WORKLOADS[name]["states"]
@@ -74,6 +100,8 @@ def workload_states(name, table, count, seed):
         return st.tree_states(table, count, seed=seed)
     if kind == "hinge":
         return st.hinge_pendulum_states(count, seed=seed)
+    if kind == "chain":
+        return st.planar_chain_states(table, count, seed=seed)
     with np.load(workload_paths(name)[1]) as z:  # knee: rigid motions of the reference's own initial state
         q0 = np.array(z["Q"][0])
     return st.rigidly_moved_states(q0, count, seed=seed, angle_max=0.3, omega_sigma=0.0)
@@ -85,55 +113,67 @@ def workload_fext(name):
         return None
     with np.load(workload_paths(name)[1]) as z:
         return np.array(z["fext_seg"]), np.array(z["fext_kind"]), np.array(z["fext_param"])
-# DRAM traffic of ONE launch of the dominant kernel at the default configuration, from the committed
-# `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum): 0.79 GB read (the 768 MB of
-# state, once) + 8.9 GB written (768 MB of state + register spills evicted from L2: the kernel runs at 128
-# registers/thread to keep 4 CTAs per SM resident; before y0 moved to tensor memory the same launch wrote
-# 66 GB).  The algorithmic bytes of the same launch are B * S * 1536 B = 153.6 GB: the state stays on chip
-# for the S steps of a launch; DRAM runs below 1 % of peak.
-NCU_TRAFFIC = {"systems_per_gpu": 1_000_000, "rk4_steps_per_launch": 100, "bytes": 792.342528e6 + 8.927182e9,
-               "source": "profiles/r01_ncu_rk4_kernel_v12_benchconfig.txt"}
-METRIC = "rk4_forward_dynamics_system_steps_per_s"
-UNIT = "system-steps/s"
 
 
-# ----------------------------------------------------------------------------- CPU side (oracle port)
+# ----------------------------------------------------------------------------- CPU side: the reference on the host cores
+def reference_available(workload) -> bool:
+    sys.path.insert(0, os.path.join(REPO, "baseline"))
+    import reference_models as rm
+
+    return rm.available() and WORKLOADS[workload]["ref"] is not None
+
+
 def _cpu_worker(args):
-    """One host core: integrate `nsys` systems for `nsteps` RK4 steps with the oracle port."""
-    seed, nsys, nsteps, workload = args
+    """One host core: integrate `nsys` systems for `nsteps` RK4 steps.  kind "reference": the unmodified reference
+    (bionc.RK4 around model.forward_dynamics, utils/ode_solver.py:8-53, :107-116); kind "port": the numpy oracle."""
+    seed, nsys, nsteps, workload, kind = args
     os.environ["OMP_NUM_THREADS"] = "1"
-    sys.path.insert(0, os.path.join(REPO, "oracle"))
-    from bionc_oracle import OracleModel  # noqa: E402  (the CPU baseline leg is allowed to run the oracle)
-
+    warnings.filterwarnings("ignore")
     from bionc_b200.bionc_cuda.model_table import ModelTable
     from bionc_b200.utils import states as st
 
+    w = WORKLOADS[workload]
     model_file = workload_paths(workload)[0]
     table = ModelTable.load(model_file)
-    om = OracleModel(model_file)
     Q, Qd = workload_states(workload, table, nsys, seed)
+    t = np.arange(nsteps + 1) * w["h"]
+    per_system = st.perturbed_inertial_parameters(table, nsys, seed=seed) if w["inertia"] else None
+    if kind == "reference":
+        sys.path.insert(0, os.path.join(REPO, "baseline"))
+        import reference_models as rm
+
+        model, fext = rm.CONFIGS[w["ref"]]["build"]()
+        t0 = time.perf_counter()
+        for s in range(nsys):
+            if per_system is not None:  # the reference carries the inertial parameters in the model object (inside the timing)
+                for i, seg in enumerate(model.segments_no_ground.values()):
+                    seg.set_natural_inertial_parameters(mass=per_system[0][s, i], natural_center_of_mass=per_system[1][s, i],
+                                                        natural_pseudo_inertia=per_system[2][s, i])
+                model._update_mass_matrix()
+            rm.reference_rk4(model, Q[s], Qd[s], t, True, fext)
+        return time.perf_counter() - t0
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    from bionc_oracle import OracleModel  # noqa: E402  (the CPU baseline leg is allowed to run the oracle)
+
+    om = OracleModel(model_file)
     fx = workload_fext(workload)
     fext = None if fx is None else [(int(a), int(b), c) for a, b, c in zip(*fx)]
-    per_system = None
-    if WORKLOADS[workload]["inertia"]:
-        per_system = st.perturbed_inertial_parameters(table, nsys, seed=seed)
-    t = np.arange(nsteps + 1) * WORKLOADS[workload]["h"]
     t0 = time.perf_counter()
     for s in range(nsys):
-        if per_system is not None:  # like the reference, one model object per parameter set (a few ms, inside the timing)
+        if per_system is not None:
             om = OracleModel(model_file, seg_mass=per_system[0][s], seg_com=per_system[1][s], seg_J=per_system[2][s])
         om.rk4(Q[s], Qd[s], t, normalize=True, fext=fext)
     return time.perf_counter() - t0
 
 
-def cpu_rate(nsys_per_core: int, nsteps: int, cores: int, seed0: int = 1000, workload: str = "lower_limb"):
+def cpu_rate(nsys_per_core: int, nsteps: int, cores: int, seed0: int = 1000, workload: str = "lower_limb", kind: str = "reference"):
     """Aggregate system-steps/s of `cores` worker processes, wall clock of the slowest worker."""
     import multiprocessing as mp
 
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
-        times = pool.map(_cpu_worker, [(seed0 + c, nsys_per_core, nsteps, workload) for c in range(cores)])
-    wall = max(times)  # integration time of the slowest worker (process start-up and imports excluded)
+        times = pool.map(_cpu_worker, [(seed0 + c, nsys_per_core, nsteps, workload, kind) for c in range(cores)])
+    wall = max(times)  # integration time of the slowest worker (process start-up, imports and model building excluded)
     return cores * nsys_per_core * nsteps / wall, wall
 
 
@@ -144,27 +184,41 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
+def cpu_kind(workload):
+    return "reference" if reference_available(workload) else "port"
+
+
+CPU_WHAT = {"reference": "unmodified bioNC: bionc.RK4 + bionc_numpy.BiomechanicalModel.forward_dynamics (baseline/_ref)",
+            "port": "numpy oracle port of the reference algorithm (dense KKT, LAPACK LU); baseline/_ref missing"}
+
+
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU algorithm on all host cores.  Each bench step is a bounded
-    sample: every core integrates `nsys` lower-limb systems for `nsteps` RK4 steps."""
+    """--impl reference: the reference's own CPU implementation on all host cores.  Each bench step is a bounded
+    sample: every core integrates `nsys` systems of the workload for `nsteps` RK4 steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = host_cores()
-    nsys, nsteps = 4, 100  # ~1 s per core per bench step at a few hundred system-steps/s/core
+    kind = cpu_kind(args.workload)
+    nsys, nsteps = (2, 25) if kind == "reference" else (4, 100)  # ~0.4 s per core per bench step
+    if WORKLOADS[args.workload]["model"] == "full_body":
+        nsys, nsteps = 1, 20
     for _ in range(args.warmup):
-        cpu_rate(nsys, nsteps, cores, workload=args.workload)
+        cpu_rate(nsys, nsteps, cores, workload=args.workload, kind=kind)
     wall = 0.0
     for k in range(args.steps):
-        wall += cpu_rate(nsys, nsteps, cores, seed0=2000 + 100 * k, workload=args.workload)[1]
+        wall += cpu_rate(nsys, nsteps, cores, seed0=2000 + 100 * k, workload=args.workload, kind=kind)[1]
     value = args.steps * cores * nsys * nsteps / wall
-    sample = f"{cores} cores x {nsys} systems x {nsteps} RK4 steps per bench step (oracle port, numpy dense KKT LU)"
+    sample = f"{cores} cores x {nsys} systems x {nsteps} RK4 steps per bench step ({CPU_WHAT[kind]})"
+    wl = WORKLOADS[args.workload]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload]["desc"], "h": WORKLOADS[args.workload]["h"], "normalize": True},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": wl["desc"], "systems_per_gpu": args.batch, "rk4_steps_per_launch": args.rk4_steps_per_launch,
+                   "h": wl["h"], "normalize": True,
+                   "sample": "the CPU arm integrates a subsample of the same workload (same model, h, normalize, state generator)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -239,12 +293,14 @@ def run_gpu_arm(args):
     cpu_baseline = None
     if not distributed and not args.no_cpu_baseline:
         cores = host_cores()
-        nsys, nsteps = 8, 1000  # ~10-25 s of CPU work per core at a few hundred system-steps/s/core
-        if WORKLOADS[args.workload]['model'] == 'full_body':
-            nsys, nsteps = 4, 250  # 2.4 ms per evaluation
-        rate, wall = cpu_rate(nsys, nsteps, cores, workload=args.workload)
-        cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"{cores} cores x {nsys} systems x {nsteps} RK4 steps, same model/h/normalize ({wall:.1f} s wall)"}
+        kind = cpu_kind(args.workload)
+        nsys, nsteps = (4, 100) if kind == "reference" else (8, 1000)  # ~3-25 s of CPU work per core
+        if WORKLOADS[args.workload]["model"] == "full_body":
+            nsys, nsteps = (2, 50) if kind == "reference" else (4, 250)
+        rate, wall = cpu_rate(nsys, nsteps, cores, workload=args.workload, kind=kind)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+                        "sample": f"{cores} cores x {nsys} systems x {nsteps} RK4 steps, same model/h/normalize/state generator "
+                                  f"({wall:.1f} s wall; {CPU_WHAT[kind]})"}
 
     import ctypes as C
 
@@ -266,12 +322,10 @@ def run_gpu_arm(args):
     h_step = wl["h"]
     model = BiomechanicalModel.load(workload_paths(args.workload)[0], device=dev)
     n = model.nb_Q
-    # seeded synthetic initial states: a pool of 2^16 consistent states (numpy), tiled to B on the device
-    pool = min(B, 1 << 16)
-    Qp, Qdp = workload_states(args.workload, model.table, pool, seed=1 + rank)
-    reps = (B + pool - 1) // pool
-    Q0 = torch.from_numpy(Qp).to(dev).repeat(reps, 1)[:B].contiguous()
-    Qd0 = torch.from_numpy(Qdp).to(dev).repeat(reps, 1)[:B].contiguous()
+    # seeded synthetic initial states: B distinct consistent states per rank (numpy generators of SURVEY 8(d))
+    Qp, Qdp = workload_states(args.workload, model.table, B, seed=1 + rank)
+    Q0 = torch.from_numpy(Qp).to(dev)
+    Qd0 = torch.from_numpy(Qdp).to(dev)
     Q, Qd = Q0.clone(), Qd0.clone()
     status = torch.zeros(B, dtype=torch.int32, device=dev)
     lib = _lib.load()
@@ -285,19 +339,19 @@ def run_gpu_arm(args):
                                    par.ctypes.data_as(_lib.c_double_p))
         keep += [seg, kind, par, fdesc]
         opt.fext = C.pointer(fdesc)
-    ip_pool = None
+    ip_host = None
     if wl["inertia"]:  # config 5: per-system natural inertial parameters (B, N, 10), resident on the device
-        mass, com, J = st.perturbed_inertial_parameters(model.table, pool, seed=100 + rank)
-        ip_pool = np.ascontiguousarray(np.concatenate(
+        mass, com, J = st.perturbed_inertial_parameters(model.table, B, seed=100 + rank)
+        ip_host = np.ascontiguousarray(np.concatenate(
             [mass[..., None], com, np.stack([J[..., 0, 0], J[..., 0, 1], J[..., 0, 2], J[..., 1, 1], J[..., 1, 2], J[..., 2, 2]], axis=-1)], axis=-1))
-        ip_dev = torch.from_numpy(ip_pool).to(dev).repeat(reps, 1, 1)[:B].contiguous()
+        ip_dev = torch.from_numpy(ip_host).to(dev)
         keep.append(ip_dev)
         opt.inertia = ip_dev.data_ptr()
     stream = torch.cuda.current_stream(dev)
 
-    def launch():
-        rc = lib.bionc_cuda_rk4(model._h, Q.data_ptr(), Qd.data_ptr(), h_step, None, S, 1, C.byref(opt), None, 1, None,
-                                status.data_ptr(), B, C.c_void_p(stream.cuda_stream))
+    def launch(o=opt, q=Q, qd=Qd, b=B):
+        rc = lib.bionc_cuda_rk4(model._h, q.data_ptr(), qd.data_ptr(), h_step, None, S, 1, C.byref(o), None, 1, None,
+                                status.data_ptr(), b, C.c_void_p(stream.cuda_stream))
         _lib.check(rc, "rk4")
 
     def barrier():
@@ -305,44 +359,69 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def timed(o=opt, q=Q, qd=Qd, b=B, steps=None):
+        """`steps` launches, each bracketed by CUDA events on the launching stream; the states go back to the initial
+        ones every `run` launches (one integration of the configuration's step count).  Returns (total device ms from the
+        first launch to the last, mean ms per launch, flagged systems at the end of the last complete integration)."""
+        steps = steps or args.steps
+        run = max(1, args.run_steps // S)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        q.copy_(Q0[:b]), qd.copy_(Qd0[:b])
+        flagged = torch.zeros((), dtype=torch.int64, device=dev)
+        barrier()
+        reset_ms = 0.0
+        resets = []
+        for k, (e0, e1) in enumerate(evs):
+            if k > 0 and k % run == 0:  # next integration: back to the initial states (untimed copy, bracketed by its own events)
+                r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                r0.record(stream)
+                q.copy_(Q0[:b]), qd.copy_(Qd0[:b])
+                r1.record(stream)
+                resets.append((r0, r1))
+            e0.record(stream)
+            launch(o, q, qd, b)
+            e1.record(stream)
+            if (k + 1) % run == 0 or k == steps - 1:
+                flagged = (status[:b] != 0).sum()  # flags are per launch: the count after the last launch of an integration
+        barrier()
+        reset_ms = sum(r0.elapsed_time(r1) for r0, r1 in resets)
+        total_ms = evs[0][0].elapsed_time(evs[-1][1]) - reset_ms
+        return total_ms, float(np.mean([e0.elapsed_time(e1) for e0, e1 in evs])), int(flagged.item())
+
     clocks = ClockSampler(local_rank)
     clocks.__enter__()
     for _ in range(args.warmup):
         launch()
     barrier()
-    # every timed launch starts from the same consistent initial states: a free-falling chain integrated
-    # for thousands of steps drifts off to large coordinates; resetting keeps the timed work representative
-    Q.copy_(Q0), Qd.copy_(Qd0)
     launches0 = lib.bionc_cuda_launch_count()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
     t_wall0 = time.perf_counter()
-    for e0, e1 in evs:
-        e0.record(stream)
-        launch()
-        e1.record(stream)
-    barrier()
+    total_ms, kernel_ms_mean, bad = timed()
     t_wall1 = time.perf_counter()
     t_wall = t_wall1 - t_wall0
     time.sleep(0.1)  # let the last samples of the window arrive
     clocks.__exit__()
     gpu_launches = int(lib.bionc_cuda_launch_count() - launches0)
-    kernel_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
-    total_ms = evs[0][0].elapsed_time(evs[-1][1])  # first launch start -> last launch end, on the device
-    bad = int((status != 0).sum().item())
+
+    # ---- the same launches with Baumgarte stabilisation (biomechanical_model.py:416-421)
+    opt_stab = _lib.BioncDynOptions()
+    opt_stab.fext, opt_stab.inertia = opt.fext, opt.inertia
+    opt_stab.use_stabilization, opt_stab.alpha, opt_stab.beta = 1, STAB["alpha"], STAB["beta"]
+    launch(opt_stab)
+    stab_steps = max(2, min(args.steps, max(1, args.run_steps // S)))
+    stab_total_ms, stab_kernel_ms, stab_bad = timed(opt_stab, steps=stab_steps)
 
     # ---- end-to-end through the C ABI with host buffers (pinned), copies inside the timed region
     Be = min(B, args.e2e_batch)
-    Qh = torch.from_numpy(np.ascontiguousarray(Qp[:Be] if Be <= pool else np.tile(Qp, (reps, 1))[:Be])).pin_memory()
-    Qdh = torch.from_numpy(np.ascontiguousarray(Qdp[:Be] if Be <= pool else np.tile(Qdp, (reps, 1))[:Be])).pin_memory()
+    Qh = torch.from_numpy(np.ascontiguousarray(Qp[:Be])).pin_memory()
+    Qdh = torch.from_numpy(np.ascontiguousarray(Qdp[:Be])).pin_memory()
     Qh0, Qdh0 = Qh.clone(), Qdh.clone()
     sth = torch.zeros(Be, dtype=torch.int32).pin_memory()
 
     opt_host = _lib.BioncDynOptions()
     opt_host.fext = opt.fext
     extra_h2d = 0
-    if ip_pool is not None:  # the host entry point takes the per-system parameters from host memory and uploads them
-        iph = torch.from_numpy(np.ascontiguousarray(ip_pool[:Be] if Be <= pool else np.tile(ip_pool, (reps, 1, 1))[:Be])).pin_memory()
+    if ip_host is not None:  # the host entry point takes the per-system parameters from host memory and uploads them
+        iph = torch.from_numpy(np.ascontiguousarray(ip_host[:Be])).pin_memory()
         keep.append(iph)
         opt_host.inertia = iph.data_ptr()
         extra_h2d = int(iph.numel() * 8)
@@ -362,21 +441,37 @@ def run_gpu_arm(args):
     e2e_s = float(np.median(e2e_times))
     barrier()
 
-    # ---- reduce over ranks: slowest rank defines the job time
+    # ---- N > 1: the configuration's own scaling run (1e6 systems IN TOTAL) and the final gather
     from bionc_b200.utils.sharding import gather_states, max_over_ranks
 
-    t = max_over_ranks([total_ms, e2e_s, float(np.mean(kernel_ms)), float(bad)], device=dev)
+    strong_ms = gather_ms = 0.0
+    gather_bytes = 0
+    Bs = max(1, args.batch // world)
     if distributed:
-        # the only collective of the workload: a final gather (of per-rank checksums by default;
-        # --gather-states gathers the full states, 768 MB per rank at the default batch)
-        ok = (status == 0).to(torch.float64)[:, None]  # a handful of systems diverge in 800+ unstabilised steps, as the reference does
-        chk = torch.stack([torch.nan_to_num(Q * ok).sum(), torch.nan_to_num(Qd * ok).sum()])[None]
-        allchk = gather_states(chk, world)
-        assert allchk.shape == (world, 2) and bool(torch.isfinite(allchk).all())
-        if args.gather_states:
-            full = gather_states(Q, world * B)
-            assert full.shape == (world * B, n)
-    total_ms, e2e_s, kernel_ms_mean, bad = t
+        qs, qds = Q[:Bs], Qd[:Bs]  # views of the resident arrays: the first B / N systems of this rank
+        launch(opt, qs, qds, Bs)
+        strong_ms, _, _ = timed(opt, qs, qds, Bs)
+        # the only collective of the workload: one all_gather_into_tensor of the final states [Q | Qdot] of the strong run
+        y = torch.cat([qs, qds], dim=1).contiguous()
+        gather_states(y, world * Bs)  # warm-up (NCCL channel set-up)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        full = gather_states(y, world * Bs)
+        g1.record(stream)
+        barrier()
+        gather_ms = g0.elapsed_time(g1)
+        gather_bytes = int(full.numel() * 8)
+        assert full.shape == (world * Bs, 2 * n)
+        del full, y
+
+    t = max_over_ranks([total_ms, e2e_s, kernel_ms_mean, float(bad), stab_total_ms, float(stab_bad), strong_ms, gather_ms], device=dev)
+    if distributed:
+        # flagged systems are summed over the ranks, times are the slowest rank's
+        cnt = torch.tensor([float(bad), float(stab_bad)], dtype=torch.float64, device=dev)
+        dist.all_reduce(cnt)
+        t[3], t[5] = float(cnt[0].item()), float(cnt[1].item())
+    total_ms, e2e_s, kernel_ms_mean, bad, stab_total_ms, stab_bad, strong_ms, gather_ms = t
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -386,31 +481,45 @@ def run_gpu_arm(args):
         per_gpu_rate = B * S / (kernel_ms_mean * 1e-3)  # dominant kernel, one launch, one GPU
         fl, by = rf.flops_per_step(model.table), rf.bytes_per_step(model.table)
         lay = model.kernel_layout()
-        general = fx is not None or any(int(t) != 0 for t in model.table.blk_type)
-        kernel_name = "rk4_kernel<%s, %d threads, %d systems per CTA%s>" % (
-            "general" if general else "lean", 32 * model.nb_segments, lay["systems_per_cta"],
-            ", y0 in tensor memory" if model.nb_segments >= 3 else "")
-        achieved_tf = per_gpu_rate * fl / 1e12
+        general = fx is not None or any(int(tt) != 0 for tt in model.table.blk_type)
+        kernel_name = "rk4_kernel<%s, %d threads, %d systems per CTA>" % (
+            "general" if general else "lean", 32 * model.nb_segments, lay["systems_per_cta"])
+        algorithmic_tf = per_gpu_rate * fl / 1e12
+        ncu = NCU.get(args.workload)
+        same_cfg = ncu is not None and (ncu["systems"], ncu["rk4_steps_per_launch"]) == (B, S)
+        executed_flop = executed_tf = frac = traffic = None
+        if ncu is not None:  # per system-step figures scale to any batch; the DRAM traffic only holds at the captured configuration
+            executed_flop = (2.0 * ncu["dfma"] + ncu["dmul"] + ncu["dadd"]) / (ncu["systems"] * ncu["rk4_steps_per_launch"])
+            executed_tf = per_gpu_rate * executed_flop / 1e12
+            frac = executed_tf / sustained.value
+            traffic = ncu["dram_bytes"] if same_cfg else None
+        alg_bytes = B * by  # one launch: the state is read once and written once, whatever the number of steps
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": wl["desc"], "systems_per_gpu": B, "rk4_steps_per_launch": S, "h": h_step, "normalize": True,
+                "integration": "%d steps from the initial states, then reset (untimed device copy): %d launches per integration" % (
+                    args.run_steps, max(1, args.run_steps // S)),
+                "states": "%d pairwise distinct seeded consistent states per GPU (SURVEY 8(d) generator)" % B,
                 "l2": "state per GPU = %.0f MB, larger than the 126 MB L2; every launch re-reads it from HBM" % (B * 2 * n * 8 / 1e6),
                 "parallelism": f"batch sharded over {world} GPU(s), no collective on the step path",
             },
             "roofline": {
-                "bound": "fp64", "achieved": achieved_tf, "peak": sustained.value, "unit": "TFLOP/s",
-                "frac": achieved_tf / sustained.value,
-                "traffic": NCU_TRAFFIC["bytes"] if (args.workload, B, S) == ("lower_limb", NCU_TRAFFIC["systems_per_gpu"], NCU_TRAFFIC["rk4_steps_per_launch"]) else None,
-                "traffic_source": NCU_TRAFFIC["source"], "algorithmic_bytes_per_launch": B * S * by,
+                "bound": "fp64", "achieved": executed_tf, "peak": sustained.value, "unit": "TFLOP/s", "frac": frac,
+                "executed_flop_per_system_step": executed_flop,
+                "fp64_pipe_active_pct_ncu": ncu.get("fp64_pipe_pct") if ncu else None,
+                "counts_source": ncu.get("source") if ncu else "no committed ncu capture for this workload",
+                "algorithmic_achieved": algorithmic_tf, "algorithmic_frac": algorithmic_tf / sustained.value,
+                "flops_per_system_step": fl,
+                "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
+                "traffic_ratio": (traffic / alg_bytes) if traffic else None,
+                "bytes_per_system_step": by, "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peak_src,
+                "dram_gbs": (traffic / (kernel_ms_mean * 1e-3) / 1e9) if traffic else None,
                 "kernel": kernel_name, "kernel_ms": kernel_ms_mean,
-                "flops_per_system_step": fl, "bytes_per_system_step": by,
                 "peak_source": "DFMA micro-benchmark in this run (bionc_cuda_measure_fp64_peak): sustained %.2f, best launch %.2f TFLOP/s"
                                % (sustained.value, best.value),
-                "hbm": {"achieved": per_gpu_rate * by / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                        "frac": per_gpu_rate * by / 1e9 / peaks.get("hbm_gbs", 6650.0), "peak_source": peak_src},
             },
             "e2e": {
                 "value": world * Be * S / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(2 * Be * n * 8) + extra_h2d,
@@ -419,9 +528,23 @@ def run_gpu_arm(args):
             },
             "gpu_launches": gpu_launches,
             "clocks": clocks.summary(t_wall0, t_wall1),
-            "status_flagged_systems": int(bad),
+            "flagged": {
+                "systems": int(bad), "of": world * B,
+                "meaning": "status != 0 after %d unstabilised steps: the drift of the rigid-body and joint constraints makes the "
+                           "joint-level matrix of these free-falling chains singular or the state non-finite (the reference raises "
+                           "LinAlgError or returns NaN there too); flagged systems keep computing, nothing is skipped" % args.run_steps,
+            },
+            "stabilized": {
+                "value": world * B * S * stab_steps / (stab_total_ms * 1e-3), "unit": UNIT, "alpha": STAB["alpha"], "beta": STAB["beta"],
+                "flagged_systems": int(stab_bad), "kernel": kernel_name.replace("<lean", "<lean + Baumgarte"),
+            },
             "wall_s": t_wall,
         }
+        if distributed:
+            line["strong"] = {"value": world * Bs * S * args.steps / (strong_ms * 1e-3), "unit": UNIT, "systems_total": world * Bs,
+                              "systems_per_gpu": Bs, "ms_per_step": strong_ms / args.steps}
+            line["gather"] = {"ms": gather_ms, "bytes": gather_bytes, "gbs": gather_bytes / (gather_ms * 1e-3) / 1e9 if gather_ms else None,
+                              "what": "all_gather_into_tensor (NCCL) of the final [Q | Qdot] of the strong run: every rank receives all systems"}
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)
@@ -438,9 +561,9 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--batch", type=int, default=1_000_000, help="systems per GPU")
     ap.add_argument("--rk4-steps-per-launch", type=int, default=100)
+    ap.add_argument("--run-steps", type=int, default=1000, help="RK4 steps of one integration (BASELINE.json: 1000); the states are reset after it")
     ap.add_argument("--e2e-batch", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather-states", action="store_true")
     ap.add_argument("--workload", default="lower_limb", choices=sorted(WORKLOADS),
                     help="default: the configuration BASELINE.json's metric is quoted on; the others are its remaining GPU configs")
     args = ap.parse_args()

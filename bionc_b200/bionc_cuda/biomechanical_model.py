@@ -233,11 +233,11 @@ class BiomechanicalModel:
         keep.append(opt)
         return opt, keep
 
-    def _eval(self, which: int, x, rows: int | None, cols: int | None, name: str, external_forces=None):
+    def _eval(self, which: int, x, rows: int | None, cols: int | None, name: str, external_forces=None, force_values=None):
         b = _Batch(x, self.nb_Q, self.device, name)
         shape = (b.B,) + ((rows,) if rows is not None else ()) + ((cols,) if cols is not None else ())
         out = torch.empty(shape, dtype=torch.float64, device=self.device)
-        opt, keep = self._options(external_forces)
+        opt, keep = self._options(external_forces, B=b.B, force_values=force_values)
         with torch.cuda.device(self.device):
             if out.numel():
                 _lib.check(self._lib.bionc_cuda_eval(self._h, which, b.t.data_ptr(), C.byref(opt), out.data_ptr(), b.B, self._stream()), "eval")
@@ -279,9 +279,10 @@ class BiomechanicalModel:
         b, out = self._eval(EVAL_BIAS_H, Qdot, self.nb_holonomic_constraints, None, "Qdot")
         return b.out(out, column=True)
 
-    def natural_external_forces(self, Q, external_forces):
-        """ExternalForceSet.to_natural_external_forces (external_force.py:143-166) -> (n, 1) / (B, n)"""
-        b, out = self._eval(EVAL_FEXT, Q, self.nb_Q, None, "Q", external_forces=external_forces)
+    def natural_external_forces(self, Q, external_forces, external_force_values=None):
+        """ExternalForceSet.to_natural_external_forces (external_force.py:143-166) -> (n, 1) / (B, n);
+        ``external_force_values`` (B, F, 6): per-system (torque, force) values."""
+        b, out = self._eval(EVAL_FEXT, Q, self.nb_Q, None, "Q", external_forces=external_forces, force_values=external_force_values)
         return b.out(out, column=True)
 
     def augmented_mass_matrix(self, Q):

@@ -8,7 +8,7 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(ROOT, "csrc", "capi.cu")
-DEPS = [os.path.join(ROOT, "csrc", f) for f in ("capi.cu", "kernels.cuh", "dynamics.cuh", "model.cuh")] + [
+DEPS = [os.path.join(ROOT, "csrc", f) for f in ("capi.cu", "kernels.cuh", "dynamics.cuh", "model.cuh", "tmem.cuh")] + [
     os.path.join(os.path.dirname(ROOT), "include", "bionc_cuda.h")
 ]
 OUT = os.path.join(ROOT, "lib", "libbionc_cuda.so")

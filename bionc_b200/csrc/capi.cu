@@ -332,12 +332,12 @@ struct DeviceGuard {
 
 // Systems per CTA and shared memory for a force table of `ftab_bytes` bytes behind the blob: 32 systems (every lane
 // busy) or 16 (upper half-warps mirror), whichever keeps more systems resident per SM.
-int make_plan(const BioncModel* M, int ftab_bytes, LaunchPlan& plan) {
+int make_plan(const BioncModel* M, int ftab_bytes, bool persys, LaunchPlan& plan) {
     const DevHeader& h = M->hdr;
     int best_resident = 0;
     plan = LaunchPlan{};
     for (int spc = 32; spc >= 16; spc >>= 1) {
-        const size_t bytes = (size_t)h.blob_bytes + ftab_bytes + (size_t)cta_smem_doubles(spc, h.N, h.nb, h.nslot, h.nslot2, h.rnl) * sizeof(double);
+        const size_t bytes = (size_t)h.blob_bytes + ftab_bytes + (size_t)cta_smem_doubles(spc, h.N, h.nb, h.nslot, h.nslot2, h.rnl, persys) * sizeof(double);
         if (bytes > (size_t)M->dev_smem_optin) continue;
         int ctas = (int)((size_t)M->sm_smem / (bytes + 1024));  // 1 KB per CTA is reserved by the driver
         const int by_threads = 2048 / (32 * h.N);
@@ -360,7 +360,7 @@ int build_blob(BioncModel* M) {
     CUDA_TRY(cudaDeviceGetAttribute(&M->dev_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, M->device));
     CUDA_TRY(cudaDeviceGetAttribute(&M->sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, M->device));
     M->hdr = h;
-    int rc = make_plan(M, 0, M->plan0);
+    int rc = make_plan(M, 0, false, M->plan0);
     if (rc != BIONC_OK) return rc;
     h.spw = M->plan0.spw;
     M->hdr = h;
@@ -567,8 +567,16 @@ int bionc_cuda_model_create(const BioncModelDesc* d, int device, BioncModel** ou
             if (B.child != i && B.parent != i) continue;
             DevSide sd{};
             sd.blk = b, sd.role = (B.child == i) ? CHILD : PARENT;
+            sd.node = B.jrow / 3, sd.lam_off = B.jrow, sd.row_h = B.row_h, sd.ground = B.parent < 0 ? 1 : 0;
+            sd.rhs_off = B.jrow + (sd.role == PARENT ? 3 * M->hdr.nb : 0);
             if (B.type == LIN3) {
                 sd.nl_slot = -1;
+                const double sgn = sd.role == CHILD ? -1.0 : 1.0;  // Phi = c0 + a_p Q_p - a_c Q_c
+                const double* a = B.p + (sd.role == CHILD ? 4 : 0);
+                sd.lev[0] = sgn * (a[1] + a[2]);
+                sd.lev[1] = sgn * a[0] - sd.lev[0] * c[0];
+                sd.lev[2] = -sgn * a[2] - sd.lev[0] * c[1];
+                sd.lev[3] = sgn * a[3] - sd.lev[0] * c[2];
             } else {
                 sd.nl_slot = nl;
                 nl += (B.type == SOP && sd.role == PARENT) ? 6 : 3;  // d1 (and d2 for the two-term row kind)
@@ -687,7 +695,8 @@ struct DynCall {
         if (rc != BIONC_OK) return rc;
         fx.args.step_stride = (long long)B * fx.args.nf * 6;
         plan = M->plan0;
-        if (fx.args.tab != nullptr && (rc = make_plan(M, fx.args.tab_bytes, plan)) != BIONC_OK) return rc;
+        const bool persys = opt != nullptr && opt->inertia != nullptr;  // per-system constants take shared memory too
+        if ((fx.args.tab != nullptr || persys) && (rc = make_plan(M, fx.args.tab_bytes, persys, plan)) != BIONC_OK) return rc;
         ks = pick_kernels(kernel_path(M, o, fx.args), 32 * M->hdr.N, plan.spw);
         return BIONC_OK;
     }
@@ -751,6 +760,21 @@ int bionc_cuda_forward_dynamics_dense(const BioncModel* M, const double* Q, cons
     return BIONC_OK;
 }
 
+// one launch of the fused integrator: steps step0 .. step0 + n_steps - 1 of a run (h_steps, traj and the force slices
+// are indexed by the global step)
+static int launch_rk4(const BioncModel* M, DynCall& call, double* Q, double* Qd, double h, const double* h_steps, long long step0,
+                      long long n_steps, int normalize, const double* inertia, double* traj, long long traj_every, int32_t* status,
+                      long long B, cudaStream_t st) {
+    const unsigned grid = (unsigned)((B + call.plan.spw - 1) / call.plan.spw), block = 32 * M->hdr.N;
+    const unsigned char* blob = M->d_blob;
+    int blob_bytes = M->blob_bytes;
+    void* args[] = {&blob, &blob_bytes, &call.fx.args, &Q, &Qd, &inertia, &call.o, &h, &h_steps, &n_steps, &step0, &normalize, &traj, &traj_every, &status, &B};
+    CUDA_TRY(cudaLaunchKernel(call.ks.rk4, dim3(grid), dim3(block), args, call.plan.smem, st));
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return BIONC_OK;
+}
+
 int bionc_cuda_rk4(const BioncModel* M, double* Q, double* Qd, double h, const double* h_steps, int64_t n_steps,
                    int32_t normalize, const BioncDynOptions* opt, double* traj, int64_t traj_every, double* lam_last,
                    int32_t* status, int64_t B, void* stream) {
@@ -764,18 +788,32 @@ int bionc_cuda_rk4(const BioncModel* M, double* Q, double* Qd, double h, const d
     if (rc != BIONC_OK) return rc;
     if (status != nullptr) CUDA_TRY(cudaMemsetAsync(status, 0, B * sizeof(int32_t), st));
     const double* inertia = opt != nullptr ? opt->inertia : nullptr;
-    const unsigned grid = (unsigned)((B + call.plan.spw - 1) / call.plan.spw), block = 32 * M->hdr.N;
     if (traj == nullptr) traj_every = 1;
     if ((rc = ensure_smem(M->device, call.ks.rk4, M->dev_smem_optin)) != BIONC_OK) return rc;
-    const unsigned char* blob = M->d_blob;
-    int blob_bytes = M->blob_bytes;
-    long long Bll = B, nsteps = n_steps, tevery = traj_every;
-    int norm = normalize;
-    void* args[] = {&blob, &blob_bytes, &call.fx.args, &Q, &Qd, &inertia, &call.o, &h, &h_steps, &nsteps, &norm, &traj, &tevery, &lam_last, &status, &Bll};
-    CUDA_TRY(cudaLaunchKernel(call.ks.rk4, dim3(grid), dim3(block), args, call.plan.smem, st));
-    g_launches++;
-    CUDA_TRY(cudaGetLastError());
-    return BIONC_OK;
+    if (lam_last == nullptr) return launch_rk4(M, call, Q, Qd, h, h_steps, 0, n_steps, normalize, inertia, traj, traj_every, status, B, st);
+    // The multipliers of the first stage of the last step are those of forward_dynamics at the state before that step:
+    // n_steps - 1 fused steps, one forward_dynamics launch for lambda (its accelerations go to a scratch array), the last
+    // step.  The integrator kernel itself carries no multiplier output path.
+    if (n_steps > 1 && (rc = launch_rk4(M, call, Q, Qd, h, h_steps, 0, n_steps - 1, normalize, inertia, traj, traj_every, status, B, st)) != BIONC_OK) return rc;
+    {
+        if ((rc = ensure_smem(M->device, call.ks.fd, M->dev_smem_optin)) != BIONC_OK) return rc;
+        double* scratch = nullptr;
+        CUDA_TRY(cudaMallocAsync(&scratch, (size_t)B * 12 * M->hdr.N * sizeof(double), st));
+        FextArgs fxl = call.fx.args;  // the force slice of the last step
+        if (fxl.vals != nullptr) fxl.vals += (n_steps - 1 < fxl.steps ? n_steps - 1 : fxl.steps - 1) * fxl.step_stride;
+        const unsigned grid = (unsigned)((B + call.plan.spw - 1) / call.plan.spw), block = 32 * M->hdr.N;
+        const unsigned char* blob = M->d_blob;
+        int blob_bytes = M->blob_bytes;
+        const double *Qc = Q, *Qdc = Qd;
+        int32_t* no_status = nullptr;  // flags of this evaluation are raised by the last step as well
+        long long Bll = B;
+        void* args[] = {&blob, &blob_bytes, &fxl, &Qc, &Qdc, &inertia, &call.o, &scratch, &lam_last, &no_status, &Bll};
+        const cudaError_t e = cudaLaunchKernel(call.ks.fd, dim3(grid), dim3(block), args, call.plan.smem, st);
+        cudaFreeAsync(scratch, st);
+        if (e != cudaSuccess) return fail(BIONC_E_CUDA, std::string("cudaLaunchKernel: ") + cudaGetErrorString(e));
+        g_launches++;
+    }
+    return launch_rk4(M, call, Q, Qd, h, h_steps, n_steps - 1, 1, normalize, inertia, traj, traj_every, status, B, st);
 }
 
 int bionc_cuda_eval(const BioncModel* M, int32_t which, const double* in, const BioncDynOptions* opt, double* out,
@@ -807,32 +845,44 @@ int bionc_cuda_eval(const BioncModel* M, int32_t which, const double* in, const 
         CUDA_TRY(cudaGetLastError());
         return BIONC_OK;
     }
-    size_t out_elems = 0;
+    int rows = 0, cols = 1;
     switch (which) {
-        case BIONC_EVAL_PHI_R: out_elems = (size_t)6 * N; break;
-        case BIONC_EVAL_K_R: out_elems = (size_t)6 * N * n; break;
-        case BIONC_EVAL_PHI_J: out_elems = mj; break;
-        case BIONC_EVAL_K_J: out_elems = (size_t)mj * n; break;
-        case BIONC_EVAL_PHI_H: case BIONC_EVAL_BIAS_H: out_elems = m; break;
-        case BIONC_EVAL_K_H: out_elems = (size_t)m * n; break;
-        case BIONC_EVAL_FEXT: out_elems = n; break;
+        case BIONC_EVAL_PHI_R: rows = 6 * N; break;
+        case BIONC_EVAL_K_R: rows = 6 * N, cols = n; break;
+        case BIONC_EVAL_PHI_J: rows = mj; break;
+        case BIONC_EVAL_K_J: rows = mj, cols = n; break;
+        case BIONC_EVAL_PHI_H: case BIONC_EVAL_BIAS_H: rows = m; break;
+        case BIONC_EVAL_K_H: rows = m, cols = n; break;
+        case BIONC_EVAL_FEXT: rows = n; break;
     }
-    if (out_elems == 0) return BIONC_OK;
+    const int out_per_sys = rows * cols;
+    if (out_per_sys == 0) return BIONC_OK;
     FextCall fx;
     if (which == BIONC_EVAL_FEXT) {
         int rc = fx.upload(M, opt != nullptr ? opt->fext : nullptr, st);
         if (rc != BIONC_OK) return rc;
         fx.args.step_stride = (long long)B * fx.args.nf * 6;
     }
-    // vector outputs are written row by row in full; only the (sparse) Jacobians need the zero fill
-    if (which == BIONC_EVAL_K_R || which == BIONC_EVAL_K_J || which == BIONC_EVAL_K_H)
-        CUDA_TRY(cudaMemsetAsync(out, 0, out_elems * B * sizeof(double), st));
+    // Tile of T systems: two input and two output images in shared memory, about 64 KB together when a system allows it
+    // (several CTAs per SM keep copies and evaluation overlapped); T x out_per_sys is kept even so that every full tile
+    // is a 16-byte multiple for the bulk copies.
+    long long T = 65536 / (16LL * (n + out_per_sys));
+    if (T > 64) T = 64;
+    if (T < 1) T = 1;
+    if ((out_per_sys & 1) && (T & 1) && T > 1) --T;
+    if (T > B) T = B;
+    const size_t smem = 128 + 2 * (size_t)T * (n + out_per_sys) * sizeof(double);
+    if (smem > (size_t)M->dev_smem_optin) return fail(BIONC_E_TOO_LARGE, "one system's output does not fit the shared-memory tile of the evaluator");
+    int rc = ensure_smem(M->device, (const void*)eval_tiled_kernel, M->dev_smem_optin);
+    if (rc != BIONC_OK) return rc;
+    int ctas = (int)((size_t)M->sm_smem / (smem + 1024));
+    if (ctas > 8) ctas = 8;
+    if (ctas < 1) ctas = 1;
+    const long long ntiles = (B + T - 1) / T;
+    long long grid = 148LL * ctas;
+    if (grid > ntiles) grid = ntiles;
     EvalArgs ea{which, N, M->hdr.nblk, mj, m};
-    const long long total = B * (long long)(N + M->hdr.nblk);
-    const int block = 128;
-    long long grid = (total + block - 1) / block;
-    if (grid > 148LL * 64) grid = 148LL * 64;
-    eval_kernel<<<(unsigned)grid, block, 0, st>>>(M->d_blob, fx.args, ea, in, out, B);
+    eval_tiled_kernel<<<(unsigned)grid, kEvalThreads, smem, st>>>(M->d_blob, fx.args, ea, in, out, (long long)B, (int)T, out_per_sys, rows, cols);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return BIONC_OK;

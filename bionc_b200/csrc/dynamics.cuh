@@ -43,6 +43,7 @@
 //   knl      : N x rnl x 32   state-dependent vectors of the non-LIN3 rows (3 or 6 doubles per row and segment)
 #pragma once
 #include "model.cuh"
+#include "tmem.cuh"
 
 namespace bionc {
 
@@ -81,6 +82,12 @@ __device__ __forceinline__ double dot(V3 a, V3 b) { return fma(a.x, b.x, fma(a.y
 __device__ __forceinline__ V3 cross(V3 a, V3 b) {
     return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
+// acc + a x b and acc - a x b in six fused multiply-adds (a standalone cross product plus an addition costs nine FP64
+// issue slots: every DMUL / DADD takes the same slot as a DFMA)
+__device__ __forceinline__ V3 cross_acc(V3 a, V3 b, V3 acc) {
+    return V3{fma(a.y, b.z, fma(-a.z, b.y, acc.x)), fma(a.z, b.x, fma(-a.x, b.z, acc.y)), fma(a.x, b.y, fma(-a.y, b.x, acc.z))};
+}
+__device__ __forceinline__ V3 cross_sub(V3 acc, V3 a, V3 b) { return cross_acc(b, a, acc); }
 // a + s * b
 __device__ __forceinline__ V3 axpy(double s, V3 b, V3 a) { return V3{fma(s, b.x, a.x), fma(s, b.y, a.y), fma(s, b.z, a.z)}; }
 __device__ __forceinline__ double comp(V3 a, int c) { return c == 0 ? a.x : (c == 1 ? a.y : a.z); }
@@ -98,10 +105,17 @@ __device__ __forceinline__ constexpr int widx(int t, int s) {
 
 // Per-lane view of one segment in one system.
 struct SegCtx {
-    // constants of the segment: from the model table, or from the per-system inertial parameters (config 5)
-    double N3[6];  // J - m c c^T, packed xx xy xz yy yz zz: second-moment matrix about the centre of mass, natural coordinates
-    double cn[3];  // natural centre of mass
-    double m, minv;
+    // Constants of the segment, 11 doubles read from shared memory where they are used (no registers held across the
+    // evaluation): kc[i * ks] = N3 (6: J - m c c^T packed xx xy xz yy yz zz, the second-moment matrix about the centre
+    // of mass in natural coordinates), natural centre of mass (3), m, 1 / m.  Model inertia: the segment's table entry
+    // (ks = 1, one broadcast address per warp); per-system inertial parameters (config 5): this lane's column of the
+    // CTA's constant area (ks = systems per CTA), filled by load_constants.
+    const double* kc;
+    int ks;
+    __device__ __forceinline__ double N3(int i) const { return kc[i * ks]; }
+    __device__ __forceinline__ double cn(int i) const { return kc[(6 + i) * ks]; }
+    __device__ __forceinline__ double m() const { return kc[9 * ks]; }
+    __device__ __forceinline__ double minv() const { return kc[10 * ks]; }
     // state-dependent, set by segment_setup
     V3 u, v, w;        // v = rp - rd
     V3 Au, Av, Aw;     // particular accelerations of u, v, w:  [Au Av Aw] = B^-T S,  S = -1/2 Bsym
@@ -117,6 +131,10 @@ __device__ __forceinline__ V3 in_basis(const SegCtx& c, double x0, double x1, do
 __device__ __forceinline__ V3 in_accel(const SegCtx& c, double x0, double x1, double x2) {
     return axpy(x0, c.Au, axpy(x1, c.Av, x2 * c.Aw));
 }
+// acc + sum_i x[i] * (Au, Av, Aw)[i]
+__device__ __forceinline__ V3 in_accel_acc(const SegCtx& c, double x0, double x1, double x2, V3 acc) {
+    return axpy(x0, c.Au, axpy(x1, c.Av, axpy(x2, c.Aw, acc)));
+}
 
 // A constant coefficient vector a over the slots (u, rp, rd, w) as seen from the centre of mass:
 // sum_s a[s] Qdd_s = sigma tc + al x rho' + kappa',  sigma = a_rp + a_rd,  rho' = B r,  kappa' = A r,
@@ -128,9 +146,9 @@ struct Lever {
 __device__ __forceinline__ Lever lever_of(const SegCtx& c, const double (&a)[4]) {
     Lever l;
     l.sigma = a[1] + a[2];
-    l.r[0] = fma(-l.sigma, c.cn[0], a[0]);
-    l.r[1] = fma(-l.sigma, c.cn[1], -a[2]);
-    l.r[2] = fma(-l.sigma, c.cn[2], a[3]);
+    l.r[0] = fma(-l.sigma, c.cn(0), a[0]);
+    l.r[1] = fma(-l.sigma, c.cn(1), -a[2]);
+    l.r[2] = fma(-l.sigma, c.cn(2), a[3]);
     return l;
 }
 
@@ -158,11 +176,13 @@ struct WarpCtx {
     const double* fvals;     // per-system (torque, force) values of this lane's system at the current step, or nullptr
     double *Qo, *Qdo, *Qsys, *Qdsys;
     double *S0, *S1, *r0, *r1, *lamv, *dinv, *knl;
+    double* kcs;  // per-system constants of this lane's segment, element i at kcs[i * spw] (allocated only for such calls)
     // symbolic factorisation tables (host, capi.cu symbolic_analysis)
     const int *slot_tab, *slot2_tab, *zero_list, *comb_list, *unit_list, *colptr, *colrow, *lvlptr, *lvlpiv, *owner, *pivmask, *pivwriter, *nscale;
     int N, mj, nb;
     int segi;  // this warp's segment
     int lane;  // this lane's system inside the CTA
+    bool persys;  // per-system inertial parameters: the levers of the model's centre of mass are corrected per system
 };
 
 
@@ -403,6 +423,19 @@ __device__ __forceinline__ V3 sym3_apply(const double (&di)[6], V3 x) {
               fma(di[3], x.x, fma(di[4], x.y, di[5] * x.z)));
 }
 
+// lever of a point-to-point side from the host-compiled constants (DevSide::lev, built for the model's own centre of
+// mass); with per-system inertial parameters r moves by sigma (c_model - c_system)
+__device__ __forceinline__ Lever lever_of_side(const WarpCtx& w, const SegCtx& c, const DevSeg& sg, const DevSide& sd) {
+    Lever l;
+    l.sigma = sd.lev[0];
+    l.r[0] = sd.lev[1], l.r[1] = sd.lev[2], l.r[2] = sd.lev[3];
+    if (w.persys) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) l.r[i] = fma(l.sigma, sg.kc[6 + i] - c.cn(i), l.r[i]);
+    }
+    return l;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Phase B: everything about this lane's segment that depends on the stage state only.
 //   B = [u v w], reciprocal basis b_i (rows of det B^-1), Ic^-1, particular accelerations A = B^-T S with
@@ -419,7 +452,7 @@ __device__ __forceinline__ void segment_setup(const WarpCtx& w, SegCtx& c, const
     if (!(fabs(det) > 0.0) || !isfinite(det)) status |= 1;
     else if (det * det < (kSmallPivot * kSmallPivot) * (guu * gvv * gww)) status |= 4;
     const double idet = fast_rcp(det);
-    const double* N = c.N3;
+    const double N[6] = {c.N3(0), c.N3(1), c.N3(2), c.N3(3), c.N3(4), c.N3(5)};
     {   // Y = B N3 B^T,  Ic = tr(Y) I - Y
         const V3 X0 = in_basis(c, N[0], N[1], N[2]), X1 = in_basis(c, N[1], N[3], N[4]), X2 = in_basis(c, N[2], N[4], N[5]);
         const double Yxx = fma(X0.x, c.u.x, fma(X1.x, c.v.x, X2.x * c.w.x));
@@ -447,18 +480,17 @@ __device__ __forceinline__ void segment_setup(const WarpCtx& w, SegCtx& c, const
     c.Aw = axpy(s02, b0, axpy(s12, b1, s22 * b2));
     {   // eta = sum_ij N3_ij B_i x A_j
         const V3 Z0 = in_accel(c, N[0], N[1], N[2]), Z1 = in_accel(c, N[1], N[3], N[4]), Z2 = in_accel(c, N[2], N[4], N[5]);
-        const V3 eta = cross(c.u, Z0) + cross(c.v, Z1) + cross(c.w, Z2);
-        c.tau0 = mk(-eta.x, -eta.y, -eta.z);
+        c.tau0 = cross_acc(Z2, c.w, cross_acc(Z1, c.v, cross(Z0, c.u)));  // -eta: the factors of every cross product swapped
     }
-    c.F0 = mk(0.0, 0.0, -9.81 * c.m);  // gravity acts at the centre of mass: no torque (natural_segment.py:562-572)
+    c.F0 = mk(0.0, 0.0, -9.81 * c.m());  // gravity acts at the centre of mass: no torque (natural_segment.py:562-572)
     if (GENERAL && w.fext != nullptr) {
         const int fb = w.ftab->begin[w.segi], fe = w.ftab->begin[w.segi + 1];
         if (fe > fb) {
             V3 te, Fe;
             external_wrench(w.fext, fb, fe, w.fvals, c.u, c.v, c.w, rp, te, Fe);
-            const V3 cbar = in_basis(c, c.cn[0], c.cn[1], c.cn[2]);
+            const V3 cbar = in_basis(c, c.cn(0), c.cn(1), c.cn(2));
             c.F0 = c.F0 + Fe;
-            c.tau0 = c.tau0 + te - cross(cbar, Fe);
+            c.tau0 = cross_sub(c.tau0 + te, cbar, Fe);
         }
     }
 }
@@ -473,7 +505,7 @@ template <bool KAP>
 __device__ __forceinline__ void row6_term(const SegCtx& c, const double* a, double scale, V3 d, Row6& r) {
     const double as[4] = {scale * a[0], scale * a[1], scale * a[2], scale * a[3]};
     const Lever lv = lever_of(c, as);
-    r.n = r.n + cross(in_basis(c, lv.r[0], lv.r[1], lv.r[2]), d);
+    r.n = cross_acc(in_basis(c, lv.r[0], lv.r[1], lv.r[2]), d, r.n);
     r.f = axpy(lv.sigma, d, r.f);
     if (KAP) r.kap += dot(d, in_accel(c, lv.r[0], lv.r[1], lv.r[2]));
 }
@@ -648,15 +680,15 @@ __device__ __forceinline__ void solve_two_leaves(const WarpCtx& w, int& status) 
 // lambda_r of this lane's segment from  Kr^T lambda_r = R,  R = f - Kj^T lambda_j - G Qdd  (the rows of the reference's
 // KKT system that the null-space form never touches).  Kr^T lambda_r reads  R_u = 2 l0 u + l1 v + l2 w,
 // R_rp = l1 u + 2 l3 v + l4 w = -R_rd,  R_w = l2 u + l4 v + 2 l5 w,  so  B^-1 [R_u R_rp R_w] = [[2 l0, l1, l2], [l1, 2 l3, l4],
-// [l2, l4, 2 l5]]; the off-diagonal pairs agree up to rounding and are averaged.  Output path only (forward_dynamics,
-// the last step of rk4 when lambda is asked for): it is kept out of line so that it does not weigh on the hot loop.
+// [l2, l4, 2 l5]]; the off-diagonal pairs agree up to rounding and are averaged.  Output path only: compiled into the
+// forward_dynamics kernel (LAM = true), never into the fused integrator.
 template <bool GENERAL, int S>
-__device__ __noinline__ void rigid_multipliers(const WarpCtx& w, const SegCtx& c, const DevSeg& sg, const Q12& Qdd, double* lam_r) {
+__device__ __forceinline__ void rigid_multipliers(const WarpCtx& w, const SegCtx& c, const DevSeg& sg, const Q12& Qdd, double* lam_r) {
     constexpr int spw = S;
     // M4 rows u, rp, w from (m, c, J), J = N3 + m c c^T   (natural_inertial_parameters.py:153-177)
-    const double m = c.m, c0 = c.cn[0], c1 = c.cn[1], c2 = c.cn[2];
-    const double J00 = fma(m * c0, c0, c.N3[0]), J01 = fma(m * c0, c1, c.N3[1]), J02 = fma(m * c0, c2, c.N3[2]);
-    const double J11 = fma(m * c1, c1, c.N3[3]), J12 = fma(m * c1, c2, c.N3[4]), J22 = fma(m * c2, c2, c.N3[5]);
+    const double m = c.m(), c0 = c.cn(0), c1 = c.cn(1), c2 = c.cn(2);
+    const double J00 = fma(m * c0, c0, c.N3(0)), J01 = fma(m * c0, c1, c.N3(1)), J02 = fma(m * c0, c2, c.N3(2));
+    const double J11 = fma(m * c1, c1, c.N3(3)), J12 = fma(m * c1, c2, c.N3(4)), J22 = fma(m * c2, c2, c.N3(5));
     const double Mu[4] = {J00, m * c0 + J01, -J01, J02};
     const double Mr[4] = {m * c0 + J01, m + 2.0 * m * c1 + J11, -(m * c1 + J11), m * c2 + J12};
     const double Mw[4] = {J02, m * c2 + J12, -J12, J22};
@@ -700,17 +732,18 @@ __device__ __noinline__ void rigid_multipliers(const WarpCtx& w, const SegCtx& c
 // ---------------------------------------------------------------------------------------------
 // One forward-dynamics evaluation for the whole warp.
 // Precondition: every lane has published its segment's stage state (Q, Qdot) in w.Qs / w.Qds.
-// Every lane receives Qddot of its segment; lambda (holonomic order) goes to lam_out if non-null.
+// Every lane receives Qddot of its segment; lambda (holonomic order) goes to lam_out if LAM and lam_out is non-null.
 // Every thread of the CTA must call this (it contains __syncthreads).
 //
 // GENERAL=false is the lean instantiation for models whose joints are all point-to-point (LIN3: spherical / ground
 // spherical / weld halves) without external forces -- the lower-limb and full-body trees; GENERAL=true handles every
 // block kind and the forces.  STAB compiles the Baumgarte terms in (they read the other segment of a joint, so the
-// caller must order the publication of a stage state with a barrier when STAB or GENERAL is set).
+// caller must order the publication of a stage state with a barrier when STAB or GENERAL is set).  PARKA: the particular
+// accelerations wait in the thread's tensor-memory columns tmA (18 words) while the joint-level phases run.
 // ---------------------------------------------------------------------------------------------
-template <bool GENERAL, bool STAB, int S>
+template <bool GENERAL, bool STAB, bool LAM, bool PARKA, int S>
 __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& c, const DynOpts& o, Q12& Qdd,
-                                                      double* lam_out, int& status) {
+                                                      double* lam_out, int& status, unsigned tmA = 0) {
     constexpr int spw = S;
     const DevSeg& sg = w.seg[w.segi];
     const bool stab = STAB && o.use_stab;
@@ -722,7 +755,10 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
     if (w.mj > 0) {
         const int nb = w.nb, mjp = 3 * nb;
         const DevHeader* hd = w.hdr;
-        const V3 afree = sym3_apply(c.Ii, c.tau0), tfree = c.minv * c.F0;  // free accelerations (no joint forces)
+        // free accelerations (no joint forces); without external forces F0 is gravity: z only
+        const V3 afree = sym3_apply(c.Ii, c.tau0);
+        const double minv = c.minv();
+        const V3 tfree = GENERAL ? minv * c.F0 : mk(0.0, 0.0, minv * c.F0.z);
 
         // ---- C. zero what the assembly does not overwrite (pure fill blocks, blocks of nodes made of single
         //         rows); padding rows get a unit diagonal and a zero right-hand side.  Lean models have
@@ -744,15 +780,15 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
         // ---- D. right-hand side rhs' = J a_free + kappa + b_j: every segment adds its share into its own copy of the
         //         row (copy `role`, written by exactly one lane); the child side also carries the row's bias terms
         for (int e = sg.side_begin; e < sg.side_end; ++e) {
-            const DevSide sd = w.side[e];
+            const DevSide& sd = w.side[e];
             const DevBlk& b = w.blk[sd.blk];
-            double* rr = (sd.role == CHILD ? w.r0 : w.r1) + b.jrow * spw;
+            double* rr = w.r0 + sd.rhs_off * spw;
             if (!GENERAL || b.type == LIN3) {
-                double as[4];
-                lin3_coefs(b, sd.role, as);
-                const Lever lv = lever_of(c, as);
+                const Lever lv = lever_of_side(w, c, sg, sd);
                 const V3 rho = in_basis(c, lv.r[0], lv.r[1], lv.r[2]);
-                V3 r = axpy(lv.sigma, tfree, cross(afree, rho) + in_accel(c, lv.r[0], lv.r[1], lv.r[2]));
+                V3 r = in_accel_acc(c, lv.r[0], lv.r[1], lv.r[2], cross(afree, rho));
+                if (GENERAL) r = axpy(lv.sigma, tfree, r);
+                else r.z = fma(lv.sigma, tfree.z, r.z);  // gravity only
                 if (stab && sd.role == CHILD) {
                     // Phi = c0 + N_p Q_p - N_c Q_c ; K Qdot = N_p Qdot_p - N_c Qdot_c
                     V3 phi = mk(b.p[8], b.p[9], b.p[10]) - lin_form<S>(w, w.Qsys, b.child, b.p + 4);
@@ -764,8 +800,8 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                     r = axpy(o.alpha, phi, axpy(o.beta, kqd, r));
                 }
                 rr[0] = r.x, rr[spw] = r.y, rr[2 * spw] = r.z;
-                if (b.parent < 0) {  // no parent lane: the child also settles the second copy
-                    double* r1p = w.r1 + b.jrow * spw;
+                if (sd.ground) {  // no parent lane: the child also settles the second copy
+                    double* r1p = w.r1 + sd.lam_off * spw;
                     r1p[0] = 0.0, r1p[spw] = 0.0, r1p[2 * spw] = 0.0;
                 }
             } else {
@@ -777,65 +813,69 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                 dst[0] = d1.x, dst[S] = d1.y, dst[2 * S] = d1.z;
                 if (nonlin_two_terms(b, sd.role)) dst[3 * S] = d2.x, dst[4 * S] = d2.y, dst[5 * S] = d2.z;
                 rr[0] = dot(r6.n, afree) + dot(r6.f, tfree) + r6.kap + bterm;
-                if (b.parent < 0) w.r1[b.jrow * spw] = 0.0;
+                if (sd.ground) w.r1[sd.lam_off * spw] = 0.0;
             }
+        }
+
+        if (PARKA) {  // A is not needed again before phase I
+            const double a9[9] = {c.Au.x, c.Au.y, c.Au.z, c.Av.x, c.Av.y, c.Av.z, c.Aw.x, c.Aw.y, c.Aw.z};
+            tmem_put(tmA, a9);
         }
 
         // ---- E. this segment's contribution to S':  S'_ab = fdir_a . fdir_b / m + n_a . Ic^-1 n_b
         for (int e = sg.side_begin; e < sg.side_end; ++e) {
-            const DevSide sd = w.side[e];
+            const DevSide& sd = w.side[e];
             const DevBlk& b = w.blk[sd.blk];
             if (!GENERAL || b.type == LIN3) {
                 // point-to-point side b against the point-to-point sides a >= b: 3x3 block gamma I + [V_c x rho_a]
-                double asb[4];
-                lin3_coefs(b, sd.role, asb);
-                const Lever lb = lever_of(c, asb);
+                const Lever lb = lever_of_side(w, c, sg, sd);
+                const V3 rho_b = in_basis(c, lb.r[0], lb.r[1], lb.r[2]);
                 V3 V[3];
-                lever_columns(c.Ii, in_basis(c, lb.r[0], lb.r[1], lb.r[2]), V);
-                const double sbm = lb.sigma * c.minv;
-                const int Jb = b.jrow / 3;
+                lever_columns(c.Ii, rho_b, V);
+                const double sbm = lb.sigma * minv;
+                const int Jb = sd.node;
                 for (int e2 = e; e2 < sg.side_end; ++e2) {
-                    const DevSide sa = w.side[e2];
-                    const DevBlk& a = w.blk[sa.blk];
-                    if (GENERAL && a.type != LIN3) continue;
-                    double asa[4];
-                    lin3_coefs(a, sa.role, asa);
-                    const Lever la = lever_of(c, asa);
-                    const V3 rho_a = in_basis(c, la.r[0], la.r[1], la.r[2]);
-                    const double gamma = la.sigma * sbm;
+                    const DevSide& sa = w.side[e2];
+                    if (GENERAL && sa.nl_slot >= 0) continue;  // a single row: handled from its own side
+                    V3 rho_a = rho_b;
+                    double gamma = lb.sigma * sbm;
+                    if (e2 != e) {
+                        const Lever la = lever_of_side(w, c, sg, sa);
+                        rho_a = in_basis(c, la.r[0], la.r[1], la.r[2]);
+                        gamma = la.sigma * sbm;
+                    }
                     // element (row r of a, row cc of b) = gamma delta + (rho_a x e_r) . V_cc = gamma delta + (V_cc x rho_a)_r
-                    const V3 col0 = cross(V[0], rho_a), col1 = cross(V[1], rho_a), col2 = cross(V[2], rho_a);
-                    const int Ia = a.jrow / 3;
+                    const V3 col0 = cross_acc(V[0], rho_a, mk(gamma, 0.0, 0.0)), col1 = cross_acc(V[1], rho_a, mk(0.0, gamma, 0.0)),
+                             col2 = cross_acc(V[2], rho_a, mk(0.0, 0.0, gamma));
+                    const int Ia = sa.node;
                     if (Ia >= Jb) {  // block (Ia, Jb): rows of a, columns of b
                         const int s2 = w.slot2_tab[Ia * nb + Jb];
                         double* Sc = (sa.role == PARENT && s2 >= 0) ? w.S1 + 9 * s2 * spw : w.S0 + 9 * w.slot_tab[Ia * nb + Jb] * spw;
-                        Sc[0 * spw] = col0.x + gamma, Sc[1 * spw] = col1.x, Sc[2 * spw] = col2.x;
-                        Sc[3 * spw] = col0.y, Sc[4 * spw] = col1.y + gamma, Sc[5 * spw] = col2.y;
-                        Sc[6 * spw] = col0.z, Sc[7 * spw] = col1.z, Sc[8 * spw] = col2.z + gamma;
+                        Sc[0 * spw] = col0.x, Sc[1 * spw] = col1.x, Sc[2 * spw] = col2.x;
+                        Sc[3 * spw] = col0.y, Sc[4 * spw] = col1.y, Sc[5 * spw] = col2.y;
+                        Sc[6 * spw] = col0.z, Sc[7 * spw] = col1.z, Sc[8 * spw] = col2.z;
                     } else {  // block (Jb, Ia): transposed; the copy follows this lane's role in the larger node b
                         const int s2 = w.slot2_tab[Jb * nb + Ia];
                         double* Sc = (sd.role == PARENT && s2 >= 0) ? w.S1 + 9 * s2 * spw : w.S0 + 9 * w.slot_tab[Jb * nb + Ia] * spw;
-                        Sc[0 * spw] = col0.x + gamma, Sc[1 * spw] = col0.y, Sc[2 * spw] = col0.z;
-                        Sc[3 * spw] = col1.x, Sc[4 * spw] = col1.y + gamma, Sc[5 * spw] = col1.z;
-                        Sc[6 * spw] = col2.x, Sc[7 * spw] = col2.y, Sc[8 * spw] = col2.z + gamma;
+                        Sc[0 * spw] = col0.x, Sc[1 * spw] = col0.y, Sc[2 * spw] = col0.z;
+                        Sc[3 * spw] = col1.x, Sc[4 * spw] = col1.y, Sc[5 * spw] = col1.z;
+                        Sc[6 * spw] = col2.x, Sc[7 * spw] = col2.y, Sc[8 * spw] = col2.z;
                     }
                 }
             } else {
                 // single row b against every point-to-point side and against the single rows a >= b
                 const Row6 rb6 = load_row6<false, S>(w, c, b, sd.role, sd.nl_slot);
-                const V3 yb = sym3_apply(c.Ii, rb6.n), fbm = c.minv * rb6.f;
-                const int Ib = b.jrow / 3, rb = b.jrow - 3 * Ib;
+                const V3 yb = sym3_apply(c.Ii, rb6.n), fbm = minv * rb6.f;
+                const int Ib = sd.node, rb = sd.lam_off - 3 * Ib;
                 for (int e2 = sg.side_begin; e2 < sg.side_end; ++e2) {
-                    const DevSide sa = w.side[e2];
+                    const DevSide& sa = w.side[e2];
                     const DevBlk& a = w.blk[sa.blk];
                     // the copy is chosen by this lane's role in the block holding the larger row
                     if (a.type == LIN3) {
-                        double asa[4];
-                        lin3_coefs(a, sa.role, asa);
-                        const Lever la = lever_of(c, asa);
+                        const Lever la = lever_of_side(w, c, sg, sa);
                         const V3 rho_a = in_basis(c, la.r[0], la.r[1], la.r[2]);
-                        const V3 r = axpy(la.sigma, fbm, cross(yb, rho_a));
-                        const int Ia = a.jrow / 3;  // LIN3 blocks are whole nodes, never Ib
+                        const V3 r = cross_acc(yb, rho_a, la.sigma * fbm);
+                        const int Ia = sa.node;  // LIN3 blocks are whole nodes, never Ib
                         if (Ia > Ib) {  // rows of a, column rb
                             const int s2 = w.slot2_tab[Ia * nb + Ib];
                             double* Sc = ((sa.role == PARENT && s2 >= 0) ? w.S1 + 9 * s2 * spw : w.S0 + 9 * w.slot_tab[Ia * nb + Ib] * spw) + rb * spw;
@@ -848,9 +888,9 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                     } else if (e2 >= e) {  // every pair of single rows once
                         const Row6 ra6 = load_row6<false, S>(w, c, a, sa.role, sa.nl_slot);
                         const double acc = dot(ra6.f, fbm) + dot(ra6.n, yb);
-                        const int Ia = a.jrow / 3, ra = a.jrow - 3 * Ia;
+                        const int Ia = sa.node, ra = sa.lam_off - 3 * Ia;
                         // the larger ROW decides the block orientation and whose role picks the copy
-                        const bool a_larger = a.jrow >= b.jrow;
+                        const bool a_larger = sa.lam_off >= sd.lam_off;
                         const int Ihi = a_larger ? Ia : Ib, Ilo = a_larger ? Ib : Ia;
                         const int rhi = a_larger ? ra : rb, rlo = a_larger ? rb : ra;
                         const int role = a_larger ? sa.role : sd.role;
@@ -906,41 +946,47 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
         }
         __syncthreads();
 
+        TmemWords<18> parked;
+        if (PARKA) tmem_stores_done(), tmem_issue(tmA, parked);  // back while phase H runs
+
         // ---- H. joint forces on this segment:  F -= sum fdir lambda,  tau -= sum n lambda
         for (int e = sg.side_begin; e < sg.side_end; ++e) {
-            const DevSide sd = w.side[e];
-            const DevBlk& b = w.blk[sd.blk];
-            const double* lj = w.lamv + b.jrow * spw;
-            if (!GENERAL || b.type == LIN3) {
-                double as[4];
-                lin3_coefs(b, sd.role, as);
-                const Lever lv = lever_of(c, as);
+            const DevSide& sd = w.side[e];
+            const double* lj = w.lamv + sd.lam_off * spw;
+            if (!GENERAL || sd.nl_slot < 0) {
+                const Lever lv = lever_of_side(w, c, sg, sd);
                 const V3 lam = mk(lj[0], lj[spw], lj[2 * spw]);
                 F = axpy(-lv.sigma, lam, F);
-                tau = tau - cross(in_basis(c, lv.r[0], lv.r[1], lv.r[2]), lam);
-                if (lam_out != nullptr && sd.role == CHILD) {
-                    lam_out[b.row_h + 0] = lam.x, lam_out[b.row_h + 1] = lam.y, lam_out[b.row_h + 2] = lam.z;
+                tau = cross_sub(tau, in_basis(c, lv.r[0], lv.r[1], lv.r[2]), lam);
+                if (LAM && lam_out != nullptr && sd.role == CHILD) {
+                    lam_out[sd.row_h + 0] = lam.x, lam_out[sd.row_h + 1] = lam.y, lam_out[sd.row_h + 2] = lam.z;
                 }
             } else {
                 const double lam = lj[0];
-                const Row6 r6 = load_row6<false, S>(w, c, b, sd.role, sd.nl_slot);
+                const Row6 r6 = load_row6<false, S>(w, c, w.blk[sd.blk], sd.role, sd.nl_slot);
                 F = axpy(-lam, r6.f, F);
                 tau = axpy(-lam, r6.n, tau);
-                if (lam_out != nullptr && sd.role == CHILD) lam_out[b.row_h] = lam;
+                if (LAM && lam_out != nullptr && sd.role == CHILD) lam_out[sd.row_h] = lam;
             }
+        }
+        if (PARKA) {
+            double a9[9];
+            tmem_wait(parked, a9);
+            c.Au = mk(a9[0], a9[1], a9[2]), c.Av = mk(a9[3], a9[4], a9[5]), c.Aw = mk(a9[6], a9[7], a9[8]);
         }
     }
 
     // ---- I. Newton-Euler and back to natural accelerations:  Qdd = T (al, tc) + q_p
     {
-        const V3 al = sym3_apply(c.Ii, tau), tc = c.minv * F;
-        const V3 cbar = in_basis(c, c.cn[0], c.cn[1], c.cn[2]);
-        Qdd.s[0] = cross(al, c.u) + c.Au;
-        Qdd.s[3] = cross(al, c.w) + c.Aw;
-        Qdd.s[1] = tc - cross(al, cbar) - in_accel(c, c.cn[0], c.cn[1], c.cn[2]);
-        Qdd.s[2] = Qdd.s[1] - (cross(al, c.v) + c.Av);
+        const double c0 = c.cn(0), c1 = c.cn(1), c2 = c.cn(2);
+        const V3 al = sym3_apply(c.Ii, tau), tc = c.minv() * F;
+        const V3 cbar = in_basis(c, c0, c1, c2);
+        Qdd.s[0] = cross_acc(al, c.u, c.Au);
+        Qdd.s[3] = cross_acc(al, c.w, c.Aw);
+        Qdd.s[1] = in_accel_acc(c, -c0, -c1, -c2, cross_sub(tc, al, cbar));
+        Qdd.s[2] = Qdd.s[1] - cross_acc(al, c.v, c.Av);
     }
-    if (lam_out != nullptr) rigid_multipliers<GENERAL, S>(w, c, sg, Qdd, lam_out + sg.rigid_row);
+    if (LAM && lam_out != nullptr) rigid_multipliers<GENERAL, S>(w, c, sg, Qdd, lam_out + sg.rigid_row);
     // No barrier here: lambda_j lives in its own array, so the next evaluation may start assembling while
     // slower warps still read it; the barriers inside the next evaluation order everything else.
 }

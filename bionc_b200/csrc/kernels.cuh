@@ -4,23 +4,14 @@
 
 namespace bionc {
 
-// Kernels are instantiated per CTA-size class (threads = 32 x segments); the register budget follows from
-// __launch_bounds__(MAXT, MinCtas<MAXT>): up to 64 threads -> 255 registers (shared memory limits residency
-// long before registers do), 96 threads x 4 CTAs -> 168 registers, 128 threads x 4 CTAs -> 128 registers (barrier waits want resident CTAs more
-// than registers), 256 x 2 -> 128, 384 x 1 -> 168, 512 x 1 -> 128, 1024 x 1 -> 64.
-template <int MAXT>
-struct MinCtas {
-    static constexpr int value = MAXT <= 32 ? 8 : (MAXT <= 64 ? 4 : (MAXT <= 128 ? 4 : (MAXT <= 256 ? 2 : 1)));
-};
-
 // What the dynamics need of the natural inertial parameters ip = [m, c(3), J00 J01 J02 J11 J12 J22]
 // (natural_inertial_parameters.py:153-177): N3 = J - m c c^T, c, m, 1/m.  No inverse of M4 is involved.
-__device__ __forceinline__ void inertia_to_constants(const double* __restrict__ ip, SegCtx& c, int& status) {
+__device__ __forceinline__ void inertia_to_constants(const double* __restrict__ ip, double* kc, int ks, int& status) {
     const double m = ip[0], c0 = ip[1], c1 = ip[2], c2 = ip[3];
-    c.N3[0] = fma(-m * c0, c0, ip[4]), c.N3[1] = fma(-m * c0, c1, ip[5]), c.N3[2] = fma(-m * c0, c2, ip[6]);
-    c.N3[3] = fma(-m * c1, c1, ip[7]), c.N3[4] = fma(-m * c1, c2, ip[8]), c.N3[5] = fma(-m * c2, c2, ip[9]);
-    c.cn[0] = c0, c.cn[1] = c1, c.cn[2] = c2;
-    c.m = m, c.minv = 1.0 / m;
+    kc[0] = fma(-m * c0, c0, ip[4]), kc[ks] = fma(-m * c0, c1, ip[5]), kc[2 * ks] = fma(-m * c0, c2, ip[6]);
+    kc[3 * ks] = fma(-m * c1, c1, ip[7]), kc[4 * ks] = fma(-m * c1, c2, ip[8]), kc[5 * ks] = fma(-m * c2, c2, ip[9]);
+    kc[6 * ks] = c0, kc[7 * ks] = c1, kc[8 * ks] = c2;
+    kc[9 * ks] = m, kc[10 * ks] = 1.0 / m;
     if (!(fabs(m) > 0.0) || !isfinite(m)) status |= 1;
 }
 
@@ -62,6 +53,7 @@ __device__ __forceinline__ void setup_cta(const unsigned char* __restrict__ blob
     w.lamv = w.r1 + 3 * S * w.nb;
     w.dinv = w.lamv + 3 * S * w.nb;
     w.knl = w.dinv + 6 * S * w.nb + S * h->rnl * w.segi;
+    w.kcs = w.dinv + 6 * S * w.nb + S * h->rnl * w.N + S * kSegConsts * w.segi;  // behind knl; present only with per-system inertia
     const int* sym = reinterpret_cast<const int*>(smem + h->off_sym);
     w.slot_tab = sym;
     w.slot2_tab = w.slot_tab + w.nb * w.nb;
@@ -96,95 +88,29 @@ __device__ __forceinline__ void store_q12(double* __restrict__ p, const Q12& q) 
     p2[5] = make_double2(q.s[3].y, q.s[3].z);
 }
 
-__device__ __forceinline__ void load_constants(const WarpCtx& w, const double* __restrict__ inertia, long long gsys,
+// Q12 <-> tensor-memory columns (tmem.cuh works on plain arrays)
+__device__ __forceinline__ void tmem_put(unsigned taddr, const Q12& q) {
+    const double x[12] = {q.s[0].x, q.s[0].y, q.s[0].z, q.s[1].x, q.s[1].y, q.s[1].z, q.s[2].x, q.s[2].y, q.s[2].z, q.s[3].x, q.s[3].y, q.s[3].z};
+    tmem_put(taddr, x);
+}
+__device__ __forceinline__ void tmem_wait(TmemWords<24>& t, Q12& q) {
+    double x[12];
+    tmem_wait(t, x);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q.s[k] = mk(x[3 * k], x[3 * k + 1], x[3 * k + 2]);
+}
+
+template <int S>
+__device__ __forceinline__ void load_constants(WarpCtx& w, const double* __restrict__ inertia, long long gsys,
                                                SegCtx& c, int& status) {
-    if (inertia != nullptr) {
-        inertia_to_constants(inertia + ((size_t)gsys * w.N + w.segi) * 10, c, status);
+    w.persys = inertia != nullptr;
+    if (inertia != nullptr) {  // this lane's column of the CTA's constant area (only this thread ever touches it)
+        inertia_to_constants(inertia + ((size_t)gsys * w.N + w.segi) * 10, w.kcs, S, status);
+        c.kc = w.kcs, c.ks = S;
     } else {
-        const DevSeg& sg = w.seg[w.segi];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) c.N3[i] = sg.kc[i];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) c.cn[i] = sg.kc[6 + i];
-        c.m = sg.kc[9], c.minv = sg.kc[10];
+        c.kc = w.seg[w.segi].kc, c.ks = 1;
     }
 }
-
-// ---- tensor memory as per-thread parking space ------------------------------------------------------
-// The fused integrator carries y0 and the k-accumulator (48 doubles per thread) across every stage
-// evaluation; in registers they would leave the evaluation ~30 registers, in local memory they turn into
-// L2 round trips and HBM write-backs.  The path issues no MMA, so the SM's 256 KB of tensor memory is
-// idle: each CTA allocates columns for its warps and every thread parks y0 (24 doubles = 48 32-bit words)
-// in its own TMEM lane (tcgen05.st / tcgen05.ld, shape 32x32b: lane = thread of the warp, columns = words).
-// A warp reaches the lane quarter 32 (warp % 4); warps 4.. of a CTA use the next group of 48 columns.
-// Measured on the lower limb (1e6 systems x 100 steps): y0 in TMEM 3.59e8 system-steps/s against 3.20e8
-// with everything left to the register allocator; parking the accumulator as well is slower (3.0e8, the
-// TMEM read port, 64 B/clk per SM, becomes the queue), so the accumulator stays with the compiler.
-template <int MAXT>
-struct TmemPark {
-    static constexpr int words = 48;  // per thread
-    static constexpr int groups = (MAXT + 127) / 128;
-    static constexpr int need = words * groups;
-    static constexpr int cols = need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : (need <= 256 ? 256 : 512)));
-    // CTAs per SM x columns must fit the 512 columns of an SM; small CTAs have registers to spare anyway
-    static constexpr bool use = MAXT >= 96 && need <= 512 && cols * MinCtas<MAXT>::value <= 512;
-};
-
-__device__ __forceinline__ void tmem_alloc(unsigned* slot_in_smem, unsigned ncols) {
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(slot_in_smem);
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(unsigned taddr, unsigned ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tmem_put(unsigned taddr, const Q12& q) {  // 12 doubles -> 24 columns
-    unsigned r[24];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        r[6 * t + 0] = __double2loint(q.s[t].x), r[6 * t + 1] = __double2hiint(q.s[t].x);
-        r[6 * t + 2] = __double2loint(q.s[t].y), r[6 * t + 3] = __double2hiint(q.s[t].y);
-        r[6 * t + 4] = __double2loint(q.s[t].z), r[6 * t + 5] = __double2hiint(q.s[t].z);
-    }
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-        : "memory");
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr + 16), "r"(r[16]),
-                 "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23])
-                 : "memory");
-}
-// loads are issued first (tmem_issue) and awaited together (tmem_wait): the registers are in/out operands of
-// the wait so that the compiler cannot read them before it
-struct TmemWords {
-    unsigned r[24];
-};
-__device__ __forceinline__ void tmem_issue(unsigned taddr, TmemWords& x) {
-    unsigned* r = x.r;
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%24];\n"
-        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%16, %17, %18, %19, %20, %21, %22, %23}, [%25];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23])
-        : "r"(taddr), "r"(taddr + 16)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_wait(TmemWords& x, Q12& q) {
-    unsigned* r = x.r;
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
-                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23])
-                 :
-                 : "memory");
-#pragma unroll
-    for (int t = 0; t < 4; ++t)
-        q.s[t] = mk(__hiloint2double(r[6 * t + 1], r[6 * t + 0]), __hiloint2double(r[6 * t + 3], r[6 * t + 2]),
-                    __hiloint2double(r[6 * t + 5], r[6 * t + 4]));
-}
-__device__ __forceinline__ void tmem_stores_done() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // forward_dynamics(Q, Qdot) -> Qddot, lambda       (biomechanical_model.py:351-429, batched)
@@ -204,7 +130,7 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
     const int n = 12 * w.N;
     int status = 0;
     SegCtx c;
-    load_constants(w, inertia, gsys, c, status);
+    load_constants<S>(w, inertia, gsys, c, status);
     if (GENERAL && fx.vals != nullptr) w.fvals = fx.vals + (size_t)gsys * fx.nf * 6;
     {
         Q12 q, qd;
@@ -216,7 +142,7 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
     __syncthreads();
     Q12 qdd;
     double* lam_sys = (lam != nullptr && live) ? lam + (size_t)gsys * w.hdr->m : nullptr;
-    eval_forward_dynamics<GENERAL, STAB, S>(w, c, o, qdd, lam_sys, status);
+    eval_forward_dynamics<GENERAL, STAB, true, false, S>(w, c, o, qdd, lam_sys, status);
     if (live) {
         store_q12(Qdd + (size_t)gsys * n + 12 * w.segi, qdd);
         if (status_out != nullptr && status != 0) atomicOr(status_out + gsys, status);
@@ -230,14 +156,16 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
 // (it has to be published there anyway for the two-segment joints); y0 is parked in tensor memory
 // (TmemPark above) and the k-accumulator is a per-thread value that the compiler keeps in registers
 // or spills to L2-resident local memory.  Per-system external-force values may change from step to
-// step (fx.steps slices, held over the four stages of a step).
+// step (fx.steps slices, held over the four stages of a step).  A launch integrates the steps step0 .. step0 +
+// n_steps - 1 of a longer run (h_steps, traj and the force slices are indexed by the global step): the host splits a
+// run in two launches around a forward_dynamics call when the multipliers of the last step are asked for.
 // ---------------------------------------------------------------------------------------------
 template <bool GENERAL, bool STAB, int MAXT, int S>
 __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
     rk4_kernel(const unsigned char* __restrict__ blob, int blob_bytes, FextArgs fx, double* __restrict__ Q, double* __restrict__ Qd,
                const double* __restrict__ inertia, DynOpts o, double h_const, const double* __restrict__ h_steps,
-               long long n_steps, int normalize, double* __restrict__ traj, long long traj_every,
-               double* __restrict__ lam_last, int* __restrict__ status_out, long long B) {
+               long long n_steps, long long step0, int normalize, double* __restrict__ traj, long long traj_every,
+               int* __restrict__ status_out, long long B) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr bool XSEG = GENERAL || STAB;  // an evaluation reads other segments' published state
     WarpCtx w;
@@ -248,13 +176,13 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
     const int n = 12 * w.N;
     int status = 0;
     SegCtx c;
-    load_constants(w, inertia, gsys, c, status);
+    load_constants<S>(w, inertia, gsys, c, status);
     const double* fvals0 = (GENERAL && fx.vals != nullptr) ? fx.vals + (size_t)gsys * fx.nf * 6 : nullptr;
     Q12 y0q, y0v;
     load_q12(Q + (size_t)gsys * n + 12 * w.segi, y0q);
     load_q12(Qd + (size_t)gsys * n + 12 * w.segi, y0v);
-    constexpr bool TM = TmemPark<MAXT>::use;
-    unsigned tm = 0;  // this thread's 48 columns: y0q, y0v (24 each)
+    constexpr int TM = TmemPark<MAXT>::level;  // 2: y0, accumulator and A in tensor memory; 1: y0; 0: nothing
+    unsigned tm = 0;  // this thread's columns (layout: tmem.cuh)
     unsigned* tm_slot = reinterpret_cast<unsigned*>(const_cast<int*>(&w.hdr->tmem_slot));  // a free word of the header copy
     if (TM) {
         if (threadIdx.x < 32) tmem_alloc(tm_slot, TmemPark<MAXT>::cols);
@@ -266,55 +194,90 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
 
 #pragma unroll 1
     for (long long step = 0; step < n_steps; ++step) {
-        const double h = h_steps != nullptr ? h_steps[step] : h_const;
-        if (GENERAL && fvals0 != nullptr) w.fvals = fvals0 + (step < fx.steps ? step : fx.steps - 1) * fx.step_stride;
+        const double h = h_steps != nullptr ? h_steps[step0 + step] : h_const;
+        if (GENERAL && fvals0 != nullptr) w.fvals = fvals0 + (step0 + step < fx.steps ? step0 + step : fx.steps - 1) * fx.step_stride;
         Q12 accq, accv;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             accq.s[t] = mk(0.0, 0.0, 0.0), accv.s[t] = mk(0.0, 0.0, 0.0);
             publish3<S>(w.Qo, t, y0q.s[t]), publish3<S>(w.Qdo, t, y0v.s[t]);
         }
-        if (TM) tmem_put(tm, y0q), tmem_put(tm + 24, y0v), tmem_stores_done();
+        if (TM) tmem_put(tm, y0q), tmem_put(tm + 24, y0v);
+        if (TM == 2) tmem_put(tm + 48, accq), tmem_put(tm + 72, accv);  // zeros: every stage then runs the same read-add-write
+        if (TM) tmem_stores_done();
         if (XSEG) __syncthreads();
+        const double h6 = h / 6.0;
 #pragma unroll 1
         for (int stage = 0; stage < 4; ++stage) {
             // k_stage = f(stage state): (stage velocity, Qddot)
             Q12 a;
-            double* lam_sys = (lam_last != nullptr && live && stage == 0 && step == n_steps - 1)
-                                  ? lam_last + (size_t)gsys * w.hdr->m : nullptr;
-            eval_forward_dynamics<GENERAL, STAB, S>(w, c, o, a, lam_sys, status);
+            eval_forward_dynamics<GENERAL, STAB, false, TM == 2, S>(w, c, o, a, nullptr, status, tm + 96);
             const double wt = (stage == 0 || stage == 3) ? 1.0 : 2.0;
             const double cn = (stage == 2) ? h : 0.5 * h;  // next stage is y0 + cn * k_stage
-            if (TM) {
-                TmemWords t0, t1;
-                tmem_issue(tm, t0), tmem_issue(tm + 24, t1);
-                tmem_wait(t0, y0q), tmem_wait(t1, y0v);
-            }
             // other segments' published state is only read before the barriers inside the evaluation: no barrier here
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const V3 sv = own3<S>(w.Qdo, t);
-                accq.s[t] = axpy(wt, sv, accq.s[t]);
-                accv.s[t] = axpy(wt, a.s[t], accv.s[t]);
+            if (TM == 2) {
+                // y0 and the accumulators come back from tensor memory one half at a time (Q, then Qdot: 48 registers in
+                // flight); the last stage turns its half into the new y0 at once instead of writing the accumulator back
+                TmemWords<24> ty, ta;
+                tmem_issue(tm, ty), tmem_issue(tm + 48, ta);
+                tmem_wait(ty, y0q), tmem_wait(ta, accq);
                 if (stage < 3) {
-                    publish3<S>(w.Qo, t, axpy(cn, sv, y0q.s[t]));
-                    publish3<S>(w.Qdo, t, axpy(cn, a.s[t], y0v.s[t]));
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const V3 sv = own3<S>(w.Qdo, t);
+                        accq.s[t] = axpy(wt, sv, accq.s[t]);
+                        publish3<S>(w.Qo, t, axpy(cn, sv, y0q.s[t]));
+                    }
+                    tmem_put(tm + 48, accq);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) y0q.s[t] = axpy(h6, own3<S>(w.Qdo, t) + accq.s[t], y0q.s[t]);
+                }
+                tmem_issue(tm + 24, ty), tmem_issue(tm + 72, ta);
+                tmem_wait(ty, y0v), tmem_wait(ta, accv);
+                if (stage < 3) {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        accv.s[t] = axpy(wt, a.s[t], accv.s[t]);
+                        publish3<S>(w.Qdo, t, axpy(cn, a.s[t], y0v.s[t]));
+                    }
+                    tmem_put(tm + 72, accv), tmem_stores_done();
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) y0v.s[t] = axpy(h6, a.s[t] + accv.s[t], y0v.s[t]);
+                }
+            } else {
+                if (TM) {
+                    TmemWords<24> t0, t1;
+                    tmem_issue(tm, t0), tmem_issue(tm + 24, t1);
+                    tmem_wait(t0, y0q), tmem_wait(t1, y0v);
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const V3 sv = own3<S>(w.Qdo, t);
+                    accq.s[t] = axpy(wt, sv, accq.s[t]);
+                    accv.s[t] = axpy(wt, a.s[t], accv.s[t]);
+                    if (stage < 3) {
+                        publish3<S>(w.Qo, t, axpy(cn, sv, y0q.s[t]));
+                        publish3<S>(w.Qdo, t, axpy(cn, a.s[t], y0v.s[t]));
+                    }
                 }
             }
             if (XSEG) __syncthreads();
         }
-        const double h6 = h / 6.0;
+        if (TM < 2) {
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            y0q.s[t] = axpy(h6, accq.s[t], y0q.s[t]);
-            y0v.s[t] = axpy(h6, accv.s[t], y0v.s[t]);
+            for (int t = 0; t < 4; ++t) {
+                y0q.s[t] = axpy(h6, accq.s[t], y0q.s[t]);
+                y0v.s[t] = axpy(h6, accv.s[t], y0v.s[t]);
+            }
         }
         if (normalize) {  // u <- u/|u|, w <- w/|w| of Q only (ode_solver.py:50-52)
             y0q.s[0] = fast_rsqrt(dot(y0q.s[0], y0q.s[0])) * y0q.s[0];
             y0q.s[3] = fast_rsqrt(dot(y0q.s[3], y0q.s[3])) * y0q.s[3];
         }
-        if (traj != nullptr && ((step + 1) % traj_every) == 0 && live) {
-            double* dst = traj + (((size_t)((step + 1) / traj_every - 1) * B + gsys) * 2) * n;
+        if (traj != nullptr && ((step0 + step + 1) % traj_every) == 0 && live) {
+            double* dst = traj + (((size_t)((step0 + step + 1) / traj_every - 1) * B + gsys) * 2) * n;
             store_q12(dst + 12 * w.segi, y0q);
             store_q12(dst + n + 12 * w.segi, y0v);
         }
@@ -352,13 +315,24 @@ __device__ __forceinline__ V3 glin(const double* __restrict__ X, int s, const do
     for (int t = 0; t < 4; ++t) r = axpy(a[t], mk(X[12 * s + 3 * t], X[12 * s + 3 * t + 1], X[12 * s + 3 * t + 2]), r);
     return r;
 }
+// Row `row` of a Jacobian restricted to segment `seg`: the 12 entries  s1 a1 (x) d1 [+ s2 a2 (x) d2]  are WRITTEN (not
+// accumulated): every structural non-zero of a system's matrix is stored exactly once, by one thread, so the tiled
+// evaluator can keep a zero background in shared memory across tiles and the dense kernel needs no read-modify-write.
 __device__ __forceinline__ void put_row(double* __restrict__ K, int ld, int row, int seg, const double* a, V3 d, double s) {
     double* dst = K + (size_t)row * ld + 12 * seg;
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-        dst[3 * t] += s * a[t] * d.x;
-        dst[3 * t + 1] += s * a[t] * d.y;
-        dst[3 * t + 2] += s * a[t] * d.z;
+        const double c = s * a[t];
+        dst[3 * t] = c * d.x, dst[3 * t + 1] = c * d.y, dst[3 * t + 2] = c * d.z;
+    }
+}
+__device__ __forceinline__ void put_row2(double* __restrict__ K, int ld, int row, int seg, const double* a1, V3 d1, double s1,
+                                         const double* a2, V3 d2, double s2) {
+    double* dst = K + (size_t)row * ld + 12 * seg;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const double c1 = s1 * a1[t], c2 = s2 * a2[t];
+        dst[3 * t] = fma(c1, d1.x, c2 * d2.x), dst[3 * t + 1] = fma(c1, d1.y, c2 * d2.y), dst[3 * t + 2] = fma(c1, d1.z, c2 * d2.z);
     }
 }
 
@@ -380,7 +354,7 @@ __device__ __forceinline__ FextView fext_view(const FextArgs& fx, long long sys)
 __device__ __forceinline__ void eval_item(const DevSeg* __restrict__ seg, const DevBlk* __restrict__ blk,
                                           const FextView& fext, const EvalArgs& ea, int which, int item,
                                           const double* __restrict__ X, double* __restrict__ vec, double* __restrict__ K,
-                                          int ldK) {
+                                          int ldK, int sub = -1) {
     if (item < ea.N) {  // ---------------- segment items
         const int i = item;
         const DevSeg& sg = seg[i];
@@ -404,12 +378,12 @@ __device__ __forceinline__ void eval_item(const DevSeg* __restrict__ seg, const 
         } else if (which == 1 || which == 5) {  // K_r rows
             const int r0 = (which == 1) ? 6 * i : sg.rigid_row;
             const double eu[4] = {1, 0, 0, 0}, ev[4] = {0, 1, -1, 0}, ew[4] = {0, 0, 0, 1};
-            put_row(K, ldK, r0 + 0, i, eu, u, 2.0);
-            put_row(K, ldK, r0 + 1, i, eu, v, 1.0), put_row(K, ldK, r0 + 1, i, ev, u, 1.0);
-            put_row(K, ldK, r0 + 2, i, eu, w, 1.0), put_row(K, ldK, r0 + 2, i, ew, u, 1.0);
-            put_row(K, ldK, r0 + 3, i, ev, v, 2.0);
-            put_row(K, ldK, r0 + 4, i, ev, w, 1.0), put_row(K, ldK, r0 + 4, i, ew, v, 1.0);
-            put_row(K, ldK, r0 + 5, i, ew, w, 2.0);
+            if (sub < 0 || sub == 0) put_row(K, ldK, r0 + 0, i, eu, u, 2.0);
+            if (sub < 0 || sub == 1) put_row2(K, ldK, r0 + 1, i, eu, v, 1.0, ev, u, 1.0);
+            if (sub < 0 || sub == 2) put_row2(K, ldK, r0 + 2, i, eu, w, 1.0, ew, u, 1.0);
+            if (sub < 0 || sub == 3) put_row(K, ldK, r0 + 3, i, ev, v, 2.0);
+            if (sub < 0 || sub == 4) put_row2(K, ldK, r0 + 4, i, ev, w, 1.0, ew, v, 1.0);
+            if (sub < 0 || sub == 5) put_row(K, ldK, r0 + 5, i, ew, w, 2.0);
         } else if (which == 7) {  // natural external forces
             double* o = vec + 12 * i;
             Q12 f;
@@ -425,6 +399,7 @@ __device__ __forceinline__ void eval_item(const DevSeg* __restrict__ seg, const 
     } else {  // ---------------- constraint-block items
         if (which == 0 || which == 1 || which == 7) return;
         const DevBlk& b = blk[item - ea.N];
+        if (sub > 2 || (sub > 0 && b.type != LIN3)) return;  // row-split callers: a block has 3 rows or 1
         const double* p = b.p;
         const bool jorder = (which == 2 || which == 3);
         const int row = jorder ? b.row_j : b.row_h;
@@ -439,11 +414,12 @@ __device__ __forceinline__ void eval_item(const DevSeg* __restrict__ seg, const 
             } else if (want_b) {
                 o[row] = 0.0, o[row + 1] = 0.0, o[row + 2] = 0.0;  // point-to-point rows are linear: no bias
             } else if (want_K) {
-                put_row(K, ldK, row, b.child, p + 4, ex, -1.0), put_row(K, ldK, row + 1, b.child, p + 4, ey, -1.0);
-                put_row(K, ldK, row + 2, b.child, p + 4, ez, -1.0);
-                if (b.parent >= 0) {
-                    put_row(K, ldK, row, b.parent, p, ex, 1.0), put_row(K, ldK, row + 1, b.parent, p, ey, 1.0);
-                    put_row(K, ldK, row + 2, b.parent, p, ez, 1.0);
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    if (sub >= 0 && sub != r) continue;
+                    const V3 e = r == 0 ? ex : (r == 1 ? ey : ez);
+                    put_row(K, ldK, row + r, b.child, p + 4, e, -1.0);
+                    if (b.parent >= 0) put_row(K, ldK, row + r, b.parent, p, e, 1.0);
                 }
             }
         } else if (b.type == DOT) {
@@ -464,7 +440,7 @@ __device__ __forceinline__ void eval_item(const DevSeg* __restrict__ seg, const 
             const V3 P = glin(X, b.parent, p), A = glin(X, b.child, p + 4), nn = glin(X, b.child, p + 8);
             if (want_phi) o[row] = dot(P - A, nn) - p[12];
             if (want_K) {
-                put_row(K, ldK, row, b.parent, p + 4, nn, -1.0), put_row(K, ldK, row, b.parent, p + 8, P - A, 1.0);
+                put_row2(K, ldK, row, b.parent, p + 4, nn, -1.0, p + 8, P - A, 1.0);
                 put_row(K, ldK, row, b.child, p, nn, 1.0);
             }
             if (want_b) o[row] = 2.0 * dot(P, nn) - 2.0 * dot(nn, A);
@@ -472,24 +448,123 @@ __device__ __forceinline__ void eval_item(const DevSeg* __restrict__ seg, const 
     }
 }
 
-__global__ void eval_kernel(const unsigned char* __restrict__ blob, FextArgs fx, EvalArgs ea, const double* __restrict__ in,
-                            double* __restrict__ out, long long B) {
+// ---- 1-D bulk copies (TMA engine; SASS UBLKCP) and their mbarrier -----------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_LOOP;\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// global -> shared, completion counted in bytes on the mbarrier; addresses and size are multiples of 16
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global as one bulk group
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {  // at most N store groups still reading their shared-memory source
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// Tiled evaluator.  The outputs are dense per system (the reference's own shapes), a Jacobian mostly zeros: what the
+// kernel has to do is write B x rows x cols doubles to HBM once, in full 16-byte-aligned bursts.  A CTA walks tiles of
+// T consecutive systems; per tile
+//   1. the states of the tile (T x 12N doubles, contiguous in global memory) arrive by one bulk copy into shared memory
+//      (prefetched one tile ahead, completion on an mbarrier);
+//   2. the threads evaluate (system, item[, row]) units from shared memory into the tile's output image in shared
+//      memory.  Every structural non-zero is written exactly once (put_row), so for Jacobians the image keeps its zero
+//      background from tile to tile: it is cleared once per CTA, not once per system;
+//   3. one bulk copy streams the image (T x rows x cols doubles, contiguous in global memory) out while the next tile
+//      is computed in the other buffer.
+// DRAM traffic = input once + output once = the algorithmic bytes; no memset, no read-modify-write on global memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int kEvalThreads = 128;
+
+__global__ void __launch_bounds__(kEvalThreads, 4)
+    eval_tiled_kernel(const unsigned char* __restrict__ blob, FextArgs fx, EvalArgs ea, const double* __restrict__ in,
+                      double* __restrict__ out, long long B, int T, int out_per_sys, int rows, int cols) {
+    extern __shared__ __align__(128) unsigned char sm[];
     const DevHeader* h = reinterpret_cast<const DevHeader*>(blob);
     const DevSeg* seg = reinterpret_cast<const DevSeg*>(blob + h->off_seg);
     const DevBlk* blk = reinterpret_cast<const DevBlk*>(blob + h->off_blk);
-    const int n = 12 * ea.N;
-    const int nitem = ea.N + ea.nblk;
-    const long long total = B * nitem;
-    const int which = ea.which;
-    const bool matrix = (which == 1 || which == 3 || which == 5);
-    const int rows = (which == 0 || which == 1) ? 6 * ea.N : ((which == 2 || which == 3) ? ea.mj : (which == 7 ? n : ea.m));
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const long long sys = idx / nitem;
-        const int item = (int)(idx - sys * nitem);
-        double* o = out + (size_t)sys * rows * (matrix ? n : 1);
-        eval_item(seg, blk, fext_view(fx, sys), ea, which, item, in + (size_t)sys * n, o, o, n);
+    const int n = 12 * ea.N, nitem = ea.N + ea.nblk, which = ea.which, tid = threadIdx.x;
+    const bool matrix = cols > 1;
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(sm);  // two mbarriers
+    double* in_tile[2];
+    double* out_tile[2];
+    in_tile[0] = reinterpret_cast<double*>(sm + 128);
+    in_tile[1] = in_tile[0] + (size_t)T * n;
+    out_tile[0] = in_tile[1] + (size_t)T * n;
+    out_tile[1] = out_tile[0] + (size_t)T * out_per_sys;
+    const long long ntiles = (B + T - 1) / T;
+    if (tid == 0) {
+        mbar_init(bar, 1), mbar_init(bar + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (matrix) {  // zero background of both output images, once
+        double2* z = reinterpret_cast<double2*>(out_tile[0]);
+        for (int i = tid; i < T * out_per_sys; i += kEvalThreads) z[i] = make_double2(0.0, 0.0);  // 2 T out_per_sys doubles
+    }
+    __syncthreads();
+    auto tile_systems = [&](long long tile) { return (int)((B - tile * T < T) ? B - tile * T : T); };
+    long long tile = blockIdx.x;
+    if (tid == 0 && tile < ntiles) {
+        const unsigned bytes = (unsigned)tile_systems(tile) * n * 8u;
+        mbar_expect_tx(bar, bytes);
+        bulk_load(in_tile[0], in + (size_t)tile * T * n, bytes, bar);
+    }
+    const int subs = matrix ? 6 : 1;  // Jacobians: one unit per (item, row)
+    for (int k = 0; tile < ntiles; tile += gridDim.x, ++k) {
+        const int buf = k & 1, ns = tile_systems(tile);
+        const long long next = tile + gridDim.x;
+        if (tid == 0) {
+            if (next < ntiles) {  // prefetch: in_tile[buf ^ 1] was last read in iteration k - 1, closed by its barrier
+                const unsigned bytes = (unsigned)tile_systems(next) * n * 8u;
+                mbar_expect_tx(bar + (buf ^ 1), bytes);
+                bulk_load(in_tile[buf ^ 1], in + (size_t)next * T * n, bytes, bar + (buf ^ 1));
+            }
+            bulk_wait_read<1>();  // the store of iteration k - 2 has finished reading out_tile[buf]
+        }
+        mbar_wait(bar + buf, (k >> 1) & 1);
+        __syncthreads();
+        const double* X0 = in_tile[buf];
+        double* O0 = out_tile[buf];
+        for (int idx = tid; idx < ns * nitem * subs; idx += kEvalThreads) {
+            const int sys = idx / (nitem * subs), r = idx - sys * (nitem * subs);
+            const int item = r / subs, sub = matrix ? r - item * subs : -1;
+            double* o = O0 + (size_t)sys * out_per_sys;
+            eval_item(seg, blk, fext_view(fx, tile * T + sys), ea, which, item, X0 + (size_t)sys * n, o, o, n, sub);
+        }
+        fence_async_smem();  // generic-proxy writes of the image become visible to the bulk-copy engine
+        __syncthreads();
+        const size_t bytes = (size_t)ns * out_per_sys * 8;
+        double* gdst = out + (size_t)tile * T * out_per_sys;
+        if ((bytes & 15) == 0) {
+            if (tid == 0) bulk_store(gdst, O0, (unsigned)bytes);
+        } else {  // odd tail: plain stores
+            for (int i = tid; i < ns * out_per_sys; i += kEvalThreads) gdst[i] = O0[i];
+        }
+    }
+    if (tid == 0) bulk_wait_all();
 }
 
 // ---------------------------------------------------------------------------------------------

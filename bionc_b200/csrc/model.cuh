@@ -66,11 +66,19 @@ struct DevBlk {
     int pad0, pad1;
 };
 
+// One (block, segment) incidence with everything the per-segment phases need resolved on the host.
 struct DevSide {
     int blk;
-    int role;     // CHILD / PARENT
-    int nl_slot;  // offset (in doubles) of the row's d-vectors in the lane's storage, -1 for LIN3
-    int pad;
+    int role;      // CHILD / PARENT
+    int nl_slot;   // offset (in doubles) of the row's d-vectors in the lane's storage, -1 for LIN3
+    int node;      // 3x3 node of the joint-level system holding the block's first row (jrow / 3)
+    int rhs_off;   // row of this side's copy of the right-hand side inside [r0 | r1]: jrow (+ 3 nb for the parent copy)
+    int lam_off;   // jrow: first row of the block in lambda_j
+    int row_h;     // first row, holonomic order
+    int ground;    // the block has no parent segment: the child also settles the second copy of the right-hand side
+    // point-to-point (LIN3) sides: the signed coefficient vector as seen from the centre of mass of the MODEL's inertial
+    // parameters, lev = (sigma, r[3]), sigma = a_rp + a_rd, r = (a_u, -a_rd, a_w) - sigma c (see Lever, dynamics.cuh)
+    double lev[4];
 };
 
 struct DevFext {
@@ -97,8 +105,10 @@ struct FextArgs {
 };
 
 // Shared-memory working set of one CTA (spc systems, one warp per segment), in doubles (layout: dynamics.cuh).
-__host__ __device__ inline int cta_smem_doubles(int spc, int N, int nb, int nslot, int nslot2, int rnl) {
+constexpr int kSegConsts = 11;  // N3 (6), natural centre of mass (3), m, 1 / m
+__host__ __device__ inline int cta_smem_doubles(int spc, int N, int nb, int nslot, int nslot2, int rnl, bool persys = false) {
     return spc * (2 * 12 * N              // published Q, Qdot of the current stage
+                 + (persys ? kSegConsts * N : 0)  // per-system segment constants (per-system inertial parameters only)
                  + 9 * (nslot + nslot2)  // stored 3x3 blocks of the joint-level Schur matrix (+ second copies)
                  + 3 * 3 * nb            // rhs copy 0 / copy 1 (-> y-hat), lambda_j
                  + 6 * nb                // inverse pivot blocks

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Where are the local-memory (spill) and FP64 instructions of a kernel?  Static SASS statistics per source line.
 
-    nvdisasm --print-line-info file.cubin > all.sass
+    nvdisasm --print-line-info-inline file.cubin > all.sass
     python profiles/sass_spills.py all.sass <substring of the mangled kernel name>
 
 Prints the instruction count, the opcode mix (DFMA / DMUL / DADD / LDS / STS / LDL / STL / BAR ...) and the source
@@ -17,13 +17,22 @@ def main():
     start = next(i for i, l in enumerate(lines) if l.startswith(".text.") and key in l)
     end = next((i for i in range(start + 1, len(lines)) if lines[i].startswith("//---------------------")), len(lines))
     cur = None
+    chain = []
     ops = collections.Counter()
     where = collections.Counter()
+    prev_was_marker = False
     for l in lines[start:end]:
         m = re.search(r'//## File "([^"]+)", line (\d+)', l)
         if m:
-            cur = (m.group(1).split("/")[-1], int(m.group(2)))
+            if not prev_was_marker:
+                chain = []
+            chain.append((m.group(1).split("/")[-1], int(m.group(2))))
+            prev_was_marker = True
+            # attribute to the outermost frame inside dynamics.cuh (the phase of the evaluation), else the outermost frame
+            dyn = [c for c in chain if c[0] == "dynamics.cuh"]
+            cur = dyn[-1] if dyn else chain[-1]
             continue
+        prev_was_marker = False
         m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", l)
         if not m:
             continue
