@@ -27,6 +27,7 @@ SYMBOLS = (
     "bionc_cuda_forward_dynamics_host",
     "bionc_cuda_rk4_host",
     "bionc_cuda_measure_fp64_peak",
+    "bionc_cuda_debug_poison",
     "bionc_cuda_launch_count",
     "bionc_cuda_last_error",
     "bionc_cuda_version",
@@ -146,6 +147,7 @@ def load():
     lib.bionc_cuda_forward_dynamics_host.argtypes = [vp, vp, vp, optp, vp, vp, vp, i64]
     lib.bionc_cuda_rk4_host.argtypes = [vp, vp, vp, dbl, vp, i64, i32, optp, vp, i64]
     lib.bionc_cuda_measure_fp64_peak.argtypes = [C.c_int, C.c_int, c_double_p, c_double_p]
+    lib.bionc_cuda_debug_poison.argtypes = [i32]
     lib.bionc_cuda_launch_count.restype = C.c_int64
     lib.bionc_cuda_last_error.restype = C.c_char_p
     lib.bionc_cuda_version.restype = C.c_char_p

@@ -179,7 +179,8 @@ class BiomechanicalModel:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _options(self, external_forces=None, stabilization=None, inertia=None, B=None, force_values=None, host=False):
+    def _options(self, external_forces=None, stabilization=None, inertia=None, B=None, force_values=None, host=False,
+                 joint_forces=None):
         """``BioncDynOptions`` of one call plus the objects it points into.  ``force_values``: optional per-system
         (torque, force) values ``(B, F, 6)`` -- or ``(steps, B, F, 6)`` for ``rk4`` -- replacing the values stored in
         ``external_forces`` (forces in the order ``ExternalForceSet.to_arrays`` lists them: by segment, then insertion);
@@ -198,6 +199,27 @@ class BiomechanicalModel:
                     "The number of segment in the model and the number of segment in the external forces must be the same"
                 )
             seg, kind, par = external_forces.to_arrays()
+        if joint_forces is not None:  # appended behind the external forces (apply_joint_generalized_forces=True)
+            from .generalized_force import JointGeneralizedForcesList
+
+            if not isinstance(joint_forces, JointGeneralizedForcesList):
+                if not hasattr(joint_forces, "joint_generalized_forces"):
+                    raise NotImplementedError(
+                        "apply_joint_generalized_forces needs a JointGeneralizedForcesList: the reference's conversion of a "
+                        "joint-dof array (add_all_joint_generalized_forces) is not lowered")
+                joint_forces = JointGeneralizedForcesList.from_reference(joint_forces)
+            if force_values is not None:
+                raise ValueError("per-system external force values cannot be combined with joint generalized forces")
+            if not len(self.table.all_joint_names):
+                raise ValueError("this model table carries no joint list (built before format 3): rebuild it with from_numpy")
+            js, jk, jp = joint_forces.to_arrays(self.table.all_joint_parent, self.table.all_joint_child)
+            if external_forces is None:
+                seg, kind, par = js, jk, jp
+            else:
+                seg, kind, par = np.concatenate([seg, js]), np.concatenate([kind, jk]), np.concatenate([par, jp])
+                seg, kind, par = np.ascontiguousarray(seg), np.ascontiguousarray(kind), np.ascontiguousarray(par)
+            external_forces = True
+        if external_forces is not None:
             if seg.size:
                 fx = _lib.BioncFextDesc(int(seg.size), _ptr(seg, _lib.c_int32_p), _ptr(kind, _lib.c_int32_p), _ptr(par, _lib.c_double_p))
                 if force_values is not None:
@@ -371,9 +393,12 @@ class BiomechanicalModel:
         return_status: bool = False,
         pivoting: str = "auto",
         external_force_values=None,
+        apply_joint_generalized_forces: bool = False,
     ):
         """biomechanical_model.py:351-429, batched.  ``joint_generalized_forces`` is accepted and ignored
-        exactly like the reference (:391-413).  ``inertial_parameters`` (B, N, 10) optionally overrides
+        exactly like the reference (:391-413) unless ``apply_joint_generalized_forces=True``: then a
+        ``JointGeneralizedForcesList`` (``bionc_cuda.generalized_force``) acts on the joints' children and reacts on
+        their parents as generalized_force.py:98-129 documents.  ``inertial_parameters`` (B, N, 10) optionally overrides
         the natural inertial parameters per system; ``external_force_values`` (B, F, 6) gives every system its own
         (torque, force) for the forces of ``external_forces`` (the reference builds one ``ExternalForceSet`` per call,
         external_force.py:143-180).  Returns ``(Qddot, lambdas)``; a single system whose
@@ -394,7 +419,8 @@ class BiomechanicalModel:
         qdd = torch.empty_like(q.t)
         lam = torch.empty((B, self.nb_holonomic_constraints), dtype=torch.float64, device=self.device)
         status = torch.empty((B,), dtype=torch.int32, device=self.device)
-        opt, keep = self._options(external_forces, stabilization, inertial_parameters, B, external_force_values)
+        opt, keep = self._options(external_forces, stabilization, inertial_parameters, B, external_force_values,
+                                  joint_forces=joint_generalized_forces if apply_joint_generalized_forces else None)
         with torch.cuda.device(self.device):
             if B > 0 and pivoting != "always":
                 rc = self._lib.bionc_cuda_forward_dynamics(
@@ -436,6 +462,8 @@ class BiomechanicalModel:
         inplace: bool = False,
         pivoting: str = "never",
         external_force_values=None,
+        joint_generalized_forces=None,
+        apply_joint_generalized_forces: bool = False,
     ):
         """Fused integrator: ``utils/ode_solver.py:8-53`` with the closure of ``:107-116`` inside the kernel.
 
@@ -476,7 +504,8 @@ class BiomechanicalModel:
             traj = torch.empty((n_steps // save_every, B, 2 * self.nb_Q), dtype=torch.float64, device=self.device)
         lam = torch.empty((B, self.nb_holonomic_constraints), dtype=torch.float64, device=self.device) if return_lambdas else None
         status = torch.empty((B,), dtype=torch.int32, device=self.device)
-        opt, keep = self._options(external_forces, stabilization, inertial_parameters, B, external_force_values)
+        opt, keep = self._options(external_forces, stabilization, inertial_parameters, B, external_force_values,
+                                  joint_forces=joint_generalized_forces if apply_joint_generalized_forces else None)
         with torch.cuda.device(self.device):
             if B > 0 and n_steps > 0:
                 rc = self._lib.bionc_cuda_rk4(

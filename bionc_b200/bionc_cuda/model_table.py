@@ -44,6 +44,7 @@ FEXT_GLOBAL_ON_PROXIMAL = 0
 FEXT_GLOBAL_LOCAL_POINT = 1
 FEXT_GLOBAL = 2
 FEXT_LOCAL = 3
+FEXT_JOINT_REACTION = 4  # reaction of a joint generalized force on the joint's parent (generalized_force.py:98-129)
 FEXT_NPARAM = 24  # [torque(3), force(3), point(3), Tinv(9)] padded
 
 
@@ -165,6 +166,11 @@ class ModelTable:
     marker_segment: np.ndarray = None  # (nmk,) int32
     marker_position: np.ndarray = None  # (nmk, 3) natural coordinates (n_u, n_v, n_w) of the marker in its segment
     marker_technical: np.ndarray = None  # (nmk,) int32 0/1
+    # every joint of the model in the reference's joint order (model.joints, free joints included): what joint
+    # generalized forces are indexed by (generalized_force.py:232-311); optional
+    all_joint_names: list[str] = field(default_factory=list)
+    all_joint_parent: np.ndarray = None  # (nj,) int32, -1 = ground
+    all_joint_child: np.ndarray = None  # (nj,) int32
 
     # ------------------------------------------------------------------ counts (protocols/biomechanical_model.py:347-453)
     @property
@@ -238,6 +244,10 @@ class ModelTable:
         assert self.marker_segment.shape == (nmk,) and self.marker_position.shape == (nmk, 3) and self.marker_technical.shape == (nmk,)
         if nmk:
             assert self.marker_segment.min() >= 0 and self.marker_segment.max() < N
+        nj = len(self.all_joint_names)
+        self.all_joint_parent = np.ascontiguousarray(self.all_joint_parent if self.all_joint_parent is not None else np.zeros(0), dtype=np.int32)
+        self.all_joint_child = np.ascontiguousarray(self.all_joint_child if self.all_joint_child is not None else np.zeros(0), dtype=np.int32)
+        assert self.all_joint_parent.shape == (nj,) and self.all_joint_child.shape == (nj,)
         assert self.seg_phi_const.shape == (N, 4) and self.seg_J.shape == (N, 3, 3)
         assert self.blk_param.shape == (self.nb_blocks, BLK_NPARAM)
         if self.nb_blocks:
@@ -255,7 +265,10 @@ class ModelTable:
     def save(self, filename: str) -> None:
         np.savez(
             filename,
-            format_version=np.int32(2),
+            format_version=np.int32(3),
+            all_joint_names=np.array(self.all_joint_names, dtype=str),
+            all_joint_parent=self.all_joint_parent,
+            all_joint_child=self.all_joint_child,
             segment_names=np.array(self.segment_names),
             marker_names=np.array(self.marker_names, dtype=str),
             marker_segment=self.marker_segment,
@@ -270,12 +283,15 @@ class ModelTable:
     def load(cls, filename: str) -> "ModelTable":
         with np.load(filename, allow_pickle=False) as z:
             version = int(z["format_version"])
-            if version not in (1, 2):  # 2 = 1 + the marker arrays
+            if version not in (1, 2, 3):  # 2 = 1 + the marker arrays, 3 = 2 + the joint list
                 raise ValueError(f"unknown model table version {version}")
             kw = {k: z[k] for k in cls._ARRAYS}
             if version >= 2:
                 kw.update(marker_names=[str(s) for s in z["marker_names"]], marker_segment=z["marker_segment"],
                           marker_position=z["marker_position"], marker_technical=z["marker_technical"])
+            if version >= 3:
+                kw.update(all_joint_names=[str(s) for s in z["all_joint_names"]], all_joint_parent=z["all_joint_parent"],
+                          all_joint_child=z["all_joint_child"])
             return cls(
                 segment_names=[str(s) for s in z["segment_names"]],
                 joint_names=[str(s) for s in z["joint_names"]],
@@ -388,6 +404,9 @@ class ModelTable:
             marker_segment=np.array(mk_seg, dtype=np.int32),
             marker_position=np.array(mk_pos, dtype=np.float64).reshape(len(mk_seg), 3),
             marker_technical=np.array(mk_tech, dtype=np.int32),
+            all_joint_names=[str(j.name) for j in model.joints.values()],
+            all_joint_parent=np.array([-1 if j.parent is None else int(j.parent.index) for j in model.joints.values()], dtype=np.int32),
+            all_joint_child=np.array([int(j.child.index) for j in model.joints.values()], dtype=np.int32),
         ).validate()
         if row_h != model.nb_holonomic_constraints:
             raise AssertionError("holonomic row count differs from the reference model")

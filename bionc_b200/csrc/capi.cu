@@ -19,6 +19,7 @@ namespace {
 
 thread_local std::string g_last_error;
 std::atomic<long long> g_launches{0};
+std::atomic<int> g_debug_poison{0};
 
 int fail(int code, const std::string& msg) {
     g_last_error = msg;
@@ -93,6 +94,9 @@ struct BioncModel {
     std::string device_err;
     unsigned char* d_blob = nullptr;
     int blob_bytes = 0;
+    // row maps of the Jacobian evaluator (row -> item * 8 + row inside the item): K_r (6N), K_j (mj, joint order), K_h (m)
+    std::vector<int> rowmap;
+    int* d_rowmap = nullptr;
     int dev_smem_optin = 0, sm_smem = 0;
     LaunchPlan plan0;  // without external forces
     // host-path scratch
@@ -221,11 +225,15 @@ int symbolic_analysis(BioncModel* M, int N) {
                 }
                 if (s2 >= 0) comb.push_back(s), comb.push_back(s2);
             }
-    // padding rows sit at the end of the node that received the last single rows
+    // padding rows sit at the end of the node that received the last single rows (after the renumbering that node may be
+    // anywhere: the kernel gets the padding rows explicitly)
     for (int I = 0; I < nb; ++I)
         if (mixed[I]) {
             int rows = (int)node_blocks[I].size();
-            for (int r = rows; r < 3; ++r) unit.push_back(9 * slot_tab[newidx[I] * nb + newidx[I]] + 4 * r);
+            for (int r = rows; r < 3; ++r) {  // (diagonal element of the padding row, the row itself)
+                unit.push_back(9 * slot_tab[newidx[I] * nb + newidx[I]] + 4 * r);
+                unit.push_back(3 * newidx[I] + r);
+            }
         }
     for (int K = 0; K < nb; ++K) {
         for (int I = K + 1; I < nb; ++I)
@@ -303,7 +311,7 @@ int symbolic_analysis(BioncModel* M, int N) {
     }
     M->hdr.nlevel = nlevel;
     M->hdr.nb = nb, M->hdr.nslot = nslot, M->hdr.nslot2 = nslot2;
-    M->hdr.nzero = (int)zero.size(), M->hdr.ncomb = (int)comb.size() / 2, M->hdr.nunit = (int)unit.size();
+    M->hdr.nzero = (int)zero.size(), M->hdr.ncomb = (int)comb.size() / 2, M->hdr.nunit = (int)unit.size() / 2;
     M->hdr.ncol = (int)colrow.size();
     return mj;
 }
@@ -373,6 +381,22 @@ int build_blob(BioncModel* M) {
     CUDA_TRY(cudaMalloc(&M->d_blob, h.blob_bytes));
     CUDA_TRY(cudaMemcpy(M->d_blob, blob.data(), h.blob_bytes, cudaMemcpyHostToDevice));
     M->blob_bytes = h.blob_bytes;
+    {
+        const int N = h.N, nblk = (int)M->blk.size();
+        std::vector<int>& rm = M->rowmap;
+        rm.assign((size_t)6 * N + h.mj + h.m, 0);
+        int* kr = rm.data();
+        int* kj = kr + 6 * N;
+        int* kh = kj + h.mj;
+        for (int i = 0; i < N; ++i)
+            for (int r = 0; r < 6; ++r) kr[6 * i + r] = i * 8 + r, kh[M->seg[i].rigid_row + r] = i * 8 + r;
+        for (int b = 0; b < nblk; ++b) {
+            const int nr = M->blk[b].type == LIN3 ? 3 : 1;
+            for (int r = 0; r < nr; ++r) kj[M->blk[b].row_j + r] = (N + b) * 8 + r, kh[M->blk[b].row_h + r] = (N + b) * 8 + r;
+        }
+        CUDA_TRY(cudaMalloc(&M->d_rowmap, rm.size() * sizeof(int)));
+        CUDA_TRY(cudaMemcpy(M->d_rowmap, rm.data(), rm.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
     return BIONC_OK;
 }
 
@@ -401,7 +425,12 @@ struct FextCall {
         if (fx->segment == nullptr || fx->kind == nullptr || fx->param == nullptr) return fail(BIONC_E_INVALID, "external force arrays missing");
         for (int i = 0; i < nf; ++i) {
             if (fx->segment[i] < 0 || fx->segment[i] >= N) return fail(BIONC_E_INVALID, "external force on a segment that does not exist");
-            if (fx->kind[i] < 0 || fx->kind[i] > 3) return fail(BIONC_E_INVALID, "unknown external force kind");
+            if (fx->kind[i] < 0 || fx->kind[i] > 4) return fail(BIONC_E_INVALID, "unknown external force kind");
+            if (fx->kind[i] == 4) {  // the segment the force itself acts on travels in param[18]
+                const double o = fx->param[(size_t)i * kFextNParam + 18];
+                if (!(o >= 0 && o < N) || o != std::floor(o) || (int)o == fx->segment[i])
+                    return fail(BIONC_E_INVALID, "joint reaction force without a valid other segment (param[18])");
+            }
         }
         const int bytes = align16((int)(sizeof(DevFextTab) + (size_t)nf * sizeof(DevFext)));
         std::vector<unsigned char> host(bytes, 0);
@@ -414,7 +443,8 @@ struct FextCall {
             for (int i = 0; i < nf; ++i)
                 if (fx->segment[i] == s) {
                     std::memcpy(f[k].p, fx->param + (size_t)i * kFextNParam, kFextNParam * sizeof(double));
-                    f[k].segment = s, f[k].kind = fx->kind[i], f[k].slot = i, f[k].pad0 = 0;
+                    f[k].segment = s, f[k].kind = fx->kind[i], f[k].slot = i;
+                    f[k].other = fx->kind[i] == 4 ? (int)f[k].p[18] : -1;
                     ++k;
                 }
         }
@@ -478,6 +508,7 @@ int ensure_smem(int device, const void* kernel, int optin_bytes) {
 
 void dyn_options(const BioncDynOptions* opt, DynOpts& o) {
     o.use_stab = (opt != nullptr && opt->use_stabilization) ? 1 : 0;
+    o.poison = g_debug_poison.load();
     o.alpha = opt != nullptr ? opt->alpha : 0.0;
     o.beta = opt != nullptr ? opt->beta : 0.0;
 }
@@ -651,6 +682,7 @@ int bionc_cuda_model_destroy(BioncModel* M) {
     }
     DeviceGuard guard(M->device);
     cudaFree(M->d_blob);
+    cudaFree(M->d_rowmap);
     cudaFree(M->d_markers);
     cudaFree(M->d_Q), cudaFree(M->d_Qd), cudaFree(M->d_Qdd), cudaFree(M->d_lam), cudaFree(M->d_inertia), cudaFree(M->d_h);
     cudaFree(M->d_status), cudaFree(M->d_fvals);
@@ -863,26 +895,43 @@ int bionc_cuda_eval(const BioncModel* M, int32_t which, const double* in, const 
         if (rc != BIONC_OK) return rc;
         fx.args.step_stride = (long long)B * fx.args.nf * 6;
     }
-    // Tile of T systems: two input and two output images in shared memory, about 64 KB together when a system allows it
-    // (several CTAs per SM keep copies and evaluation overlapped); T x out_per_sys is kept even so that every full tile
-    // is a 16-byte multiple for the bulk copies.
-    long long T = 65536 / (16LL * (n + out_per_sys));
-    if (T > 64) T = 64;
-    if (T < 1) T = 1;
-    if ((out_per_sys & 1) && (T & 1) && T > 1) --T;
-    if (T > B) T = B;
-    const size_t smem = 128 + 2 * (size_t)T * (n + out_per_sys) * sizeof(double);
-    if (smem > (size_t)M->dev_smem_optin) return fail(BIONC_E_TOO_LARGE, "one system's output does not fit the shared-memory tile of the evaluator");
-    int rc = ensure_smem(M->device, (const void*)eval_tiled_kernel, M->dev_smem_optin);
-    if (rc != BIONC_OK) return rc;
-    int ctas = (int)((size_t)M->sm_smem / (smem + 1024));
-    if (ctas > 8) ctas = 8;
-    if (ctas < 1) ctas = 1;
-    const long long ntiles = (B + T - 1) / T;
-    long long grid = 148LL * ctas;
-    if (grid > ntiles) grid = ntiles;
     EvalArgs ea{which, N, M->hdr.nblk, mj, m};
-    eval_tiled_kernel<<<(unsigned)grid, kEvalThreads, smem, st>>>(M->d_blob, fx.args, ea, in, out, (long long)B, (int)T, out_per_sys, rows, cols);
+    const size_t budget = 65536;  // two input and two output images per CTA: several CTAs per SM keep copies and evaluation overlapped
+    if (cols == 1) {
+        // vectors: tile of T systems; T x rows is kept even so that every full tile is a 16-byte multiple for the bulk copies
+        long long T = (long long)(budget / (16 * (size_t)(n + rows)));
+        if (T > 64) T = 64;
+        if (T < 1) T = 1;
+        if ((rows & 1) && (T & 1) && T > 1) --T;
+        if (T > B) T = B;
+        const size_t smem = 128 + 2 * (size_t)T * (n + rows) * sizeof(double);
+        int rc = ensure_smem(M->device, (const void*)eval_vec_kernel, M->dev_smem_optin);
+        if (rc != BIONC_OK) return rc;
+        int ctas = (int)((size_t)M->sm_smem / (smem + 1024));
+        ctas = ctas > 8 ? 8 : (ctas < 1 ? 1 : ctas);
+        const long long ntiles = (B + T - 1) / T;
+        long long grid = 148LL * ctas;
+        if (grid > ntiles) grid = ntiles;
+        eval_vec_kernel<<<(unsigned)grid, kEvalThreads, smem, st>>>(M->d_blob, fx.args, ea, in, out, (long long)B, (int)T, rows);
+    } else {
+        // Jacobians: tile of G consecutive rows of the (B rows) x n output; whole systems per tile when one fits the budget
+        const int* rowmap = M->d_rowmap + (which == BIONC_EVAL_K_R ? 0 : (which == BIONC_EVAL_K_J ? 6 * N : 6 * N + mj));
+        long long G = (long long)(budget / 4 / ((size_t)n * sizeof(double)));  // rows per output image of budget / 4 bytes
+        if (G < 1) G = 1;
+        if (G >= rows) G = G / rows * rows;
+        const long long grows = (long long)B * rows;
+        if (G > grows) G = grows;
+        const int in_systems = (int)((G + rows - 1) / rows) + 1;
+        const size_t smem = 128 + 2 * ((size_t)in_systems + (size_t)G) * n * sizeof(double);
+        int rc = ensure_smem(M->device, (const void*)eval_mat_kernel, M->dev_smem_optin);
+        if (rc != BIONC_OK) return rc;
+        int ctas = (int)((size_t)M->sm_smem / (smem + 1024));
+        ctas = ctas > 8 ? 8 : (ctas < 1 ? 1 : ctas);
+        const long long ntiles = (grows + G - 1) / G;
+        long long grid = 148LL * ctas;
+        if (grid > ntiles) grid = ntiles;
+        eval_mat_kernel<<<(unsigned)grid, kEvalThreads, smem, st>>>(M->d_blob, rowmap, ea, in, out, (long long)B, (int)G, rows, in_systems);
+    }
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return BIONC_OK;
@@ -1109,6 +1158,10 @@ int bionc_cuda_measure_fp64_peak(int device, int repeats, double* tflops_best, d
     return BIONC_OK;
 }
 
+int bionc_cuda_debug_poison(int32_t mask) {
+    g_debug_poison.store(mask);
+    return BIONC_OK;
+}
 int64_t bionc_cuda_launch_count(void) { return g_launches.load(); }
 const char* bionc_cuda_last_error(void) { return g_last_error.c_str(); }
 const char* bionc_cuda_version(void) { return "bionc_cuda 0.1.0 (sm_100a, fp64)"; }

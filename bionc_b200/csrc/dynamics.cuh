@@ -198,6 +198,7 @@ __device__ __forceinline__ V3 lin_form(const WarpCtx& w, const double* Xsys, int
 
 struct DynOpts {
     int use_stab;
+    int poison;  // debug (bionc_cuda_debug_poison): bit mask of working-set regions filled with NaN before the first evaluation
     double alpha, beta;
 };
 
@@ -302,9 +303,11 @@ __device__ __forceinline__ Q12 load_nonlin_k(const WarpCtx& w, const DevBlk& b, 
 // External forces (external_force.py:143-180 and the four force classes).  The force table lives outside the model
 // blob: DevFextTab | DevFext[nf], sorted by segment (begin[s] .. begin[s+1]).  `vals` (optional) holds per-system
 // values: 6 doubles (torque, force) per force, indexed by the force's position in the caller's list (DevFext::slot).
-// fext_transport returns the force and its torque about rp.
+// fext_transport returns the force and its torque about rp.  Kind 4 is the reaction of a joint generalized force
+// (generalized_force.py:98-129: the force acts on the joint's child at its proximal point, `rp_other`; the parent gets
+// the opposite wrench transported to its own proximal point, external_force_global_on_proximal.py:117-147 as coded).
 __device__ __forceinline__ void fext_transport(const DevFext& fe, const double* __restrict__ vals, V3 u, V3 v, V3 w, V3 rp,
-                                               V3& tau, V3& F) {
+                                               V3 rp_other, V3& tau, V3& F) {
     if (vals != nullptr) {
         const double* x = vals + 6 * fe.slot;
         tau = mk(x[0], x[1], x[2]), F = mk(x[3], x[4], x[5]);
@@ -328,20 +331,24 @@ __device__ __forceinline__ void fext_transport(const DevFext& fe, const double* 
         tau = tau + cross(lever, F);
     } else if (fe.kind == 2) {  // global application point (external_force_global.py:67-96)
         tau = tau + cross(rp - pt, F);
+    } else if (fe.kind == 4) {  // -(tau + (rp - rp_other) x F, F)
+        tau = cross_acc(rp - rp_other, F, tau);
+        tau = mk(-tau.x, -tau.y, -tau.z), F = mk(-F.x, -F.y, -F.z);
     }
 }
 
 // Natural external forces of one segment as the reference forms them: the torque goes through the pseudo
 // interpolation matrix (natural_coordinates.py:132-158), f = N_prox^T F + N*^T tau.  Used by the FEXT evaluator, the
 // dense kernel and the lambda_r output; the dynamics only need the wrench (below).
+template <typename RpOf>  // RpOf(segment) -> proximal point of another segment of the same system (kind 4 only)
 __device__ __forceinline__ Q12 external_forces(const DevFext* __restrict__ fext, int begin, int end,
-                                               const double* __restrict__ vals, V3 u, V3 v, V3 w, V3 rp) {
+                                               const double* __restrict__ vals, V3 u, V3 v, V3 w, V3 rp, RpOf rp_of) {
     Q12 f;
 #pragma unroll
     for (int t = 0; t < 4; ++t) f.s[t] = mk(0.0, 0.0, 0.0);
     for (int e = begin; e < end; ++e) {
         V3 tau, F;
-        fext_transport(fext[e], vals, u, v, w, rp, tau, F);
+        fext_transport(fext[e], vals, u, v, w, rp, fext[e].kind == 4 ? rp_of(fext[e].other) : rp, tau, F);
         // solve [w x u, u x v, -v x w] x = tau
         const V3 b0 = cross(w, u), b1 = cross(u, v), b2 = cross(w, v);  // -v x w = w x v
         const double det = dot(b0, cross(b1, b2));
@@ -359,12 +366,13 @@ __device__ __forceinline__ Q12 external_forces(const DevFext* __restrict__ fext,
 
 // The same forces as a wrench about rp.  T^T f of the natural force above is exactly (tau, F): the pseudo interpolation
 // is built so that u x f_u - v x f_rd + w x f_w = tau, hence the dynamics never need the 3x3 solve.
+template <typename RpOf>
 __device__ __forceinline__ void external_wrench(const DevFext* __restrict__ fext, int begin, int end,
-                                                const double* __restrict__ vals, V3 u, V3 v, V3 w, V3 rp, V3& tau_sum, V3& F_sum) {
+                                                const double* __restrict__ vals, V3 u, V3 v, V3 w, V3 rp, RpOf rp_of, V3& tau_sum, V3& F_sum) {
     tau_sum = mk(0.0, 0.0, 0.0), F_sum = mk(0.0, 0.0, 0.0);
     for (int e = begin; e < end; ++e) {
         V3 tau, F;
-        fext_transport(fext[e], vals, u, v, w, rp, tau, F);
+        fext_transport(fext[e], vals, u, v, w, rp, fext[e].kind == 4 ? rp_of(fext[e].other) : rp, tau, F);
         tau_sum = tau_sum + tau, F_sum = F_sum + F;
     }
 }
@@ -487,7 +495,9 @@ __device__ __forceinline__ void segment_setup(const WarpCtx& w, SegCtx& c, const
         const int fb = w.ftab->begin[w.segi], fe = w.ftab->begin[w.segi + 1];
         if (fe > fb) {
             V3 te, Fe;
-            external_wrench(w.fext, fb, fe, w.fvals, c.u, c.v, c.w, rp, te, Fe);
+            const double* Qsys = w.Qsys;
+            auto rp_of = [Qsys](int sgm) { return mk(Qsys[(12 * sgm + 3) * S], Qsys[(12 * sgm + 4) * S], Qsys[(12 * sgm + 5) * S]); };
+            external_wrench(w.fext, fb, fe, w.fvals, c.u, c.v, c.w, rp, rp_of, te, Fe);
             const V3 cbar = in_basis(c, c.cn(0), c.cn(1), c.cn(2));
             c.F0 = c.F0 + Fe;
             c.tau0 = cross_sub(c.tau0 + te, cbar, Fe);
@@ -696,7 +706,9 @@ __device__ __forceinline__ void rigid_multipliers(const WarpCtx& w, const SegCtx
     const double g = -9.81 * m;
     V3 Ru = mk(0.0, 0.0, g * c0), Rr = mk(0.0, 0.0, g * (1.0 + c1)), Rw = mk(0.0, 0.0, g * c2);
     if (GENERAL && w.fext != nullptr) {
-        const Q12 fe = external_forces(w.fext, w.ftab->begin[w.segi], w.ftab->begin[w.segi + 1], w.fvals, c.u, c.v, c.w, rp);
+        const double* Qsys = w.Qsys;
+        auto rp_of = [Qsys](int sgm) { return mk(Qsys[(12 * sgm + 3) * S], Qsys[(12 * sgm + 4) * S], Qsys[(12 * sgm + 5) * S]); };
+        const Q12 fe = external_forces(w.fext, w.ftab->begin[w.segi], w.ftab->begin[w.segi + 1], w.fvals, c.u, c.v, c.w, rp, rp_of);
         Ru = Ru + fe.s[0], Rr = Rr + fe.s[1], Rw = Rw + fe.s[3];
     }
 #pragma unroll
@@ -753,7 +765,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
     V3 tau = c.tau0, F = c.F0;  // Newton-Euler right-hand sides, joint multipliers subtracted in phase H
 
     if (w.mj > 0) {
-        const int nb = w.nb, mjp = 3 * nb;
+        const int nb = w.nb;
         const DevHeader* hd = w.hdr;
         // free accelerations (no joint forces); without external forces F0 is gravity: z only
         const V3 afree = sym3_apply(c.Ii, c.tau0);
@@ -772,8 +784,11 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
             }
             __syncthreads();
             if (w.segi == 0) {
-                for (int it = 0; it < hd->nunit; ++it) w.S0[w.unit_list[it] * spw] = 1.0;
-                for (int r = w.mj; r < mjp; ++r) w.r0[r * spw] = 0.0, w.r1[r * spw] = 0.0;
+                for (int it = 0; it < hd->nunit; ++it) {
+                    w.S0[w.unit_list[2 * it] * spw] = 1.0;
+                    const int r = w.unit_list[2 * it + 1];
+                    w.r0[r * spw] = 0.0, w.r1[r * spw] = 0.0;
+                }
             }
         }
 

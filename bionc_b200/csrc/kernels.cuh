@@ -18,7 +18,7 @@ __device__ __forceinline__ void inertia_to_constants(const double* __restrict__ 
 // ---- per-CTA setup: copy the model blob to shared memory, carve the working set ----------------------
 template <int S>
 __device__ __forceinline__ void setup_cta(const unsigned char* __restrict__ blob, int blob_bytes, const FextArgs& fx,
-                                          unsigned char* smem, WarpCtx& w) {
+                                          unsigned char* smem, WarpCtx& w, int poison = 0) {
     {
         const int4* src = reinterpret_cast<const int4*>(blob);
         int4* dst = reinterpret_cast<int4*>(smem);
@@ -54,13 +54,25 @@ __device__ __forceinline__ void setup_cta(const unsigned char* __restrict__ blob
     w.dinv = w.lamv + 3 * S * w.nb;
     w.knl = w.dinv + 6 * S * w.nb + S * h->rnl * w.segi;
     w.kcs = w.dinv + 6 * S * w.nb + S * h->rnl * w.N + S * kSegConsts * w.segi;  // behind knl; present only with per-system inertia
+    if (poison != 0) {
+        // Debug aid: a correct evaluation writes every word of the working set before it reads it, so filling the regions
+        // with NaN first must not change any result (tests/test_gpu_scale.py).  Bits: 0 S0, 1 S1, 2 r0, 3 r1, 4 lambda_j,
+        // 5 inverse pivots, 6 row vectors of the non-LIN3 blocks.  Shared memory of a fresh CTA holds whatever ran before.
+        const double nan = __longlong_as_double(0x7ff8dead0000beefLL);
+        double* reg[7] = {Qds + 12 * S * w.N, w.S1 - w.lane, w.r0 - w.lane, w.r1 - w.lane, w.lamv - w.lane, w.dinv - w.lane, w.dinv - w.lane + 6 * S * w.nb};
+        const int len[7] = {9 * S * h->nslot, 9 * S * h->nslot2, 3 * S * w.nb, 3 * S * w.nb, 3 * S * w.nb, 6 * S * w.nb, S * h->rnl * w.N};
+        for (int r = 0; r < 7; ++r)
+            if ((poison >> r) & 1)
+                for (int i = threadIdx.x; i < len[r]; i += blockDim.x) reg[r][i] = nan;
+        __syncthreads();
+    }
     const int* sym = reinterpret_cast<const int*>(smem + h->off_sym);
     w.slot_tab = sym;
     w.slot2_tab = w.slot_tab + w.nb * w.nb;
     w.zero_list = w.slot2_tab + w.nb * w.nb;
     w.comb_list = w.zero_list + h->nzero;
     w.unit_list = w.comb_list + 2 * h->ncomb;
-    w.colptr = w.unit_list + h->nunit;
+    w.colptr = w.unit_list + 2 * h->nunit;
     w.colrow = w.colptr + w.nb + 1;
     w.lvlptr = w.colrow + h->ncol;
     w.lvlpiv = w.lvlptr + h->nlevel + 1;
@@ -123,7 +135,7 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
                             long long B) {
     extern __shared__ __align__(16) unsigned char smem[];
     WarpCtx w;
-    setup_cta<S>(blob, blob_bytes, fx, smem, w);
+    setup_cta<S>(blob, blob_bytes, fx, smem, w, o.poison);
     long long gsys = (long long)blockIdx.x * S + w.lane;
     const bool live = (int)(threadIdx.x & 31) < S && gsys < B;
     if (gsys >= B) gsys = B - 1;  // tail lanes recompute the last system, stores are masked
@@ -169,7 +181,7 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr bool XSEG = GENERAL || STAB;  // an evaluation reads other segments' published state
     WarpCtx w;
-    setup_cta<S>(blob, blob_bytes, fx, smem, w);
+    setup_cta<S>(blob, blob_bytes, fx, smem, w, o.poison);
     long long gsys = (long long)blockIdx.x * S + w.lane;
     const bool live = (int)(threadIdx.x & 31) < S && gsys < B;
     if (gsys >= B) gsys = B - 1;
@@ -388,7 +400,8 @@ __device__ __forceinline__ void eval_item(const DevSeg* __restrict__ seg, const 
             double* o = vec + 12 * i;
             Q12 f;
             if (fext.tab != nullptr) {
-                f = external_forces(fext.f, fext.tab->begin[i], fext.tab->begin[i + 1], fext.vals, u, v, w, rp);
+                auto rp_of = [X](int sgm) { return mk(X[12 * sgm + 3], X[12 * sgm + 4], X[12 * sgm + 5]); };
+                f = external_forces(fext.f, fext.tab->begin[i], fext.tab->begin[i + 1], fext.vals, u, v, w, rp, rp_of);
             } else {
 #pragma unroll
                 for (int t = 0; t < 4; ++t) f.s[t] = mk(0.0, 0.0, 0.0);
@@ -485,84 +498,150 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
-// Tiled evaluator.  The outputs are dense per system (the reference's own shapes), a Jacobian mostly zeros: what the
-// kernel has to do is write B x rows x cols doubles to HBM once, in full 16-byte-aligned bursts.  A CTA walks tiles of
-// T consecutive systems; per tile
-//   1. the states of the tile (T x 12N doubles, contiguous in global memory) arrive by one bulk copy into shared memory
-//      (prefetched one tile ahead, completion on an mbarrier);
-//   2. the threads evaluate (system, item[, row]) units from shared memory into the tile's output image in shared
-//      memory.  Every structural non-zero is written exactly once (put_row), so for Jacobians the image keeps its zero
-//      background from tile to tile: it is cleared once per CTA, not once per system;
-//   3. one bulk copy streams the image (T x rows x cols doubles, contiguous in global memory) out while the next tile
-//      is computed in the other buffer.
+// Tiled evaluators.  The outputs are dense per system (the reference's own shapes), a Jacobian mostly zeros: what the
+// kernels have to do is write B x rows x cols doubles to HBM once, in full 16-byte-aligned bursts.  A CTA walks tiles;
+// per tile
+//   1. the states the tile needs (consecutive systems, contiguous in global memory) arrive by one bulk copy into shared
+//      memory (prefetched one tile ahead, completion on an mbarrier);
+//   2. the threads evaluate their units from shared memory into the tile's output image in shared memory;
+//   3. one bulk copy streams the image (contiguous in global memory) out while the next tile is computed in the other
+//      buffer.
 // DRAM traffic = input once + output once = the algorithmic bytes; no memset, no read-modify-write on global memory.
+//   eval_vec_kernel: vector outputs (Phi_r, Phi_j, Phi_h, bias, f_ext); tile = T systems, unit = (system, item).
+//   eval_mat_kernel: Jacobians (K_r, K_j, K_h); tile = G consecutive rows of the (B rows) x 12N output, whatever system
+//                    they belong to (one row is 96 N bytes: any tile is a 16-byte multiple and any model fits), unit = one
+//                    row, found through the host-built row map (row -> item, row inside the item).  Every structural
+//                    non-zero is written exactly once (put_row); when a tile holds whole systems the image keeps its
+//                    zero background from tile to tile, otherwise it is cleared per tile.
 // ---------------------------------------------------------------------------------------------
 constexpr int kEvalThreads = 128;
 
+struct TilePipe {  // the two-buffer pipeline shared by both kernels
+    unsigned long long* bar;
+    double* in_tile[2];
+    double* out_tile[2];
+};
+__device__ __forceinline__ TilePipe tile_pipe(unsigned char* sm, size_t in_doubles, size_t out_doubles) {
+    TilePipe p;
+    p.bar = reinterpret_cast<unsigned long long*>(sm);
+    p.in_tile[0] = reinterpret_cast<double*>(sm + 128);
+    p.in_tile[1] = p.in_tile[0] + in_doubles;
+    p.out_tile[0] = p.in_tile[1] + in_doubles;
+    p.out_tile[1] = p.out_tile[0] + out_doubles;
+    if (threadIdx.x == 0) {
+        mbar_init(p.bar, 1), mbar_init(p.bar + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    return p;
+}
+
 __global__ void __launch_bounds__(kEvalThreads, 4)
-    eval_tiled_kernel(const unsigned char* __restrict__ blob, FextArgs fx, EvalArgs ea, const double* __restrict__ in,
-                      double* __restrict__ out, long long B, int T, int out_per_sys, int rows, int cols) {
+    eval_vec_kernel(const unsigned char* __restrict__ blob, FextArgs fx, EvalArgs ea, const double* __restrict__ in,
+                    double* __restrict__ out, long long B, int T, int rows) {
     extern __shared__ __align__(128) unsigned char sm[];
     const DevHeader* h = reinterpret_cast<const DevHeader*>(blob);
     const DevSeg* seg = reinterpret_cast<const DevSeg*>(blob + h->off_seg);
     const DevBlk* blk = reinterpret_cast<const DevBlk*>(blob + h->off_blk);
     const int n = 12 * ea.N, nitem = ea.N + ea.nblk, which = ea.which, tid = threadIdx.x;
-    const bool matrix = cols > 1;
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(sm);  // two mbarriers
-    double* in_tile[2];
-    double* out_tile[2];
-    in_tile[0] = reinterpret_cast<double*>(sm + 128);
-    in_tile[1] = in_tile[0] + (size_t)T * n;
-    out_tile[0] = in_tile[1] + (size_t)T * n;
-    out_tile[1] = out_tile[0] + (size_t)T * out_per_sys;
+    const TilePipe p = tile_pipe(sm, (size_t)T * n, (size_t)T * rows);
     const long long ntiles = (B + T - 1) / T;
-    if (tid == 0) {
-        mbar_init(bar, 1), mbar_init(bar + 1, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (matrix) {  // zero background of both output images, once
-        double2* z = reinterpret_cast<double2*>(out_tile[0]);
-        for (int i = tid; i < T * out_per_sys; i += kEvalThreads) z[i] = make_double2(0.0, 0.0);  // 2 T out_per_sys doubles
-    }
     __syncthreads();
     auto tile_systems = [&](long long tile) { return (int)((B - tile * T < T) ? B - tile * T : T); };
     long long tile = blockIdx.x;
     if (tid == 0 && tile < ntiles) {
         const unsigned bytes = (unsigned)tile_systems(tile) * n * 8u;
-        mbar_expect_tx(bar, bytes);
-        bulk_load(in_tile[0], in + (size_t)tile * T * n, bytes, bar);
+        mbar_expect_tx(p.bar, bytes);
+        bulk_load(p.in_tile[0], in + (size_t)tile * T * n, bytes, p.bar);
     }
-    const int subs = matrix ? 6 : 1;  // Jacobians: one unit per (item, row)
     for (int k = 0; tile < ntiles; tile += gridDim.x, ++k) {
         const int buf = k & 1, ns = tile_systems(tile);
         const long long next = tile + gridDim.x;
         if (tid == 0) {
             if (next < ntiles) {  // prefetch: in_tile[buf ^ 1] was last read in iteration k - 1, closed by its barrier
                 const unsigned bytes = (unsigned)tile_systems(next) * n * 8u;
-                mbar_expect_tx(bar + (buf ^ 1), bytes);
-                bulk_load(in_tile[buf ^ 1], in + (size_t)next * T * n, bytes, bar + (buf ^ 1));
+                mbar_expect_tx(p.bar + (buf ^ 1), bytes);
+                bulk_load(p.in_tile[buf ^ 1], in + (size_t)next * T * n, bytes, p.bar + (buf ^ 1));
             }
             bulk_wait_read<1>();  // the store of iteration k - 2 has finished reading out_tile[buf]
         }
-        mbar_wait(bar + buf, (k >> 1) & 1);
+        mbar_wait(p.bar + buf, (k >> 1) & 1);
         __syncthreads();
-        const double* X0 = in_tile[buf];
-        double* O0 = out_tile[buf];
-        for (int idx = tid; idx < ns * nitem * subs; idx += kEvalThreads) {
-            const int sys = idx / (nitem * subs), r = idx - sys * (nitem * subs);
-            const int item = r / subs, sub = matrix ? r - item * subs : -1;
-            double* o = O0 + (size_t)sys * out_per_sys;
-            eval_item(seg, blk, fext_view(fx, tile * T + sys), ea, which, item, X0 + (size_t)sys * n, o, o, n, sub);
+        const double* X0 = p.in_tile[buf];
+        double* O0 = p.out_tile[buf];
+        for (int idx = tid; idx < ns * nitem; idx += kEvalThreads) {
+            const int sys = idx / nitem, item = idx - sys * nitem;
+            double* o = O0 + (size_t)sys * rows;
+            eval_item(seg, blk, fext_view(fx, tile * T + sys), ea, which, item, X0 + (size_t)sys * n, o, nullptr, 0);
         }
         fence_async_smem();  // generic-proxy writes of the image become visible to the bulk-copy engine
         __syncthreads();
-        const size_t bytes = (size_t)ns * out_per_sys * 8;
-        double* gdst = out + (size_t)tile * T * out_per_sys;
+        const size_t bytes = (size_t)ns * rows * 8;
+        double* gdst = out + (size_t)tile * T * rows;
         if ((bytes & 15) == 0) {
             if (tid == 0) bulk_store(gdst, O0, (unsigned)bytes);
-        } else {  // odd tail: plain stores
-            for (int i = tid; i < ns * out_per_sys; i += kEvalThreads) gdst[i] = O0[i];
+        } else {  // odd tail (T x rows is even for every full tile): plain stores
+            for (int i = tid; i < ns * rows; i += kEvalThreads) gdst[i] = O0[i];
         }
+    }
+    if (tid == 0) bulk_wait_all();
+}
+
+__global__ void __launch_bounds__(kEvalThreads, 4)
+    eval_mat_kernel(const unsigned char* __restrict__ blob, const int* __restrict__ rowmap, EvalArgs ea, const double* __restrict__ in,
+                    double* __restrict__ out, long long B, int G, int rows, int in_systems) {
+    extern __shared__ __align__(128) unsigned char sm[];
+    const DevHeader* h = reinterpret_cast<const DevHeader*>(blob);
+    const DevSeg* seg = reinterpret_cast<const DevSeg*>(blob + h->off_seg);
+    const DevBlk* blk = reinterpret_cast<const DevBlk*>(blob + h->off_blk);
+    const int n = 12 * ea.N, which = ea.which, tid = threadIdx.x;
+    const TilePipe p = tile_pipe(sm, (size_t)in_systems * n, (size_t)G * n);
+    const long long grows = B * rows, ntiles = (grows + G - 1) / G;
+    const bool whole = (G % rows) == 0;  // tiles hold whole systems: the non-zero pattern of the image never changes
+    {
+        double2* z = reinterpret_cast<double2*>(p.out_tile[0]);
+        for (int i = tid; i < G * n; i += kEvalThreads) z[i] = make_double2(0.0, 0.0);  // both images: 2 G n doubles
+    }
+    __syncthreads();
+    // systems a tile needs: those of its first and last row
+    auto first_sys = [&](long long tile) { return tile * G / rows; };
+    auto last_sys = [&](long long tile) { const long long e = (tile + 1) * G < grows ? (tile + 1) * G : grows; return (e - 1) / rows; };
+    long long tile = blockIdx.x;
+    if (tid == 0 && tile < ntiles) {
+        const unsigned bytes = (unsigned)(last_sys(tile) - first_sys(tile) + 1) * n * 8u;
+        mbar_expect_tx(p.bar, bytes);
+        bulk_load(p.in_tile[0], in + (size_t)first_sys(tile) * n, bytes, p.bar);
+    }
+    const FextView nofx{nullptr, nullptr, nullptr};
+    for (int k = 0; tile < ntiles; tile += gridDim.x, ++k) {
+        const int buf = k & 1;
+        const long long g0 = tile * G, s0 = first_sys(tile), next = tile + gridDim.x;
+        const int ng = (int)(grows - g0 < G ? grows - g0 : G);
+        if (tid == 0) {
+            if (next < ntiles) {
+                const unsigned bytes = (unsigned)(last_sys(next) - first_sys(next) + 1) * n * 8u;
+                mbar_expect_tx(p.bar + (buf ^ 1), bytes);
+                bulk_load(p.in_tile[buf ^ 1], in + (size_t)first_sys(next) * n, bytes, p.bar + (buf ^ 1));
+            }
+            bulk_wait_read<1>();
+        }
+        mbar_wait(p.bar + buf, (k >> 1) & 1);
+        __syncthreads();
+        double* O0 = p.out_tile[buf];
+        if (!whole && k >= 2) {  // the image still holds the rows of iteration k - 2: clear it (the first two are clean)
+            double2* z = reinterpret_cast<double2*>(O0);
+            for (int i = tid; i < G * n / 2; i += kEvalThreads) z[i] = make_double2(0.0, 0.0);
+            __syncthreads();
+        }
+        for (int idx = tid; idx < ng; idx += kEvalThreads) {
+            const long long g = g0 + idx, sys = g / rows;
+            const int r = (int)(g - sys * rows), code = rowmap[r];
+            // eval_item addresses the matrix of one system: its row 0 sits (sys rows - g0) rows from the image's start
+            double* K = O0 + (sys * rows - g0) * n;
+            eval_item(seg, blk, nofx, ea, which, code >> 3, p.in_tile[buf] + (size_t)(sys - s0) * n, nullptr, K, n, code & 7);
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) bulk_store(out + (size_t)g0 * n, O0, (unsigned)((size_t)ng * n * 8));
     }
     if (tid == 0) bulk_wait_all();
 }

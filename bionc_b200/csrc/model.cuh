@@ -35,10 +35,10 @@ struct DevHeader {
     int nslot2;   // blocks that can receive contributions from two segments (second, exclusive-writer copy)
     int nzero;    // entries of the zero list (slots that are not fully overwritten by the assembly)
     int ncomb;    // entries of the combine list (slot, slot2) pairs
-    int nunit;    // entries of the unit list: diagonal elements of padding rows
+    int nunit;    // entries of the unit list: (diagonal element, row) of every padding row
     int ncol;     // total length of the column lists
     int off_sym;  // byte offset of the symbolic tables (ints): slot_tab[nb*nb] slot2_tab[nb*nb] zero[nzero]
-                  // comb[2*ncomb] unit[nunit] colptr[nb+1] colrow[ncol] lvlptr[nlevel+1] lvlpiv[nb]
+                  // comb[2*ncomb] unit[2*nunit] colptr[nb+1] colrow[ncol] lvlptr[nlevel+1] lvlpiv[nb]
                   // owner[nb] (warp of block row I) pivmask[nb] (warps taking part in pivot K)
                   // pivwriter[nb] (warp that stores the inverse pivot and y-hat of pivot K)
                   // nscale[nb] (float bits: nominal diagonal scale of each node)
@@ -84,8 +84,8 @@ struct DevSide {
 struct DevFext {
     double p[kFextNParam];  // torque(3) force(3) point(3) Tinv(9, row-major)
     int segment, kind;
-    int slot;  // position in the caller's force list: per-system values are (B, F, 6) in that order
-    int pad0;
+    int slot;   // position in the caller's force list: per-system values are (B, F, 6) in that order
+    int other;  // kind 4 (reaction of a joint force): the segment the force itself acts on (the joint's child)
 };
 
 // header of a call's force table; the forces follow it, sorted by segment

@@ -39,7 +39,10 @@ extern "C" {
 #define BIONC_FEXT_GLOBAL_LOCAL_POINT 1
 #define BIONC_FEXT_GLOBAL 2
 #define BIONC_FEXT_LOCAL 3
-#define BIONC_FEXT_NPARAM 24 /* torque(3) force(3) point(3) Tinv(9) pad(6) */
+#define BIONC_FEXT_JOINT_REACTION 4 /* reaction of a joint generalized force on the joint's parent (generalized_force.py:98-129):
+                                       `segment` is the parent, param[18] the index of the child the force (torque, force) itself
+                                       acts on; the parent receives -(torque + (rp_parent - rp_child) x force, force) */
+#define BIONC_FEXT_NPARAM 24 /* torque(3) force(3) point(3) Tinv(9) other segment(1, kind 4) pad(5) */
 
 /* per-system status bits written by forward_dynamics / rk4 */
 #define BIONC_STATUS_OK 0
@@ -182,6 +185,11 @@ int bionc_cuda_rk4_host(BioncModel* model, double* Q, double* Qdot, double h, co
 /* FP64 roofline denominator: DFMA-only micro-benchmark timed with CUDA events (best single launch and
  * the average over `repeats` back-to-back launches), in TFLOP/s */
 int bionc_cuda_measure_fp64_peak(int device, int repeats, double* tflops_best, double* tflops_sustained);
+
+/* debug aid: the dynamics kernels fill the selected regions of their shared-memory working set with NaN before the first
+ * evaluation (bit 0 S', 1 second copies, 2 / 3 right-hand-side copies, 4 lambda_j, 5 inverse pivots, 6 row vectors of the
+ * non-LIN3 blocks).  A correct kernel writes every word before reading it, so no result may change; 0 switches it off. */
+int bionc_cuda_debug_poison(int32_t mask);
 
 /* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
 int64_t bionc_cuda_launch_count(void);

@@ -26,7 +26,7 @@ import numpy as np
 
 BLK_LIN3, BLK_DOT, BLK_CLEN, BLK_SOP = 0, 1, 2, 3
 BLK_ROWS = {BLK_LIN3: 3, BLK_DOT: 1, BLK_CLEN: 1, BLK_SOP: 1}
-FEXT_GLOBAL_ON_PROXIMAL, FEXT_GLOBAL_LOCAL_POINT, FEXT_GLOBAL, FEXT_LOCAL = 0, 1, 2, 3
+FEXT_GLOBAL_ON_PROXIMAL, FEXT_GLOBAL_LOCAL_POINT, FEXT_GLOBAL, FEXT_LOCAL, FEXT_JOINT_REACTION = 0, 1, 2, 3, 4
 
 _ARRAYS = (
     "seg_phi_const seg_mass seg_com seg_J seg_rigid_row blk_type blk_parent blk_child "
@@ -365,6 +365,13 @@ class OracleModel:
                 tau = tau + np.cross(rp - P_app, F)
             elif kind == FEXT_GLOBAL:  # external_force_global.py:67-96
                 tau = tau + np.cross(rp - pt, F)
+            elif kind == FEXT_JOINT_REACTION:
+                # reaction of a joint generalized force on the joint's parent (generalized_force.py:98-129): the force acts on
+                # the child par[18] at its proximal point; transported to this segment's proximal point as
+                # external_force_global_on_proximal.py:117-147 codes it (lever = new point - old point), then negated
+                rp_child = Q[12 * int(par[18]) + 3 : 12 * int(par[18]) + 6]
+                tau = -(tau + np.cross(rp - rp_child, F))
+                F = -F
             # external_force_global_on_proximal.py:65-115 + natural_coordinates.py:132-158
             left = np.zeros((12, 3))
             left[9:12, 0] = u

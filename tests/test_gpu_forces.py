@@ -166,3 +166,54 @@ def test_two_devices_in_one_process():
     ra = m1.rk4(Q, Qd, h=1e-3, n_steps=5)
     rb = m0.rk4(Q, Qd, h=1e-3, n_steps=5)
     assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1])
+
+
+def test_joint_generalized_forces_behind_the_flag():
+    """SURVEY 8(f) rank 3.  Default: accepted and ignored exactly like the reference (call site commented out,
+    biomechanical_model.py:391-413).  With apply_joint_generalized_forces=True: the documented semantics of
+    generalized_force.py:98-129, against vectors composed from the reference's own existing methods
+    (tests/golden/generate_joint_forces.py -- the reference's to_natural_joint_forces itself raises AttributeError)."""
+    import os
+
+    from helpers import GOLDEN
+    from bionc_b200.bionc_cuda import BiomechanicalModel, ExternalForceSet
+    from bionc_b200.bionc_cuda.generalized_force import JointGeneralizedForces, JointGeneralizedForcesList
+    from bionc_b200.bionc_cuda.model_table import ModelTable
+
+    with np.load(os.path.join(GOLDEN, "cases_extra", "joint_forces_lower_limb.npz")) as z:
+        g = {k: np.array(z[k]) for k in z.files}
+    table = ModelTable.load(model_path("lower_limb"))
+    table.all_joint_names = [f"j{k}" for k in range(g["all_joint_parent"].size)]  # the committed table predates format 3
+    table.all_joint_parent, table.all_joint_child = g["all_joint_parent"], g["all_joint_child"]
+    model = BiomechanicalModel.from_table(table)
+    jl = JointGeneralizedForcesList.empty_from_nb_joint(len(table.all_joint_names))
+    for j, v in zip(g["joint_index"], g["joint_force"]):
+        jl.add_generalized_force(int(j), JointGeneralizedForces(v, np.zeros(3)))
+    Q, Qd = g["Q"], g["Qdot"]
+    plain = model.forward_dynamics(Q, Qd)
+    ignored = model.forward_dynamics(Q, Qd, joint_generalized_forces=jl)
+    assert np.array_equal(plain[0], ignored[0]) and np.array_equal(plain[1], ignored[1])  # the reference's behaviour
+    qdd, lam, status = model.forward_dynamics(Q, Qd, joint_generalized_forces=jl, apply_joint_generalized_forces=True, return_status=True)
+    assert not status.any()
+    for s in range(Q.shape[0]):
+        assert rel_err(qdd[s], g["ref_Qddot"][s]) < TOL_EVAL and rel_err(lam[s], g["ref_lam"][s]) < TOL_EVAL, s
+    assert rel_err(qdd, plain[0]) > 1e-3  # and they do act
+    # the natural joint forces themselves, through the force evaluator
+    seg, kind, par = jl.to_arrays(table.all_joint_parent, table.all_joint_child)
+    fs = ExternalForceSet.empty_from_nb_segment(model.nb_segments)
+    for s_, k_, p_ in zip(seg, kind, par):
+        fs.external_forces[int(s_)].append((int(k_), p_))
+    fn = model.natural_external_forces(Q, fs)
+    assert rel_err(fn, g["ref_natural_joint_forces"]) < 1e-12
+    # fused integrator and dense kernel take the same table
+    qd2, lam2 = model.forward_dynamics(Q, Qd, joint_generalized_forces=jl, apply_joint_generalized_forces=True, pivoting="always")
+    assert rel_err(qd2, qdd) < 1e-9 and rel_err(lam2, lam) < 1e-9
+    from bionc_oracle import OracleModel
+
+    om = OracleModel(model_path("lower_limb"))
+    fext = [(int(a), int(b), c) for a, b, c in zip(seg, kind, par)]
+    t = np.linspace(0.0, 0.05, 26)
+    Qf, Qdf = model.rk4(Q[:2], Qd[:2], t=t, joint_generalized_forces=jl, apply_joint_generalized_forces=True)
+    for s in range(2):
+        rq, rqd = om.rk4(Q[s], Qd[s], t, normalize=True, fext=fext)
+        assert rel_err(np.concatenate([Qf[s], Qdf[s]]), np.concatenate([rq, rqd])) < TOL_TRAJ

@@ -291,3 +291,47 @@ def test_full_body_perturbed_inertia_full_batch():
     got = np.concatenate([Qf[s].cpu().numpy(), Qdf[s].cpu().numpy()])
     ref = np.concatenate([rq, rqd])
     assert np.abs(got - ref).max() / max(1.0, np.abs(ref).max()) < 1e-8
+
+
+@pytest.mark.parametrize("name", ["lower_limb", "knee_feikes", "n_link_4", "full_body", "pendulum_force_batch", "tj_universal"])
+def test_no_shared_memory_word_is_read_before_it_is_written(name):
+    """bionc_cuda_debug_poison fills regions of a CTA's working set with NaN before the first evaluation.  A fresh CTA
+    inherits whatever the previous one left in shared memory, so an evaluation must write every word before reading it:
+    no output may change, for any region.  (Round 1 zeroed the right-hand side of the padding rows at the END of the
+    joint-level system although the fill-reducing ordering moves the padded node: 0 x garbage, visible only as sporadic
+    NaNs at large batches.)"""
+    from bionc_b200.bionc_cuda import _lib
+
+    lib = _lib.load()
+    case, model = load_case(name), _model(name)
+    Q, Qd = np.tile(case["Q"], (40, 1))[:67], np.tile(case["Qdot"], (40, 1))[:67]
+
+    def run():
+        return (model.forward_dynamics(Q, Qd, pivoting="never") + model.rk4(Q, Qd, h=1e-4, n_steps=3)
+                + model.forward_dynamics(Q, Qd, pivoting="never", stabilization=dict(alpha=1.0, beta=1.0)))
+
+    try:
+        lib.bionc_cuda_debug_poison(0)
+        ref = run()
+        for bit in range(7):
+            lib.bionc_cuda_debug_poison(1 << bit)
+            out = run()
+            assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(ref, out)), f"region {bit}"
+    finally:
+        lib.bionc_cuda_debug_poison(0)
+
+
+def test_forward_dynamics_repeats_bit_for_bit_at_scale():
+    """The single-evaluation kernel on 150 001 hinge-chain systems (16 systems per CTA, level-parallel schedule, a padded
+    node in the middle of the ordering), three times."""
+    from bionc_b200.utils import states as st
+
+    model = _model("n_link_4")
+    Qn, Qdn = st.planar_chain_states(model.table, 1 << 14, seed=31)
+    Q = torch.from_numpy(Qn).cuda().repeat(10, 1)[:150_001].contiguous()
+    Qd = torch.from_numpy(Qdn).cuda().repeat(10, 1)[:150_001].contiguous()
+    ref = model.forward_dynamics(Q, Qd, pivoting="never", return_status=True)
+    assert not bool(torch.isnan(ref[0]).any()) and not bool(ref[2].any())
+    for _ in range(3):
+        out = model.forward_dynamics(Q, Qd, pivoting="never", return_status=True)
+        assert all(torch.equal(a, b) for a, b in zip(ref, out))
