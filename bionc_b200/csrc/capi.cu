@@ -411,8 +411,9 @@ int ensure_device(const BioncModel* Mc) {
     return BIONC_OK;
 }
 
-// External forces of one call: the table (a few hundred bytes) is built on the host, uploaded into a stream-ordered
-// allocation on the caller's stream and freed on that stream after the launch; nothing of it is kept in the model.
+// External forces of one call: the table (a few hundred bytes) is built on the host, written into a stream-ordered
+// allocation on the caller's stream by a parameter-carrying kernel and freed on that stream after the launch; nothing of
+// it is kept in the model and no host memory is referenced after the call returns.
 struct FextCall {
     FextArgs args{};
     void* d_tab = nullptr;
@@ -450,8 +451,14 @@ struct FextCall {
         }
         for (int s = N; s < kMaxSegments + 4; ++s) tab->begin[s] = k;
         CUDA_TRY(cudaMallocAsync(&d_tab, bytes, st));
-        // pageable source: the runtime stages it before returning, so `host` may go out of scope
-        CUDA_TRY(cudaMemcpyAsync(d_tab, host.data(), bytes, cudaMemcpyHostToDevice, st));
+        // the table travels in kernel parameters (copied at launch): no host buffer has to outlive this call
+        for (int off = 0; off < bytes; off += (int)sizeof(ParamChunk)) {
+            ParamChunk chunk;
+            const int nbytes = bytes - off < (int)sizeof(ParamChunk) ? bytes - off : (int)sizeof(ParamChunk);
+            std::memcpy(chunk.bytes, host.data() + off, nbytes);
+            param_upload_kernel<<<1, 64, 0, st>>>(chunk, static_cast<unsigned char*>(d_tab) + off, nbytes);
+            CUDA_TRY(cudaGetLastError());
+        }
         args.tab = static_cast<const unsigned char*>(d_tab);
         args.tab_bytes = bytes, args.nf = nf;
         args.vals = fx->values;
@@ -734,6 +741,17 @@ struct DynCall {
     }
 };
 
+// The single-evaluation kernel is persistent: as many CTAs as fit the device at once, each walking tiles of systems, so
+// the per-CTA set-up (model blob to shared memory) is paid once per CTA instead of once per 32 systems.
+static unsigned fd_grid(const BioncModel* M, const DynCall& call, int64_t B) {
+    const long long ntiles = (B + call.plan.spw - 1) / call.plan.spw;
+    int per_sm = 0, sms = 148;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, call.ks.fd, 32 * M->hdr.N, call.plan.smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, M->device);
+    const long long resident = (long long)per_sm * sms;
+    return (unsigned)(ntiles < resident ? ntiles : resident);
+}
+
 int bionc_cuda_forward_dynamics(const BioncModel* M, const double* Q, const double* Qd, const BioncDynOptions* opt,
                                 double* Qdd, double* lam, int32_t* status, int64_t B, void* stream) {
     if (M == nullptr || Q == nullptr || Qd == nullptr || Qdd == nullptr || B < 0) return fail(BIONC_E_INVALID, "null argument");
@@ -745,8 +763,9 @@ int bionc_cuda_forward_dynamics(const BioncModel* M, const double* Q, const doub
     if (rc != BIONC_OK) return rc;
     if (status != nullptr) CUDA_TRY(cudaMemsetAsync(status, 0, B * sizeof(int32_t), st));
     const double* inertia = opt != nullptr ? opt->inertia : nullptr;
-    const unsigned grid = (unsigned)((B + call.plan.spw - 1) / call.plan.spw), block = 32 * M->hdr.N;
+    const unsigned block = 32 * M->hdr.N;
     if ((rc = ensure_smem(M->device, call.ks.fd, M->dev_smem_optin)) != BIONC_OK) return rc;
+    const unsigned grid = fd_grid(M, call, B);
     const unsigned char* blob = M->d_blob;
     int blob_bytes = M->blob_bytes;
     long long Bll = B;
@@ -833,7 +852,7 @@ int bionc_cuda_rk4(const BioncModel* M, double* Q, double* Qd, double h, const d
         CUDA_TRY(cudaMallocAsync(&scratch, (size_t)B * 12 * M->hdr.N * sizeof(double), st));
         FextArgs fxl = call.fx.args;  // the force slice of the last step
         if (fxl.vals != nullptr) fxl.vals += (n_steps - 1 < fxl.steps ? n_steps - 1 : fxl.steps - 1) * fxl.step_stride;
-        const unsigned grid = (unsigned)((B + call.plan.spw - 1) / call.plan.spw), block = 32 * M->hdr.N;
+        const unsigned grid = fd_grid(M, call, B), block = 32 * M->hdr.N;
         const unsigned char* blob = M->d_blob;
         int blob_bytes = M->blob_bytes;
         const double *Qc = Q, *Qdc = Qd;

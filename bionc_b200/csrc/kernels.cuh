@@ -135,29 +135,33 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
                             long long B) {
     extern __shared__ __align__(16) unsigned char smem[];
     WarpCtx w;
-    setup_cta<S>(blob, blob_bytes, fx, smem, w, o.poison);
-    long long gsys = (long long)blockIdx.x * S + w.lane;
-    const bool live = (int)(threadIdx.x & 31) < S && gsys < B;
-    if (gsys >= B) gsys = B - 1;  // tail lanes recompute the last system, stores are masked
+    setup_cta<S>(blob, blob_bytes, fx, smem, w, o.poison);  // once per CTA: the grid is persistent, a CTA walks tiles of S systems
     const int n = 12 * w.N;
-    int status = 0;
-    SegCtx c;
-    load_constants<S>(w, inertia, gsys, c, status);
-    if (GENERAL && fx.vals != nullptr) w.fvals = fx.vals + (size_t)gsys * fx.nf * 6;
-    {
-        Q12 q, qd;
-        load_q12(Q + (size_t)gsys * n + 12 * w.segi, q);
-        load_q12(Qd + (size_t)gsys * n + 12 * w.segi, qd);
+    const long long ntiles = (B + S - 1) / S;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        long long gsys = tile * S + w.lane;
+        const bool live = (int)(threadIdx.x & 31) < S && gsys < B;
+        if (gsys >= B) gsys = B - 1;  // tail lanes recompute the last system, stores are masked
+        int status = 0;
+        SegCtx c;
+        load_constants<S>(w, inertia, gsys, c, status);
+        if (GENERAL && fx.vals != nullptr) w.fvals = fx.vals + (size_t)gsys * fx.nf * 6;
+        {
+            Q12 q, qd;
+            load_q12(Q + (size_t)gsys * n + 12 * w.segi, q);
+            load_q12(Qd + (size_t)gsys * n + 12 * w.segi, qd);
 #pragma unroll
-        for (int t = 0; t < 4; ++t) publish3<S>(w.Qo, t, q.s[t]), publish3<S>(w.Qdo, t, qd.s[t]);
-    }
-    __syncthreads();
-    Q12 qdd;
-    double* lam_sys = (lam != nullptr && live) ? lam + (size_t)gsys * w.hdr->m : nullptr;
-    eval_forward_dynamics<GENERAL, STAB, true, false, S>(w, c, o, qdd, lam_sys, status);
-    if (live) {
-        store_q12(Qdd + (size_t)gsys * n + 12 * w.segi, qdd);
-        if (status_out != nullptr && status != 0) atomicOr(status_out + gsys, status);
+            for (int t = 0; t < 4; ++t) publish3<S>(w.Qo, t, q.s[t]), publish3<S>(w.Qdo, t, qd.s[t]);
+        }
+        __syncthreads();
+        Q12 qdd;
+        double* lam_sys = (lam != nullptr && live) ? lam + (size_t)gsys * w.hdr->m : nullptr;
+        eval_forward_dynamics<GENERAL, STAB, true, false, S>(w, c, o, qdd, lam_sys, status);
+        if (live) {
+            store_q12(Qdd + (size_t)gsys * n + 12 * w.segi, qdd);
+            if (status_out != nullptr && status != 0) atomicOr(status_out + gsys, status);
+        }
+        __syncthreads();  // the next tile overwrites what slower warps may still read (lambda_j, row vectors, published state)
     }
 }
 
@@ -985,6 +989,16 @@ __global__ void __launch_bounds__(kDenseThreads)
         const int any_bad = __syncthreads_or(bad ? 1 : 0);
         if (tid == 0 && status_out != nullptr) status_out[sys] = st | (any_bad && !singular ? 2 : 0);
     }
+}
+
+// A few KB of host data to device memory without any host buffer that has to outlive the call: the bytes travel in the
+// kernel parameters (copied at launch time, stream-ordered, legal inside a graph capture).  Used for the per-call force
+// table: cudaMemcpyAsync from pageable memory may read the source only when the stream gets there.
+struct alignas(16) ParamChunk {
+    unsigned char bytes[3072];
+};
+__global__ void param_upload_kernel(ParamChunk chunk, unsigned char* __restrict__ dst, int n) {
+    for (int i = threadIdx.x; i < n / 16; i += blockDim.x) reinterpret_cast<int4*>(dst)[i] = reinterpret_cast<const int4*>(chunk.bytes)[i];
 }
 
 // FP64 peak probe: nothing but dependent-chain DFMAs, 8 chains per thread

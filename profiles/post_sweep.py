@@ -49,12 +49,29 @@ def main():
         ("holonomic_constraints", lambda: model.holonomic_constraints(Qt), n + m),
         ("holonomic_constraints_acceleration_bias", lambda: model.holonomic_constraints_acceleration_bias(Qdt), n + m),
     ]
-    if B <= 200_000:
-        cases.append(("holonomic_constraints_jacobian", lambda: model.holonomic_constraints_jacobian(Qt), n + 2 * m * n))  # memset + write
+    mj = model.nb_joint_constraints
+    cases += [
+        ("rigid_body_constraints", lambda: model.rigid_body_constraints(Qt), n + 6 * N),
+        ("joint_constraints", lambda: model.joint_constraints(Qt), n + mj),
+        # the single-evaluation kernel behind the Python-level RK4 closure: Q, Qdot in; Qddot, lambda, status out
+        ("forward_dynamics (one evaluation, pivoting='never')", lambda: model.forward_dynamics(Qt, Qdt, pivoting="never"), 3 * n + m + 0.5),
+    ]
     for name, fn, doubles in cases:
         ms = timed(fn)
         gbs = B * doubles * 8 / (ms * 1e-3) / 1e9
         rows.append({"evaluator": name, "systems": B, "ms": ms, "algorithmic_bytes": B * doubles * 8, "GB_per_s": gbs, "frac_of_hbm_peak": gbs / hbm, "hbm_peak_GB_per_s": hbm})
+        print(json.dumps(rows[-1]))
+    # the Jacobians are dense (B, rows, 12N) outputs: 1e5 systems are 1.3 GB for K_h, ten times the L2
+    Bk = min(B, 100_000)
+    Qk = Qt[:Bk].contiguous()
+    for name, fn, doubles in [
+        ("rigid_body_constraints_jacobian", lambda: model.rigid_body_constraints_jacobian(Qk), n + 6 * N * n),
+        ("joint_constraints_jacobian", lambda: model.joint_constraints_jacobian(Qk), n + mj * n),
+        ("holonomic_constraints_jacobian", lambda: model.holonomic_constraints_jacobian(Qk), n + m * n),
+    ]:
+        ms = timed(fn)
+        gbs = Bk * doubles * 8 / (ms * 1e-3) / 1e9
+        rows.append({"evaluator": name, "systems": Bk, "ms": ms, "algorithmic_bytes": Bk * doubles * 8, "GB_per_s": gbs, "frac_of_hbm_peak": gbs / hbm, "hbm_peak_GB_per_s": hbm})
         print(json.dumps(rows[-1]))
 
 

@@ -217,3 +217,25 @@ def test_joint_generalized_forces_behind_the_flag():
     for s in range(2):
         rq, rqd = om.rk4(Q[s], Qd[s], t, normalize=True, fext=fext)
         assert rel_err(np.concatenate([Qf[s], Qdf[s]]), np.concatenate([rq, rqd])) < TOL_TRAJ
+
+
+def test_force_table_does_not_reference_host_memory_after_the_call():
+    """The per-call force table is written to the device by a parameter-carrying kernel.  A call queued behind a long
+    kernel on a busy stream (where an asynchronous copy from pageable memory would read its source late) gives the
+    same bits as on an idle stream, and the force description may be dropped as soon as the call returns."""
+    name = "pendulum_force_batch"
+    case, model = load_case(name), _model(name)
+    B = 300_000
+    rng = np.random.default_rng(2)
+    idx = rng.integers(0, case["Q"].shape[0], B)
+    Q, Qd = torch.from_numpy(case["Q"][idx]).cuda(), torch.from_numpy(case["Qdot"][idx]).cuda()
+    fext = _fext(model, case)
+    ref = model.forward_dynamics(Q[:4096], Qd[:4096], external_forces=fext, pivoting="never")
+    torch.cuda.synchronize()
+    outs = []
+    for _ in range(3):
+        model.rk4(Q, Qd, h=1e-3, n_steps=300, external_forces=fext)  # tens of milliseconds of queued work
+        outs.append(model.forward_dynamics(Q[:4096], Qd[:4096], external_forces=_fext(model, case), pivoting="never"))
+    torch.cuda.synchronize()
+    for out in outs:
+        assert torch.equal(out[0], ref[0]) and torch.equal(out[1], ref[1])
