@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib", "libbionc_cuda.so")
+LIB_PATH = os.environ.get("BIONC_CUDA_LIB") or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib", "libbionc_cuda.so")
 
 # every symbol include/bionc_cuda.h declares (tests/test_c_abi.py checks the header against this list)
 SYMBOLS = (

@@ -11,7 +11,9 @@ SRC = os.path.join(ROOT, "csrc", "capi.cu")
 DEPS = [os.path.join(ROOT, "csrc", f) for f in ("capi.cu", "kernels.cuh", "dynamics.cuh", "model.cuh", "tmem.cuh")] + [
     os.path.join(os.path.dirname(ROOT), "include", "bionc_cuda.h")
 ]
-OUT = os.path.join(ROOT, "lib", "libbionc_cuda.so")
+# BIONC_LIB_SUFFIX builds an experimental variant next to the library (profiles/: occupancy sweeps); _lib.py loads
+# $BIONC_CUDA_LIB instead of the default when it is set
+OUT = os.path.join(ROOT, "lib", "libbionc_cuda%s.so" % os.environ.get("BIONC_LIB_SUFFIX", ""))
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

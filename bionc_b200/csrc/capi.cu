@@ -94,9 +94,14 @@ struct BioncModel {
     std::string device_err;
     unsigned char* d_blob = nullptr;
     int blob_bytes = 0;
-    // row maps of the Jacobian evaluator (row -> item * 8 + row inside the item): K_r (6N), K_j (mj, joint order), K_h (m)
-    std::vector<int> rowmap;
-    int* d_rowmap = nullptr;
+    // host-compiled sparse affine maps of the Jacobians K_r, K_j, K_h (compile_evaluators), freed at destroy
+    struct Jac {
+        int* ptr = nullptr;
+        int* off = nullptr;
+        double* coef = nullptr;
+        double* c0 = nullptr;
+        int E = 0;
+    } jac[3];
     int dev_smem_optin = 0, sm_smem = 0;
     LaunchPlan plan0;  // without external forces
     // host-path scratch
@@ -338,6 +343,16 @@ struct DeviceGuard {
         if (rc__ != BIONC_OK) return rc__;                                                      \
     }
 
+// resident CTAs per SM the launch bounds of a CTA-size class are sized for (MinCtas, tmem.cuh)
+int class_ctas(int threads) {
+    if (threads <= 32) return MinCtas<32>::value;
+    if (threads <= 64) return MinCtas<64>::value;
+    if (threads <= 96) return MinCtas<96>::value;
+    if (threads <= 128) return MinCtas<128>::value;
+    if (threads <= 256) return MinCtas<256>::value;
+    return 1;
+}
+
 // Systems per CTA and shared memory for a force table of `ftab_bytes` bytes behind the blob: 32 systems (every lane
 // busy) or 16 (upper half-warps mirror), whichever keeps more systems resident per SM.
 int make_plan(const BioncModel* M, int ftab_bytes, bool persys, LaunchPlan& plan) {
@@ -350,10 +365,170 @@ int make_plan(const BioncModel* M, int ftab_bytes, bool persys, LaunchPlan& plan
         int ctas = (int)((size_t)M->sm_smem / (bytes + 1024));  // 1 KB per CTA is reserved by the driver
         const int by_threads = 2048 / (32 * h.N);
         if (ctas > by_threads) ctas = by_threads;
-        if (ctas > 32) ctas = 32;
-        if (ctas * spc > best_resident) best_resident = ctas * spc, plan.spw = spc, plan.smem = bytes;
+        const int by_class = class_ctas(32 * h.N);  // registers and tensor-memory columns of the kernel's CTA-size class
+        if (ctas > by_class) ctas = by_class;
+        if (ctas * spc >= best_resident && ctas > 0) best_resident = ctas * spc, plan.spw = spc, plan.smem = bytes;  // ties: more CTAs, more warps
     }
     if (plan.spw == 0) return fail(BIONC_E_TOO_LARGE, "model needs more shared memory per CTA than one SM has");
+    return BIONC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host compilation of the Jacobian evaluator: every constraint row is  scale * sum_comp A(comp) B(comp) + c0  with two
+// linear forms over the coordinates (rigid row u.v - L cos g: A = u, B = rp - rd; point-to-point row: B = 1; D_p . D_c -
+// cos; |d|^2 - l^2; (P - A) . n - r), so every Jacobian entry is an affine function of the coordinates: the dense
+// (rows x 12N) matrix of a system is a constant sparse affine map of its coordinate vector (jacobian_kernel).
+// ---------------------------------------------------------------------------------------------
+struct HostForm {
+    std::vector<std::pair<int, double>> t;  // (offset of component 0, coefficient)
+    bool is_const = false;
+    double cst[3] = {0, 0, 0};
+};
+struct HostRow {
+    HostForm A, B;
+    bool b_one = false;
+    double scale = 1.0, c0 = 0.0;
+    int comp0 = 0, ncomp = 3;
+    const DevBlk* sop = nullptr;  // sphere-on-plane row: its Jacobian blocks are stored as the reference codes them
+};
+
+void add_lin(HostForm& f, int seg, const double* a, double sign) {
+    for (int t = 0; t < 4; ++t)
+        if (a[t] != 0.0) f.t.emplace_back(12 * seg + 3 * t, sign * a[t]);
+}
+
+// row `sub` of item `item` (segment: rigid-body rows; block: joint rows); bias = acceleration-bias row (forms of Qdot)
+HostRow make_row(const BioncModel* M, int item, int sub, bool bias) {
+    HostRow r;
+    const int N = M->hdr.N;
+    if (item < N) {
+        const int i = item;
+        static const int pa[6] = {0, 0, 0, 1, 1, 2}, pb[6] = {0, 1, 2, 1, 2, 2};
+        auto vec = [&](int k, HostForm& f) {
+            if (k == 0) f.t = {{12 * i, 1.0}};
+            else if (k == 1) f.t = {{12 * i + 3, 1.0}, {12 * i + 6, -1.0}};
+            else f.t = {{12 * i + 9, 1.0}};
+        };
+        vec(pa[sub], r.A), vec(pb[sub], r.B);
+        const double* pc = M->seg[i].phic;
+        const double cst[6] = {1.0, pc[0], pc[1], pc[2], pc[3], 1.0};
+        r.scale = bias ? 2.0 : 1.0, r.c0 = bias ? 0.0 : -cst[sub];
+        return r;
+    }
+    const DevBlk& b = M->blk[item - N];
+    const double* p = b.p;
+    if (b.type == LIN3) {
+        r.b_one = true, r.comp0 = sub, r.ncomp = 1;
+        if (!bias) {
+            if (b.parent >= 0) add_lin(r.A, b.parent, p, 1.0);
+            add_lin(r.A, b.child, p + 4, -1.0);
+            r.c0 = p[8 + sub];
+        }
+        return r;  // bias: a zero row
+    }
+    r.scale = bias ? 2.0 : 1.0;
+    if (b.type == DOT) {
+        if (b.parent >= 0) add_lin(r.A, b.parent, p, 1.0);
+        else if (!bias) r.A.is_const = true, r.A.cst[0] = p[0], r.A.cst[1] = p[1], r.A.cst[2] = p[2];
+        else r.scale = 0.0;  // a ground axis does not move
+        add_lin(r.B, b.child, p + 4, 1.0);
+        r.c0 = bias ? 0.0 : -p[8];
+    } else if (b.type == CLEN) {
+        add_lin(r.A, b.parent, p, 1.0), add_lin(r.A, b.child, p + 4, -1.0);
+        r.B = r.A;
+        r.c0 = bias ? 0.0 : -p[8];
+    } else {  // SOP
+        add_lin(r.A, b.parent, p, 1.0), add_lin(r.A, b.child, p + 4, -1.0);
+        add_lin(r.B, b.child, p + 8, 1.0);
+        r.c0 = bias ? 0.0 : -p[12];
+        r.sop = &b;
+    }
+    return r;
+}
+
+template <typename T>
+int upload(T*& dst, const std::vector<T>& v) {
+    dst = nullptr;
+    if (v.empty()) return BIONC_OK;
+    CUDA_TRY(cudaMalloc(&dst, v.size() * sizeof(T)));
+    CUDA_TRY(cudaMemcpy(dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return BIONC_OK;
+}
+
+int compile_evaluators(BioncModel* M) {
+    const int N = M->hdr.N, n = 12 * N, nblk = (int)M->blk.size(), mj = M->hdr.mj, m = M->hdr.m;
+    // (item, sub) of every row in the three row orders: rigid (6N), joint-index (mj), holonomic (m)
+    std::vector<std::pair<int, int>> ord[3];
+    ord[0].resize(6 * N), ord[1].resize(mj), ord[2].resize(m);
+    for (int i = 0; i < N; ++i)
+        for (int k = 0; k < 6; ++k) ord[0][6 * i + k] = {i, k}, ord[2][M->seg[i].rigid_row + k] = {i, k};
+    for (int b = 0; b < nblk; ++b) {
+        const int nr = M->blk[b].type == LIN3 ? 3 : 1;
+        for (int k = 0; k < nr; ++k) ord[1][M->blk[b].row_j + k] = {N + b, k}, ord[2][M->blk[b].row_h + k] = {N + b, k};
+    }
+    // ---- Jacobians: element (row, col) = c0 + sum coef * X[off]
+    for (int w = 0; w < 3; ++w) {
+        const auto& rows = ord[w];
+        const int E = (int)rows.size() * n;
+        std::vector<std::vector<std::pair<int, double>>> el(E);
+        std::vector<double> c0(E + 2, 0.0);
+        auto add = [&](int row, int col, int off, double coef) {
+            if (coef == 0.0) return;
+            auto& v = el[(size_t)row * n + col];
+            for (auto& t : v)
+                if (t.first == off) {
+                    t.second += coef;
+                    return;
+                }
+            v.emplace_back(off, coef);
+        };
+        for (int r = 0; r < (int)rows.size(); ++r) {
+            const HostRow hr = make_row(M, rows[r].first, rows[r].second, false);
+            if (hr.sop != nullptr) {  // joints.py:676-698 as coded: the two blocks swapped between parent and child columns
+                const DevBlk& b = *hr.sop;
+                const double* p = b.p;
+                for (int t = 0; t < 4; ++t)
+                    for (int comp = 0; comp < 3; ++comp) {
+                        const int colp = 12 * b.parent + 3 * t + comp, colc = 12 * b.child + 3 * t + comp;
+                        for (int u = 0; u < 4; ++u) {
+                            add(r, colp, 12 * b.child + 3 * u + comp, -p[4 + t] * p[8 + u]);   // -n^T N_A
+                            add(r, colp, 12 * b.parent + 3 * u + comp, p[8 + t] * p[u]);        // (P - A)^T N_n
+                            add(r, colp, 12 * b.child + 3 * u + comp, -p[8 + t] * p[4 + u]);
+                            add(r, colc, 12 * b.child + 3 * u + comp, p[t] * p[8 + u]);         // n^T N_P
+                        }
+                    }
+                continue;
+            }
+            for (int comp = hr.comp0; comp < hr.comp0 + hr.ncomp; ++comp) {
+                for (auto& ta : hr.A.t) {  // d/dX[offA + comp] = scale a B(comp)
+                    const int col = ta.first + comp;
+                    if (hr.b_one) c0[(size_t)r * n + col] += hr.scale * ta.second;
+                    else
+                        for (auto& tb : hr.B.t) add(r, col, tb.first + comp, hr.scale * ta.second * tb.second);
+                }
+                if (!hr.b_one)
+                    for (auto& tb : hr.B.t) {  // d/dX[offB + comp] = scale b A(comp)
+                        const int col = tb.first + comp;
+                        if (hr.A.is_const) c0[(size_t)r * n + col] += hr.scale * tb.second * hr.A.cst[comp];
+                        else
+                            for (auto& ta : hr.A.t) add(r, col, ta.first + comp, hr.scale * tb.second * ta.second);
+                    }
+            }
+        }
+        std::vector<int> ptr(E + 3, 0), off;
+        std::vector<double> coef;
+        for (int e = 0; e < E; ++e) {
+            for (auto& t : el[e]) off.push_back(t.first), coef.push_back(t.second);
+            ptr[e + 1] = (int)off.size();
+        }
+        ptr[E + 1] = ptr[E + 2] = ptr[E];
+        BioncModel::Jac& J = M->jac[w];
+        J.E = E;
+        int rc;
+        if ((rc = upload(J.ptr, ptr)) != BIONC_OK || (rc = upload(J.off, off)) != BIONC_OK || (rc = upload(J.coef, coef)) != BIONC_OK ||
+            (rc = upload(J.c0, c0)) != BIONC_OK)
+            return rc;
+    }
     return BIONC_OK;
 }
 
@@ -382,20 +557,8 @@ int build_blob(BioncModel* M) {
     CUDA_TRY(cudaMemcpy(M->d_blob, blob.data(), h.blob_bytes, cudaMemcpyHostToDevice));
     M->blob_bytes = h.blob_bytes;
     {
-        const int N = h.N, nblk = (int)M->blk.size();
-        std::vector<int>& rm = M->rowmap;
-        rm.assign((size_t)6 * N + h.mj + h.m, 0);
-        int* kr = rm.data();
-        int* kj = kr + 6 * N;
-        int* kh = kj + h.mj;
-        for (int i = 0; i < N; ++i)
-            for (int r = 0; r < 6; ++r) kr[6 * i + r] = i * 8 + r, kh[M->seg[i].rigid_row + r] = i * 8 + r;
-        for (int b = 0; b < nblk; ++b) {
-            const int nr = M->blk[b].type == LIN3 ? 3 : 1;
-            for (int r = 0; r < nr; ++r) kj[M->blk[b].row_j + r] = (N + b) * 8 + r, kh[M->blk[b].row_h + r] = (N + b) * 8 + r;
-        }
-        CUDA_TRY(cudaMalloc(&M->d_rowmap, rm.size() * sizeof(int)));
-        CUDA_TRY(cudaMemcpy(M->d_rowmap, rm.data(), rm.size() * sizeof(int), cudaMemcpyHostToDevice));
+        const int rc2 = compile_evaluators(M);
+        if (rc2 != BIONC_OK) return rc2;
     }
     return BIONC_OK;
 }
@@ -494,6 +657,8 @@ KernelSet pick_kernels(int path, int threads, int spc) {
     }
     // 16 systems per CTA (upper half-warps mirror the lower ones): models whose working set for 32 systems
     // would leave fewer systems resident per SM
+    if (threads <= 32) return BIONC_PICK(32, 16);
+    if (threads <= 64) return BIONC_PICK(64, 16);
     if (threads <= 128) return BIONC_PICK(128, 16);
     if (threads <= 256) return BIONC_PICK(256, 16);
     return BIONC_PICK(1024, 16);
@@ -616,8 +781,16 @@ int bionc_cuda_model_create(const BioncModelDesc* d, int device, BioncModel** ou
                 sd.lev[2] = -sgn * a[2] - sd.lev[0] * c[1];
                 sd.lev[3] = sgn * a[3] - sd.lev[0] * c[2];
             } else {
+                // the row's 6-vector (n, f_dir); f_dir = sigma d vanishes identically for rows made of directions only
+                // (sigma = a_rp + a_rd = 0: the rotation rows of hinge / universal joints), which then store n alone
+                bool has_f = false;
+                auto sigma_of = [](const double* a) { return a[1] + a[2]; };
+                if (B.type == DOT) has_f = sigma_of(sd.role == CHILD ? B.p + 4 : B.p) != 0.0;
+                else if (B.type == CLEN) has_f = true;
+                else has_f = sd.role == CHILD ? sigma_of(B.p) != 0.0 : (sigma_of(B.p + 4) != 0.0 || sigma_of(B.p + 8) != 0.0);
+                if (has_f) sd.ground |= 2;
                 sd.nl_slot = nl;
-                nl += (B.type == SOP && sd.role == PARENT) ? 6 : 3;  // d1 (and d2 for the two-term row kind)
+                nl += has_f ? 6 : 3;
             }
             M->side.push_back(sd);
         }
@@ -689,7 +862,7 @@ int bionc_cuda_model_destroy(BioncModel* M) {
     }
     DeviceGuard guard(M->device);
     cudaFree(M->d_blob);
-    cudaFree(M->d_rowmap);
+    for (auto& j : M->jac) cudaFree(j.ptr), cudaFree(j.off), cudaFree(j.coef), cudaFree(j.c0);
     cudaFree(M->d_markers);
     cudaFree(M->d_Q), cudaFree(M->d_Qd), cudaFree(M->d_Qdd), cudaFree(M->d_lam), cudaFree(M->d_inertia), cudaFree(M->d_h);
     cudaFree(M->d_status), cudaFree(M->d_fvals);
@@ -743,13 +916,17 @@ struct DynCall {
 
 // The single-evaluation kernel is persistent: as many CTAs as fit the device at once, each walking tiles of systems, so
 // the per-CTA set-up (model blob to shared memory) is paid once per CTA instead of once per 32 systems.
-static unsigned fd_grid(const BioncModel* M, const DynCall& call, int64_t B) {
-    const long long ntiles = (B + call.plan.spw - 1) / call.plan.spw;
+// grid of a persistent kernel: exactly the CTAs the device holds at once (a larger grid would run its surplus CTAs as a
+// second wave after the first has walked all its tiles), or fewer if there are fewer tiles
+static unsigned resident_grid(const BioncModel* M, const void* kernel, int threads, size_t smem, long long ntiles) {
     int per_sm = 0, sms = 148;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, call.ks.fd, 32 * M->hdr.N, call.plan.smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, M->device);
     const long long resident = (long long)per_sm * sms;
     return (unsigned)(ntiles < resident ? ntiles : resident);
+}
+static unsigned fd_grid(const BioncModel* M, const DynCall& call, int64_t B) {
+    return resident_grid(M, call.ks.fd, 32 * M->hdr.N, call.plan.smem, (B + call.plan.spw - 1) / call.plan.spw);
 }
 
 int bionc_cuda_forward_dynamics(const BioncModel* M, const double* Q, const double* Qd, const BioncDynOptions* opt,
@@ -914,42 +1091,31 @@ int bionc_cuda_eval(const BioncModel* M, int32_t which, const double* in, const 
         if (rc != BIONC_OK) return rc;
         fx.args.step_stride = (long long)B * fx.args.nf * 6;
     }
-    EvalArgs ea{which, N, M->hdr.nblk, mj, m};
-    const size_t budget = 65536;  // two input and two output images per CTA: several CTAs per SM keep copies and evaluation overlapped
-    if (cols == 1) {
-        // vectors: tile of T systems; T x rows is kept even so that every full tile is a 16-byte multiple for the bulk copies
-        long long T = (long long)(budget / (16 * (size_t)(n + rows)));
-        if (T > 64) T = 64;
-        if (T < 1) T = 1;
-        if ((rows & 1) && (T & 1) && T > 1) --T;
+    if (which == BIONC_EVAL_FEXT) {
+        // natural external forces: tile of T systems (T even: every full tile is a 16-byte multiple for the bulk copies)
+        EvalArgs ea{which, N, M->hdr.nblk, mj, m};
+        long long T = 65536 / (16LL * (n + rows));
+        T = T > 64 ? 64 : (T < 2 ? 2 : T & ~1LL);
         if (T > B) T = B;
         const size_t smem = 128 + 2 * (size_t)T * (n + rows) * sizeof(double);
         int rc = ensure_smem(M->device, (const void*)eval_vec_kernel, M->dev_smem_optin);
         if (rc != BIONC_OK) return rc;
-        int ctas = (int)((size_t)M->sm_smem / (smem + 1024));
-        ctas = ctas > 8 ? 8 : (ctas < 1 ? 1 : ctas);
-        const long long ntiles = (B + T - 1) / T;
-        long long grid = 148LL * ctas;
-        if (grid > ntiles) grid = ntiles;
-        eval_vec_kernel<<<(unsigned)grid, kEvalThreads, smem, st>>>(M->d_blob, fx.args, ea, in, out, (long long)B, (int)T, rows);
-    } else {
-        // Jacobians: tile of G consecutive rows of the (B rows) x n output; whole systems per tile when one fits the budget
-        const int* rowmap = M->d_rowmap + (which == BIONC_EVAL_K_R ? 0 : (which == BIONC_EVAL_K_J ? 6 * N : 6 * N + mj));
-        long long G = (long long)(budget / 4 / ((size_t)n * sizeof(double)));  // rows per output image of budget / 4 bytes
-        if (G < 1) G = 1;
-        if (G >= rows) G = G / rows * rows;
-        const long long grows = (long long)B * rows;
-        if (G > grows) G = grows;
-        const int in_systems = (int)((G + rows - 1) / rows) + 1;
-        const size_t smem = 128 + 2 * ((size_t)in_systems + (size_t)G) * n * sizeof(double);
-        int rc = ensure_smem(M->device, (const void*)eval_mat_kernel, M->dev_smem_optin);
+        const unsigned grid = resident_grid(M, (const void*)eval_vec_kernel, kEvalThreads, smem, (B + T - 1) / T);
+        eval_vec_kernel<<<grid, kEvalThreads, smem, st>>>(M->d_blob, fx.args, ea, in, out, (long long)B, (int)T, rows);
+    } else if (cols == 1) {
+        // constraint vectors: 32 systems per tile, lane = system, one item per instruction stream
+        EvalArgs ea{which, N, M->hdr.nblk, mj, m};
+        const size_t smem = ((size_t)kItemSystems * (n + 1) + (size_t)kItemSystems * (rows | 1)) * sizeof(double);
+        if (smem > (size_t)M->dev_smem_optin) return fail(BIONC_E_TOO_LARGE, "model too large for the constraint evaluator tile");
+        int rc = ensure_smem(M->device, (const void*)items_kernel, M->dev_smem_optin);
         if (rc != BIONC_OK) return rc;
-        int ctas = (int)((size_t)M->sm_smem / (smem + 1024));
-        ctas = ctas > 8 ? 8 : (ctas < 1 ? 1 : ctas);
-        const long long ntiles = (grows + G - 1) / G;
-        long long grid = 148LL * ctas;
-        if (grid > ntiles) grid = ntiles;
-        eval_mat_kernel<<<(unsigned)grid, kEvalThreads, smem, st>>>(M->d_blob, rowmap, ea, in, out, (long long)B, (int)G, rows, in_systems);
+        const unsigned grid = resident_grid(M, (const void*)items_kernel, kItemThreads, smem, (B + kItemSystems - 1) / kItemSystems);
+        items_kernel<<<grid, kItemThreads, smem, st>>>(M->d_blob, ea, rows, in, out, (long long)B);
+    } else {
+        const BioncModel::Jac& J = M->jac[which == BIONC_EVAL_K_R ? 0 : (which == BIONC_EVAL_K_J ? 1 : 2)];
+        const size_t smem = (size_t)kJacSystems * n * sizeof(double);
+        const unsigned grid = resident_grid(M, (const void*)jacobian_kernel, kJacThreads, smem, (B + kJacSystems - 1) / kJacSystems);
+        jacobian_kernel<<<grid, kJacThreads, smem, st>>>(J.ptr, J.off, J.coef, J.c0, J.E, n, in, out, (long long)B);
     }
     g_launches++;
     CUDA_TRY(cudaGetLastError());

@@ -40,7 +40,7 @@
 //   S0, S1   : 9 nslot x 32, 9 nslot2 x 32   stored 3x3 blocks of the joint-level Schur matrix; a block that
 //              two segments contribute to has a second copy written by the PARENT-role warp -> no atomics
 //   r0, r1, lamv, dinv : 3 nb, 3 nb, 3 nb, 6 nb (x 32)   rhs (child / parent copies), y-hat -> lambda_j, pivots
-//   knl      : N x rnl x 32   state-dependent vectors of the non-LIN3 rows (3 or 6 doubles per row and segment)
+//   knl      : N x rnl x 32   the 6-vector (n, f_dir) of every non-LIN3 row touching the segment (6 doubles per row)
 #pragma once
 #include "model.cuh"
 #include "tmem.cuh"
@@ -292,11 +292,15 @@ __device__ __forceinline__ void nonlin_row(const WarpCtx& w, const DevBlk& b, in
 // the stored state-dependent vectors of a non-LIN3 row of this lane: d1 at offset q (in doubles), d2 behind
 // it for the only two-term row kind (sphere-on-plane, parent side)
 __device__ __forceinline__ bool nonlin_two_terms(const DevBlk& b, int role) { return b.type == SOP && role == PARENT; }
+// the 12-vector of a non-LIN3 row restricted to this lane's segment, rebuilt from the published state (multiplier
+// output path only: the hot path keeps the row's 6-vector instead, load_row6)
 template <int S>
-__device__ __forceinline__ Q12 load_nonlin_k(const WarpCtx& w, const DevBlk& b, int role, int q) {
-    const double* src = w.knl + q * S;
-    const V3 d1 = mk(src[0], src[S], src[2 * S]);
-    const V3 d2 = nonlin_two_terms(b, role) ? mk(src[3 * S], src[4 * S], src[5 * S]) : mk(0.0, 0.0, 0.0);
+__device__ __forceinline__ Q12 rebuild_nonlin_k(const WarpCtx& w, const DevBlk& b, int role) {
+    V3 d1, d2;
+    double bterm;
+    DynOpts none;
+    none.use_stab = 0, none.poison = 0, none.alpha = 0.0, none.beta = 0.0;
+    nonlin_row<S>(w, b, role, none, d1, d2, bterm);
     return nonlin_k(b, role, d1, d2);
 }
 
@@ -537,12 +541,14 @@ __device__ __forceinline__ Row6 nonlin_row6(const SegCtx& c, const DevBlk& b, in
     }
     return r;
 }
-template <bool KAP, int S>
-__device__ __forceinline__ Row6 load_row6(const WarpCtx& w, const SegCtx& c, const DevBlk& b, int role, int q) {
-    const double* src = w.knl + q * S;
-    const V3 d1 = mk(src[0], src[S], src[2 * S]);
-    const V3 d2 = nonlin_two_terms(b, role) ? mk(src[3 * S], src[4 * S], src[5 * S]) : mk(0.0, 0.0, 0.0);
-    return nonlin_row6<KAP>(c, b, role, d1, d2);
+// the stored 6-vector of a non-LIN3 row of this lane (written in phase D)
+template <int S>
+__device__ __forceinline__ Row6 load_row6(const WarpCtx& w, const DevSide& sd) {
+    const double* src = w.knl + sd.nl_slot * S;
+    Row6 r;
+    r.n = mk(src[0], src[S], src[2 * S]), r.kap = 0.0;
+    r.f = (sd.ground & 2) ? mk(src[3 * S], src[4 * S], src[5 * S]) : mk(0.0, 0.0, 0.0);  // rows of directions only: f_dir = 0
+    return r;
 }
 
 // Ic^-1 (rho x e_c), c = 0..2: the three columns of Ic^-1 [rho]x^T a point-to-point side needs for its pair blocks
@@ -727,7 +733,7 @@ __device__ __forceinline__ void rigid_multipliers(const WarpCtx& w, const SegCtx
             const V3 lam = mk(lj[0], lj[spw], lj[2 * spw]);
             Ru = axpy(-as[0], lam, Ru), Rr = axpy(-as[1], lam, Rr), Rw = axpy(-as[3], lam, Rw);
         } else {
-            const Q12 k = load_nonlin_k<S>(w, b, sd.role, sd.nl_slot);
+            const Q12 k = rebuild_nonlin_k<S>(w, b, sd.role);
             Ru = axpy(-lj[0], k.s[0], Ru), Rr = axpy(-lj[0], k.s[1], Rr), Rw = axpy(-lj[0], k.s[3], Rw);
         }
     }
@@ -815,7 +821,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                     r = axpy(o.alpha, phi, axpy(o.beta, kqd, r));
                 }
                 rr[0] = r.x, rr[spw] = r.y, rr[2 * spw] = r.z;
-                if (sd.ground) {  // no parent lane: the child also settles the second copy
+                if (sd.ground & 1) {  // no parent lane: the child also settles the second copy
                     double* r1p = w.r1 + sd.lam_off * spw;
                     r1p[0] = 0.0, r1p[spw] = 0.0, r1p[2 * spw] = 0.0;
                 }
@@ -824,17 +830,20 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                 double bterm;
                 nonlin_row<S>(w, b, sd.role, o, d1, d2, bterm);
                 const Row6 r6 = nonlin_row6<true>(c, b, sd.role, d1, d2);
-                double* dst = w.knl + sd.nl_slot * S;
-                dst[0] = d1.x, dst[S] = d1.y, dst[2 * S] = d1.z;
-                if (nonlin_two_terms(b, sd.role)) dst[3 * S] = d2.x, dst[4 * S] = d2.y, dst[5 * S] = d2.z;
+                double* dst = w.knl + sd.nl_slot * S;  // the row's 6-vector stays for the pair products and the back-substitution
+                dst[0] = r6.n.x, dst[S] = r6.n.y, dst[2 * S] = r6.n.z;
+                if (sd.ground & 2) dst[3 * S] = r6.f.x, dst[4 * S] = r6.f.y, dst[5 * S] = r6.f.z;
                 rr[0] = dot(r6.n, afree) + dot(r6.f, tfree) + r6.kap + bterm;
-                if (sd.ground) w.r1[sd.lam_off * spw] = 0.0;
+                if (sd.ground & 1) w.r1[sd.lam_off * spw] = 0.0;
             }
         }
 
         if (PARKA) {  // A is not needed again before phase I
             const double a9[9] = {c.Au.x, c.Au.y, c.Au.z, c.Av.x, c.Av.y, c.Av.z, c.Aw.x, c.Aw.y, c.Aw.z};
             tmem_put(tmA, a9);
+#ifdef BIONC_WAITST_EARLY
+            tmem_stores_done();
+#endif
         }
 
         // ---- E. this segment's contribution to S':  S'_ab = fdir_a . fdir_b / m + n_a . Ic^-1 n_b
@@ -879,7 +888,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                 }
             } else {
                 // single row b against every point-to-point side and against the single rows a >= b
-                const Row6 rb6 = load_row6<false, S>(w, c, b, sd.role, sd.nl_slot);
+                const Row6 rb6 = load_row6<S>(w, sd);
                 const V3 yb = sym3_apply(c.Ii, rb6.n), fbm = minv * rb6.f;
                 const int Ib = sd.node, rb = sd.lam_off - 3 * Ib;
                 for (int e2 = sg.side_begin; e2 < sg.side_end; ++e2) {
@@ -901,7 +910,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                             Sc[0] = r.x, Sc[spw] = r.y, Sc[2 * spw] = r.z;
                         }
                     } else if (e2 >= e) {  // every pair of single rows once
-                        const Row6 ra6 = load_row6<false, S>(w, c, a, sa.role, sa.nl_slot);
+                        const Row6 ra6 = load_row6<S>(w, sa);
                         const double acc = dot(ra6.f, fbm) + dot(ra6.n, yb);
                         const int Ia = sa.node, ra = sa.lam_off - 3 * Ia;
                         // the larger ROW decides the block orientation and whose role picks the copy
@@ -962,7 +971,11 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
         __syncthreads();
 
         TmemWords<18> parked;
+#ifdef BIONC_WAITST_EARLY
+        if (PARKA) tmem_issue(tmA, parked);  // back while phase H runs
+#else
         if (PARKA) tmem_stores_done(), tmem_issue(tmA, parked);  // back while phase H runs
+#endif
 
         // ---- H. joint forces on this segment:  F -= sum fdir lambda,  tau -= sum n lambda
         for (int e = sg.side_begin; e < sg.side_end; ++e) {
@@ -978,7 +991,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                 }
             } else {
                 const double lam = lj[0];
-                const Row6 r6 = load_row6<false, S>(w, c, w.blk[sd.blk], sd.role, sd.nl_slot);
+                const Row6 r6 = load_row6<S>(w, sd);
                 F = axpy(-lam, r6.f, F);
                 tau = axpy(-lam, r6.n, tau);
                 if (LAM && lam_out != nullptr && sd.role == CHILD) lam_out[sd.row_h] = lam;

@@ -127,8 +127,19 @@ __device__ __forceinline__ void load_constants(WarpCtx& w, const double* __restr
 // ---------------------------------------------------------------------------------------------
 // forward_dynamics(Q, Qdot) -> Qddot, lambda       (biomechanical_model.py:351-429, batched)
 // ---------------------------------------------------------------------------------------------
+// The single evaluation carries no integrator state but has the multiplier output path: its register budget is set
+// separately from the fused integrator's.
+template <int MAXT>
+struct FdMinCtas {
+#ifdef BIONC_EXP_FD128
+    static constexpr int value = (MAXT > 64 && MAXT <= 128) ? BIONC_EXP_FD128 : MinCtas<MAXT>::value;
+#else
+    static constexpr int value = MinCtas<MAXT>::value;
+#endif
+};
+
 template <bool GENERAL, bool STAB, int MAXT, int S>
-__global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
+__global__ void __launch_bounds__(MAXT, FdMinCtas<MAXT>::value)
     forward_dynamics_kernel(const unsigned char* __restrict__ blob, int blob_bytes, FextArgs fx, const double* __restrict__ Q,
                             const double* __restrict__ Qd, const double* __restrict__ inertia, DynOpts o,
                             double* __restrict__ Qdd, double* __restrict__ lam, int* __restrict__ status_out,
@@ -150,6 +161,16 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
             Q12 q, qd;
             load_q12(Q + (size_t)gsys * n + 12 * w.segi, q);
             load_q12(Qd + (size_t)gsys * n + 12 * w.segi, qd);
+            // the tile this CTA takes next: into L2 while this one is evaluated (its loads then wait for L2, not for HBM)
+            const long long nsys = (tile + gridDim.x) * S + w.lane;
+            if (nsys < B) {
+                const double* nq = Q + (size_t)nsys * n + 12 * w.segi;
+                const double* nqd = Qd + (size_t)nsys * n + 12 * w.segi;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nq));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nq + 11));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nqd));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nqd + 11));
+            }
 #pragma unroll
             for (int t = 0; t < 4; ++t) publish3<S>(w.Qo, t, q.s[t]), publish3<S>(w.Qdo, t, qd.s[t]);
         }
@@ -164,6 +185,13 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
         __syncthreads();  // the next tile overwrites what slower warps may still read (lambda_j, row vectors, published state)
     }
 }
+
+#ifndef BIONC_PARKA
+#define BIONC_PARKA 1  // particular accelerations parked in tensor memory during the joint-level phases (experiment switch)
+#endif
+#ifndef BIONC_EPI_WAIT_LATE
+#define BIONC_EPI_WAIT_LATE 0  // tcgen05.wait::st of the accumulator stores just before they are read again instead of right after them
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // RK4 with the forward-dynamics closure fused in (utils/ode_solver.py:8-53, :107-120).
@@ -227,7 +255,7 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
         for (int stage = 0; stage < 4; ++stage) {
             // k_stage = f(stage state): (stage velocity, Qddot)
             Q12 a;
-            eval_forward_dynamics<GENERAL, STAB, false, TM == 2, S>(w, c, o, a, nullptr, status, tm + 96);
+            eval_forward_dynamics<GENERAL, STAB, false, (TM == 2) && BIONC_PARKA, S>(w, c, o, a, nullptr, status, tm + 96);
             const double wt = (stage == 0 || stage == 3) ? 1.0 : 2.0;
             const double cn = (stage == 2) ? h : 0.5 * h;  // next stage is y0 + cn * k_stage
             // other segments' published state is only read before the barriers inside the evaluation: no barrier here
@@ -235,6 +263,7 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
                 // y0 and the accumulators come back from tensor memory one half at a time (Q, then Qdot: 48 registers in
                 // flight); the last stage turns its half into the new y0 at once instead of writing the accumulator back
                 TmemWords<24> ty, ta;
+                if (BIONC_EPI_WAIT_LATE) tmem_stores_done();
                 tmem_issue(tm, ty), tmem_issue(tm + 48, ta);
                 tmem_wait(ty, y0q), tmem_wait(ta, accq);
                 if (stage < 3) {
@@ -257,7 +286,8 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
                         accv.s[t] = axpy(wt, a.s[t], accv.s[t]);
                         publish3<S>(w.Qdo, t, axpy(cn, a.s[t], y0v.s[t]));
                     }
-                    tmem_put(tm + 72, accv), tmem_stores_done();
+                    tmem_put(tm + 72, accv);
+                    if (!BIONC_EPI_WAIT_LATE) tmem_stores_done();
                 } else {
 #pragma unroll
                     for (int t = 0; t < 4; ++t) y0v.s[t] = axpy(h6, a.s[t] + accv.s[t], y0v.s[t]);
@@ -511,12 +541,8 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 //   3. one bulk copy streams the image (contiguous in global memory) out while the next tile is computed in the other
 //      buffer.
 // DRAM traffic = input once + output once = the algorithmic bytes; no memset, no read-modify-write on global memory.
-//   eval_vec_kernel: vector outputs (Phi_r, Phi_j, Phi_h, bias, f_ext); tile = T systems, unit = (system, item).
-//   eval_mat_kernel: Jacobians (K_r, K_j, K_h); tile = G consecutive rows of the (B rows) x 12N output, whatever system
-//                    they belong to (one row is 96 N bytes: any tile is a 16-byte multiple and any model fits), unit = one
-//                    row, found through the host-built row map (row -> item, row inside the item).  Every structural
-//                    non-zero is written exactly once (put_row); when a tile holds whole systems the image keeps its
-//                    zero background from tile to tile, otherwise it is cleared per tile.
+//   eval_vec_kernel: natural external forces (f_ext); tile = T systems, unit = (system, segment).  The constraint
+//                    vectors and Jacobians have their own table-driven kernels below.
 // ---------------------------------------------------------------------------------------------
 constexpr int kEvalThreads = 128;
 
@@ -590,64 +616,106 @@ __global__ void __launch_bounds__(kEvalThreads, 4)
     if (tid == 0) bulk_wait_all();
 }
 
-__global__ void __launch_bounds__(kEvalThreads, 4)
-    eval_mat_kernel(const unsigned char* __restrict__ blob, const int* __restrict__ rowmap, EvalArgs ea, const double* __restrict__ in,
-                    double* __restrict__ out, long long B, int G, int rows, int in_systems) {
-    extern __shared__ __align__(128) unsigned char sm[];
+// ---------------------------------------------------------------------------------------------
+// Constraint vectors: Phi_r, Phi_j, Phi_h, acceleration bias.  LANE = SYSTEM, one ITEM (segment or constraint block) per
+// instruction stream: a CTA takes tiles of 32 consecutive systems, stages their coordinates in shared memory with an odd
+// row stride (coalesced 16-byte loads in, conflict-free reads by lane = system); warp w evaluates items w, w + 4, ... for
+// its 32 systems -- the item's table entry is one broadcast read, no lane diverges, a segment's twelve coordinates serve
+// its six rigid rows -- into a shared-memory image [system][row | 1], and the image (contiguous in global memory) leaves
+// with coalesced stores.  (A first version evaluated every ROW as a product of two generic linear forms from a
+// host-compiled table: 48 shared-memory loads per row, LSU-bound at 0.12 of the HBM peak.)
+// ---------------------------------------------------------------------------------------------
+constexpr int kItemThreads = 128, kItemSystems = 32;
+
+__global__ void __launch_bounds__(kItemThreads, 4)
+    items_kernel(const unsigned char* __restrict__ blob, EvalArgs ea, int rows, const double* __restrict__ in, double* __restrict__ out, long long B) {
+    extern __shared__ __align__(16) double fsm[];
     const DevHeader* h = reinterpret_cast<const DevHeader*>(blob);
     const DevSeg* seg = reinterpret_cast<const DevSeg*>(blob + h->off_seg);
     const DevBlk* blk = reinterpret_cast<const DevBlk*>(blob + h->off_blk);
-    const int n = 12 * ea.N, which = ea.which, tid = threadIdx.x;
-    const TilePipe p = tile_pipe(sm, (size_t)in_systems * n, (size_t)G * n);
-    const long long grows = B * rows, ntiles = (grows + G - 1) / G;
-    const bool whole = (G % rows) == 0;  // tiles hold whole systems: the non-zero pattern of the image never changes
-    {
-        double2* z = reinterpret_cast<double2*>(p.out_tile[0]);
-        for (int i = tid; i < G * n; i += kEvalThreads) z[i] = make_double2(0.0, 0.0);  // both images: 2 G n doubles
-    }
-    __syncthreads();
-    // systems a tile needs: those of its first and last row
-    auto first_sys = [&](long long tile) { return tile * G / rows; };
-    auto last_sys = [&](long long tile) { const long long e = (tile + 1) * G < grows ? (tile + 1) * G : grows; return (e - 1) / rows; };
-    long long tile = blockIdx.x;
-    if (tid == 0 && tile < ntiles) {
-        const unsigned bytes = (unsigned)(last_sys(tile) - first_sys(tile) + 1) * n * 8u;
-        mbar_expect_tx(p.bar, bytes);
-        bulk_load(p.in_tile[0], in + (size_t)first_sys(tile) * n, bytes, p.bar);
-    }
+    const int n = 12 * ea.N, nitem = ea.N + ea.nblk;
+    const int ldx = n + 1, ldo = rows | 1, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double* Xs = fsm;                          // [32][n + 1]
+    double* Os = fsm + kItemSystems * ldx;     // [32][rows | 1]
     const FextView nofx{nullptr, nullptr, nullptr};
-    for (int k = 0; tile < ntiles; tile += gridDim.x, ++k) {
-        const int buf = k & 1;
-        const long long g0 = tile * G, s0 = first_sys(tile), next = tile + gridDim.x;
-        const int ng = (int)(grows - g0 < G ? grows - g0 : G);
-        if (tid == 0) {
-            if (next < ntiles) {
-                const unsigned bytes = (unsigned)(last_sys(next) - first_sys(next) + 1) * n * 8u;
-                mbar_expect_tx(p.bar + (buf ^ 1), bytes);
-                bulk_load(p.in_tile[buf ^ 1], in + (size_t)first_sys(next) * n, bytes, p.bar + (buf ^ 1));
+    const long long ntiles = (B + kItemSystems - 1) / kItemSystems;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long s0 = tile * kItemSystems;
+        const int ns = (int)(B - s0 < kItemSystems ? B - s0 : kItemSystems);
+        {   // ns * n contiguous doubles; n is a multiple of 12, the tile starts 16-byte aligned
+            const double2* src = reinterpret_cast<const double2*>(in + (size_t)s0 * n);
+            for (int i = tid; i < ns * n / 2; i += kItemThreads) {
+                const double2 v = src[i];
+                const int e = 2 * i, sy = e / n, k = e - sy * n;
+                Xs[sy * ldx + k] = v.x, Xs[sy * ldx + k + 1] = v.y;
             }
-            bulk_wait_read<1>();
         }
-        mbar_wait(p.bar + buf, (k >> 1) & 1);
         __syncthreads();
-        double* O0 = p.out_tile[buf];
-        if (!whole && k >= 2) {  // the image still holds the rows of iteration k - 2: clear it (the first two are clean)
-            double2* z = reinterpret_cast<double2*>(O0);
-            for (int i = tid; i < G * n / 2; i += kEvalThreads) z[i] = make_double2(0.0, 0.0);
-            __syncthreads();
-        }
-        for (int idx = tid; idx < ng; idx += kEvalThreads) {
-            const long long g = g0 + idx, sys = g / rows;
-            const int r = (int)(g - sys * rows), code = rowmap[r];
-            // eval_item addresses the matrix of one system: its row 0 sits (sys rows - g0) rows from the image's start
-            double* K = O0 + (sys * rows - g0) * n;
-            eval_item(seg, blk, nofx, ea, which, code >> 3, p.in_tile[buf] + (size_t)(sys - s0) * n, nullptr, K, n, code & 7);
-        }
-        fence_async_smem();
+        const double* X = Xs + (lane < ns ? lane : 0) * ldx;
+        double* o = Os + lane * ldo;
+        for (int item = wid; item < nitem; item += kItemThreads / 32) eval_item(seg, blk, nofx, ea, ea.which, item, X, o, nullptr, 0);
         __syncthreads();
-        if (tid == 0) bulk_store(out + (size_t)g0 * n, O0, (unsigned)((size_t)ng * n * 8));
+        double* dst = out + (size_t)s0 * rows;
+        for (int i = tid; i < ns * rows; i += kItemThreads) {
+            const int sy = i / rows, r = i - sy * rows;
+            dst[i] = Os[sy * ldo + r];
+        }
+        __syncthreads();
     }
-    if (tid == 0) bulk_wait_all();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Jacobians K_r, K_j, K_h.  Every entry of a constraint Jacobian of these models is an affine function of the
+// coordinates (the constraints are at most quadratic), so the dense (rows x 12N) matrix of one system is a constant
+// sparse affine map of its coordinate vector, compiled once per model on the host: element e = c0[e] + sum_j coef[j]
+// X[off[j]], j in ptr[e] .. ptr[e+1] (most elements have no term: structural zeros).  A CTA stages KS systems'
+// coordinates in shared memory; a thread owns element PAIRS (e, e + 1) and keeps KS accumulators per element, so the
+// element's terms are read once per tile, and for a fixed system consecutive threads store consecutive 16-byte pairs:
+// the B x rows x 12N doubles go to HBM exactly once in full coalesced bursts, with no zero fill and no scatter.
+// ---------------------------------------------------------------------------------------------
+constexpr int kJacThreads = 256, kJacSystems = 8;
+
+__global__ void __launch_bounds__(kJacThreads, 4)
+    jacobian_kernel(const int* __restrict__ ptr, const int* __restrict__ off, const double* __restrict__ coef, const double* __restrict__ c0,
+                    int E, int n, const double* __restrict__ in, double* __restrict__ out, long long B) {
+    extern __shared__ __align__(16) double jsm[];  // [KS][n]
+    const int tid = threadIdx.x;
+    const long long ntiles = (B + kJacSystems - 1) / kJacSystems;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long s0 = tile * kJacSystems;
+        const int ns = (int)(B - s0 < kJacSystems ? B - s0 : kJacSystems);
+        {
+            const double2* src = reinterpret_cast<const double2*>(in + (size_t)s0 * n);
+            double2* dst = reinterpret_cast<double2*>(jsm);
+            for (int i = tid; i < ns * n / 2; i += kJacThreads) dst[i] = src[i];
+            for (int i = ns * n / 2 + tid; i < kJacSystems * n / 2; i += kJacThreads) dst[i] = make_double2(0.0, 0.0);  // tail tile
+        }
+        __syncthreads();
+        for (int e = 2 * tid; e < E; e += 2 * kJacThreads) {
+            double a0[kJacSystems], a1[kJacSystems];
+            const double k0 = c0[e], k1 = c0[e + 1];
+#pragma unroll
+            for (int s = 0; s < kJacSystems; ++s) a0[s] = k0, a1[s] = k1;
+            const int p0 = ptr[e], p1 = ptr[e + 1], p2 = ptr[e + 2];
+            for (int j = p0; j < p1; ++j) {
+                const double c = coef[j];
+                const double* x = jsm + off[j];
+#pragma unroll
+                for (int s = 0; s < kJacSystems; ++s) a0[s] = fma(c, x[s * n], a0[s]);
+            }
+            for (int j = p1; j < p2; ++j) {
+                const double c = coef[j];
+                const double* x = jsm + off[j];
+#pragma unroll
+                for (int s = 0; s < kJacSystems; ++s) a1[s] = fma(c, x[s * n], a1[s]);
+            }
+            double* o = out + (size_t)s0 * E + e;
+#pragma unroll
+            for (int s = 0; s < kJacSystems; ++s)
+                if (s < ns) *reinterpret_cast<double2*>(o + (size_t)s * E) = make_double2(a0[s], a1[s]);
+        }
+        __syncthreads();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -26,7 +26,7 @@ struct DevHeader {
     int nb;       // 3x3 block rows ("nodes") of the joint-level Schur system (mj padded up to a multiple of 3)
     int m;        // holonomic rows = mj + 6 N
     int spw;      // systems per CTA without external forces: 32 (one lane per system), or 16 when the working set of 32 does not fit
-    int rnl;      // doubles of shared memory per lane for the d-vectors of the non-LIN3 rows touching a segment
+    int rnl;      // doubles of shared memory per lane for the 6-vectors of the non-LIN3 rows touching a segment
     int pad0;
     int blob_bytes;
     int off_seg, off_blk, off_side, pad1;  // byte offsets inside the blob
@@ -70,12 +70,13 @@ struct DevBlk {
 struct DevSide {
     int blk;
     int role;      // CHILD / PARENT
-    int nl_slot;   // offset (in doubles) of the row's d-vectors in the lane's storage, -1 for LIN3
+    int nl_slot;   // offset (in doubles) of the row's 6-vector in the lane's storage, -1 for LIN3
     int node;      // 3x3 node of the joint-level system holding the block's first row (jrow / 3)
     int rhs_off;   // row of this side's copy of the right-hand side inside [r0 | r1]: jrow (+ 3 nb for the parent copy)
     int lam_off;   // jrow: first row of the block in lambda_j
     int row_h;     // first row, holonomic order
-    int ground;    // the block has no parent segment: the child also settles the second copy of the right-hand side
+    int ground;    // bit 0: the block has no parent segment (the child also settles the second copy of the right-hand side);
+                   // bit 1: non-LIN3 row whose force direction f_dir is not identically zero (6 stored doubles instead of 3)
     // point-to-point (LIN3) sides: the signed coefficient vector as seen from the centre of mass of the MODEL's inertial
     // parameters, lev = (sigma, r[3]), sigma = a_rp + a_rd, r = (a_u, -a_rd, a_w) - sigma c (see Lever, dynamics.cuh)
     double lev[4];

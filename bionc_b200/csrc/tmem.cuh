@@ -5,16 +5,25 @@
 namespace bionc {
 
 // Kernels are instantiated per CTA-size class (threads = 32 x segments); the register budget follows from
-// __launch_bounds__(MAXT, MinCtas<MAXT>): up to 64 threads -> 255 registers (shared memory limits residency
-// long before registers do), 96 threads x 4 CTAs -> 168 registers, 128 threads x 4 CTAs -> 128 registers (barrier waits want resident CTAs more
-// than registers), 256 x 2 -> 128, 384 x 1 -> 168, 512 x 1 -> 128, 1024 x 1 -> 64.
+// __launch_bounds__(MAXT, MinCtas<MAXT>): residency is what hides the latency of the dependent 3x3 chains and of the block
+// barriers: 128 threads x 4 CTAs, 256 x 2 and 512 x 1 run 16 warps per SM at 128 registers per thread and the tensor-
+// memory parking below takes what no longer fits the registers.  One- and two-segment models (32 / 64 threads) are
+// limited by shared memory to fewer CTAs than that anyway and keep 255 registers (measured: pendulum 1.12e9 system-steps/s
+// at 255 registers against 8.4e8 at 128; knee 1.9e8 with 32 systems per CTA at 255 registers against 1.2e8 with 16
+// systems per CTA at 128); 96 x 4 and 384 x 1 get 168 registers, 1024 x 1 gets 64.
 template <int MAXT>
 struct MinCtas {
-#ifdef BIONC_EXP_MINCTAS128
-    static constexpr int value = MAXT <= 32 ? 8 : (MAXT <= 64 ? 4 : (MAXT <= 128 ? BIONC_EXP_MINCTAS128 : (MAXT <= 256 ? 2 : 1)));
+#ifdef BIONC_EXP_MINCTAS32
+    static constexpr int c32 = BIONC_EXP_MINCTAS32;
 #else
-    static constexpr int value = MAXT <= 32 ? 8 : (MAXT <= 64 ? 4 : (MAXT <= 128 ? 4 : (MAXT <= 256 ? 2 : 1)));
+    static constexpr int c32 = 8;
 #endif
+#ifdef BIONC_EXP_MINCTAS64
+    static constexpr int c64 = BIONC_EXP_MINCTAS64;
+#else
+    static constexpr int c64 = 4;
+#endif
+    static constexpr int value = MAXT <= 32 ? c32 : (MAXT <= 64 ? c64 : (MAXT <= 128 ? 4 : (MAXT <= 256 ? 2 : 1)));
 };
 
 // ---- tensor memory as per-thread parking space ------------------------------------------------------
@@ -33,9 +42,10 @@ struct TmemPark {
     static constexpr int words_full = 114, words_y0 = 48;
     static constexpr int budget = 512 / MinCtas<MAXT>::value;  // columns one CTA may take
     static constexpr int pow2(int need) { return need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : (need <= 256 ? 256 : 512))); }
-    // level 2: y0, accumulator and A; level 1: y0 only (CTAs too large for the full set); level 0: nothing (small
-    // CTAs run at 255 registers and need no parking)
-    static constexpr int level = MAXT < 96 ? 0 : (pow2(words_full * groups) <= budget ? 2 : (pow2(words_y0 * groups) <= budget ? 1 : 0));
+    // level 2: y0, accumulator and A; level 1: y0 only (the full set does not fit the CTA's share of the columns);
+    // level 0: nothing (classes that run at 255 registers per thread need no parking; neither set fits)
+    static constexpr int regs = 65536 / (MAXT * MinCtas<MAXT>::value);
+    static constexpr int level = regs > 200 ? 0 : (pow2(words_full * groups) <= budget ? 2 : (pow2(words_y0 * groups) <= budget ? 1 : 0));
     static constexpr int words = level == 2 ? words_full : words_y0;  // per thread
     static constexpr int cols = pow2(words * groups);
 };

@@ -56,12 +56,17 @@ def main():
         # the single-evaluation kernel behind the Python-level RK4 closure: Q, Qdot in; Qddot, lambda, status out
         ("forward_dynamics (one evaluation, pivoting='never')", lambda: model.forward_dynamics(Qt, Qdt, pivoting="never"), 3 * n + m + 0.5),
     ]
+    only = os.environ.get("POST_SWEEP_ONLY")
+    if only:
+        cases = [c for c in cases if only in c[0]]
     for name, fn, doubles in cases:
         ms = timed(fn)
         gbs = B * doubles * 8 / (ms * 1e-3) / 1e9
         rows.append({"evaluator": name, "systems": B, "ms": ms, "algorithmic_bytes": B * doubles * 8, "GB_per_s": gbs, "frac_of_hbm_peak": gbs / hbm, "hbm_peak_GB_per_s": hbm})
         print(json.dumps(rows[-1]))
     # the Jacobians are dense (B, rows, 12N) outputs: 1e5 systems are 1.3 GB for K_h, ten times the L2
+    if only:
+        return
     Bk = min(B, 100_000)
     Qk = Qt[:Bk].contiguous()
     for name, fn, doubles in [

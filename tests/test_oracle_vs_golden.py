@@ -1,12 +1,14 @@
 """Pin the CPU oracle (oracle/bionc_oracle.py) against outputs of the UNMODIFIED reference
 (tests/golden/cases/*.npz, written by tests/golden/generate_golden.py in the build container) and
 against literal known-answer vectors transcribed from the reference's own test-suite."""
+import os
+
 import numpy as np
 import pytest
 
 from bionc_oracle import OracleModel, rk4_generic
 from conftest import golden_case_names
-from helpers import fext_list, load_case, model_path, rel_err
+from helpers import GOLDEN, fext_list, load_case, model_path, rel_err
 
 CASES = golden_case_names()
 
@@ -173,3 +175,29 @@ def test_full_body_perturbed_inertial_parameters():
         qdd, lam = om.forward_dynamics(case["Q"][s], case["Qdot"][s])
         assert rel_err(qdd, case["ref_Qddot"][s]) < 1e-10
         assert rel_err(lam, case["ref_lam"][s]) < 1e-10
+
+
+def test_joint_generalized_forces_against_the_reference_building_blocks():
+    """the oracle's joint-reaction force kind and the lowering of a JointGeneralizedForcesList against
+    vectors composed from the reference's own methods (tests/golden/generate_joint_forces.py)."""
+    from bionc_oracle import OracleModel
+
+    from bionc_b200.bionc_cuda.generalized_force import JointGeneralizedForces, JointGeneralizedForcesList
+
+    with np.load(os.path.join(GOLDEN, "cases_extra", "joint_forces_lower_limb.npz")) as z:
+        g = {k: np.array(z[k]) for k in z.files}
+    om = OracleModel(model_path("lower_limb"))
+    jl = JointGeneralizedForcesList.empty_from_nb_joint(g["all_joint_parent"].size)
+    for j, v in zip(g["joint_index"], g["joint_force"]):
+        jl.add_generalized_force(int(j), JointGeneralizedForces(v))
+    seg, kind, par = jl.to_arrays(g["all_joint_parent"], g["all_joint_child"])
+    assert set(kind.tolist()) == {1, 4}  # forces on the children, reactions on the parents
+    fext = [(int(a), int(b), c) for a, b, c in zip(seg, kind, par)]
+    for s in range(g["Q"].shape[0]):
+        assert np.abs(om.natural_external_forces(g["Q"][s], fext) - g["ref_natural_joint_forces"][s]).max() < 1e-12
+        qdd, lam = om.forward_dynamics(g["Q"][s], g["Qdot"][s], fext)
+        assert rel_err(qdd, g["ref_Qddot"][s]) < 1e-10 and rel_err(lam, g["ref_lam"][s]) < 1e-10
+    with pytest.raises(ValueError):
+        JointGeneralizedForcesList.empty_from_nb_joint(2).to_arrays(g["all_joint_parent"], g["all_joint_child"])
+    with pytest.raises(NotImplementedError):
+        JointGeneralizedForces(np.zeros(6), application_point_in_local=[0, 0.1, 0])
