@@ -453,16 +453,17 @@ def run_gpu_arm(args):
         strong_ms, _, _ = timed(opt, qs, qds, Bs)
         # the only collective of the workload: one all_gather_into_tensor of the final states [Q | Qdot] of the strong run
         y = torch.cat([qs, qds], dim=1).contiguous()
-        gather_states(y, world * Bs)  # warm-up (NCCL channel set-up)
+        full = torch.empty((world * Bs, 2 * n), dtype=torch.float64, device=dev)  # equal shards: rank r's rows are [r Bs, (r + 1) Bs)
+        dist.all_gather_into_tensor(full, y)  # warm-up (NCCL channel set-up)
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record(stream)
-        full = gather_states(y, world * Bs)
+        dist.all_gather_into_tensor(full, y)
         g1.record(stream)
         barrier()
         gather_ms = g0.elapsed_time(g1)
         gather_bytes = int(full.numel() * 8)
-        assert full.shape == (world * Bs, 2 * n)
+        assert torch.equal(full[rank * Bs : (rank + 1) * Bs], y) and torch.equal(gather_states(y, world * Bs), full)
         del full, y
 
     t = max_over_ranks([total_ms, e2e_s, kernel_ms_mean, float(bad), stab_total_ms, float(stab_bad), strong_ms, gather_ms], device=dev)

@@ -397,6 +397,7 @@ __device__ __forceinline__ FextView fext_view(const FextArgs& fx, long long sys)
     return v;
 }
 
+template <bool VEC = false>  // VEC: vector quantities only (the Jacobian branches are compiled out)
 __device__ __forceinline__ void eval_item(const DevSeg* __restrict__ seg, const DevBlk* __restrict__ blk,
                                           const FextView& fext, const EvalArgs& ea, int which, int item,
                                           const double* __restrict__ X, double* __restrict__ vec, double* __restrict__ K,
@@ -421,7 +422,7 @@ __device__ __forceinline__ void eval_item(const DevSeg* __restrict__ seg, const 
             double* o = vec + sg.rigid_row;
             o[0] = 2.0 * dot(u, u), o[1] = 2.0 * dot(u, v), o[2] = 2.0 * dot(u, w);
             o[3] = 2.0 * dot(v, v), o[4] = 2.0 * dot(v, w), o[5] = 2.0 * dot(w, w);
-        } else if (which == 1 || which == 5) {  // K_r rows
+        } else if (!VEC && (which == 1 || which == 5)) {  // K_r rows
             const int r0 = (which == 1) ? 6 * i : sg.rigid_row;
             const double eu[4] = {1, 0, 0, 0}, ev[4] = {0, 1, -1, 0}, ew[4] = {0, 0, 0, 1};
             if (sub < 0 || sub == 0) put_row(K, ldK, r0 + 0, i, eu, u, 2.0);
@@ -450,7 +451,7 @@ __device__ __forceinline__ void eval_item(const DevSeg* __restrict__ seg, const 
         const double* p = b.p;
         const bool jorder = (which == 2 || which == 3);
         const int row = jorder ? b.row_j : b.row_h;
-        const bool want_phi = (which == 2 || which == 4), want_K = (which == 3 || which == 5), want_b = (which == 6);
+        const bool want_phi = (which == 2 || which == 4), want_K = !VEC && (which == 3 || which == 5), want_b = (which == 6);
         double* o = vec;
         const V3 ex = mk(1, 0, 0), ey = mk(0, 1, 0), ez = mk(0, 0, 1);
         if (b.type == LIN3) {
@@ -601,7 +602,7 @@ __global__ void __launch_bounds__(kEvalThreads, 4)
         for (int idx = tid; idx < ns * nitem; idx += kEvalThreads) {
             const int sys = idx / nitem, item = idx - sys * nitem;
             double* o = O0 + (size_t)sys * rows;
-            eval_item(seg, blk, fext_view(fx, tile * T + sys), ea, which, item, X0 + (size_t)sys * n, o, nullptr, 0);
+            eval_item<true>(seg, blk, fext_view(fx, tile * T + sys), ea, which, item, X0 + (size_t)sys * n, o, nullptr, 0);
         }
         fence_async_smem();  // generic-proxy writes of the image become visible to the bulk-copy engine
         __syncthreads();
@@ -627,7 +628,7 @@ __global__ void __launch_bounds__(kEvalThreads, 4)
 // ---------------------------------------------------------------------------------------------
 constexpr int kItemThreads = 128, kItemSystems = 32;
 
-__global__ void __launch_bounds__(kItemThreads, 4)
+__global__ void __launch_bounds__(kItemThreads, 8)
     items_kernel(const unsigned char* __restrict__ blob, EvalArgs ea, int rows, const double* __restrict__ in, double* __restrict__ out, long long B) {
     extern __shared__ __align__(16) double fsm[];
     const DevHeader* h = reinterpret_cast<const DevHeader*>(blob);
@@ -653,7 +654,7 @@ __global__ void __launch_bounds__(kItemThreads, 4)
         __syncthreads();
         const double* X = Xs + (lane < ns ? lane : 0) * ldx;
         double* o = Os + lane * ldo;
-        for (int item = wid; item < nitem; item += kItemThreads / 32) eval_item(seg, blk, nofx, ea, ea.which, item, X, o, nullptr, 0);
+        for (int item = wid; item < nitem; item += kItemThreads / 32) eval_item<true>(seg, blk, nofx, ea, ea.which, item, X, o, nullptr, 0);
         __syncthreads();
         double* dst = out + (size_t)s0 * rows;
         for (int i = tid; i < ns * rows; i += kItemThreads) {

@@ -30,6 +30,9 @@ for w in ("lower_limb", "pendulum_force", "knee", "full_body", "n_link_4"):
         scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e-3, "us": 1e-6, "s": 1.0}.get(unit, 1.0)
         return x * scale
 
+    def fp64(op):  # the raw page lists the per-cycle rate of the sum over the SM sub-partitions
+        return float(d[f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum.per_cycle_elapsed"]) * float(d["smsp__cycles_elapsed.avg"])
+
     csvp = os.path.join(REPO, "scratch", f"{TAG}_{w}_raw.csv")
     os.makedirs(os.path.dirname(csvp), exist_ok=True)
     open(csvp, "w").write(raw)
@@ -40,14 +43,11 @@ for w in ("lower_limb", "pendulum_force", "knee", "full_body", "n_link_4"):
         f.write(f"# ncu --set full --clock-control none, one launch of the fused integrator, bench.py --workload {w} (1e6 systems x 100 steps)\n")
         f.write(f"# kernel: {spc_line}\n")
         f.write(summary)
-        for k in ("smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum",
-                  "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum"):
-            f.write(f"{k:75s} {d[k]:>18s} {u[k]}\n")
+        for op in ("dfma", "dmul", "dadd"):
+            f.write(f"{'smsp__sass_thread_inst_executed_op_' + op + '_pred_on.sum  (= .sum.per_cycle_elapsed x smsp__cycles_elapsed.avg)':110s} {fp64(op):.6e} inst\n")
     out[w] = {
         "systems": 1_000_000, "rk4_steps_per_launch": 100,
-        "dfma": val("smsp__sass_thread_inst_executed_op_dfma_pred_on.sum"),
-        "dmul": val("smsp__sass_thread_inst_executed_op_dmul_pred_on.sum"),
-        "dadd": val("smsp__sass_thread_inst_executed_op_dadd_pred_on.sum"),
+        "dfma": fp64("dfma"), "dmul": fp64("dmul"), "dadd": fp64("dadd"),
         "warp_instructions": val("smsp__inst_executed.sum"),
         "fp64_pipe_pct": float(d["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed"]),
         "issue_active_pct": float(d["smsp__issue_active.avg.pct_of_peak_sustained_active"]),

@@ -222,3 +222,39 @@ print("tables ok")
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(os.path.dirname(GOLDEN)))
     for token in ("tables ok", "ValueError ok", "ground ok", "fext ok"):
         assert token in res.stdout, res.stdout + res.stderr
+
+
+def test_model_table_format_3_keeps_the_joint_list(tmp_path):
+    """Format 3 adds every joint's (parent, child) in the reference's joint order -- what joint generalized forces are
+    indexed by; older files load with an empty list."""
+    t = ModelTable.load(model_path("lower_limb"))
+    assert t.all_joint_names == [] and t.all_joint_parent.size == 0  # committed before format 3
+    t.all_joint_names = ["free_joint_PELVIS", "hip", "knee", "ankle"]
+    t.all_joint_parent, t.all_joint_child = np.array([-1, 0, 1, 2]), np.array([0, 1, 2, 3])
+    f = tmp_path / "ll3.npz"
+    t.validate().save(str(f))
+    t2 = ModelTable.load(str(f))
+    assert t2.all_joint_names == t.all_joint_names
+    assert np.array_equal(t2.all_joint_parent, [-1, 0, 1, 2]) and np.array_equal(t2.all_joint_child, [0, 1, 2, 3])
+    assert t2.all_joint_parent.dtype == np.int32
+
+
+def test_model_compiler_records_the_reference_joint_order():
+    """from_numpy on the live reference (when it is installed in baseline/_ref): the joint list of the lower limb."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "baseline"))
+    import reference_models as rm
+
+    if not rm.available():
+        pytest.skip("baseline/_ref not installed")
+    import warnings
+
+    warnings.filterwarnings("ignore")
+    t = ModelTable.from_numpy(rm.lower_limb_model())
+    assert t.all_joint_names == ["free_joint_PELVIS", "hip", "knee", "ankle"]
+    assert t.all_joint_parent.tolist() == [-1, 0, 1, 2] and t.all_joint_child.tolist() == [0, 1, 2, 3]
+    committed = ModelTable.load(model_path("lower_limb"))
+    for k in ModelTable._ARRAYS:
+        assert np.array_equal(getattr(t, k), getattr(committed, k)), k
