@@ -664,6 +664,15 @@ KernelSet pick_kernels(int path, int threads, int spc) {
     return BIONC_PICK(1024, 16);
 }
 
+// forward_dynamics_rows_kernel by CTA size (nullptr: no instantiation that large)
+const void* fd_rows_kernel(unsigned threads) {
+    if (threads <= 64) return (const void*)forward_dynamics_rows_kernel<64>;
+    if (threads <= 128) return (const void*)forward_dynamics_rows_kernel<128>;
+    if (threads <= 256) return (const void*)forward_dynamics_rows_kernel<256>;
+    if (threads <= 512) return (const void*)forward_dynamics_rows_kernel<512>;
+    return nullptr;
+}
+
 // opt a kernel in to the device's full shared memory, once per (device, kernel)
 int ensure_smem(int device, const void* kernel, int optin_bytes) {
     static std::mutex mu;
@@ -941,11 +950,27 @@ int bionc_cuda_forward_dynamics(const BioncModel* M, const double* Q, const doub
     if (status != nullptr) CUDA_TRY(cudaMemsetAsync(status, 0, B * sizeof(int32_t), st));
     const double* inertia = opt != nullptr ? opt->inertia : nullptr;
     const unsigned block = 32 * M->hdr.N;
-    if ((rc = ensure_smem(M->device, call.ks.fd, M->dev_smem_optin)) != BIONC_OK) return rc;
-    const unsigned grid = fd_grid(M, call, B);
     const unsigned char* blob = M->d_blob;
     int blob_bytes = M->blob_bytes;
     long long Bll = B;
+    // lean path with everything 16-byte aligned: the kernel that moves whole system rows with the bulk-copy engine
+    const void* rows_kernel = fd_rows_kernel(block);
+    // + the padding of the two row areas and a second buffer of Qdot rows
+    const size_t rows_smem = call.plan.smem + (size_t)32 * (2 * 2 + 12 * M->hdr.N + 2) * sizeof(double);
+    auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    if (kernel_path(M, call.o, call.fx.args) == 0 && call.plan.spw == 32 && inertia == nullptr && rows_kernel != nullptr &&
+        aligned(Q) && aligned(Qd) && aligned(Qdd) && aligned(lam) && M->hdr.mj > 0 && M->hdr.m <= 9 * (M->hdr.nslot + M->hdr.nslot2) &&
+        rows_smem <= (size_t)M->dev_smem_optin && (g_debug_poison.load() & 0x100) == 0) {
+        if ((rc = ensure_smem(M->device, rows_kernel, M->dev_smem_optin)) != BIONC_OK) return rc;
+        const unsigned grid = resident_grid(M, rows_kernel, block, rows_smem, (B + 31) / 32);
+        void* args[] = {&blob, &blob_bytes, &Q, &Qd, &call.o, &Qdd, &lam, &status, &Bll};
+        CUDA_TRY(cudaLaunchKernel(rows_kernel, dim3(grid), dim3(block), args, rows_smem, st));
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+        return BIONC_OK;
+    }
+    if ((rc = ensure_smem(M->device, call.ks.fd, M->dev_smem_optin)) != BIONC_OK) return rc;
+    const unsigned grid = fd_grid(M, call, B);
     void* args[] = {&blob, &blob_bytes, &call.fx.args, &Q, &Qd, &inertia, &call.o, &Qdd, &lam, &status, &Bll};
     CUDA_TRY(cudaLaunchKernel(call.ks.fd, dim3(grid), dim3(block), args, call.plan.smem, st));
     g_launches++;

@@ -118,6 +118,7 @@ struct SegCtx {
     __device__ __forceinline__ double minv() const { return kc[10 * ks]; }
     // state-dependent, set by segment_setup
     V3 u, v, w;        // v = rp - rd
+    V3 rp;             // proximal point (read again only by the multiplier output of the system-row layout)
     V3 Au, Av, Aw;     // particular accelerations of u, v, w:  [Au Av Aw] = B^-T S,  S = -1/2 Bsym
     double Ii[6];      // inverse of the inertia tensor about the centre of mass (sym3_inverse layout: 00 10 11 20 21 22)
     V3 tau0, F0;       // applied wrench about the centre of mass, gyroscopic term eta already subtracted from tau0
@@ -454,10 +455,12 @@ __device__ __forceinline__ Lever lever_of_side(const WarpCtx& w, const SegCtx& c
 //   S = -1/2 Bsym,  Bsym = 2 Ud^T Ud  (+ alpha Phi_r + beta Kr Qdot as symmetric matrices when stabilised:
 //   natural_segment.py:429-448, :508-545, biomechanical_model.py:416-421), gyroscopic term eta, applied wrench.
 // ---------------------------------------------------------------------------------------------
-template <bool GENERAL, bool STAB, int S>
+template <bool GENERAL, bool STAB, int S, int ES = S>
 __device__ __forceinline__ void segment_setup(const WarpCtx& w, SegCtx& c, const DevSeg& sg, const DynOpts& o, int& status) {
-    const V3 rp = own3<S>(w.Qo, 1);
-    c.u = own3<S>(w.Qo, 0), c.v = rp - own3<S>(w.Qo, 2), c.w = own3<S>(w.Qo, 3);
+    // ES: element stride of this lane's own state (S in the lane-minor layout, 1 when the state lies in system rows)
+    const V3 rp = own3<ES>(w.Qo, 1);
+    c.rp = rp;
+    c.u = own3<ES>(w.Qo, 0), c.v = rp - own3<ES>(w.Qo, 2), c.w = own3<ES>(w.Qo, 3);
     const V3 b0 = cross(c.v, c.w), b1 = cross(c.w, c.u), b2 = cross(c.u, c.v);
     const double det = dot(c.u, b0);
     const double guu = dot(c.u, c.u), gvv = dot(c.v, c.v), gww = dot(c.w, c.w);
@@ -475,7 +478,7 @@ __device__ __forceinline__ void segment_setup(const WarpCtx& w, SegCtx& c, const
         const double Yyz = fma(X0.y, c.u.z, fma(X1.y, c.v.z, X2.y * c.w.z));
         sym3_inverse(Yyy + Yzz, -Yxy, Yxx + Yzz, -Yxz, -Yyz, Yxx + Yyy, c.Ii, status);
     }
-    const V3 ud = own3<S>(w.Qdo, 0), vd = own3<S>(w.Qdo, 1) - own3<S>(w.Qdo, 2), wd = own3<S>(w.Qdo, 3);
+    const V3 ud = own3<ES>(w.Qdo, 0), vd = own3<ES>(w.Qdo, 1) - own3<ES>(w.Qdo, 2), wd = own3<ES>(w.Qdo, 3);
     double s00 = -dot(ud, ud), s01 = -dot(ud, vd), s02 = -dot(ud, wd), s11 = -dot(vd, vd), s12 = -dot(vd, wd), s22 = -dot(wd, wd);
     if (STAB && o.use_stab) {
         const double ha = 0.5 * o.alpha, hb = 0.5 * o.beta;
@@ -698,7 +701,7 @@ __device__ __forceinline__ void solve_two_leaves(const WarpCtx& w, int& status) 
 // R_rp = l1 u + 2 l3 v + l4 w = -R_rd,  R_w = l2 u + l4 v + 2 l5 w,  so  B^-1 [R_u R_rp R_w] = [[2 l0, l1, l2], [l1, 2 l3, l4],
 // [l2, l4, 2 l5]]; the off-diagonal pairs agree up to rounding and are averaged.  Output path only: compiled into the
 // forward_dynamics kernel (LAM = true), never into the fused integrator.
-template <bool GENERAL, int S>
+template <bool GENERAL, int S, int ES = S>
 __device__ __forceinline__ void rigid_multipliers(const WarpCtx& w, const SegCtx& c, const DevSeg& sg, const Q12& Qdd, double* lam_r) {
     constexpr int spw = S;
     // M4 rows u, rp, w from (m, c, J), J = N3 + m c c^T   (natural_inertial_parameters.py:153-177)
@@ -708,7 +711,7 @@ __device__ __forceinline__ void rigid_multipliers(const WarpCtx& w, const SegCtx
     const double Mu[4] = {J00, m * c0 + J01, -J01, J02};
     const double Mr[4] = {m * c0 + J01, m + 2.0 * m * c1 + J11, -(m * c1 + J11), m * c2 + J12};
     const double Mw[4] = {J02, m * c2 + J12, -J12, J22};
-    const V3 rp = own3<S>(w.Qo, 1);
+    const V3 rp = ES == 1 ? c.rp : own3<ES>(w.Qo, 1);  // system rows: the state may already belong to the next tile
     const double g = -9.81 * m;
     V3 Ru = mk(0.0, 0.0, g * c0), Rr = mk(0.0, 0.0, g * (1.0 + c1)), Rw = mk(0.0, 0.0, g * c2);
     if (GENERAL && w.fext != nullptr) {
@@ -759,15 +762,26 @@ __device__ __forceinline__ void rigid_multipliers(const WarpCtx& w, const SegCtx
 // caller must order the publication of a stage state with a barrier when STAB or GENERAL is set).  PARKA: the particular
 // accelerations wait in the thread's tensor-memory columns tmA (18 words) while the joint-level phases run.
 // ---------------------------------------------------------------------------------------------
-template <bool GENERAL, bool STAB, bool LAM, bool PARKA, int S>
+struct NoHook {
+    __device__ __forceinline__ void before_assembly() const {}
+    __device__ __forceinline__ void operator()() const {}
+};
+
+// hook (forward_dynamics_rows_kernel): before_assembly() is called by every thread before the first write to the joint-
+// level matrix (whose area holds the previous tile's multiplier image while it is stored); operator() right after the
+// first barrier that follows the assembly -- from there on no thread reads the stage state of the lean, unstabilised
+// path again, so the next tile's copies may start.
+template <bool GENERAL, bool STAB, bool LAM, bool PARKA, int S, bool ROWS = false, class Hook = NoHook>
 __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& c, const DynOpts& o, Q12& Qdd,
-                                                      double* lam_out, int& status, unsigned tmA = 0) {
+                                                      double* lam_out, int& status, unsigned tmA = 0, Hook hook = Hook()) {
     constexpr int spw = S;
     const DevSeg& sg = w.seg[w.segi];
     const bool stab = STAB && o.use_stab;
 
     // ---- B. segment-local quantities
-    segment_setup<GENERAL, STAB, S>(w, c, sg, o, status);
+    constexpr int ES = ROWS ? 1 : S;  // ROWS: this lane's state lies in its system's row (lean path without stabilisation only)
+    static_assert(!ROWS || (!GENERAL && !STAB), "system-row state layout: own-segment reads only");
+    segment_setup<GENERAL, STAB, S, ES>(w, c, sg, o, status);
     V3 tau = c.tau0, F = c.F0;  // Newton-Euler right-hand sides, joint multipliers subtracted in phase H
 
     if (w.mj > 0) {
@@ -847,6 +861,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
         }
 
         // ---- E. this segment's contribution to S':  S'_ab = fdir_a . fdir_b / m + n_a . Ic^-1 n_b
+        hook.before_assembly();
         for (int e = sg.side_begin; e < sg.side_end; ++e) {
             const DevSide& sd = w.side[e];
             const DevBlk& b = w.blk[sd.blk];
@@ -933,11 +948,13 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
         //    G. backward substitution: lambda_K = y-hat_K - D_K^-1 sum_I S_IK^T lambda_I.
         if (hd->serial_solve == 2) {
             __syncthreads();  // closes the assembly
+            hook();
             solve_two_leaves<S>(w, status);
         } else if (hd->serial_solve != 0) {
             // serial schedule (host decision: the elimination offers no parallelism across warps): the first warp
             // factors and solves everything between two barriers -- no barrier per level, no pivot inverted twice.
             __syncthreads();
+            hook();
             if (w.segi == 0) {
 #pragma unroll 1
                 for (int K = 0; K < nb; ++K) eliminate_pivot<true, S>(w, K, status);
@@ -951,6 +968,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
 #pragma unroll 1
             for (int lv = 0; lv < hd->nlevel; ++lv) {
                 __syncthreads();
+                if (lv == 0) hook();
 #pragma unroll 1
                 for (int pi = w.lvlptr[lv]; pi < w.lvlptr[lv + 1]; ++pi) {
                     const int K = w.lvlpiv[pi];
@@ -1014,7 +1032,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
         Qdd.s[1] = in_accel_acc(c, -c0, -c1, -c2, cross_sub(tc, al, cbar));
         Qdd.s[2] = Qdd.s[1] - cross_acc(al, c.v, c.Av);
     }
-    if (LAM && lam_out != nullptr) rigid_multipliers<GENERAL, S>(w, c, sg, Qdd, lam_out + sg.rigid_row);
+    if (LAM && lam_out != nullptr) rigid_multipliers<GENERAL, S, ES>(w, c, sg, Qdd, lam_out + sg.rigid_row);
     // No barrier here: lambda_j lives in its own array, so the next evaluation may start assembling while
     // slower warps still read it; the barriers inside the next evaluation order everything else.
 }

@@ -18,7 +18,7 @@ __device__ __forceinline__ void inertia_to_constants(const double* __restrict__ 
 // ---- per-CTA setup: copy the model blob to shared memory, carve the working set ----------------------
 template <int S>
 __device__ __forceinline__ void setup_cta(const unsigned char* __restrict__ blob, int blob_bytes, const FextArgs& fx,
-                                          unsigned char* smem, WarpCtx& w, int poison = 0) {
+                                          unsigned char* smem, WarpCtx& w, int poison = 0, int qpad = 0) {
     {
         const int4* src = reinterpret_cast<const int4*>(blob);
         int4* dst = reinterpret_cast<int4*>(smem);
@@ -42,11 +42,12 @@ __device__ __forceinline__ void setup_cta(const unsigned char* __restrict__ blob
     w.segi = threadIdx.x >> 5;       // warp = segment
     w.lane = threadIdx.x & (S - 1);  // lane = system; with S < 32 systems per CTA the upper lanes mirror the lower ones
     double* base = reinterpret_cast<double*>(smem + blob_bytes + (fx.tab != nullptr ? fx.tab_bytes : 0));
+    // qpad: extra doubles per system in each of the two state areas (forward_dynamics_rows_kernel keeps padded rows there)
     double* Qs = base;
-    double* Qds = Qs + 12 * S * w.N;
+    double* Qds = Qs + (12 * w.N + qpad) * S;
     w.Qsys = Qs + w.lane, w.Qdsys = Qds + w.lane;
     w.Qo = w.Qsys + 12 * S * w.segi, w.Qdo = w.Qdsys + 12 * S * w.segi;
-    w.S0 = Qds + 12 * S * w.N + w.lane;
+    w.S0 = Qds + (12 * w.N + qpad) * S + w.lane;
     w.S1 = w.S0 + 9 * S * h->nslot;
     w.r0 = w.S1 + 9 * S * h->nslot2;
     w.r1 = w.r0 + 3 * S * w.nb;
@@ -59,7 +60,7 @@ __device__ __forceinline__ void setup_cta(const unsigned char* __restrict__ blob
         // with NaN first must not change any result (tests/test_gpu_scale.py).  Bits: 0 S0, 1 S1, 2 r0, 3 r1, 4 lambda_j,
         // 5 inverse pivots, 6 row vectors of the non-LIN3 blocks.  Shared memory of a fresh CTA holds whatever ran before.
         const double nan = __longlong_as_double(0x7ff8dead0000beefLL);
-        double* reg[7] = {Qds + 12 * S * w.N, w.S1 - w.lane, w.r0 - w.lane, w.r1 - w.lane, w.lamv - w.lane, w.dinv - w.lane, w.dinv - w.lane + 6 * S * w.nb};
+        double* reg[7] = {w.S0 - w.lane, w.S1 - w.lane, w.r0 - w.lane, w.r1 - w.lane, w.lamv - w.lane, w.dinv - w.lane, w.dinv - w.lane + 6 * S * w.nb};
         const int len[7] = {9 * S * h->nslot, 9 * S * h->nslot2, 3 * S * w.nb, 3 * S * w.nb, 3 * S * w.nb, 6 * S * w.nb, S * h->rnl * w.N};
         for (int r = 0; r < 7; ++r)
             if ((poison >> r) & 1)
@@ -531,6 +532,129 @@ __device__ __forceinline__ void bulk_wait_read() {  // at most N store groups st
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// forward_dynamics for the lean path (point-to-point joints, no forces, no stabilisation, model constants): all global
+// traffic goes through the bulk-copy engine instead of per-lane strided loads and stores, which kept the L1 data pipe at
+// 63 % for the kernel above (profiles/r02_ncu_fd.txt) -- a lane's 96-byte slice of a 384-byte system row is 32 sectors
+// per request.  Per tile of 32 systems:
+//   in   one bulk copy per system row (12 N doubles) of Q and of Qdot into rows padded by 16 bytes, so that the lanes'
+//        16-byte reads of their own segment fall on distinct banks; the evaluation reads its state straight from the
+//        rows (ROWS layout), nothing is transposed.  The copies of the NEXT tile start inside the evaluation, right
+//        after the barrier that closes the assembly (nothing reads the state after it): Q into the same rows, Qdot into
+//        the other of two row buffers;
+//   out  Qddot overwrites the lane's slice of the tile's Qdot rows (dead after phase B), one bulk store per row; the
+//        multipliers are written as the tile's contiguous (systems, m) image into the area of the joint-level matrix
+//        (dead after the back-substitution) and leave as one bulk store.  Nobody waits for the stores: the warp that
+//        issued them checks that they have read their source when it starts the next copies, one evaluation later.
+// Needs: joints (mj > 0), 16-byte aligned Q, Qdot, Qddot, lambda; 8 m <= 72 (nslot + nslot2) bytes per system (checked
+// by the host).  A partial last tile loads the last system into the spare rows and writes its outputs with plain stores.
+// ---------------------------------------------------------------------------------------------
+template <int MAXT>
+struct FdRowsMinCtas {
+#ifdef BIONC_EXP_FDROWS128
+    static constexpr int value = (MAXT > 64 && MAXT <= 128) ? BIONC_EXP_FDROWS128 : MinCtas<MAXT>::value;
+#else
+    static constexpr int value = (MAXT > 64 && MAXT <= 128) ? 3 : MinCtas<MAXT>::value;  // three CTAs of 74 KB per SM: 168 registers
+#endif
+};
+
+struct RowsPrefetch {
+    unsigned long long *bar, *img_bar;
+    unsigned img_parity;
+    double *qrows, *qdrows;  // destination rows of the next tile
+    const double *Q, *Qd;    // this lane's source rows, nullptr when there is no next tile
+    unsigned bytes;
+    int ld;
+    // the bulk store of the previous tile's multiplier image has read it (thread 0 arrives on img_bar when it has)
+    __device__ __forceinline__ void before_assembly() const { mbar_wait(img_bar, img_parity); }
+    __device__ __forceinline__ void operator()() const {
+        // the copies are the business of the LAST warp: in the two-leaves and the serial schedule it has nothing to do
+        // between the barriers of the joint-level solve, while the first warp is on the critical path there
+        if (threadIdx.x >= blockDim.x - 32 && Q != nullptr) {
+            const unsigned lane = threadIdx.x & 31;
+            bulk_wait_read<0>();  // the stores of the previous tile have read the buffers written next
+            if (lane == 0) mbar_expect_tx(bar, 2u * 32u * bytes);
+            __syncwarp();
+            bulk_load(qrows + lane * ld, Q, bytes, bar);
+            bulk_load(qdrows + lane * ld, Qd, bytes, bar);
+        }
+    }
+};
+
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, FdRowsMinCtas<MAXT>::value)
+    forward_dynamics_rows_kernel(const unsigned char* __restrict__ blob, int blob_bytes, const double* __restrict__ Q,
+                                 const double* __restrict__ Qd, DynOpts o, double* __restrict__ Qdd, double* __restrict__ lam,
+                                 int* __restrict__ status_out, long long B) {
+    constexpr int S = 32;
+    extern __shared__ __align__(16) unsigned char smem[];
+    WarpCtx w;
+    FextArgs nofx{};
+    setup_cta<S>(blob, blob_bytes, nofx, smem, w, o.poison, 2);
+    const int n = 12 * w.N, ld = n + 2, m = w.hdr->m;
+    double* Qrows = w.Qsys - w.lane;
+    double* Qdrows0 = w.Qdsys - w.lane;
+    double* lam_img = w.S0 - w.lane;
+    // second Qdot row buffer: behind the working set (the host adds it to the launch's shared memory)
+    double* Qdrows1 = w.dinv - w.lane + 6 * S * w.nb + S * w.hdr->rnl * w.N;
+    unsigned long long* const barp = reinterpret_cast<unsigned long long*>(Qrows + n);  // the padding of the first row
+    unsigned long long* const imgp = reinterpret_cast<unsigned long long*>(Qrows + ld + n);  // of the second
+    w.Qo = Qrows + w.lane * ld + 12 * w.segi;
+    w.persys = false;
+    if (threadIdx.x == 0) {
+        mbar_init(barp, 1), mbar_init(imgp, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const long long ntiles = (B + S - 1) / S;
+    auto src_row = [&](long long tile) {  // the system this lane's row of a tile comes from
+        const long long s = tile * S + w.lane;
+        return s < B ? s : B - 1;
+    };
+    {
+        RowsPrefetch first{barp, imgp, 1u, Qrows, Qdrows0, nullptr, nullptr, n * 8u, ld};
+        if ((long long)blockIdx.x < ntiles) first.Q = Q + (size_t)src_row(blockIdx.x) * n, first.Qd = Qd + (size_t)src_row(blockIdx.x) * n;
+        first();
+    }
+    unsigned it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const long long sys0 = tile * S;
+        const int nlive = (int)(B - sys0 < S ? B - sys0 : S);
+        double* Qdcur = (it & 1) ? Qdrows1 : Qdrows0;
+        w.Qdo = Qdcur + w.lane * ld + 12 * w.segi;
+        mbar_wait(barp, it & 1);
+        // image barrier: phase it - 1 is completed by thread 0 after the stores of the previous tile (a fresh barrier reports
+        // the phase before its first as complete)
+        RowsPrefetch next{barp, imgp, (it & 1) ^ 1u, Qrows, (it & 1) ? Qdrows0 : Qdrows1, nullptr, nullptr, n * 8u, ld};
+        if (tile + gridDim.x < ntiles) next.Q = Q + (size_t)src_row(tile + gridDim.x) * n, next.Qd = Qd + (size_t)src_row(tile + gridDim.x) * n;
+        int status = 0;
+        SegCtx c;
+        c.kc = w.seg[w.segi].kc, c.ks = 1;
+        Q12 qdd;
+        eval_forward_dynamics<false, false, true, false, S, true, RowsPrefetch>(w, c, o, qdd, lam != nullptr ? lam_img + w.lane * m : nullptr,
+                                                                               status, 0, next);
+        store_q12(w.Qdo, qdd);
+        if (w.lane < nlive && status_out != nullptr && status != 0) atomicOr(status_out + sys0 + w.lane, status);
+        fence_async_smem();
+        __syncthreads();
+        if (nlive == S) {
+            if (threadIdx.x >= blockDim.x - 32) {
+                bulk_store(Qdd + (size_t)(sys0 + w.lane) * n, Qdcur + w.lane * ld, n * 8u);
+                if (w.lane == 0) {
+                    if (lam != nullptr) bulk_store(lam + (size_t)sys0 * m, lam_img, (unsigned)(S * m * 8));
+                    bulk_wait_read<0>();  // only this thread waits; the others meet it at before_assembly() of the next tile
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(imgp)) : "memory");
+                }
+            }
+        } else {  // only ever the last tile of the grid
+            for (int i = threadIdx.x; i < nlive * n; i += blockDim.x) Qdd[(size_t)sys0 * n + i] = Qdcur[(i / n) * ld + i % n];
+            if (lam != nullptr)
+                for (int i = threadIdx.x; i < nlive * m; i += blockDim.x) lam[(size_t)sys0 * m + i] = lam_img[i];
+        }
+    }
+    if (threadIdx.x >= blockDim.x - 32) bulk_wait_all();
+}
 
 // ---------------------------------------------------------------------------------------------
 // Tiled evaluators.  The outputs are dense per system (the reference's own shapes), a Jacobian mostly zeros: what the

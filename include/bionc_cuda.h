@@ -188,7 +188,9 @@ int bionc_cuda_measure_fp64_peak(int device, int repeats, double* tflops_best, d
 
 /* debug aid: the dynamics kernels fill the selected regions of their shared-memory working set with NaN before the first
  * evaluation (bit 0 S', 1 second copies, 2 / 3 right-hand-side copies, 4 lambda_j, 5 inverse pivots, 6 row vectors of the
- * non-LIN3 blocks).  A correct kernel writes every word before reading it, so no result may change; 0 switches it off. */
+ * non-LIN3 blocks).  A correct kernel writes every word before reading it, so no result may change; 0 switches it off.
+ * Bit 8 makes bionc_cuda_forward_dynamics use its per-lane load/store kernel where it would pick the bulk-copy one
+ * (forward_dynamics_rows_kernel), so that tests and measurements can compare the two. */
 int bionc_cuda_debug_poison(int32_t mask);
 
 /* number of kernel launches issued through this library since load (bench.py's gpu_launches) */

@@ -335,3 +335,25 @@ def test_forward_dynamics_repeats_bit_for_bit_at_scale():
     for _ in range(3):
         out = model.forward_dynamics(Q, Qd, pivoting="never", return_status=True)
         assert all(torch.equal(a, b) for a, b in zip(ref, out))
+
+
+@pytest.mark.parametrize("name,kind", [("lower_limb", "tree"), ("full_body", "tree")])
+@pytest.mark.parametrize("B", [1, 31, 32, 33, 1000, 150_001])
+def test_bulk_copy_forward_dynamics_matches_the_per_lane_kernel(name, kind, B):
+    """forward_dynamics on the lean path moves whole system rows with the bulk-copy engine and evaluates from them
+    (forward_dynamics_rows_kernel); bit 8 of bionc_cuda_debug_poison selects the per-lane load/store kernel instead.  Same
+    arithmetic, so accelerations, multipliers and flags must agree bit for bit -- full tiles, partial tiles, one system."""
+    from bionc_b200.bionc_cuda import _lib
+
+    lib = _lib.load()
+    case, model = load_case(name), _model(name)
+    Q, Qd = _tiled_states(kind, model, case, B, seed=5)
+    try:
+        lib.bionc_cuda_debug_poison(0)
+        rows = model.forward_dynamics(Q, Qd, pivoting="never", return_status=True)
+        lib.bionc_cuda_debug_poison(0x100)
+        lanes = model.forward_dynamics(Q, Qd, pivoting="never", return_status=True)
+    finally:
+        lib.bionc_cuda_debug_poison(0)
+    assert not bool(torch.isnan(rows[0]).any()) and not bool(torch.isnan(rows[1]).any())
+    assert all(torch.equal(a, b) for a, b in zip(rows, lanes))
