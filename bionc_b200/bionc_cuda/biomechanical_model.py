@@ -56,6 +56,8 @@ class _Batch:
         if t.dim() != 2 or t.shape[1] != n:
             raise ValueError(f"{name} must have shape ({n},), ({n}, 1) or (B, {n}); got {shape}")
         self.t = t.to(device=device, dtype=torch.float64).contiguous()
+        if self.t.data_ptr() % 16:  # a view at an odd double of a larger buffer: the kernels use 16-byte accesses
+            self.t = self.t.clone()
         self.B = int(self.t.shape[0])
 
     def out(self, t: torch.Tensor, column: bool = False):

@@ -33,6 +33,8 @@ int fail(int code, const std::string& msg) {
     } while (0)
 
 int align16(int x) { return (x + 15) & ~15; }
+// the kernels read and write the per-system arrays with 16-byte vector accesses
+bool misaligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
 
 // robust inverse of a 4x4 (Gauss-Jordan, full pivoting, long double): the host has time to spare
 bool invert4(const double M[4][4], double W[4][4]) {
@@ -941,6 +943,7 @@ static unsigned fd_grid(const BioncModel* M, const DynCall& call, int64_t B) {
 int bionc_cuda_forward_dynamics(const BioncModel* M, const double* Q, const double* Qd, const BioncDynOptions* opt,
                                 double* Qdd, double* lam, int32_t* status, int64_t B, void* stream) {
     if (M == nullptr || Q == nullptr || Qd == nullptr || Qdd == nullptr || B < 0) return fail(BIONC_E_INVALID, "null argument");
+    if (misaligned16(Q) || misaligned16(Qd) || misaligned16(Qdd)) return fail(BIONC_E_INVALID, "Q, Qdot and Qddot must be 16-byte aligned");
     if (B == 0) return BIONC_OK;
     BIONC_ON_DEVICE(M);
     cudaStream_t st = (cudaStream_t)stream;
@@ -1033,6 +1036,7 @@ int bionc_cuda_rk4(const BioncModel* M, double* Q, double* Qd, double h, const d
                    int32_t* status, int64_t B, void* stream) {
     if (M == nullptr || Q == nullptr || Qd == nullptr || B < 0 || n_steps < 0) return fail(BIONC_E_INVALID, "null argument");
     if (traj != nullptr && traj_every < 1) return fail(BIONC_E_INVALID, "traj_every must be >= 1");
+    if (misaligned16(Q) || misaligned16(Qd) || misaligned16(traj)) return fail(BIONC_E_INVALID, "Q, Qdot and traj must be 16-byte aligned");
     if (B == 0 || n_steps == 0) return BIONC_OK;
     BIONC_ON_DEVICE(M);
     cudaStream_t st = (cudaStream_t)stream;
@@ -1072,6 +1076,7 @@ int bionc_cuda_rk4(const BioncModel* M, double* Q, double* Qd, double h, const d
 int bionc_cuda_eval(const BioncModel* M, int32_t which, const double* in, const BioncDynOptions* opt, double* out,
                     int64_t B, void* stream) {
     if (M == nullptr || in == nullptr || out == nullptr || B < 0 || which < 0 || which > 12) return fail(BIONC_E_INVALID, "bad argument");
+    if (misaligned16(in) || misaligned16(out)) return fail(BIONC_E_INVALID, "in and out must be 16-byte aligned");
     if (B == 0) return BIONC_OK;
     BIONC_ON_DEVICE(M);
     const int N = M->hdr.N, n = 12 * N, mj = M->hdr.mj, m = M->hdr.m;

@@ -137,6 +137,10 @@ int bionc_cuda_model_layout(const BioncModel* model, int32_t* out);
  * symbolic analysis); lets a host program replay the block elimination.  out: nb_blocks values */
 int bionc_cuda_model_joint_rows(const BioncModel* model, int32_t* first_row_of_block);
 
+/* Device entry points: the per-system arrays (Q, Qdot, Qddot, traj, the in / out of bionc_cuda_eval) are read and
+ * written with 16-byte vector accesses and must be 16-byte aligned (cudaMalloc and every row of a (B, 12 N) array are;
+ * a misaligned pointer returns BIONC_E_INVALID, no launch).  The _host entry points take any alignment. */
+
 /* replaces BiomechanicalModel.forward_dynamics (bionc_numpy/biomechanical_model.py:351-429), batched.
  * lambda and status may be NULL. */
 int bionc_cuda_forward_dynamics(const BioncModel* model, const double* Q, const double* Qdot,

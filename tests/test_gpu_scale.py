@@ -357,3 +357,32 @@ def test_bulk_copy_forward_dynamics_matches_the_per_lane_kernel(name, kind, B):
         lib.bionc_cuda_debug_poison(0)
     assert not bool(torch.isnan(rows[0]).any()) and not bool(torch.isnan(rows[1]).any())
     assert all(torch.equal(a, b) for a, b in zip(rows, lanes))
+
+
+def test_misaligned_device_arrays_are_refused_and_the_mirror_realigns():
+    """The kernels use 16-byte accesses on the per-system arrays.  The C ABI refuses a pointer at an odd double (no launch,
+    no CUDA fault that would poison the context); the Python mirror copies such a view to an aligned tensor."""
+    import ctypes as C
+
+    from bionc_b200.bionc_cuda import _lib
+
+    lib = _lib.load()
+    case, model = load_case("lower_limb"), _model("lower_limb")
+    B, n = 64, model.nb_Q
+    Q, Qd = _tiled_states("tree", model, case, B, seed=9)
+    ref = model.forward_dynamics(Q, Qd, pivoting="never")
+    buf = torch.zeros(B * n + 1, dtype=torch.float64, device="cuda")
+    odd = buf[1:].view(B, n)
+    odd.copy_(Q)
+    assert odd.data_ptr() % 16 == 8 and odd.is_contiguous()
+    out = model.forward_dynamics(odd, Qd, pivoting="never")
+    assert all(torch.equal(a, b) for a, b in zip(ref, out))
+    qdd = torch.empty_like(Q)
+    rc = lib.bionc_cuda_forward_dynamics(model._h, C.c_void_p(odd.data_ptr()), C.c_void_p(Qd.data_ptr()), None,
+                                         C.c_void_p(qdd.data_ptr()), None, None, B, None)
+    assert rc != 0 and b"aligned" in lib.bionc_cuda_last_error()
+    rc = lib.bionc_cuda_rk4(model._h, C.c_void_p(odd.data_ptr()), C.c_void_p(Qd.data_ptr()), 1e-3, None, 1, 1, None, None, 1, None,
+                            None, B, None)
+    assert rc != 0 and b"aligned" in lib.bionc_cuda_last_error()
+    torch.cuda.synchronize()  # the context is intact
+    assert all(torch.equal(a, b) for a, b in zip(ref, model.forward_dynamics(Q, Qd, pivoting="never")))
