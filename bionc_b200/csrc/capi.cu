@@ -640,12 +640,18 @@ struct FextCall {
 //   0 lean (point-to-point blocks only, no forces)   1 lean + Baumgarte   2 general (every block kind, forces, Baumgarte)
 struct KernelSet {
     const void* fd;
-    const void* rk4;
+    // integrator variants: lean paths [0] model constants, [1] per-system inertial parameters; general path [0] without,
+    // [1] with external forces (per-system inertial parameters are a run-time choice there).  What is fixed at compile time
+    // is what the compiler would otherwise re-derive from the kernel parameters all over the evaluation.
+    const void* rk4[2];
 };
-#define BIONC_PICK(T, S)                                                                                                         \
-    (path == 2   ? KernelSet{(const void*)forward_dynamics_kernel<true, true, T, S>, (const void*)rk4_kernel<true, true, T, S>}    \
-     : path == 1 ? KernelSet{(const void*)forward_dynamics_kernel<false, true, T, S>, (const void*)rk4_kernel<false, true, T, S>}  \
-                 : KernelSet{(const void*)forward_dynamics_kernel<false, false, T, S>, (const void*)rk4_kernel<false, false, T, S>})
+#define BIONC_PICK(T, S)                                                                                               \
+    (path == 2   ? KernelSet{(const void*)forward_dynamics_kernel<true, true, T, S>,                                   \
+                             {(const void*)rk4_kernel<true, true, T, S, 2, false>, (const void*)rk4_kernel<true, true, T, S, 2, true>}} \
+     : path == 1 ? KernelSet{(const void*)forward_dynamics_kernel<false, true, T, S>,                                  \
+                             {(const void*)rk4_kernel<false, true, T, S, 0, false>, (const void*)rk4_kernel<false, true, T, S, 1, false>}} \
+                 : KernelSet{(const void*)forward_dynamics_kernel<false, false, T, S>,                                 \
+                             {(const void*)rk4_kernel<false, false, T, S, 0, false>, (const void*)rk4_kernel<false, false, T, S, 1, false>}})
 KernelSet pick_kernels(int path, int threads, int spc) {
     if (spc == 32) {
         if (threads <= 32) return BIONC_PICK(32, 32);
@@ -912,6 +918,10 @@ struct DynCall {
     FextCall fx;
     LaunchPlan plan;
     KernelSet ks{};
+    int path = 0;
+    const void* rk4_entry(const double* inertia) const {
+        return ks.rk4[path == 2 ? (fx.args.tab != nullptr ? 1 : 0) : (inertia != nullptr ? 1 : 0)];
+    }
     int prepare(const BioncModel* M, const BioncDynOptions* opt, int64_t B, cudaStream_t st) {
         dyn_options(opt, o);
         int rc = fx.upload(M, opt != nullptr ? opt->fext : nullptr, st);
@@ -920,7 +930,8 @@ struct DynCall {
         plan = M->plan0;
         const bool persys = opt != nullptr && opt->inertia != nullptr;  // per-system constants take shared memory too
         if ((fx.args.tab != nullptr || persys) && (rc = make_plan(M, fx.args.tab_bytes, persys, plan)) != BIONC_OK) return rc;
-        ks = pick_kernels(kernel_path(M, o, fx.args), 32 * M->hdr.N, plan.spw);
+        path = kernel_path(M, o, fx.args);
+        ks = pick_kernels(path, 32 * M->hdr.N, plan.spw);
         return BIONC_OK;
     }
 };
@@ -1025,7 +1036,7 @@ static int launch_rk4(const BioncModel* M, DynCall& call, double* Q, double* Qd,
     const unsigned char* blob = M->d_blob;
     int blob_bytes = M->blob_bytes;
     void* args[] = {&blob, &blob_bytes, &call.fx.args, &Q, &Qd, &inertia, &call.o, &h, &h_steps, &n_steps, &step0, &normalize, &traj, &traj_every, &status, &B};
-    CUDA_TRY(cudaLaunchKernel(call.ks.rk4, dim3(grid), dim3(block), args, call.plan.smem, st));
+    CUDA_TRY(cudaLaunchKernel(call.rk4_entry(inertia), dim3(grid), dim3(block), args, call.plan.smem, st));
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return BIONC_OK;
@@ -1046,7 +1057,7 @@ int bionc_cuda_rk4(const BioncModel* M, double* Q, double* Qd, double h, const d
     if (status != nullptr) CUDA_TRY(cudaMemsetAsync(status, 0, B * sizeof(int32_t), st));
     const double* inertia = opt != nullptr ? opt->inertia : nullptr;
     if (traj == nullptr) traj_every = 1;
-    if ((rc = ensure_smem(M->device, call.ks.rk4, M->dev_smem_optin)) != BIONC_OK) return rc;
+    if ((rc = ensure_smem(M->device, call.rk4_entry(inertia), M->dev_smem_optin)) != BIONC_OK) return rc;
     if (lam_last == nullptr) return launch_rk4(M, call, Q, Qd, h, h_steps, 0, n_steps, normalize, inertia, traj, traj_every, status, B, st);
     // The multipliers of the first stage of the last step are those of forward_dynamics at the state before that step:
     // n_steps - 1 fused steps, one forward_dynamics launch for lambda (its accelerations go to a scratch array), the last

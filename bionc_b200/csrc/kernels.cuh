@@ -16,14 +16,18 @@ __device__ __forceinline__ void inertia_to_constants(const double* __restrict__ 
 }
 
 // ---- per-CTA setup: copy the model blob to shared memory, carve the working set ----------------------
-template <int S>
+// FX = false: a kernel that never carries a force table (the lean path).  The compiler re-derives the working-set base
+// wherever it is short of registers; without the table's pointer and size that is one constant load instead of three and
+// a select (4 % of the stall samples of the lean integrator were on those loads).
+template <int S, bool FX = true>
 __device__ __forceinline__ void setup_cta(const unsigned char* __restrict__ blob, int blob_bytes, const FextArgs& fx,
                                           unsigned char* smem, WarpCtx& w, int poison = 0, int qpad = 0) {
+    const bool has_tab = FX && fx.tab != nullptr;
     {
         const int4* src = reinterpret_cast<const int4*>(blob);
         int4* dst = reinterpret_cast<int4*>(smem);
         for (int i = threadIdx.x; i < blob_bytes / 16; i += blockDim.x) dst[i] = src[i];
-        if (fx.tab != nullptr) {  // this call's force table behind the blob
+        if (has_tab) {  // this call's force table behind the blob
             const int4* fsrc = reinterpret_cast<const int4*>(fx.tab);
             int4* fdst = reinterpret_cast<int4*>(smem + blob_bytes);
             for (int i = threadIdx.x; i < fx.tab_bytes / 16; i += blockDim.x) fdst[i] = fsrc[i];
@@ -35,13 +39,13 @@ __device__ __forceinline__ void setup_cta(const unsigned char* __restrict__ blob
     w.seg = reinterpret_cast<const DevSeg*>(smem + h->off_seg);
     w.blk = reinterpret_cast<const DevBlk*>(smem + h->off_blk);
     w.side = reinterpret_cast<const DevSide*>(smem + h->off_side);
-    w.ftab = fx.tab != nullptr ? reinterpret_cast<const DevFextTab*>(smem + blob_bytes) : nullptr;
-    w.fext = fx.tab != nullptr ? reinterpret_cast<const DevFext*>(smem + blob_bytes + sizeof(DevFextTab)) : nullptr;
+    w.ftab = has_tab ? reinterpret_cast<const DevFextTab*>(smem + blob_bytes) : nullptr;
+    w.fext = has_tab ? reinterpret_cast<const DevFext*>(smem + blob_bytes + sizeof(DevFextTab)) : nullptr;
     w.fvals = nullptr;
     w.N = h->N, w.mj = h->mj, w.nb = h->nb;
     w.segi = threadIdx.x >> 5;       // warp = segment
     w.lane = threadIdx.x & (S - 1);  // lane = system; with S < 32 systems per CTA the upper lanes mirror the lower ones
-    double* base = reinterpret_cast<double*>(smem + blob_bytes + (fx.tab != nullptr ? fx.tab_bytes : 0));
+    double* base = reinterpret_cast<double*>(smem + blob_bytes + (has_tab ? fx.tab_bytes : 0));
     // qpad: extra doubles per system in each of the two state areas (forward_dynamics_rows_kernel keeps padded rows there)
     double* Qs = base;
     double* Qds = Qs + (12 * w.N + qpad) * S;
@@ -113,11 +117,15 @@ __device__ __forceinline__ void tmem_wait(TmemWords<24>& t, Q12& q) {
     for (int k = 0; k < 4; ++k) q.s[k] = mk(x[3 * k], x[3 * k + 1], x[3 * k + 2]);
 }
 
-template <int S>
+// PS: 0 the model's constants, 1 per-system inertial parameters, 2 decided by the call (inertia != nullptr).  The lean
+// integrator is instantiated for 0 and 1: with the run-time choice the compiler re-derives the constants' base and stride
+// from the kernel parameter wherever they are used (eight constant loads and selects inside the evaluation).
+template <int S, int PS = 2>
 __device__ __forceinline__ void load_constants(WarpCtx& w, const double* __restrict__ inertia, long long gsys,
                                                SegCtx& c, int& status) {
-    w.persys = inertia != nullptr;
-    if (inertia != nullptr) {  // this lane's column of the CTA's constant area (only this thread ever touches it)
+    const bool persys = PS == 2 ? inertia != nullptr : PS == 1;
+    w.persys = persys;
+    if (persys) {  // this lane's column of the CTA's constant area (only this thread ever touches it)
         inertia_to_constants(inertia + ((size_t)gsys * w.N + w.segi) * 10, w.kcs, S, status);
         c.kc = w.kcs, c.ks = S;
     } else {
@@ -147,7 +155,7 @@ __global__ void __launch_bounds__(MAXT, FdMinCtas<MAXT>::value)
                             long long B) {
     extern __shared__ __align__(16) unsigned char smem[];
     WarpCtx w;
-    setup_cta<S>(blob, blob_bytes, fx, smem, w, o.poison);  // once per CTA: the grid is persistent, a CTA walks tiles of S systems
+    setup_cta<S, GENERAL>(blob, blob_bytes, fx, smem, w, o.poison);  // once per CTA: the grid is persistent, a CTA walks tiles of S systems
     const int n = 12 * w.N;
     const long long ntiles = (B + S - 1) / S;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -205,7 +213,9 @@ __global__ void __launch_bounds__(MAXT, FdMinCtas<MAXT>::value)
 // n_steps - 1 of a longer run (h_steps, traj and the force slices are indexed by the global step): the host splits a
 // run in two launches around a forward_dynamics call when the multipliers of the last step are asked for.
 // ---------------------------------------------------------------------------------------------
-template <bool GENERAL, bool STAB, int MAXT, int S>
+// PS: see load_constants.  FX: the call carries external forces (general path only; compiled both ways for the same
+// reason as PS).
+template <bool GENERAL, bool STAB, int MAXT, int S, int PS, bool FX>
 __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
     rk4_kernel(const unsigned char* __restrict__ blob, int blob_bytes, FextArgs fx, double* __restrict__ Q, double* __restrict__ Qd,
                const double* __restrict__ inertia, DynOpts o, double h_const, const double* __restrict__ h_steps,
@@ -214,15 +224,16 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr bool XSEG = GENERAL || STAB;  // an evaluation reads other segments' published state
     WarpCtx w;
-    setup_cta<S>(blob, blob_bytes, fx, smem, w, o.poison);
+    static_assert(GENERAL || !FX, "forces go through the general path");
+    setup_cta<S, FX>(blob, blob_bytes, fx, smem, w, o.poison);
     long long gsys = (long long)blockIdx.x * S + w.lane;
     const bool live = (int)(threadIdx.x & 31) < S && gsys < B;
     if (gsys >= B) gsys = B - 1;
     const int n = 12 * w.N;
     int status = 0;
     SegCtx c;
-    load_constants<S>(w, inertia, gsys, c, status);
-    const double* fvals0 = (GENERAL && fx.vals != nullptr) ? fx.vals + (size_t)gsys * fx.nf * 6 : nullptr;
+    load_constants<S, PS>(w, inertia, gsys, c, status);
+    const double* fvals0 = (FX && fx.vals != nullptr) ? fx.vals + (size_t)gsys * fx.nf * 6 : nullptr;
     Q12 y0q, y0v;
     load_q12(Q + (size_t)gsys * n + 12 * w.segi, y0q);
     load_q12(Qd + (size_t)gsys * n + 12 * w.segi, y0v);
@@ -240,7 +251,7 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
 #pragma unroll 1
     for (long long step = 0; step < n_steps; ++step) {
         const double h = h_steps != nullptr ? h_steps[step0 + step] : h_const;
-        if (GENERAL && fvals0 != nullptr) w.fvals = fvals0 + (step0 + step < fx.steps ? step0 + step : fx.steps - 1) * fx.step_stride;
+        if (FX && fvals0 != nullptr) w.fvals = fvals0 + (step0 + step < fx.steps ? step0 + step : fx.steps - 1) * fx.step_stride;
         Q12 accq, accv;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -591,7 +602,7 @@ __global__ void __launch_bounds__(MAXT, FdRowsMinCtas<MAXT>::value)
     extern __shared__ __align__(16) unsigned char smem[];
     WarpCtx w;
     FextArgs nofx{};
-    setup_cta<S>(blob, blob_bytes, nofx, smem, w, o.poison, 2);
+    setup_cta<S, false>(blob, blob_bytes, nofx, smem, w, o.poison, 2);
     const int n = 12 * w.N, ld = n + 2, m = w.hdr->m;
     double* Qrows = w.Qsys - w.lane;
     double* Qdrows0 = w.Qdsys - w.lane;
