@@ -5,10 +5,14 @@ from __future__ import annotations
 import os
 import shutil
 import subprocess
+import tempfile
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(ROOT, "csrc", "capi.cu")
-DEPS = [os.path.join(ROOT, "csrc", f) for f in ("capi.cu", "kernels.cuh", "dynamics.cuh", "model.cuh", "tmem.cuh")] + [
+# translation units: the C ABI with the evaluator kernels, and the dynamics kernels' instantiations (csrc/instances.cuh),
+# compiled in parallel and linked into one library
+UNITS = ("capi", "inst_fd", "inst_rk4_lean", "inst_rk4_general_nofx", "inst_rk4_general_fx")
+HEADERS = ("kernels.cuh", "dynamics.cuh", "model.cuh", "tmem.cuh", "instances.cuh")
+DEPS = [os.path.join(ROOT, "csrc", f) for f in tuple(u + ".cu" for u in UNITS) + HEADERS] + [
     os.path.join(os.path.dirname(ROOT), "include", "bionc_cuda.h")
 ]
 # BIONC_LIB_SUFFIX builds an experimental variant next to the library (profiles/: occupancy sweeps); _lib.py loads
@@ -18,7 +22,7 @@ OUT = os.path.join(ROOT, "lib", "libbionc_cuda%s.so" % os.environ.get("BIONC_LIB
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
 
 
@@ -37,17 +41,27 @@ def is_stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile ``csrc/capi.cu`` into ``lib/libbionc_cuda.so`` if sources are newer than the library."""
+    """Compile ``csrc/*.cu`` into ``lib/libbionc_cuda.so`` if sources are newer than the library."""
     if not force and not is_stale():
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     extra = os.environ.get("BIONC_NVCC_EXTRA", "").split()
-    cmd = [nvcc_path(), *NVCC_FLAGS, *extra] + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    flags = [*NVCC_FLAGS, *extra] + (["-Xptxas", "-v"] if verbose else [])
+    with tempfile.TemporaryDirectory(prefix="bionc_build_") as tmp:
+        objs = [os.path.join(tmp, u + ".o") for u in UNITS]
+        cmds = [[nvcc_path(), *flags, "-c", "-o", o, os.path.join(ROOT, "csrc", u + ".cu")] for u, o in zip(UNITS, objs)]
+        procs = [subprocess.Popen(c, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for c in cmds]
+        logs = [p.communicate()[0] for p in procs]
+        for c, p, log in zip(cmds, procs, logs):
+            if p.returncode != 0:
+                raise RuntimeError("nvcc failed:\n" + " ".join(c) + "\n" + log)
+        link = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT + ".tmp", *objs]
+        res = subprocess.run(link, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("link failed:\n" + " ".join(link) + "\n" + res.stdout + res.stderr)
+        os.replace(OUT + ".tmp", OUT)
     if verbose:
-        print(res.stderr)
+        print("\n".join(logs))
     return OUT
 
 

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/bionc_cuda.h"
+#include "instances.cuh"
 #include "kernels.cuh"
 
 using namespace bionc;
@@ -636,49 +637,18 @@ struct FextCall {
     }
 };
 
-// kernel instantiations by CTA-size class (threads = 32 x segments) and path:
-//   0 lean (point-to-point blocks only, no forces)   1 lean + Baumgarte   2 general (every block kind, forces, Baumgarte)
+// the dynamics kernels of a call (instances.cuh): paths 0 lean, 1 lean + Baumgarte, 2 general
 struct KernelSet {
     const void* fd;
-    // integrator variants: lean paths [0] model constants, [1] per-system inertial parameters; general path [0] without,
-    // [1] with external forces (per-system inertial parameters are a run-time choice there).  What is fixed at compile time
-    // is what the compiler would otherwise re-derive from the kernel parameters all over the evaluation.
-    const void* rk4[2];
+    const void* rk4[4];  // index = 2 * (per-system inertial parameters) + (external forces; general path only)
 };
-#define BIONC_PICK(T, S)                                                                                               \
-    (path == 2   ? KernelSet{(const void*)forward_dynamics_kernel<true, true, T, S>,                                   \
-                             {(const void*)rk4_kernel<true, true, T, S, 2, false>, (const void*)rk4_kernel<true, true, T, S, 2, true>}} \
-     : path == 1 ? KernelSet{(const void*)forward_dynamics_kernel<false, true, T, S>,                                  \
-                             {(const void*)rk4_kernel<false, true, T, S, 0, false>, (const void*)rk4_kernel<false, true, T, S, 1, false>}} \
-                 : KernelSet{(const void*)forward_dynamics_kernel<false, false, T, S>,                                 \
-                             {(const void*)rk4_kernel<false, false, T, S, 0, false>, (const void*)rk4_kernel<false, false, T, S, 1, false>}})
 KernelSet pick_kernels(int path, int threads, int spc) {
-    if (spc == 32) {
-        if (threads <= 32) return BIONC_PICK(32, 32);
-        if (threads <= 64) return BIONC_PICK(64, 32);
-        if (threads <= 96) return BIONC_PICK(96, 32);
-        if (threads <= 128) return BIONC_PICK(128, 32);
-        if (threads <= 256) return BIONC_PICK(256, 32);
-        if (threads <= 384) return BIONC_PICK(384, 32);
-        if (threads <= 512) return BIONC_PICK(512, 32);
-        return BIONC_PICK(1024, 32);
+    KernelSet k{fd_entry(path, threads, spc), {nullptr, nullptr, nullptr, nullptr}};
+    for (int ps = 0; ps < 2; ++ps) {
+        if (path == 2) k.rk4[2 * ps] = rk4_entry_general(threads, spc, ps != 0, false), k.rk4[2 * ps + 1] = rk4_entry_general(threads, spc, ps != 0, true);
+        else k.rk4[2 * ps] = rk4_entry_lean(path == 1, threads, spc, ps != 0);
     }
-    // 16 systems per CTA (upper half-warps mirror the lower ones): models whose working set for 32 systems
-    // would leave fewer systems resident per SM
-    if (threads <= 32) return BIONC_PICK(32, 16);
-    if (threads <= 64) return BIONC_PICK(64, 16);
-    if (threads <= 128) return BIONC_PICK(128, 16);
-    if (threads <= 256) return BIONC_PICK(256, 16);
-    return BIONC_PICK(1024, 16);
-}
-
-// forward_dynamics_rows_kernel by CTA size (nullptr: no instantiation that large)
-const void* fd_rows_kernel(unsigned threads) {
-    if (threads <= 64) return (const void*)forward_dynamics_rows_kernel<64>;
-    if (threads <= 128) return (const void*)forward_dynamics_rows_kernel<128>;
-    if (threads <= 256) return (const void*)forward_dynamics_rows_kernel<256>;
-    if (threads <= 512) return (const void*)forward_dynamics_rows_kernel<512>;
-    return nullptr;
+    return k;
 }
 
 // opt a kernel in to the device's full shared memory, once per (device, kernel)
@@ -920,7 +890,7 @@ struct DynCall {
     KernelSet ks{};
     int path = 0;
     const void* rk4_entry(const double* inertia) const {
-        return ks.rk4[path == 2 ? (fx.args.tab != nullptr ? 1 : 0) : (inertia != nullptr ? 1 : 0)];
+        return ks.rk4[(inertia != nullptr ? 2 : 0) + (fx.args.tab != nullptr ? 1 : 0)];  // a force table implies path 2
     }
     int prepare(const BioncModel* M, const BioncDynOptions* opt, int64_t B, cudaStream_t st) {
         dyn_options(opt, o);
@@ -968,7 +938,7 @@ int bionc_cuda_forward_dynamics(const BioncModel* M, const double* Q, const doub
     int blob_bytes = M->blob_bytes;
     long long Bll = B;
     // lean path with everything 16-byte aligned: the kernel that moves whole system rows with the bulk-copy engine
-    const void* rows_kernel = fd_rows_kernel(block);
+    const void* rows_kernel = fd_rows_entry((int)block);
     // + the padding of the two row areas and a second buffer of Qdot rows
     const size_t rows_smem = call.plan.smem + (size_t)32 * (2 * 2 + 12 * M->hdr.N + 2) * sizeof(double);
     auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };

@@ -667,6 +667,8 @@ __global__ void __launch_bounds__(MAXT, FdRowsMinCtas<MAXT>::value)
     if (threadIdx.x >= blockDim.x - 32) bulk_wait_all();
 }
 
+#ifndef BIONC_DYNAMICS_ONLY  // the rest of this file is compiled into capi.cu only (see instances.cuh)
+
 // ---------------------------------------------------------------------------------------------
 // Tiled evaluators.  The outputs are dense per system (the reference's own shapes), a Jacobian mostly zeros: what the
 // kernels have to do is write B x rows x cols doubles to HBM once, in full 16-byte-aligned bursts.  A CTA walks tiles;
@@ -1215,5 +1217,7 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* __restrict__ out
     }
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
+
+#endif  // BIONC_DYNAMICS_ONLY
 
 }  // namespace bionc
