@@ -18,6 +18,9 @@ SYMBOLS = (
     "bionc_cuda_model_counts",
     "bionc_cuda_model_layout",
     "bionc_cuda_model_joint_rows",
+    "bionc_cuda_model_specialize",
+    "bionc_cuda_model_spec_source",
+    "bionc_cuda_model_specialized",
     "bionc_cuda_forward_dynamics",
     "bionc_cuda_dense_workspace_bytes",
     "bionc_cuda_forward_dynamics_dense",
@@ -137,6 +140,9 @@ def load():
     lib.bionc_cuda_model_counts.argtypes = [vp, c_int32_p, c_int32_p, c_int32_p]
     lib.bionc_cuda_model_layout.argtypes = [vp, c_int32_p]
     lib.bionc_cuda_model_joint_rows.argtypes = [vp, c_int32_p]
+    lib.bionc_cuda_model_specialize.argtypes = [vp, optp, i32, i32]
+    lib.bionc_cuda_model_spec_source.argtypes = [vp, optp, i32, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.bionc_cuda_model_specialized.argtypes = [vp, C.POINTER(i64)]
     lib.bionc_cuda_forward_dynamics.argtypes = [vp, vp, vp, optp, vp, vp, vp, i64, vp]
     lib.bionc_cuda_dense_workspace_bytes.argtypes = [vp, i64]
     lib.bionc_cuda_dense_workspace_bytes.restype = C.c_size_t

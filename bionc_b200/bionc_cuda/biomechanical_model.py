@@ -257,6 +257,29 @@ class BiomechanicalModel:
         keep.append(opt)
         return opt, keep
 
+    def specialize(self, external_forces=None, stabilization=None, per_system_inertia: bool = False, joint_forces=None) -> float:
+        """Compile this model's own build of the fused RK4 kernel (NVRTC, sm_100a) for calls shaped like the arguments
+        -- Baumgarte on / off, external forces present or not, per-system inertial parameters or not -- and load it:
+        ``rk4`` / ``rk4_host`` calls of that shape then run it instead of the generic kernel (the model tables are
+        compile-time constants in it; same results to rounding).  The counterpart, for this
+        path, of the reference's code generation ``model.to_mx()`` (bionc_casadi/biomechanical_model.py).  Returns the
+        host seconds spent (0.0 if that shape was compiled already)."""
+        import time
+
+        opt, keep = self._options(external_forces, stabilization, None, None, None, joint_forces=joint_forces)
+        if per_system_inertia:
+            opt.inertia = 1  # only the presence is read
+        before = self._lib.bionc_cuda_model_specialized(self._h, None)
+        t0 = time.perf_counter()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.bionc_cuda_model_specialize(self._h, C.byref(opt), 0, 1), "model_specialize")
+        dt = time.perf_counter() - t0
+        return dt if self._lib.bionc_cuda_model_specialized(self._h, None) > before else 0.0
+
+    def specialized_kernels(self) -> int:
+        """number of loaded model-specialised kernels"""
+        return int(self._lib.bionc_cuda_model_specialized(self._h, None))
+
     def _eval(self, which: int, x, rows: int | None, cols: int | None, name: str, external_forces=None, force_values=None):
         b = _Batch(x, self.nb_Q, self.device, name)
         shape = (b.B,) + ((rows,) if rows is not None else ()) + ((cols,) if cols is not None else ())

@@ -6,12 +6,14 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
 
 #include "../../include/bionc_cuda.h"
 #include "instances.cuh"
+#include "jit.cuh"
 #include "kernels.cuh"
 
 using namespace bionc;
@@ -107,6 +109,10 @@ struct BioncModel {
     } jac[3];
     int dev_smem_optin = 0, sm_smem = 0;
     LaunchPlan plan0;  // without external forces
+    // model-specialised integrator kernels (bionc_cuda_model_specialize, jit.cuh): compiled and loaded on request,
+    // looked up by the call shape at launch; never removed before destroy
+    std::mutex jit_mu;
+    std::vector<std::unique_ptr<jit::Compiled>> jit_kernels;
     // host-path scratch
     std::mutex host_mu;
     cudaStream_t stream = nullptr;
@@ -536,13 +542,18 @@ int compile_evaluators(BioncModel* M) {
 }
 
 // The model blob: built and uploaded once (ensure_device).
-int build_blob(BioncModel* M) {
-    DevHeader h = M->hdr;
+// byte offsets of the tables inside the blob (host only)
+void layout_blob(DevHeader& h, const BioncModel* M) {
     h.off_seg = align16(sizeof(DevHeader));
     h.off_blk = align16(h.off_seg + (int)(M->seg.size() * sizeof(DevSeg)));
     h.off_side = align16(h.off_blk + (int)(M->blk.size() * sizeof(DevBlk)));
     h.off_sym = align16(h.off_side + (int)(M->side.size() * sizeof(DevSide)));
     h.blob_bytes = align16(h.off_sym + (int)(M->sym.size() * sizeof(int)));
+}
+
+int build_blob(BioncModel* M) {
+    DevHeader h = M->hdr;
+    layout_blob(h, M);
     CUDA_TRY(cudaDeviceGetAttribute(&M->dev_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, M->device));
     CUDA_TRY(cudaDeviceGetAttribute(&M->sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, M->device));
     M->hdr = h;
@@ -676,6 +687,35 @@ void dyn_options(const BioncDynOptions* opt, DynOpts& o) {
 int kernel_path(const BioncModel* M, const DynOpts& o, const FextArgs& fx) {
     if (M->hdr.rnl > 0 || fx.tab != nullptr) return 2;
     return o.use_stab != 0 ? 1 : 0;
+}
+
+// CTA-size class of a launch (BIONC_BY_CLASS, instances.cuh)
+int class_maxt(int threads, int spc) {
+    if (spc == 32) {
+        for (int c : {32, 64, 96, 128, 256, 384, 512})
+            if (threads <= c) return c;
+        return 1024;
+    }
+    for (int c : {32, 64, 128, 256})
+        if (threads <= c) return c;
+    return 1024;
+}
+
+// integrator variant of a call shape (the template arguments pick_kernels / DynCall::rk4_entry choose)
+jit::Variant jit_variant(const BioncModel* M, int path, bool persys, bool forces, int spc) {
+    jit::Variant v;
+    v.general = path == 2, v.stab = path >= 1, v.persys = persys, v.forces = forces && path == 2;
+    v.maxt = class_maxt(32 * M->hdr.N, spc), v.spc = spc;
+    return v;
+}
+
+// the loaded model-specialised kernel of a variant, or nullptr
+CUfunction jit_lookup(const BioncModel* Mc, const jit::Variant& v) {
+    BioncModel* M = const_cast<BioncModel*>(Mc);
+    std::lock_guard<std::mutex> lock(M->jit_mu);
+    for (auto& k : M->jit_kernels)
+        if (k->v == v && k->fn != nullptr) return k->fn;
+    return nullptr;
 }
 
 }  // namespace
@@ -837,6 +877,7 @@ int bionc_cuda_model_create(const BioncModelDesc* d, int device, BioncModel** ou
         }
         M->nb_markers = d->nb_markers;
     }
+    layout_blob(M->hdr, M);
     *out = M;
     return BIONC_OK;
 }
@@ -848,6 +889,8 @@ int bionc_cuda_model_destroy(BioncModel* M) {
         return BIONC_OK;
     }
     DeviceGuard guard(M->device);
+    for (auto& k : M->jit_kernels)
+        if (k->mod != nullptr) jit::api().ModuleUnload(k->mod);
     cudaFree(M->d_blob);
     for (auto& j : M->jac) cudaFree(j.ptr), cudaFree(j.off), cudaFree(j.coef), cudaFree(j.c0);
     cudaFree(M->d_markers);
@@ -858,6 +901,85 @@ int bionc_cuda_model_destroy(BioncModel* M) {
         if (ps != nullptr) cudaStreamDestroy(ps);
     delete M;
     return BIONC_OK;
+}
+
+// shape of a call for the model-specialised kernels: what DynCall::prepare derives from the options (no upload)
+static int spec_shape(const BioncModel* M, const BioncDynOptions* opt, int32_t systems_per_cta, jit::Variant& v) {
+    DynOpts o;
+    dyn_options(opt, o);
+    const bool forces = opt != nullptr && opt->fext != nullptr && opt->fext->nb_forces > 0;
+    const bool persys = opt != nullptr && opt->inertia != nullptr;  // only tested against nullptr
+    FextArgs fa{};
+    fa.tab = forces ? reinterpret_cast<const unsigned char*>(M) : nullptr;  // only tested against nullptr
+    const int path = kernel_path(M, o, fa);
+    int spc = systems_per_cta;
+    if (spc == 0) {
+        BIONC_ON_DEVICE(M);
+        LaunchPlan plan = M->plan0;
+        if (forces || persys) {
+            const int ftab = forces ? align16((int)(sizeof(DevFextTab) + (size_t)opt->fext->nb_forces * sizeof(DevFext))) : 0;
+            const int rc = make_plan(M, ftab, persys, plan);
+            if (rc != BIONC_OK) return rc;
+        }
+        spc = plan.spw;
+    }
+    if (spc != 16 && spc != 32) return fail(BIONC_E_INVALID, "systems_per_cta must be 0 (the device's plan), 16 or 32");
+    v = jit_variant(M, path, persys, forces, spc);
+    return BIONC_OK;
+}
+
+int bionc_cuda_model_spec_source(const BioncModel* M, const BioncDynOptions* opt, int32_t systems_per_cta, char* buf, size_t cap, size_t* needed) {
+    if (M == nullptr) return fail(BIONC_E_INVALID, "null model");
+    jit::Variant v;
+    int rc = spec_shape(M, opt, systems_per_cta, v);
+    if (rc != BIONC_OK) return rc;
+    DevHeader h = M->hdr;
+    h.spw = v.spc;
+    const std::string src = jit::source(h, M->seg, M->blk, M->side, M->sym, v);
+    if (needed != nullptr) *needed = src.size() + 1;
+    if (buf != nullptr && cap > 0) {
+        const size_t n = src.size() < cap - 1 ? src.size() : cap - 1;
+        std::memcpy(buf, src.data(), n);
+        buf[n] = '\0';
+    }
+    return BIONC_OK;
+}
+
+int bionc_cuda_model_specialize(BioncModel* M, const BioncDynOptions* opt, int32_t systems_per_cta, int32_t load) {
+    if (M == nullptr) return fail(BIONC_E_INVALID, "null model");
+    jit::Variant v;
+    int rc = spec_shape(M, opt, load ? 0 : systems_per_cta, v);
+    if (rc != BIONC_OK) return rc;
+    {
+        std::lock_guard<std::mutex> lock(M->jit_mu);
+        for (auto& k : M->jit_kernels)
+            if (k->v == v && (k->fn != nullptr || !load)) return BIONC_OK;
+    }
+    DevHeader h = M->hdr;
+    h.spw = v.spc;
+    std::unique_ptr<jit::Compiled> c(new jit::Compiled());
+    std::string err = jit::compile(jit::source(h, M->seg, M->blk, M->side, M->sym, v), v, *c);
+    if (!err.empty()) return fail(BIONC_E_CUDA, "model-specialised kernel: " + err);
+    if (load) {
+        BIONC_ON_DEVICE(M);
+        CUDA_TRY(cudaFree(nullptr));  // the runtime's primary context is current on this thread from here on
+        err = jit::load(*c, M->dev_smem_optin);
+        if (!err.empty()) return fail(BIONC_E_CUDA, "model-specialised kernel: " + err);
+    }
+    std::lock_guard<std::mutex> lock(M->jit_mu);
+    M->jit_kernels.push_back(std::move(c));
+    return BIONC_OK;
+}
+
+int bionc_cuda_model_specialized(const BioncModel* Mc, int64_t* cubin_bytes) {
+    if (Mc == nullptr) return 0;
+    BioncModel* M = const_cast<BioncModel*>(Mc);
+    std::lock_guard<std::mutex> lock(M->jit_mu);
+    int n = 0;
+    int64_t bytes = 0;
+    for (auto& k : M->jit_kernels) n += k->fn != nullptr ? 1 : 0, bytes += (int64_t)k->cubin.size();
+    if (cubin_bytes != nullptr) *cubin_bytes = bytes;
+    return n;
 }
 
 int bionc_cuda_model_counts(const BioncModel* M, int32_t* nseg, int32_t* mj, int32_t* m) {
@@ -889,6 +1011,7 @@ struct DynCall {
     LaunchPlan plan;
     KernelSet ks{};
     int path = 0;
+    CUfunction jit_fn = nullptr;  // model-specialised integrator of this call shape, if the model has one
     const void* rk4_entry(const double* inertia) const {
         return ks.rk4[(inertia != nullptr ? 2 : 0) + (fx.args.tab != nullptr ? 1 : 0)];  // a force table implies path 2
     }
@@ -902,6 +1025,7 @@ struct DynCall {
         if ((fx.args.tab != nullptr || persys) && (rc = make_plan(M, fx.args.tab_bytes, persys, plan)) != BIONC_OK) return rc;
         path = kernel_path(M, o, fx.args);
         ks = pick_kernels(path, 32 * M->hdr.N, plan.spw);
+        jit_fn = jit_lookup(M, jit_variant(M, path, persys, fx.args.tab != nullptr, plan.spw));
         return BIONC_OK;
     }
 };
@@ -1006,6 +1130,12 @@ static int launch_rk4(const BioncModel* M, DynCall& call, double* Q, double* Qd,
     const unsigned char* blob = M->d_blob;
     int blob_bytes = M->blob_bytes;
     void* args[] = {&blob, &blob_bytes, &call.fx.args, &Q, &Qd, &inertia, &call.o, &h, &h_steps, &n_steps, &step0, &normalize, &traj, &traj_every, &status, &B};
+    if (call.jit_fn != nullptr) {  // this model's own build of the same kernel (bionc_cuda_model_specialize)
+        const CUresult r = jit::api().LaunchKernel(call.jit_fn, grid, 1, 1, block, 1, 1, (unsigned)call.plan.smem, (CUstream)st, args, nullptr);
+        if (r != CUDA_SUCCESS) return fail(BIONC_E_CUDA, "cuLaunchKernel (model-specialised integrator): " + jit::cu_error(r));
+        g_launches++;
+        return BIONC_OK;
+    }
     CUDA_TRY(cudaLaunchKernel(call.rk4_entry(inertia), dim3(grid), dim3(block), args, call.plan.smem, st));
     g_launches++;
     CUDA_TRY(cudaGetLastError());
@@ -1027,7 +1157,7 @@ int bionc_cuda_rk4(const BioncModel* M, double* Q, double* Qd, double h, const d
     if (status != nullptr) CUDA_TRY(cudaMemsetAsync(status, 0, B * sizeof(int32_t), st));
     const double* inertia = opt != nullptr ? opt->inertia : nullptr;
     if (traj == nullptr) traj_every = 1;
-    if ((rc = ensure_smem(M->device, call.rk4_entry(inertia), M->dev_smem_optin)) != BIONC_OK) return rc;
+    if (call.jit_fn == nullptr && (rc = ensure_smem(M->device, call.rk4_entry(inertia), M->dev_smem_optin)) != BIONC_OK) return rc;
     if (lam_last == nullptr) return launch_rk4(M, call, Q, Qd, h, h_steps, 0, n_steps, normalize, inertia, traj, traj_every, status, B, st);
     // The multipliers of the first stage of the last step are those of forward_dynamics at the state before that step:
     // n_steps - 1 fused steps, one forward_dynamics launch for lambda (its accelerations go to a scratch array), the last

@@ -45,6 +45,18 @@
 #include "model.cuh"
 #include "tmem.cuh"
 
+// Model-specialised builds (BIONC_SPEC, spec.cuh): the model tables are constants of the translation unit and a warp's
+// segment is a template parameter, so the loops over the tables have compile-time trip counts.  BIONC_TAB_LOOP marks
+// them: unrolled completely there (every table entry folds into the instruction stream), left to the compiler otherwise;
+// BIONC_TAB_LOOP1 marks the ones the generic build keeps rolled.
+#ifdef BIONC_SPEC
+#define BIONC_TAB_LOOP _Pragma("unroll")
+#define BIONC_TAB_LOOP1 _Pragma("unroll")
+#else
+#define BIONC_TAB_LOOP
+#define BIONC_TAB_LOOP1 _Pragma("unroll 1")
+#endif
+
 namespace bionc {
 
 // A pivot (or 3x3 pivot determinant) this small relative to the diagonal scale raises the SMALL_PIVOT status
@@ -589,7 +601,7 @@ __device__ __forceinline__ void eliminate_pivot(const WarpCtx& w, int K, int& st
         for (int i = 0; i < 6; ++i) w.dinv[(6 * K + i) * spw] = di[i];
         w.lamv[(3 * K) * spw] = yh.x, w.lamv[(3 * K + 1) * spw] = yh.y, w.lamv[(3 * K + 2) * spw] = yh.z;  // y-hat = D^-1 y
     }
-#pragma unroll 1
+BIONC_TAB_LOOP1
     for (int ci = c0; ci < c1; ++ci) {
         const int I = w.colrow[ci];
         if (!ALL && w.owner[I] != w.segi) continue;
@@ -604,7 +616,7 @@ __device__ __forceinline__ void eliminate_pivot(const WarpCtx& w, int K, int& st
             const V3 t = sym3_apply(di, mk(A[3 * r], A[3 * r + 1], A[3 * r + 2]));
             T[3 * r] = t.x, T[3 * r + 1] = t.y, T[3 * r + 2] = t.z;
         }
-#pragma unroll 1
+BIONC_TAB_LOOP1
         for (int cj = c0; cj <= ci; ++cj) {  // every J <= I of the same column: (I, J) is in the pattern
             const int J = w.colrow[cj];
             double Bj[9];
@@ -627,7 +639,7 @@ __device__ __forceinline__ void back_substitute(const WarpCtx& w, int K) {
     const int c0 = w.colptr[K], c1 = w.colptr[K + 1];
     if (c0 == c1) return;  // root: lambda = y-hat
     V3 acc = mk(0.0, 0.0, 0.0);
-#pragma unroll 1
+BIONC_TAB_LOOP1
     for (int ci = c0; ci < c1; ++ci) {
         const int I = w.colrow[ci];
         double A[9];
@@ -652,8 +664,14 @@ __device__ __forceinline__ void back_substitute(const WarpCtx& w, int K) {
 template <int spw>
 __device__ __forceinline__ void solve_two_leaves(const WarpCtx& w, int& status) {
     constexpr int nb = 3;
-    if (w.segi < 2) {
-        const int K = w.segi;
+#ifndef BIONC_SOLVE_W1
+#define BIONC_SOLVE_W1 1
+#endif
+#ifndef BIONC_SOLVE_NAMED
+#define BIONC_SOLVE_NAMED 0
+#endif
+    const int K = w.segi == 0 ? 0 : (w.segi == BIONC_SOLVE_W1 ? 1 : -1);
+    if (K >= 0) {
         double D[9], di[6], A[9], T[9];
         load_block<spw>(w, K * nb + K, D);
         sym3_inverse(D[0], D[3], D[4], D[6], D[7], D[8], di, status);
@@ -680,9 +698,12 @@ __device__ __forceinline__ void solve_two_leaves(const WarpCtx& w, int& status) 
 #pragma unroll
         for (int e = 0; e < 9; ++e) Sa[e * spw] = T[e];
     }
-    __syncthreads();
-    if (w.segi < 2) {
-        const int K = w.segi;
+    if (BIONC_SOLVE_NAMED) {
+        if (K >= 0) asm volatile("bar.sync 1, 64;" ::: "memory");
+    } else {
+        __syncthreads();
+    }
+    if (K >= 0) {
         double D[9], di[6], T[9];
         load_block<spw>(w, 2 * nb + 2, D);
         sym3_inverse(D[0], D[3], D[4], D[6], D[7], D[8], di, status);
@@ -726,6 +747,7 @@ __device__ __forceinline__ void rigid_multipliers(const WarpCtx& w, const SegCtx
         Rr = axpy(-Mr[t], Qdd.s[t], Rr);
         Rw = axpy(-Mw[t], Qdd.s[t], Rw);
     }
+    BIONC_TAB_LOOP
     for (int e = sg.side_begin; e < sg.side_end; ++e) {
         const DevSide sd = w.side[e];
         const DevBlk& b = w.blk[sd.blk];
@@ -796,6 +818,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
         //         rows); padding rows get a unit diagonal and a zero right-hand side.  Lean models have
         //         neither, so this phase and its barrier vanish for them.
         if (hd->nzero > 0 || hd->nunit > 0) {
+            BIONC_TAB_LOOP
             for (int zi = w.segi; zi < hd->nzero; zi += w.N) {
                 const int z = w.zero_list[zi];
                 double* dst = z >= 0 ? w.S0 + 9 * z * spw : w.S1 + 9 * (-z - 1) * spw;
@@ -804,6 +827,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
             }
             __syncthreads();
             if (w.segi == 0) {
+                BIONC_TAB_LOOP
                 for (int it = 0; it < hd->nunit; ++it) {
                     w.S0[w.unit_list[2 * it] * spw] = 1.0;
                     const int r = w.unit_list[2 * it + 1];
@@ -814,6 +838,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
 
         // ---- D. right-hand side rhs' = J a_free + kappa + b_j: every segment adds its share into its own copy of the
         //         row (copy `role`, written by exactly one lane); the child side also carries the row's bias terms
+        BIONC_TAB_LOOP
         for (int e = sg.side_begin; e < sg.side_end; ++e) {
             const DevSide& sd = w.side[e];
             const DevBlk& b = w.blk[sd.blk];
@@ -862,6 +887,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
 
         // ---- E. this segment's contribution to S':  S'_ab = fdir_a . fdir_b / m + n_a . Ic^-1 n_b
         hook.before_assembly();
+        BIONC_TAB_LOOP
         for (int e = sg.side_begin; e < sg.side_end; ++e) {
             const DevSide& sd = w.side[e];
             const DevBlk& b = w.blk[sd.blk];
@@ -873,6 +899,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                 lever_columns(c.Ii, rho_b, V);
                 const double sbm = lb.sigma * minv;
                 const int Jb = sd.node;
+                BIONC_TAB_LOOP
                 for (int e2 = e; e2 < sg.side_end; ++e2) {
                     const DevSide& sa = w.side[e2];
                     if (GENERAL && sa.nl_slot >= 0) continue;  // a single row: handled from its own side
@@ -906,6 +933,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
                 const Row6 rb6 = load_row6<S>(w, sd);
                 const V3 yb = sym3_apply(c.Ii, rb6.n), fbm = minv * rb6.f;
                 const int Ib = sd.node, rb = sd.lam_off - 3 * Ib;
+                BIONC_TAB_LOOP
                 for (int e2 = sg.side_begin; e2 < sg.side_end; ++e2) {
                     const DevSide& sa = w.side[e2];
                     const DevBlk& a = w.blk[sa.blk];
@@ -956,20 +984,20 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
             __syncthreads();
             hook();
             if (w.segi == 0) {
-#pragma unroll 1
+BIONC_TAB_LOOP1
                 for (int K = 0; K < nb; ++K) eliminate_pivot<true, S>(w, K, status);
-#pragma unroll 1
+BIONC_TAB_LOOP1
                 for (int K = nb - 1; K >= 0; --K) back_substitute<S>(w, K);
             }
         } else {
             // level by level of the elimination tree (pivots of one level are independent: one barrier per level, the
             // first one also closes the assembly).  A block row I is always handled by warp owner[I], so concurrent
             // pivots never write the same block.
-#pragma unroll 1
+BIONC_TAB_LOOP1
             for (int lv = 0; lv < hd->nlevel; ++lv) {
                 __syncthreads();
                 if (lv == 0) hook();
-#pragma unroll 1
+BIONC_TAB_LOOP1
                 for (int pi = w.lvlptr[lv]; pi < w.lvlptr[lv + 1]; ++pi) {
                     const int K = w.lvlpiv[pi];
                     if (((w.pivmask[K] >> w.segi) & 1) == 0) continue;  // neither the pivot's writer nor the owner of a row of column K
@@ -979,10 +1007,10 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
             // Back substitution level by level from the roots down, the pivots of a level spread over the warps (they
             // only read lambda of higher levels); the barrier of a level also closes the y-hat / inverse pivots that the
             // factorisation stored above it.
-#pragma unroll 1
+BIONC_TAB_LOOP1
             for (int lv = hd->nlevel - 2; lv >= 0; --lv) {  // the last level holds roots only: lambda = y-hat already
                 __syncthreads();
-#pragma unroll 1
+BIONC_TAB_LOOP1
                 for (int pi = w.lvlptr[lv] + w.segi; pi < w.lvlptr[lv + 1]; pi += w.N) back_substitute<S>(w, w.lvlpiv[pi]);
             }
         }
@@ -996,6 +1024,7 @@ __device__ __forceinline__ void eval_forward_dynamics(const WarpCtx& w, SegCtx& 
 #endif
 
         // ---- H. joint forces on this segment:  F -= sum fdir lambda,  tau -= sum n lambda
+        BIONC_TAB_LOOP
         for (int e = sg.side_begin; e < sg.side_end; ++e) {
             const DevSide& sd = w.side[e];
             const double* lj = w.lamv + sd.lam_off * spw;

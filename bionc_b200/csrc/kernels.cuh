@@ -19,10 +19,27 @@ __device__ __forceinline__ void inertia_to_constants(const double* __restrict__ 
 // FX = false: a kernel that never carries a force table (the lean path).  The compiler re-derives the working-set base
 // wherever it is short of registers; without the table's pointer and size that is one constant load instead of three and
 // a select (4 % of the stall samples of the lean integrator were on those loads).
-template <int S, bool FX = true>
+// SEGI >= 0 (model-specialised builds, spec.cuh): this warp's segment as a compile-time constant.
+template <int S, bool FX = true, int SEGI = -1>
 __device__ __forceinline__ void setup_cta(const unsigned char* __restrict__ blob, int blob_bytes, const FextArgs& fx,
                                           unsigned char* smem, WarpCtx& w, int poison = 0, int qpad = 0) {
     const bool has_tab = FX && fx.tab != nullptr;
+#ifdef BIONC_SPEC
+    // The model tables are constants of this translation unit: nothing is copied, every table entry the evaluation reads
+    // folds into its instruction stream.  Shared memory keeps the generic layout (the blob's area only holds the scratch
+    // words of the header), so the launch geometry of the generic kernels applies unchanged.
+    blob_bytes = spec::hdr.blob_bytes;
+    if (has_tab) {
+        const int4* fsrc = reinterpret_cast<const int4*>(fx.tab);
+        int4* fdst = reinterpret_cast<int4*>(smem + blob_bytes);
+        for (int i = threadIdx.x; i < fx.tab_bytes / 16; i += blockDim.x) fdst[i] = fsrc[i];
+    }
+    __syncthreads();
+    const DevHeader* h = &spec::hdr;
+    w.hdr = h;
+    w.seg = spec::seg, w.blk = spec::blk, w.side = spec::side;
+    const int* sym = spec::sym;
+#else
     {
         const int4* src = reinterpret_cast<const int4*>(blob);
         int4* dst = reinterpret_cast<int4*>(smem);
@@ -39,11 +56,13 @@ __device__ __forceinline__ void setup_cta(const unsigned char* __restrict__ blob
     w.seg = reinterpret_cast<const DevSeg*>(smem + h->off_seg);
     w.blk = reinterpret_cast<const DevBlk*>(smem + h->off_blk);
     w.side = reinterpret_cast<const DevSide*>(smem + h->off_side);
+    const int* sym = reinterpret_cast<const int*>(smem + h->off_sym);
+#endif
     w.ftab = has_tab ? reinterpret_cast<const DevFextTab*>(smem + blob_bytes) : nullptr;
     w.fext = has_tab ? reinterpret_cast<const DevFext*>(smem + blob_bytes + sizeof(DevFextTab)) : nullptr;
     w.fvals = nullptr;
     w.N = h->N, w.mj = h->mj, w.nb = h->nb;
-    w.segi = threadIdx.x >> 5;       // warp = segment
+    w.segi = SEGI >= 0 ? SEGI : (int)(threadIdx.x >> 5);  // warp = segment
     w.lane = threadIdx.x & (S - 1);  // lane = system; with S < 32 systems per CTA the upper lanes mirror the lower ones
     double* base = reinterpret_cast<double*>(smem + blob_bytes + (has_tab ? fx.tab_bytes : 0));
     // qpad: extra doubles per system in each of the two state areas (forward_dynamics_rows_kernel keeps padded rows there)
@@ -71,7 +90,6 @@ __device__ __forceinline__ void setup_cta(const unsigned char* __restrict__ blob
                 for (int i = threadIdx.x; i < len[r]; i += blockDim.x) reg[r][i] = nan;
         __syncthreads();
     }
-    const int* sym = reinterpret_cast<const int*>(smem + h->off_sym);
     w.slot_tab = sym;
     w.slot2_tab = w.slot_tab + w.nb * w.nb;
     w.zero_list = w.slot2_tab + w.nb * w.nb;
@@ -215,17 +233,17 @@ __global__ void __launch_bounds__(MAXT, FdMinCtas<MAXT>::value)
 // ---------------------------------------------------------------------------------------------
 // PS: see load_constants.  FX: the call carries external forces (general path only; compiled both ways for the same
 // reason as PS).
-template <bool GENERAL, bool STAB, int MAXT, int S, int PS, bool FX>
-__global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
-    rk4_kernel(const unsigned char* __restrict__ blob, int blob_bytes, FextArgs fx, double* __restrict__ Q, double* __restrict__ Qd,
-               const double* __restrict__ inertia, DynOpts o, double h_const, const double* __restrict__ h_steps,
-               long long n_steps, long long step0, int normalize, double* __restrict__ traj, long long traj_every,
-               int* __restrict__ status_out, long long B) {
-    extern __shared__ __align__(16) unsigned char smem[];
+// SEGI: see setup_cta (the generic kernels run it with -1: a warp reads its segment from its index).
+template <bool GENERAL, bool STAB, int MAXT, int S, int PS, bool FX, int SEGI>
+__device__ __forceinline__ void rk4_body(unsigned char* smem, const unsigned char* __restrict__ blob, int blob_bytes, const FextArgs& fx,
+                                         double* __restrict__ Q, double* __restrict__ Qd, const double* __restrict__ inertia, const DynOpts& o,
+                                         double h_const, const double* __restrict__ h_steps, long long n_steps, long long step0,
+                                         int normalize, double* __restrict__ traj, long long traj_every, int* __restrict__ status_out,
+                                         long long B) {
     constexpr bool XSEG = GENERAL || STAB;  // an evaluation reads other segments' published state
     WarpCtx w;
     static_assert(GENERAL || !FX, "forces go through the general path");
-    setup_cta<S, FX>(blob, blob_bytes, fx, smem, w, o.poison);
+    setup_cta<S, FX, SEGI>(blob, blob_bytes, fx, smem, w, o.poison);
     long long gsys = (long long)blockIdx.x * S + w.lane;
     const bool live = (int)(threadIdx.x & 31) < S && gsys < B;
     if (gsys >= B) gsys = B - 1;
@@ -239,7 +257,7 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
     load_q12(Qd + (size_t)gsys * n + 12 * w.segi, y0v);
     constexpr int TM = TmemPark<MAXT>::level;  // 2: y0, accumulator and A in tensor memory; 1: y0; 0: nothing
     unsigned tm = 0;  // this thread's columns (layout: tmem.cuh)
-    unsigned* tm_slot = reinterpret_cast<unsigned*>(const_cast<int*>(&w.hdr->tmem_slot));  // a free word of the header copy
+    unsigned* tm_slot = reinterpret_cast<unsigned*>(&reinterpret_cast<DevHeader*>(smem)->tmem_slot);  // a free word of the header copy
     if (TM) {
         if (threadIdx.x < 32) tmem_alloc(tm_slot, TmemPark<MAXT>::cols);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -355,6 +373,39 @@ __global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
         store_q12(Qd + (size_t)gsys * n + 12 * w.segi, y0v);
         if (status_out != nullptr && status != 0) atomicOr(status_out + gsys, status);
     }
+}
+
+#ifdef BIONC_SPEC
+// model-specialised build: every warp runs the copy of the integrator compiled for its segment
+template <bool GENERAL, bool STAB, int MAXT, int S, int PS, bool FX, int SEGI>
+struct Rk4BySegment {
+    template <class... A>
+    static __device__ __forceinline__ void run(unsigned warp, A&&... a) {
+        if (warp == SEGI) rk4_body<GENERAL, STAB, MAXT, S, PS, FX, SEGI>(a...);
+        else Rk4BySegment<GENERAL, STAB, MAXT, S, PS, FX, SEGI + 1>::run(warp, a...);
+    }
+};
+template <bool GENERAL, bool STAB, int MAXT, int S, int PS, bool FX>
+struct Rk4BySegment<GENERAL, STAB, MAXT, S, PS, FX, spec::kSegments> {
+    template <class... A>
+    static __device__ __forceinline__ void run(unsigned, A&&...) {}
+};
+#endif
+
+template <bool GENERAL, bool STAB, int MAXT, int S, int PS, bool FX>
+__global__ void __launch_bounds__(MAXT, MinCtas<MAXT>::value)
+    rk4_kernel(const unsigned char* __restrict__ blob, int blob_bytes, FextArgs fx, double* __restrict__ Q, double* __restrict__ Qd,
+               const double* __restrict__ inertia, DynOpts o, double h_const, const double* __restrict__ h_steps,
+               long long n_steps, long long step0, int normalize, double* __restrict__ traj, long long traj_every,
+               int* __restrict__ status_out, long long B) {
+    extern __shared__ __align__(16) unsigned char smem[];
+#ifdef BIONC_SPEC
+    Rk4BySegment<GENERAL, STAB, MAXT, S, PS, FX, 0>::run(threadIdx.x >> 5, smem, blob, blob_bytes, fx, Q, Qd, inertia, o, h_const, h_steps, n_steps,
+                                                         step0, normalize, traj, traj_every, status_out, B);
+#else
+    rk4_body<GENERAL, STAB, MAXT, S, PS, FX, -1>(smem, blob, blob_bytes, fx, Q, Qd, inertia, o, h_const, h_steps, n_steps, step0, normalize, traj,
+                                                 traj_every, status_out, B);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------

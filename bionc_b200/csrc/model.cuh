@@ -7,7 +7,9 @@
 // not part of the model: a call that has them passes its own table (DevFextTab | DevFext[nf]), copied
 // to shared memory behind the blob.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <stdint.h>
+#endif
 
 namespace bionc {
 

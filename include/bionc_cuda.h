@@ -127,6 +127,22 @@ int bionc_cuda_model_destroy(BioncModel* model);
 int bionc_cuda_model_counts(const BioncModel* model, int32_t* nb_segments, int32_t* nb_joint_constraints,
                             int32_t* nb_holonomic_constraints);
 
+/* Model-specialised integrator (optional; the counterpart of the reference's model.to_mx() code generation,
+ * bionc_casadi/biomechanical_model.py, for this path).  Compiles, with NVRTC for sm_100a, a build of the fused RK4 kernel
+ * in which this model's tables are compile-time constants, for calls shaped like `options` (stabilisation on / off,
+ * external forces present, per-system inertial parameters present: only the presence of fext / inertia is read), and --
+ * load != 0 -- loads it on the model's device.  bionc_cuda_rk4 / _rk4_host calls of that shape then launch it instead
+ * of the generic kernel; every other call is unaffected.  Seconds of host time per shape, once; results agree with the
+ * generic kernel to rounding.  systems_per_cta: 0 = the device's launch plan (needs the device), or 16 / 32 (load == 0:
+ * compile only, e.g. on a machine without a GPU).  Without libnvrtc / libcuda at run time: BIONC_E_CUDA, the generic
+ * kernels remain. */
+int bionc_cuda_model_specialize(BioncModel* model, const BioncDynOptions* options, int32_t systems_per_cta, int32_t load);
+/* the generated CUDA source of that kernel (diagnostics); needed: bytes including the terminator */
+int bionc_cuda_model_spec_source(const BioncModel* model, const BioncDynOptions* options, int32_t systems_per_cta, char* buf,
+                                 size_t cap, size_t* needed);
+/* number of loaded model-specialised kernels; cubin_bytes (optional): total size of the compiled images */
+int bionc_cuda_model_specialized(const BioncModel* model, int64_t* cubin_bytes);
+
 /* diagnostics: how the model was laid out for the kernels.  out[11] = {segments, joint rows, 3x3 nodes of the
  * joint-level system, stored blocks, second copies, elimination-tree levels, doubles of per-segment row
  * storage, zero-list entries, systems per CTA, shared-memory bytes per CTA, serial joint-level schedule (0/1)};

@@ -8,6 +8,7 @@ import csv
 import io
 import json
 import os
+import re
 import subprocess
 import sys
 
@@ -38,15 +39,21 @@ for w in ("lower_limb", "pendulum_force", "knee", "full_body", "n_link_4"):
     open(csvp, "w").write(raw)
     summary = subprocess.run([sys.executable, os.path.join(REPO, "profiles", "ncu_raw_summary.py"), csvp], capture_output=True, text=True).stdout
     grid, spc_line = int(float(d["launch__grid_size"])), d["Kernel Name"]
+    # systems of the captured launch: CTAs x systems per CTA (4th template argument); the launch log says which build ran
+    targs = [int(x) for x in re.findall(r"\d+", spc_line[spc_line.index("<"):spc_line.index(">")])]
+    systems = min(1_000_000, grid * targs[3])
+    logp = os.path.join(REPO, "gpurun_out", f"r02_launch_{w}.log")
+    specialised = os.path.exists(logp) and "specialised in" in open(logp).read()
     txt = os.path.join(REPO, "profiles", f"{TAG}_ncu_{w}.txt")
     with open(txt, "w") as f:
-        f.write(f"# ncu --set full --clock-control none, one launch of the fused integrator, bench.py --workload {w} (1e6 systems x 100 steps)\n")
+        f.write(f"# ncu --set full --clock-control none, one launch of the fused integrator, bench.py --workload {w} ({systems} systems x 100 steps)"
+                f"{', model-specialised build of the kernel (bionc_cuda_model_specialize)' if specialised else ''}\n")
         f.write(f"# kernel: {spc_line}\n")
         f.write(summary)
         for op in ("dfma", "dmul", "dadd"):
             f.write(f"{'smsp__sass_thread_inst_executed_op_' + op + '_pred_on.sum  (= .sum.per_cycle_elapsed x smsp__cycles_elapsed.avg)':110s} {fp64(op):.6e} inst\n")
     out[w] = {
-        "systems": 1_000_000, "rk4_steps_per_launch": 100,
+        "systems": systems, "rk4_steps_per_launch": 100, "build": "model-specialised" if specialised else "generic",
         "dfma": fp64("dfma"), "dmul": fp64("dmul"), "dadd": fp64("dadd"),
         "warp_instructions": val("smsp__inst_executed.sum"),
         "fp64_pipe_pct": float(d["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed"]),
@@ -56,7 +63,7 @@ for w in ("lower_limb", "pendulum_force", "knee", "full_body", "n_link_4"):
         "registers": int(float(d["launch__registers_per_thread"])),
         "kernel": d["Kernel Name"], "source": f"profiles/{TAG}_ncu_{w}.txt",
     }
-    flop = (2 * out[w]["dfma"] + out[w]["dmul"] + out[w]["dadd"]) / 1e8
+    flop = (2 * out[w]["dfma"] + out[w]["dmul"] + out[w]["dadd"]) / (systems * 100.0)
     print(f"{w:16s} {out[w]['kernel_ms_under_ncu']:9.2f} ms  fp64 pipe {out[w]['fp64_pipe_pct']:5.1f} %  issue {out[w]['issue_active_pct']:5.1f} %  "
           f"executed flop/system-step {flop:9.0f}  dram {out[w]['dram_bytes'] / 1e9:7.2f} GB  regs {out[w]['registers']}")
 with open(os.path.join(REPO, "profiles", "ncu_constants.json"), "w") as f:
