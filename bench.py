@@ -59,13 +59,13 @@ WORKLOAD = "lower_limb_4seg (BASELINE.json configs[2]; PELVIS free + 3 spherical
 # baseline/reference_models.py (the live reference).
 WORKLOADS = {
     "lower_limb": dict(model="lower_limb", ref="lower_limb", states="tree", h=0.01, fext=False, inertia=False, desc=WORKLOAD),
-    "pendulum_force": dict(model="pendulum_force_batch", ref="pendulum_force", states="hinge", h=1.0 / 60.0, fext=True, inertia=False,
+    "pendulum_force": dict(model="pendulum_force_batch", ref="pendulum_force", states="hinge", h=1.0 / 60.0, fext=True, inertia=False, specialize=True,
                            desc="pendulum_with_force.nmod + no_equilibrium force (BASELINE.json configs[1]; ground hinge, n=12, m=11)"),
-    "knee": dict(model="knee_feikes", ref="knee", states="knee", h=5e-5, fext=False, inertia=False,
+    "knee": dict(model="knee_feikes", ref="knee", states="knee", h=5e-5, fext=False, inertia=False, specialize=True,
                  desc="knee_feikes parallel mechanism (BASELINE.json configs[3]; closed loops, n=24, m=20)"),
     "full_body": dict(model="full_body", ref="full_body", states="tree", h=0.001, fext=False, inertia=True,
                       desc="synthetic full body, per-system inertial parameters (BASELINE.json configs[4]; 10 segments, n=120, m=87)"),
-    "n_link_4": dict(model="n_link_4", ref=None, states="chain", h=0.005, fext=False, inertia=False,
+    "n_link_4": dict(model="n_link_4", ref=None, states="chain", h=0.005, fext=False, inertia=False, specialize=True,
                      desc="4-link hinge pendulum (tests/test_forward_dynamics.py of the reference; 4 hinges, n=48, m=44)"),
 }
 STAB = dict(alpha=50.0, beta=20.0)  # Baumgarte gains of the stabilised leg: examples/forward_dynamics/actuated_3d_pendulum.py:155
@@ -348,6 +348,18 @@ def run_gpu_arm(args):
         keep.append(ip_dev)
         opt.inertia = ip_dev.data_ptr()
     stream = torch.cuda.current_stream(dev)
+    # General-path workloads run the model's own build of the integrator (bionc_cuda_model_specialize: the model tables as
+    # compile-time constants, NVRTC): a per-model compilation step like model_create, outside the timed region.  The lean
+    # workloads (lower limb, full body) keep the generic kernel, which is faster for them.
+    spec_seconds = None
+    if wl.get("specialize") and not args.no_specialize:
+        t_spec = time.perf_counter()
+        _lib.check(lib.bionc_cuda_model_specialize(model._h, C.byref(opt), 0, 1), "model_specialize")
+        sopt = _lib.BioncDynOptions()
+        C.memmove(C.byref(sopt), C.byref(opt), C.sizeof(opt))
+        sopt.use_stabilization = 1  # the stabilised leg's shape (the same kernel on the general path)
+        _lib.check(lib.bionc_cuda_model_specialize(model._h, C.byref(sopt), 0, 1), "model_specialize")
+        spec_seconds = time.perf_counter() - t_spec
 
     def launch(o=opt, q=Q, qd=Qd, b=B):
         rc = lib.bionc_cuda_rk4(model._h, q.data_ptr(), qd.data_ptr(), h_step, None, S, 1, C.byref(o), None, 1, None,
@@ -488,8 +500,12 @@ def run_gpu_arm(args):
         general = fx is not None or any(int(tt) != 0 for tt in model.table.blk_type)
         kernel_name = "rk4_kernel<%s, %d threads, %d systems per CTA>" % (
             "general" if general else "lean", 32 * model.nb_segments, lay["systems_per_cta"])
+        if spec_seconds is not None:
+            kernel_name += ", model-specialised build (NVRTC, %.1f s once per model, outside the timed region)" % spec_seconds
         algorithmic_tf = per_gpu_rate * fl / 1e12
         ncu = NCU.get(args.workload)
+        if ncu is not None and (ncu.get("build", "generic") == "model-specialised") != (spec_seconds is not None):
+            ncu = None  # the committed capture is of the other build of the kernel
         same_cfg = ncu is not None and (ncu["systems"], ncu["rk4_steps_per_launch"]) == (B, S)
         executed_flop = executed_tf = frac = traffic = None
         if ncu is not None:  # per system-step figures scale to any batch; the DRAM traffic only holds at the captured configuration
@@ -568,6 +584,7 @@ def main():
     ap.add_argument("--run-steps", type=int, default=1000, help="RK4 steps of one integration (BASELINE.json: 1000); the states are reset after it")
     ap.add_argument("--e2e-batch", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-specialize", action="store_true", help="general-path workloads: the generic kernel instead of the model-specialised build")
     ap.add_argument("--workload", default="lower_limb", choices=sorted(WORKLOADS),
                     help="default: the configuration BASELINE.json's metric is quoted on; the others are its remaining GPU configs")
     args = ap.parse_args()

@@ -79,6 +79,7 @@ bool invert4(const double M[4][4], double W[4][4]) {
 struct LaunchPlan {
     int spw = 0;        // systems per CTA (32 or 16)
     size_t smem = 0;    // dynamic shared memory per CTA
+    int ctas = 0;       // CTAs resident per SM (shared memory, threads, CTA-size class)
 };
 
 // Immutable after bionc_cuda_model_create: the device entry points only read it (re-entrant, any stream, any host
@@ -376,7 +377,7 @@ int make_plan(const BioncModel* M, int ftab_bytes, bool persys, LaunchPlan& plan
         if (ctas > by_threads) ctas = by_threads;
         const int by_class = class_ctas(32 * h.N);  // registers and tensor-memory columns of the kernel's CTA-size class
         if (ctas > by_class) ctas = by_class;
-        if (ctas * spc >= best_resident && ctas > 0) best_resident = ctas * spc, plan.spw = spc, plan.smem = bytes;  // ties: more CTAs, more warps
+        if (ctas * spc >= best_resident && ctas > 0) best_resident = ctas * spc, plan.spw = spc, plan.smem = bytes, plan.ctas = ctas;  // ties: more CTAs, more warps
     }
     if (plan.spw == 0) return fail(BIONC_E_TOO_LARGE, "model needs more shared memory per CTA than one SM has");
     return BIONC_OK;
@@ -912,19 +913,27 @@ static int spec_shape(const BioncModel* M, const BioncDynOptions* opt, int32_t s
     FextArgs fa{};
     fa.tab = forces ? reinterpret_cast<const unsigned char*>(M) : nullptr;  // only tested against nullptr
     const int path = kernel_path(M, o, fa);
-    int spc = systems_per_cta;
+    int spc = systems_per_cta, ctas = 0;
+    const int ftab = forces ? align16((int)(sizeof(DevFextTab) + (size_t)opt->fext->nb_forces * sizeof(DevFext))) : 0;
     if (spc == 0) {
         BIONC_ON_DEVICE(M);
         LaunchPlan plan = M->plan0;
         if (forces || persys) {
-            const int ftab = forces ? align16((int)(sizeof(DevFextTab) + (size_t)opt->fext->nb_forces * sizeof(DevFext))) : 0;
             const int rc = make_plan(M, ftab, persys, plan);
             if (rc != BIONC_OK) return rc;
         }
-        spc = plan.spw;
+        spc = plan.spw, ctas = plan.ctas;
+    } else if (spc == 16 || spc == 32) {  // no device: residency as on a B200 (228 KB of shared memory per SM)
+        const DevHeader& h = M->hdr;
+        const size_t bytes = (size_t)h.blob_bytes + ftab + (size_t)cta_smem_doubles(spc, h.N, h.nb, h.nslot, h.nslot2, h.rnl, persys) * sizeof(double);
+        ctas = (int)(233472 / (bytes + 1024));
+        if (ctas > 2048 / (32 * h.N)) ctas = 2048 / (32 * h.N);
+        if (ctas > class_ctas(32 * h.N)) ctas = class_ctas(32 * h.N);
+        if (ctas < 1) return fail(BIONC_E_TOO_LARGE, "model needs more shared memory per CTA than one SM has");
     }
     if (spc != 16 && spc != 32) return fail(BIONC_E_INVALID, "systems_per_cta must be 0 (the device's plan), 16 or 32");
     v = jit_variant(M, path, persys, forces, spc);
+    v.ctas = ctas;
     return BIONC_OK;
 }
 

@@ -129,6 +129,7 @@ inline void emit_array(std::string& out, const char* type, const char* name, con
 struct Variant {
     bool general = false, stab = false, persys = false, forces = false;
     int maxt = 128, spc = 32;
+    int ctas = 0;  // CTAs resident per SM for this call shape (launch plan): sizes the register budget of the build
     bool operator==(const Variant& o) const {
         return general == o.general && stab == o.stab && persys == o.persys && forces == o.forces && maxt == o.maxt && spc == o.spc;
     }
@@ -150,7 +151,9 @@ inline std::string source(const DevHeader& hdr, const std::vector<DevSeg>& seg, 
     static_assert(sizeof(DevSide) == 8 * 4 + 4 * 8, "DevSide: update the schema below");
     std::string s;
     s += "// generated by bionc_cuda (jit.cuh): model tables as constants + the generic kernel sources\n";
-    s += "#define BIONC_SPEC 1\n#define BIONC_DYNAMICS_ONLY 1\n#include \"model.cuh\"\nnamespace bionc {\nnamespace spec {\n";
+    s += "#define BIONC_SPEC 1\n#define BIONC_DYNAMICS_ONLY 1\n";
+    if (v.ctas > 0) s += "#define BIONC_SPEC_MINCTAS " + std::to_string(v.ctas) + "\n";
+    s += "#include \"model.cuh\"\nnamespace bionc {\nnamespace spec {\n";
     s += "constexpr int kSegments = " + std::to_string(hdr.N) + ";\n";
     s += "__device__ const DevHeader hdr = ";
     emit_struct(s, &hdr, repeat("i", (int)(sizeof(DevHeader) / 4)).c_str());

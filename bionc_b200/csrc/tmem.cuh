@@ -23,7 +23,13 @@ struct MinCtas {
 #else
     static constexpr int c64 = 4;
 #endif
+#ifdef BIONC_SPEC_MINCTAS
+    // model-specialised build (jit.cuh): the CTAs this model's working set really leaves resident per SM -- a class's
+    // register budget assumes the class's full residency, a model limited by shared memory to fewer CTAs gets the rest
+    static constexpr int value = BIONC_SPEC_MINCTAS;
+#else
     static constexpr int value = MAXT <= 32 ? c32 : (MAXT <= 64 ? c64 : (MAXT <= 128 ? 4 : (MAXT <= 256 ? 2 : 1)));
+#endif
 };
 
 // ---- tensor memory as per-thread parking space ------------------------------------------------------

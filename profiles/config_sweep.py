@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--steps-per-launch", type=int, default=10)
     ap.add_argument("--launches", type=int, default=5)
     ap.add_argument("--out", default=os.path.join(REPO, "gpurun_out", "config_sweep.json"))
+    ap.add_argument("--no-specialize", action="store_true", help="general-path models: the generic kernel")
     ap.add_argument("--only", default=None, help="substring of the model name to restrict the sweep to")
     args = ap.parse_args()
     B, S = args.batch, args.steps_per_launch
@@ -77,6 +78,9 @@ def main():
             mass, com, J = st.perturbed_inertial_parameters(model.table, pool, seed=3)
             ipn = np.concatenate([mass[..., None], com, np.stack([J[..., 0, 0], J[..., 0, 1], J[..., 0, 2], J[..., 1, 1], J[..., 1, 2], J[..., 2, 2]], -1)], -1)
             ip = torch.from_numpy(ipn).cuda().repeat(reps, 1, 1)[:B].contiguous()
+        # general-path models run their own build of the kernel, like bench.py's workloads
+        general = fext is not None or any(int(t) != 0 for t in model.table.blk_type)
+        spec_s = model.specialize(external_forces=fext, per_system_inertia=per_sys) if (general and not args.no_specialize) else None
         kw = dict(h=h, n_steps=S, normalize=True, external_forces=fext, inertial_parameters=ip, inplace=False)
         for _ in range(3):
             model.rk4(Qt, Qdt, **kw)
@@ -101,6 +105,7 @@ def main():
             "flops_per_system_step": fl, "algorithmic_tflops": rate * fl / 1e12,
             "frac_of_measured_fp64_peak": rate * fl / 1e12 / sus.value, "fp64_peak_tflops": sus.value,
             "flagged": int((status != 0).sum().item()), "layout": model.kernel_layout(),
+            "kernel_build": "generic" if spec_s is None else "model-specialised (NVRTC, %.1f s)" % spec_s,
         }
         print(json.dumps(res), flush=True)
         results.append(res)
