@@ -85,6 +85,7 @@ class BiomechanicalModel:
         desc, self._keep = _lib.model_desc(self.table)
         handle = C.c_void_p()
         _lib.check(self._lib.bionc_cuda_model_create(C.byref(desc), self.device.index or 0, C.byref(handle)), "model_create")
+        self._no_jit = False  # set when a model-specialised kernel could not be built here (rk4(specialize="auto"))
         self._h = handle
         self._mass_matrix = None
 
@@ -489,8 +490,14 @@ class BiomechanicalModel:
         external_force_values=None,
         joint_generalized_forces=None,
         apply_joint_generalized_forces: bool = False,
+        specialize="auto",
     ):
         """Fused integrator: ``utils/ode_solver.py:8-53`` with the closure of ``:107-116`` inside the kernel.
+
+        ``specialize``: ``"auto"`` compiles this model's own build of the kernel (:meth:`specialize`) the first time a
+        large call (>= 2e6 system-steps) of a shape that profits from it arrives -- models with other than
+        point-to-point joints, or calls with forces, of at most 4 segments; ``True`` always, ``False`` never.  Where
+        NVRTC is missing, ``"auto"`` keeps the generic kernel.
 
         Either a constant step ``h`` with ``n_steps``, or a time grid ``t`` (then ``h_i = t[i+1] - t[i]``
         exactly as the reference computes it, :41).  ``normalize=True`` is the reference's
@@ -531,6 +538,15 @@ class BiomechanicalModel:
         status = torch.empty((B,), dtype=torch.int32, device=self.device)
         opt, keep = self._options(external_forces, stabilization, inertial_parameters, B, external_force_values,
                                   joint_forces=joint_generalized_forces if apply_joint_generalized_forces else None)
+        if specialize is True or (specialize == "auto" and not self._no_jit and B * int(n_steps) >= 2_000_000 and self.nb_segments <= 4
+                                  and (opt.fext or any(int(t) != 0 for t in self.table.blk_type))):
+            try:
+                with torch.cuda.device(self.device):
+                    _lib.check(self._lib.bionc_cuda_model_specialize(self._h, C.byref(opt), 0, 1), "model_specialize")
+            except _lib.BioncCudaError:
+                if specialize is True:
+                    raise
+                self._no_jit = True  # no NVRTC / driver library here: the generic kernels serve every call
         with torch.cuda.device(self.device):
             if B > 0 and n_steps > 0:
                 rc = self._lib.bionc_cuda_rk4(

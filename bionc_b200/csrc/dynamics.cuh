@@ -49,7 +49,12 @@
 // segment is a template parameter, so the loops over the tables have compile-time trip counts.  BIONC_TAB_LOOP marks
 // them: unrolled completely there (every table entry folds into the instruction stream), left to the compiler otherwise;
 // BIONC_TAB_LOOP1 marks the ones the generic build keeps rolled.
-#ifdef BIONC_SPEC
+#if defined(BIONC_SPEC) && defined(BIONC_SPEC_ROLL_SOLVE)
+// ... except the factorisation of the joint-level system when the generated unit asks to keep its loops: unrolled, the
+// elimination of a 7-node system is 150 KB of straight-line code per CTA against a 32 KB instruction cache
+#define BIONC_TAB_LOOP _Pragma("unroll")
+#define BIONC_TAB_LOOP1 _Pragma("unroll 1")
+#elif defined(BIONC_SPEC)
 #define BIONC_TAB_LOOP _Pragma("unroll")
 #define BIONC_TAB_LOOP1 _Pragma("unroll")
 #else
@@ -191,7 +196,7 @@ struct WarpCtx {
     double *S0, *S1, *r0, *r1, *lamv, *dinv, *knl;
     double* kcs;  // per-system constants of this lane's segment, element i at kcs[i * spw] (allocated only for such calls)
     // symbolic factorisation tables (host, capi.cu symbolic_analysis)
-    const int *slot_tab, *slot2_tab, *zero_list, *comb_list, *unit_list, *colptr, *colrow, *lvlptr, *lvlpiv, *owner, *pivmask, *pivwriter, *nscale;
+    const int *slot_rt, *slot_tab, *slot2_tab, *zero_list, *comb_list, *unit_list, *colptr, *colrow, *lvlptr, *lvlpiv, *owner, *pivmask, *pivwriter, *nscale;
     int N, mj, nb;
     int segi;  // this warp's segment
     int lane;  // this lane's system inside the CTA
@@ -415,7 +420,7 @@ __device__ __forceinline__ void load9(const double* p, double (&A)[9]) {
 // update goes to the first copy.
 template <int spw>
 __device__ __forceinline__ void load_block(const WarpCtx& w, int idx, double (&A)[9]) {
-    load9<spw>(w.S0 + 9 * w.slot_tab[idx] * spw, A);
+    load9<spw>(w.S0 + 9 * w.slot_rt[idx] * spw, A);
     const int s2 = w.slot2_tab[idx];
     if (s2 >= 0) {
         const double* p2 = w.S1 + 9 * s2 * spw;
@@ -621,7 +626,7 @@ BIONC_TAB_LOOP1
             const int J = w.colrow[cj];
             double Bj[9];
             load_block<spw>(w, J * nb + K, Bj);
-            double* Sij = w.S0 + 9 * w.slot_tab[I * nb + J] * spw;
+            double* Sij = w.S0 + 9 * w.slot_rt[I * nb + J] * spw;
 #pragma unroll
             for (int r = 0; r < 3; ++r)
 #pragma unroll

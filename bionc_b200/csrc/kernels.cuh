@@ -29,6 +29,13 @@ __device__ __forceinline__ void setup_cta(const unsigned char* __restrict__ blob
     // folds into its instruction stream.  Shared memory keeps the generic layout (the blob's area only holds the scratch
     // words of the header), so the launch geometry of the generic kernels applies unchanged.
     blob_bytes = spec::hdr.blob_bytes;
+#ifdef BIONC_SPEC_ROLL_SOLVE
+    {  // the joint-level factorisation keeps its loops (below): its tables are read from the shared-memory copy of the blob
+        const int4* src = reinterpret_cast<const int4*>(blob);
+        int4* dst = reinterpret_cast<int4*>(smem);
+        for (int i = threadIdx.x; i < blob_bytes / 16; i += blockDim.x) dst[i] = src[i];
+    }
+#endif
     if (has_tab) {
         const int4* fsrc = reinterpret_cast<const int4*>(fx.tab);
         int4* fdst = reinterpret_cast<int4*>(smem + blob_bytes);
@@ -39,6 +46,11 @@ __device__ __forceinline__ void setup_cta(const unsigned char* __restrict__ blob
     w.hdr = h;
     w.seg = spec::seg, w.blk = spec::blk, w.side = spec::side;
     const int* sym = spec::sym;
+#ifdef BIONC_SPEC_ROLL_SOLVE
+    const int* symrt = reinterpret_cast<const int*>(smem + spec::hdr.off_sym);
+#else
+    const int* symrt = sym;
+#endif
 #else
     {
         const int4* src = reinterpret_cast<const int4*>(blob);
@@ -57,6 +69,7 @@ __device__ __forceinline__ void setup_cta(const unsigned char* __restrict__ blob
     w.blk = reinterpret_cast<const DevBlk*>(smem + h->off_blk);
     w.side = reinterpret_cast<const DevSide*>(smem + h->off_side);
     const int* sym = reinterpret_cast<const int*>(smem + h->off_sym);
+    const int* symrt = sym;
 #endif
     w.ftab = has_tab ? reinterpret_cast<const DevFextTab*>(smem + blob_bytes) : nullptr;
     w.fext = has_tab ? reinterpret_cast<const DevFext*>(smem + blob_bytes + sizeof(DevFextTab)) : nullptr;
@@ -95,7 +108,9 @@ __device__ __forceinline__ void setup_cta(const unsigned char* __restrict__ blob
     w.zero_list = w.slot2_tab + w.nb * w.nb;
     w.comb_list = w.zero_list + h->nzero;
     w.unit_list = w.comb_list + 2 * h->ncomb;
-    w.colptr = w.unit_list + 2 * h->nunit;
+    // tables of the joint-level factorisation and substitution (indexed at run time wherever their loops are kept)
+    w.slot_rt = symrt;
+    w.colptr = symrt + 2 * w.nb * w.nb + h->nzero + 2 * h->ncomb + 2 * h->nunit;
     w.colrow = w.colptr + w.nb + 1;
     w.lvlptr = w.colrow + h->ncol;
     w.lvlpiv = w.lvlptr + h->nlevel + 1;

@@ -81,7 +81,7 @@ def main():
         # general-path models run their own build of the kernel, like bench.py's workloads
         general = fext is not None or any(int(t) != 0 for t in model.table.blk_type)
         spec_s = model.specialize(external_forces=fext, per_system_inertia=per_sys) if (general and not args.no_specialize) else None
-        kw = dict(h=h, n_steps=S, normalize=True, external_forces=fext, inertial_parameters=ip, inplace=False)
+        kw = dict(h=h, n_steps=S, normalize=True, external_forces=fext, inertial_parameters=ip, inplace=False, specialize=False)
         for _ in range(3):
             model.rk4(Qt, Qdt, **kw)
         torch.cuda.synchronize()

@@ -209,7 +209,8 @@ def test_status_flags_mirror_the_reference_linalg_error():
     Qf, Qdf, status = model.rk4(Q, Qd, t=t, normalize=True, return_status=True)
     bad, good = np.nonzero(status)[0], np.nonzero(status == 0)[0]
     assert good.size > 0
-    for s in bad[:2]:
+    # a spread of the flagged and of the unflagged systems (an oracle trajectory is a second of numpy each)
+    for s in bad[:: max(1, bad.size // 5)][:5]:
         with np.errstate(all="ignore"):
             try:
                 rq, rqd = om.rk4(Q[s], Qd[s], t, normalize=True)
@@ -217,7 +218,7 @@ def test_status_flags_mirror_the_reference_linalg_error():
             except np.linalg.LinAlgError:
                 failed = True
         assert failed, f"system {s} flagged by the kernel but fine in the oracle"
-    for s in good[:2]:
+    for s in good[:: max(1, good.size // 5)][:5]:
         rq, rqd = om.rk4(Q[s], Qd[s], t, normalize=True)
         assert np.abs(np.concatenate([Qf[s] - rq, Qdf[s] - rqd])).max() < 1e-8
 

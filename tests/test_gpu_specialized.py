@@ -102,3 +102,23 @@ def test_specialized_host_buffer_entry_point():
     spec.rk4_host(Qa, Qda, 5e-5, 40)
     gen.rk4_host(Qb, Qdb, 5e-5, 40)
     assert rel_err(np.concatenate([Qa, Qda], axis=1), np.concatenate([Qb, Qdb], axis=1)) < TOL_SAME
+
+
+def test_rk4_specialises_large_general_path_calls_by_itself():
+    case = load_case("pendulum_force_batch")
+    spec, gen = _pair("pendulum_force_batch")
+    fext = _fext(spec, case)
+    Q, Qd = _states("hinge", spec, case, 20000, seed=4)
+    small = spec.rk4(Q[:100], Qd[:100], h=1.0 / 60.0, n_steps=100, external_forces=fext)
+    assert spec.specialized_kernels() == 0  # 1e4 system-steps: not worth a compilation
+    a = spec.rk4(Q, Qd, h=1.0 / 60.0, n_steps=100, external_forces=fext)  # 2e6 system-steps of a general-path shape
+    assert spec.specialized_kernels() == 1
+    b = gen.rk4(Q, Qd, h=1.0 / 60.0, n_steps=100, external_forces=fext, specialize=False)
+    assert gen.specialized_kernels() == 0
+    assert rel_err(np.concatenate([a[0], a[1]], axis=1), np.concatenate([b[0], b[1]], axis=1)) < TOL_SAME
+    assert np.array_equal(small[0], b[0][:100])
+    # the lean path keeps the generic kernel
+    lean = _model("lower_limb")
+    Ql, Qdl = _states("tree", lean, load_case("lower_limb"), 20000, seed=4)
+    lean.rk4(Ql, Qdl, h=0.01, n_steps=100)
+    assert lean.specialized_kernels() == 0
