@@ -975,15 +975,6 @@ int bionc_cuda_model_specialize(BioncModel* M, const BioncDynOptions* opt, int32
     std::unique_ptr<jit::Compiled> c(new jit::Compiled());
     std::string err = jit::compile(jit::source(h, M->seg, M->blk, M->side, M->sym, v), v, *c);
     if (!err.empty()) return fail(BIONC_E_CUDA, "model-specialised kernel: " + err);
-    if (c->spill_bytes > 256 && c->registers > 200) {
-        // The one- and two-segment classes run at 255 registers and park nothing in tensor memory (tmem.cuh); an unrolled
-        // evaluation that spills all the same (ptxas report) is built again with the integrator state parked, and the
-        // build that spills less is kept (knee: 680 + 1528 B -> 0).
-        jit::Variant vp = v;
-        vp.park = true;
-        std::unique_ptr<jit::Compiled> cp(new jit::Compiled());
-        if (jit::compile(jit::source(h, M->seg, M->blk, M->side, M->sym, vp), vp, *cp).empty() && cp->spill_bytes < c->spill_bytes) c = std::move(cp);
-    }
     if (load) {
         BIONC_ON_DEVICE(M);
         CUDA_TRY(cudaFree(nullptr));  // the runtime's primary context is current on this thread from here on

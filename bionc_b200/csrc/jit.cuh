@@ -11,7 +11,6 @@
 #include <nvrtc.h>
 
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -132,7 +131,6 @@ struct Variant {
     int maxt = 128, spc = 32;
     int ctas = 0;  // CTAs resident per SM for this call shape (launch plan): sizes the register budget of the build
     bool roll_solve = false;  // keep the loops of the joint-level factorisation (instruction footprint)
-    bool park = false;        // 255-register classes: park the integrator state in tensor memory all the same (the build spilled)
     bool operator==(const Variant& o) const {
         return general == o.general && stab == o.stab && persys == o.persys && forces == o.forces && maxt == o.maxt && spc == o.spc;
     }
@@ -157,7 +155,6 @@ inline std::string source(const DevHeader& hdr, const std::vector<DevSeg>& seg, 
     s += "#define BIONC_SPEC 1\n#define BIONC_DYNAMICS_ONLY 1\n";
     if (v.ctas > 0) s += "#define BIONC_SPEC_MINCTAS " + std::to_string(v.ctas) + "\n";
     if (v.roll_solve) s += "#define BIONC_SPEC_ROLL_SOLVE 1\n";
-    if (v.park) s += "#define BIONC_SPEC_PARK 1\n";
     s += "#include \"model.cuh\"\nnamespace bionc {\nnamespace spec {\n";
     s += "constexpr int kSegments = " + std::to_string(hdr.N) + ";\n";
     s += "__device__ const DevHeader hdr = ";
@@ -180,7 +177,6 @@ struct Compiled {
     Variant v;
     std::vector<char> cubin;
     std::string lowered;
-    int registers = 0, spill_bytes = 0;  // ptxas report of the kernel: registers per thread, spill stores + loads
     // per device: module and function
     CUmodule mod = nullptr;
     CUfunction fn = nullptr;
@@ -195,8 +191,8 @@ inline std::string compile(const std::string& src, const Variant& v, Compiled& o
     if (r != NVRTC_SUCCESS) return std::string("nvrtcCreateProgram: ") + a.GetErrorString(r);
     const std::string expr = v.name();
     a.AddNameExpression(prog, expr.c_str());
-    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device", "--ptxas-options=-v"};
-    r = a.CompileProgram(prog, 5, opts);
+    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device"};
+    r = a.CompileProgram(prog, 4, opts);
     size_t log_size = 0;
     a.GetProgramLogSize(prog, &log_size);
     std::string log(log_size, '\0');
@@ -219,19 +215,6 @@ inline std::string compile(const std::string& src, const Variant& v, Compiled& o
     a.GetCUBIN(prog, out.cubin.data());
     a.DestroyProgram(&prog);
     out.v = v;
-    {  // "... N bytes spill stores, M bytes spill loads" / "Used R registers" of the one kernel in the unit
-        int st = 0, ld = 0, regs = 0;
-        const size_t p0 = log.find("bytes spill stores");
-        if (p0 != std::string::npos) {
-            size_t b = log.rfind(',', p0);
-            if (b != std::string::npos) st = std::atoi(log.c_str() + b + 1);
-            const size_t p1 = log.find("bytes spill loads", p0);
-            if (p1 != std::string::npos) ld = std::atoi(log.c_str() + log.rfind(',', p1) + 1);
-        }
-        const size_t p2 = log.find("Used ");
-        if (p2 != std::string::npos) regs = std::atoi(log.c_str() + p2 + 5);
-        out.registers = regs, out.spill_bytes = st + ld;
-    }
     return n > 0 ? "" : "NVRTC produced no cubin";
 }
 

@@ -51,13 +51,7 @@ struct TmemPark {
     // level 2: y0, accumulator and A; level 1: y0 only (the full set does not fit the CTA's share of the columns);
     // level 0: nothing (classes that run at 255 registers per thread need no parking; neither set fits)
     static constexpr int regs = 65536 / (MAXT * MinCtas<MAXT>::value);
-#ifdef BIONC_SPEC_PARK
-    // model-specialised builds whose unrolled evaluation spills even at 255 registers park the integrator state as well
-    static constexpr bool roomy = false;
-#else
-    static constexpr bool roomy = regs > 200;
-#endif
-    static constexpr int level = roomy ? 0 : (pow2(words_full * groups) <= budget ? 2 : (pow2(words_y0 * groups) <= budget ? 1 : 0));
+    static constexpr int level = regs > 200 ? 0 : (pow2(words_full * groups) <= budget ? 2 : (pow2(words_y0 * groups) <= budget ? 1 : 0));
     static constexpr int words = level == 2 ? words_full : words_y0;  // per thread
     static constexpr int cols = pow2(words * groups);
 };
