@@ -711,13 +711,19 @@ jit::Variant jit_variant(const BioncModel* M, int path, bool persys, bool forces
     return v;
 }
 
-// the loaded model-specialised kernel of a variant, or nullptr
-CUfunction jit_lookup(const BioncModel* Mc, const jit::Variant& v) {
+// the loaded model-specialised kernel of a variant, or nullptr (entries are never removed before destroy)
+const jit::Compiled* jit_lookup(const BioncModel* Mc, const jit::Variant& v) {
     BioncModel* M = const_cast<BioncModel*>(Mc);
     std::lock_guard<std::mutex> lock(M->jit_mu);
     for (auto& k : M->jit_kernels)
-        if (k->v == v && k->fn != nullptr) return k->fn;
+        if (k->v == v && k->fn != nullptr) return k.get();
     return nullptr;
+}
+
+// Shared memory a compact specialised build gives back per CTA: the blob's area but the header's scratch words, and the
+// inverse pivots (stored in their dead diagonal blocks).  Serial joint-level schedule without kept loops only.
+size_t compact_savings(const BioncModel* M, int spc) {
+    return (size_t)(M->hdr.blob_bytes - align16((int)sizeof(DevHeader))) + (size_t)6 * M->hdr.nb * spc * sizeof(double);
 }
 
 }  // namespace
@@ -935,10 +941,25 @@ static int spec_shape(const BioncModel* M, const BioncDynOptions* opt, int32_t s
     if (spc != 16 && spc != 32) return fail(BIONC_E_INVALID, "systems_per_cta must be 0 (the device's plan), 16 or 32");
     v = jit_variant(M, path, persys, forces, spc);
     v.ctas = ctas;
+    {  // BIONC_SPEC_COMPACT=0/1 overrides the rule (experiment switch)
+        const char* e = std::getenv("BIONC_SPEC_COMPACT");
+        v.compact = e != nullptr ? std::atoi(e) != 0 : (M->hdr.serial_solve == 1 && M->hdr.mj > 0);
+    }
     {  // Joint-level systems of more than four nodes keep the loops of their factorisation (measured: 4-link hinge chain,
         // 7 nodes, 1140 -> 956 ms per 1e6 x 100 steps; knee, 3 nodes, 151 -> 192 ms).  BIONC_SPEC_ROLL=0/1 overrides.
         const char* e = std::getenv("BIONC_SPEC_ROLL");
         v.roll_solve = e != nullptr ? std::atoi(e) != 0 : M->hdr.nb > 4;
+        if (v.roll_solve || M->hdr.serial_solve != 1) v.compact = false;  // kept loops read the blob; parallel schedules re-read the pivot block
+    }
+    if (v.compact) {  // residency with the smaller working set (the class's CTA count still caps it)
+        const DevHeader& h = M->hdr;
+        const size_t bytes = (size_t)h.blob_bytes + ftab + (size_t)cta_smem_doubles(spc, h.N, h.nb, h.nslot, h.nslot2, h.rnl, persys) * sizeof(double) -
+                             compact_savings(M, spc);
+        const size_t sm_smem = M->sm_smem > 0 ? (size_t)M->sm_smem : (size_t)233472;
+        int c = (int)(sm_smem / (bytes + 1024));
+        if (c > 2048 / (32 * h.N)) c = 2048 / (32 * h.N);
+        if (c > class_ctas(32 * h.N)) c = class_ctas(32 * h.N);
+        if (c > v.ctas) v.ctas = c;
     }
     return BIONC_OK;
 }
@@ -1026,7 +1047,7 @@ struct DynCall {
     LaunchPlan plan;
     KernelSet ks{};
     int path = 0;
-    CUfunction jit_fn = nullptr;  // model-specialised integrator of this call shape, if the model has one
+    const jit::Compiled* jit = nullptr;  // model-specialised integrator of this call shape, if the model has one
     const void* rk4_entry(const double* inertia) const {
         return ks.rk4[(inertia != nullptr ? 2 : 0) + (fx.args.tab != nullptr ? 1 : 0)];  // a force table implies path 2
     }
@@ -1040,7 +1061,7 @@ struct DynCall {
         if ((fx.args.tab != nullptr || persys) && (rc = make_plan(M, fx.args.tab_bytes, persys, plan)) != BIONC_OK) return rc;
         path = kernel_path(M, o, fx.args);
         ks = pick_kernels(path, 32 * M->hdr.N, plan.spw);
-        jit_fn = jit_lookup(M, jit_variant(M, path, persys, fx.args.tab != nullptr, plan.spw));
+        jit = jit_lookup(M, jit_variant(M, path, persys, fx.args.tab != nullptr, plan.spw));
         return BIONC_OK;
     }
 };
@@ -1145,8 +1166,9 @@ static int launch_rk4(const BioncModel* M, DynCall& call, double* Q, double* Qd,
     const unsigned char* blob = M->d_blob;
     int blob_bytes = M->blob_bytes;
     void* args[] = {&blob, &blob_bytes, &call.fx.args, &Q, &Qd, &inertia, &call.o, &h, &h_steps, &n_steps, &step0, &normalize, &traj, &traj_every, &status, &B};
-    if (call.jit_fn != nullptr) {  // this model's own build of the same kernel (bionc_cuda_model_specialize)
-        const CUresult r = jit::api().LaunchKernel(call.jit_fn, grid, 1, 1, block, 1, 1, (unsigned)call.plan.smem, (CUstream)st, args, nullptr);
+    if (call.jit != nullptr) {  // this model's own build of the same kernel (bionc_cuda_model_specialize)
+        const size_t smem = call.plan.smem - (call.jit->v.compact ? compact_savings(M, call.plan.spw) : 0);
+        const CUresult r = jit::api().LaunchKernel(call.jit->fn, grid, 1, 1, block, 1, 1, (unsigned)smem, (CUstream)st, args, nullptr);
         if (r != CUDA_SUCCESS) return fail(BIONC_E_CUDA, "cuLaunchKernel (model-specialised integrator): " + jit::cu_error(r));
         g_launches++;
         return BIONC_OK;
@@ -1172,7 +1194,7 @@ int bionc_cuda_rk4(const BioncModel* M, double* Q, double* Qd, double h, const d
     if (status != nullptr) CUDA_TRY(cudaMemsetAsync(status, 0, B * sizeof(int32_t), st));
     const double* inertia = opt != nullptr ? opt->inertia : nullptr;
     if (traj == nullptr) traj_every = 1;
-    if (call.jit_fn == nullptr && (rc = ensure_smem(M->device, call.rk4_entry(inertia), M->dev_smem_optin)) != BIONC_OK) return rc;
+    if (call.jit == nullptr && (rc = ensure_smem(M->device, call.rk4_entry(inertia), M->dev_smem_optin)) != BIONC_OK) return rc;
     if (lam_last == nullptr) return launch_rk4(M, call, Q, Qd, h, h_steps, 0, n_steps, normalize, inertia, traj, traj_every, status, B, st);
     // The multipliers of the first stage of the last step are those of forward_dynamics at the state before that step:
     // n_steps - 1 fused steps, one forward_dynamics launch for lambda (its accelerations go to a scratch array), the last

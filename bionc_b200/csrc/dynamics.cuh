@@ -588,6 +588,18 @@ __device__ __forceinline__ void lin3_coefs(const DevBlk& b, int role, double (&a
 
 // Pivot K of the blocked LDL^T: invert D_K, y-hat_K = D_K^-1 r_K, then for the rows I of column K that this warp
 // owns (ALL: every row) the fused forward substitution and the Schur updates S_IJ -= S_IK D_K^-1 S_JK^T.
+// the six unique entries of the inverse of pivot K, element i at [i * spw]
+template <int spw>
+__device__ __forceinline__ double* dinv_of(const WarpCtx& w, int K) {
+#ifdef BIONC_SPEC_COMPACT
+    // serial schedule only (one warp factors and solves): the diagonal block is dead once its pivot has been inverted, and
+    // the next evaluation's assembly rewrites it
+    return w.S0 + 9 * w.slot_rt[K * w.nb + K] * spw;
+#else
+    return w.dinv + 6 * K * spw;
+#endif
+}
+
 template <bool ALL, int spw>
 __device__ __forceinline__ void eliminate_pivot(const WarpCtx& w, int K, int& status) {
     const int nb = w.nb;
@@ -603,7 +615,7 @@ __device__ __forceinline__ void eliminate_pivot(const WarpCtx& w, int K, int& st
                                     w.r0[(3 * K + 2) * spw] + w.r1[(3 * K + 2) * spw]));
     if (ALL || w.segi == w.pivwriter[K]) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) w.dinv[(6 * K + i) * spw] = di[i];
+        for (int i = 0; i < 6; ++i) dinv_of<spw>(w, K)[i * spw] = di[i];
         w.lamv[(3 * K) * spw] = yh.x, w.lamv[(3 * K + 1) * spw] = yh.y, w.lamv[(3 * K + 2) * spw] = yh.z;  // y-hat = D^-1 y
     }
 BIONC_TAB_LOOP1
@@ -654,7 +666,7 @@ BIONC_TAB_LOOP1
     }
     double di[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) di[i] = w.dinv[(6 * K + i) * spw];
+    for (int i = 0; i < 6; ++i) di[i] = dinv_of<spw>(w, K)[i * spw];
     const V3 corr = sym3_apply(di, acc);
     w.lamv[(3 * K) * spw] -= corr.x;
     w.lamv[(3 * K + 1) * spw] -= corr.y;

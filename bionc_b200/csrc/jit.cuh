@@ -131,6 +131,7 @@ struct Variant {
     int maxt = 128, spc = 32;
     int ctas = 0;  // CTAs resident per SM for this call shape (launch plan): sizes the register budget of the build
     bool roll_solve = false;  // keep the loops of the joint-level factorisation (instruction footprint)
+    bool compact = false;     // compact working set (serial joint-level schedule): no blob area, inverse pivots in place
     bool operator==(const Variant& o) const {
         return general == o.general && stab == o.stab && persys == o.persys && forces == o.forces && maxt == o.maxt && spc == o.spc;
     }
@@ -155,6 +156,7 @@ inline std::string source(const DevHeader& hdr, const std::vector<DevSeg>& seg, 
     s += "#define BIONC_SPEC 1\n#define BIONC_DYNAMICS_ONLY 1\n";
     if (v.ctas > 0) s += "#define BIONC_SPEC_MINCTAS " + std::to_string(v.ctas) + "\n";
     if (v.roll_solve) s += "#define BIONC_SPEC_ROLL_SOLVE 1\n";
+    if (v.compact) s += "#define BIONC_SPEC_COMPACT 1\n";
     s += "#include \"model.cuh\"\nnamespace bionc {\nnamespace spec {\n";
     s += "constexpr int kSegments = " + std::to_string(hdr.N) + ";\n";
     s += "__device__ const DevHeader hdr = ";

@@ -29,6 +29,12 @@ __device__ __forceinline__ void setup_cta(const unsigned char* __restrict__ blob
     // folds into its instruction stream.  Shared memory keeps the generic layout (the blob's area only holds the scratch
     // words of the header), so the launch geometry of the generic kernels applies unchanged.
     blob_bytes = spec::hdr.blob_bytes;
+#ifdef BIONC_SPEC_COMPACT
+    // compact working set (serial joint-level schedule, nothing read from a shared-memory blob): the blob's area shrinks to
+    // the header's scratch words and the inverse pivots live in their dead diagonal blocks (dinv_of, dynamics.cuh); the
+    // host sizes the launch accordingly (launch_rk4)
+    blob_bytes = (int)((sizeof(DevHeader) + 15) / 16 * 16);
+#endif
 #ifdef BIONC_SPEC_ROLL_SOLVE
     {  // the joint-level factorisation keeps its loops (below): its tables are read from the shared-memory copy of the blob
         const int4* src = reinterpret_cast<const int4*>(blob);
@@ -89,15 +95,20 @@ __device__ __forceinline__ void setup_cta(const unsigned char* __restrict__ blob
     w.r1 = w.r0 + 3 * S * w.nb;
     w.lamv = w.r1 + 3 * S * w.nb;
     w.dinv = w.lamv + 3 * S * w.nb;
-    w.knl = w.dinv + 6 * S * w.nb + S * h->rnl * w.segi;
-    w.kcs = w.dinv + 6 * S * w.nb + S * h->rnl * w.N + S * kSegConsts * w.segi;  // behind knl; present only with per-system inertia
+#ifdef BIONC_SPEC_COMPACT
+    const int dinv_doubles = 0;
+#else
+    const int dinv_doubles = 6 * S * w.nb;
+#endif
+    w.knl = w.dinv + dinv_doubles + S * h->rnl * w.segi;
+    w.kcs = w.dinv + dinv_doubles + S * h->rnl * w.N + S * kSegConsts * w.segi;  // behind knl; present only with per-system inertia
     if (poison != 0) {
         // Debug aid: a correct evaluation writes every word of the working set before it reads it, so filling the regions
         // with NaN first must not change any result (tests/test_gpu_scale.py).  Bits: 0 S0, 1 S1, 2 r0, 3 r1, 4 lambda_j,
         // 5 inverse pivots, 6 row vectors of the non-LIN3 blocks.  Shared memory of a fresh CTA holds whatever ran before.
         const double nan = __longlong_as_double(0x7ff8dead0000beefLL);
-        double* reg[7] = {w.S0 - w.lane, w.S1 - w.lane, w.r0 - w.lane, w.r1 - w.lane, w.lamv - w.lane, w.dinv - w.lane, w.dinv - w.lane + 6 * S * w.nb};
-        const int len[7] = {9 * S * h->nslot, 9 * S * h->nslot2, 3 * S * w.nb, 3 * S * w.nb, 3 * S * w.nb, 6 * S * w.nb, S * h->rnl * w.N};
+        double* reg[7] = {w.S0 - w.lane, w.S1 - w.lane, w.r0 - w.lane, w.r1 - w.lane, w.lamv - w.lane, w.dinv - w.lane, w.dinv - w.lane + dinv_doubles};
+        const int len[7] = {9 * S * h->nslot, 9 * S * h->nslot2, 3 * S * w.nb, 3 * S * w.nb, 3 * S * w.nb, dinv_doubles, S * h->rnl * w.N};
         for (int r = 0; r < 7; ++r)
             if ((poison >> r) & 1)
                 for (int i = threadIdx.x; i < len[r]; i += blockDim.x) reg[r][i] = nan;
