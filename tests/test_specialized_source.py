@@ -81,3 +81,26 @@ def test_nvrtc_compiles_the_specialised_kernel_without_a_gpu(name, spc, forces):
         assert cubin.value > 10_000
     finally:
         lib.bionc_cuda_model_destroy(h)
+
+
+def test_build_decisions_follow_the_model():
+    """Serial joint-level schedule -> compact working set; more than four joint-level nodes -> the factorisation keeps its
+    loops (and the blob in shared memory, so no compact layout); the register budget follows the residency on a B200."""
+    from bionc_b200.bionc_cuda import _lib
+
+    expect = {
+        "knee_feikes": (32, ["#define BIONC_SPEC_COMPACT 1", "#define BIONC_SPEC_MINCTAS 4"], ["BIONC_SPEC_ROLL_SOLVE"]),
+        "pendulum_root": (32, ["#define BIONC_SPEC_COMPACT 1", "#define BIONC_SPEC_MINCTAS 8"], ["BIONC_SPEC_ROLL_SOLVE"]),
+        "n_link_4": (16, ["#define BIONC_SPEC_ROLL_SOLVE 1", "#define BIONC_SPEC_MINCTAS 3"], ["BIONC_SPEC_COMPACT"]),
+        "lower_limb": (32, ["#define BIONC_SPEC_MINCTAS 4"], ["BIONC_SPEC_COMPACT", "BIONC_SPEC_ROLL_SOLVE"]),
+    }
+    for name, (spc, present, absent) in expect.items():
+        lib, h, table = _handle(name)
+        try:
+            head = _source(lib, h, _lib.BioncDynOptions(), spc).split('#include "model.cuh"')[0]
+            for text in present:
+                assert text in head, (name, text, head)
+            for text in absent:
+                assert text not in head, (name, text, head)
+        finally:
+            lib.bionc_cuda_model_destroy(h)
