@@ -204,3 +204,27 @@ def test_indefinite_pseudo_inertia_fuzz():
             assert ok or status[s] != 0, (trial, N, s, cond)
             checked += 1
     assert checked > 100
+
+
+@pytest.mark.parametrize("seed,N,loops", [c for c in CASES if c[1] <= 6])
+def test_random_model_specialised_kernel_matches_generic_kernel(seed, N, loops):
+    """The model-specialised build of the integrator (every block kind, open and closed topologies, serial and
+    level-parallel joint-level schedules, with and without forces / Baumgarte) against the generic kernel on the same
+    inputs: the same arithmetic in the same order, so 1e-12 on the scale of the state."""
+    from bionc_b200.bionc_cuda import BiomechanicalModel, ExternalForceSet
+
+    table = random_table(1000 + seed, N, loops)
+    spec, gen = BiomechanicalModel.from_table(table), BiomechanicalModel.from_table(table)
+    Q, Qd = random_states(table, 40, seed)
+    fext = ExternalForceSet.empty_from_nb_segment(N)
+    rng = np.random.default_rng(seed)
+    fext.add_in_global_local_point(int(rng.integers(0, N)), rng.normal(size=6), point_in_local=rng.normal(size=3) * 0.2)
+    stab = dict(alpha=0.3, beta=0.7)
+    for kw in ({}, dict(external_forces=fext, stabilization=stab)):
+        assert spec.specialize(**kw) > 0.0
+        a = spec.rk4(Q, Qd, h=0.002, n_steps=10, return_status=True, **kw)
+        b = gen.rk4(Q, Qd, h=0.002, n_steps=10, return_status=True, specialize=False, **kw)
+        assert gen.specialized_kernels() == 0
+        assert np.array_equal(a[2], b[2])
+        ok = (b[2] & 3) == 0
+        assert rel_err(np.concatenate([a[0], a[1]], axis=1)[ok], np.concatenate([b[0], b[1]], axis=1)[ok]) < 1e-12, (seed, N, loops)
