@@ -264,7 +264,12 @@ class BiomechanicalModel:
         ``rk4`` / ``rk4_host`` calls of that shape then run it instead of the generic kernel (the model tables are
         compile-time constants in it; same results to rounding).  The counterpart, for this
         path, of the reference's code generation ``model.to_mx()`` (bionc_casadi/biomechanical_model.py).  Returns the
-        host seconds spent (0.0 if that shape was compiled already)."""
+        host seconds spent (0.0 if that shape was compiled already).
+
+        Measured: it pays for models with other than point-to-point joints and for calls with
+        forces, up to about four segments (pendulum 2.8x, knee 3.3x, 4-link hinge chain 1.5x); models on the lean path
+        (point-to-point joints only, no forces: lower limb, full body) are faster on the generic kernel, whose code all
+        warps share.  ``rk4(specialize="auto")`` applies exactly that rule."""
         import time
 
         opt, keep = self._options(external_forces, stabilization, None, None, None, joint_forces=joint_forces)
