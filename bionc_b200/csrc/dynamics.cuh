@@ -681,6 +681,8 @@ BIONC_TAB_LOOP1
 template <int spw>
 __device__ __forceinline__ void solve_two_leaves(const WarpCtx& w, int& status) {
     constexpr int nb = 3;
+    // experiment switches (both measured, neither kept): second solver warp; leaves / root barrier as
+    // a 64-thread named barrier of the two solver warps
 #ifndef BIONC_SOLVE_W1
 #define BIONC_SOLVE_W1 1
 #endif
