@@ -84,7 +84,8 @@ struct LaunchPlan {
 };
 
 // Immutable after bionc_cuda_model_create: the device entry points only read it (re-entrant, any stream, any host
-// thread).  The scratch of the host-buffer entry points is the one mutable part; it is guarded by host_mu.
+// thread).  Two parts are mutable, each behind its own mutex: the scratch of the host-buffer entry points (host_mu) and the
+// append-only list of model-specialised kernels (jit_mu).
 struct BioncModel {
     int device = 0;
     DevHeader hdr{};
