@@ -25,3 +25,16 @@ def rel_err(a, b):
     """max |a - b| / max(1, max|b|): relative on the vector's scale (lambda ~ 0 in free fall)."""
     a, b = np.asarray(a, float), np.asarray(b, float)
     return float(np.max(np.abs(a - b)) / max(1.0, float(np.max(np.abs(b))))) if a.size else 0.0
+
+
+def nvrtc_available() -> bool:
+    """The model-specialised kernels need libnvrtc at run time (opened with dlopen by the library)."""
+    import ctypes
+
+    for name in ("libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so"):
+        try:
+            ctypes.CDLL(name)
+            return True
+        except OSError:
+            continue
+    return False
