@@ -6,11 +6,12 @@ import numpy as np
 import pytest
 
 torch = pytest.importorskip("torch")
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not nvrtc_available(), reason="libnvrtc not installed: the generic kernels serve every call")]
 
 from conftest import golden_case_names  # noqa: E402
 from helpers import load_case, model_path, nvrtc_available, rel_err  # noqa: E402
 from test_gpu_parity import TOL_TRAJ, _fext, _model, _states, _traj_tags  # noqa: E402
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not nvrtc_available(), reason="libnvrtc not installed: the generic kernels serve every call")]
 
 TOL_SAME = 1e-12
 TRAJ_CASES = [n for n in golden_case_names() if _traj_tags(load_case(n))]
